@@ -1,0 +1,128 @@
+"""Krylov callers of the hot path, restated (TEST INFRASTRUCTURE ONLY).
+
+``gmres`` follows ``IterativeMethod::GMRES`` (include/HPDDM_GMRES.hpp:31-158)
+with the reference defaults (include/HPDDM_iterative.hpp:197-212): right
+preconditioning, classical Gram-Schmidt, restart 40, tol 1e-6, max_it 100,
+D-weighted inner products, convergence test |s_i| / ||b||_D <= tol
+(iterative.hpp:98-127,455-468), Givens-rotated Hessenberg (Arnoldi,
+iterative.hpp:669-710), solution update x += M^{-1} (V y) at restart/exit
+(updateSol/addSol, iterative.hpp:272-336).
+
+The operator is duck-typed like the reference's ``Operator`` concept
+(GMRES.hpp:57-62,113-117): it needs ``start(b,x)``, ``apply(v)``, ``GMV(v)``,
+``dot(x,y)``.  Vectors are per-rank lists of (n_loc, mu) arrays; every column
+runs its own (pseudo-block) GMRES exactly like the reference's non-block
+driver.  Returns (iterations, x, applies).
+"""
+import numpy as np
+
+
+def _axpy(a, x, y):
+    for r in range(len(x)):
+        y[r] += x[r] * a
+
+
+def gmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40, verbose=False):
+    P = len(b)
+    mu = b[0].shape[1]
+    x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [np.array(v, order="F", copy=True) for v in x0]
+    x = op.start(b, x)                                   # initializeNorm -> A.start (iterative.hpp:444)
+    norm = np.sqrt(op.dot(b, b))                         # ||b||_D (iterative.hpp:455-468)
+    norm = np.where(norm < 1e-12, 1.0, norm)             # GMRES.hpp:73
+    m = restart
+    applies = 0
+    conv = np.full(mu, -m, dtype=int)                    # hasConverged sentinel
+    j = 1
+    while j <= max_it:
+        Ax = op.GMV(x)
+        v = [[b[r] - Ax[r] for r in range(P)]]           # right variant: v0 = b - A x
+        sn0 = op.dot(v[0], v[0])
+        if j == 1 and np.any(sn0 < np.finfo(float).eps ** 2):
+            j = 0
+            break
+        s = np.zeros((m + 1, mu))
+        s[0] = np.sqrt(sn0)
+        for r in range(P):
+            v[0][r] = v[0][r] / s[0]
+        conv[conv > 0] = 0
+        H = np.zeros((m + 1, m, mu))
+        cs = np.zeros((m, mu))
+        sn = np.zeros((m, mu))
+        i = 0
+        done = False
+        while i < m and j <= max_it:
+            z = op.apply(v[i])                           # M^{-1} v_i       (GMRES.hpp:116)
+            applies += 1
+            w = op.GMV(z)                                # A M^{-1} v_i     (GMRES.hpp:117)
+            # classical Gram-Schmidt (iterative.hpp:489-540): all dots first
+            h = np.array([op.dot(v[k], w) for k in range(i + 1)])
+            for k in range(i + 1):
+                for r in range(P):
+                    w[r] -= v[k][r] * h[k]
+            hn = np.sqrt(op.dot(w, w))
+            H[:i + 1, i] = h
+            H[i + 1, i] = hn
+            if i < m - 1:
+                for r in range(P):
+                    w[r] = w[r] / np.where(hn == 0, 1.0, hn)
+            v.append(w)
+            for k in range(i):                           # previous rotations
+                g = cs[k] * H[k, i] + sn[k] * H[k + 1, i]
+                H[k + 1, i] = -sn[k] * H[k, i] + cs[k] * H[k + 1, i]
+                H[k, i] = g
+            delta = np.hypot(H[i, i], H[i + 1, i])
+            sn[i] = H[i + 1, i] / delta
+            cs[i] = H[i, i] / delta
+            H[i, i] = delta
+            H[i + 1, i] = 0.0
+            s[i + 1] = -sn[i] * s[i]
+            s[i] = s[i] * cs[i]
+            i += 1
+            res = np.abs(s[i])
+            newly = (conv == -m) & (res / norm <= tol)
+            conv[newly] = i
+            if verbose:
+                print(f"GMRES: {j:3d} {res.max():.6e} {(res / norm).max():.6e} < {tol}")
+            if not np.any(conv == -m):
+                done = True
+                break
+            j += 1
+        # updateSol: y = H^{-1} s per column with its own dimension
+        work = [np.zeros_like(x[r]) for r in range(P)]
+        for nu in range(mu):
+            dim = abs(conv[nu]) if conv[nu] != 0 else 0
+            if not done and conv[nu] == -m:
+                dim = i
+            if dim == 0:
+                continue
+            y = np.linalg.solve(np.triu(H[:dim, :dim, nu]), s[:dim, nu])
+            for k in range(dim):
+                for r in range(P):
+                    work[r][:, nu] += v[k][r][:, nu] * y[k]
+        corr = op.apply(work)                            # addSol right variant (iterative.hpp:314-329)
+        applies += 1
+        for r in range(P):
+            x[r] += corr[r]
+        if done or j > max_it:
+            break
+    return min(j, max_it), x, applies
+
+
+class OracleOperator:
+    """Adapter SchwarzWorld -> Krylov operator concept."""
+
+    def __init__(self, world, correction=None):
+        self.w = world
+        self.correction = correction
+
+    def start(self, b, x):
+        return self.w.start(b, x)
+
+    def apply(self, v):
+        return self.w.apply(v, self.correction)
+
+    def GMV(self, v):
+        return self.w.GMV(v)
+
+    def dot(self, x, y):
+        return self.w.dot(x, y)
