@@ -1,0 +1,302 @@
+// Vector-level kernels of the RAS apply: partition-of-unity scaling fused into
+// the producing kernels, CSR SpMV, tall-skinny deflation products, halo
+// pack / deterministic unpack-add, D-weighted dots, replicated coarse solve.
+//
+// Reference counterparts: Wrapper::diag (include/HPDDM_wrapper.hpp:820-831),
+// Wrapper::gthr (314-318), generic csrmm (697-733), the two GEMMs of
+// Schwarz::deflation (include/HPDDM_schwarz.hpp:1616,1618), the gather /
+// scatter-add loops of Subdomain::exchange (include/HPDDM_subdomain.hpp:118-127),
+// the coarse solve of CoarseOperator::callSolver
+// (include/HPDDM_coarse_operator_impl.hpp:1706-1720).
+#include "hb_internal.h"
+
+namespace hb {
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void kk_scale(int n, int mu, const double *__restrict__ d, const double *__restrict__ in, double *out) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < (int64_t)n * mu) out[t] = d[t % n] * in[t];
+}
+__global__ void kk_axpy(int64_t n, double a, const double *__restrict__ x, double *y) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n) y[t] += a * x[t];
+}
+__global__ void kk_copy(int64_t n, const double *__restrict__ x, double *y) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n) y[t] = x[t];
+}
+__global__ void kk_fill(int64_t n, double v, double *y) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n) y[t] = v;
+}
+
+// out[i,c] = (d ? d[i] : 1) * (beta * yin[i,c] + alpha * sum_k a[k] x[ja[k],c])
+__global__ void kk_spmv(int n, int mu, const int *__restrict__ ia, const int *__restrict__ ja, const double *__restrict__ a, double alpha,
+                        const double *__restrict__ x, double beta, const double *__restrict__ yin, double *out, const double *__restrict__ d) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k0 = ia[i], k1 = ia[i + 1];
+  const double di = d ? d[i] : 1.0;
+  for (int c = 0; c < mu; ++c) {
+    const double *xc = x + (int64_t)c * n;
+    double acc = 0.0;
+    for (int k = k0; k < k1; ++k) acc = fma(a[k], xc[ja[k]], acc);
+    double v = alpha * acc;
+    if (beta != 0.0) v += beta * yin[i + (int64_t)c * n];
+    out[i + (int64_t)c * n] = di * v;
+  }
+}
+
+// T[k + ldT*c] += sum_i Z[i + k*n] * d[i] * x[i + c*n] ; 1024 rows per CTA, Z read once per column group
+template <int MB>
+__global__ void __launch_bounds__(256) kk_zt(int n, int nu, int c0, const double *__restrict__ Z, const double *__restrict__ d, const double *__restrict__ x,
+                                             double *T, int ldT) {
+  __shared__ double red[8][MB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int base = blockIdx.x * 1024;
+  double w[4][MB];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = base + tid + 256 * q;
+#pragma unroll
+    for (int m = 0; m < MB; ++m) w[q][m] = (i < n) ? d[i] * x[i + (int64_t)(c0 + m) * n] : 0.0;
+  }
+  for (int k = 0; k < nu; ++k) {
+    const double *zk = Z + (int64_t)k * n;
+    double acc[MB];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) acc[m] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = base + tid + 256 * q;
+      const double z = (i < n) ? zk[i] : 0.0;
+#pragma unroll
+      for (int m = 0; m < MB; ++m) acc[m] = fma(z, w[q][m], acc[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      acc[m] = warp_sum(acc[m]);
+      if (lane == 0) red[warp][m] = acc[m];
+    }
+    __syncthreads();
+    if (tid < MB) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += red[q][tid];
+      atomicAdd(&T[k + (int64_t)ldT * (c0 + tid)], s);
+    }
+    __syncthreads();
+  }
+}
+
+// out[i + c*n] = d[i] * sum_k Z[i + k*n] * Y[k + ldY*c]
+template <int MB>
+__global__ void __launch_bounds__(256) kk_zexp(int n, int nu, int c0, const double *__restrict__ Z, const double *__restrict__ d, const double *__restrict__ Y,
+                                               int ldY, double *out) {
+  extern __shared__ double ys[];  // nu * MB
+  for (int t = threadIdx.x; t < nu * MB; t += blockDim.x) ys[t] = Y[(t % nu) + (int64_t)ldY * (c0 + t / nu)];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc[MB];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) acc[m] = 0.0;
+  for (int k = 0; k < nu; ++k) {
+    const double z = Z[i + (int64_t)k * n];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) acc[m] = fma(z, ys[k + nu * m], acc[m]);
+  }
+  const double di = d[i];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) out[i + (int64_t)(c0 + m) * n] = di * acc[m];
+}
+
+// send[ebase*mu + c*esize + (e - ebase)] = x[map[e] + c*n]
+__global__ void kk_pack(int h, int n, int mu, const int *__restrict__ map, const int *__restrict__ ebase, const int *__restrict__ esize,
+                        const double *__restrict__ x, double *send) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)h * mu) return;
+  const int e = (int)(t % h), c = (int)(t / h);
+  send[(int64_t)ebase[e] * mu + (int64_t)c * esize[e] + (e - ebase[e])] = x[map[e] + (int64_t)c * n];
+}
+// deterministic unpack-add: one thread per unique target dof, contributions summed in neighbour order
+__global__ void kk_unpack(int nuniq, int n, int mu, const int *__restrict__ uidx, const int *__restrict__ useg, const int *__restrict__ upos,
+                          const int *__restrict__ ebase, const int *__restrict__ esize, const double *__restrict__ recv, double *x) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)nuniq * mu) return;
+  const int u = (int)(t % nuniq), c = (int)(t / nuniq);
+  double acc = x[uidx[u] + (int64_t)c * n];
+  for (int q = useg[u]; q < useg[u + 1]; ++q) {
+    const int e = upos[q];
+    acc += recv[(int64_t)ebase[e] * mu + (int64_t)c * esize[e] + (e - ebase[e])];
+  }
+  x[uidx[u] + (int64_t)c * n] = acc;
+}
+
+__global__ void __launch_bounds__(256) kk_dot(int n, int mu, const double *__restrict__ d, const double *__restrict__ x, const double *__restrict__ y, double *res) {
+  __shared__ double red[8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int c = 0; c < mu; ++c) {
+    double acc = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x) acc = fma(d[i] * x[i + (int64_t)c * n], y[i + (int64_t)c * n], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int q = 0; q < 8; ++q) s += red[q];
+      atomicAdd(&res[c], s);
+    }
+    __syncthreads();
+  }
+}
+
+// Replicated coarse solve (one CTA): Y = Einv T ; R = T - E Y ; Y += Einv R.
+// Coarse vectors use the communication layout [proc][col][row-in-proc]:
+//   v(r, c) = buf[(r / Lnu) * Lnu * mu + c * Lnu + r % Lnu]
+__global__ void __launch_bounds__(256) kk_coarse(int Nc, int mu, int Lnu, const double *__restrict__ E, const double *__restrict__ Einv,
+                                                 const double *__restrict__ T, double *Y, double *R) {
+  auto at = [&](int r, int c) -> int64_t { return (int64_t)(r / Lnu) * Lnu * mu + (int64_t)c * Lnu + r % Lnu; };
+  for (int c = 0; c < mu; ++c) {
+    for (int r = threadIdx.x; r < Nc; r += blockDim.x) {
+      double acc = 0.0;
+      for (int k = 0; k < Nc; ++k) acc = fma(Einv[r + (int64_t)k * Nc], T[at(k, c)], acc);
+      Y[at(r, c)] = acc;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < Nc; r += blockDim.x) {
+      double acc = T[at(r, c)];
+      for (int k = 0; k < Nc; ++k) acc = fma(-E[r + (int64_t)k * Nc], Y[at(k, c)], acc);
+      R[r] = acc;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < Nc; r += blockDim.x) {
+      double acc = 0.0;
+      for (int k = 0; k < Nc; ++k) acc = fma(Einv[r + (int64_t)k * Nc], R[k], acc);
+      Y[at(r, c)] += acc;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void kk_bc(int nbc, int n, int mu, const int *__restrict__ idx, const double *__restrict__ val, const double *__restrict__ b, double *x) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbc * mu) return;
+  const int q = t % nbc, c = t / nbc;
+  x[idx[q] + (int64_t)c * n] = b[idx[q] + (int64_t)c * n] / val[q];
+}
+
+inline unsigned grid1(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace
+
+#define HB_LAUNCH_END(c)       \
+  (c)->launches++;             \
+  HB_CUDA(cudaGetLastError()); \
+  return 0
+
+int k_scale(Ctx *c, int n, int mu, const double *d, const double *in, double *out) {
+  if ((int64_t)n * mu == 0) return 0;
+  kk_scale<<<grid1((int64_t)n * mu), 256, 0, c->stream>>>(n, mu, d, in, out);
+  HB_LAUNCH_END(c);
+}
+int k_axpy(Ctx *c, int64_t n, double a, const double *x, double *y) {
+  if (n == 0) return 0;
+  kk_axpy<<<grid1(n), 256, 0, c->stream>>>(n, a, x, y);
+  HB_LAUNCH_END(c);
+}
+int k_copy(Ctx *c, int64_t n, const double *x, double *y) {
+  if (n == 0 || x == y) return 0;
+  kk_copy<<<grid1(n), 256, 0, c->stream>>>(n, x, y);
+  HB_LAUNCH_END(c);
+}
+int k_fill(Ctx *c, int64_t n, double v, double *y) {
+  if (n == 0) return 0;
+  kk_fill<<<grid1(n), 256, 0, c->stream>>>(n, v, y);
+  HB_LAUNCH_END(c);
+}
+int k_spmv(Ctx *c, const Sub *s, int mu, double alpha, const double *x, double beta, const double *yin, double *out, const double *d) {
+  if (s->n == 0) return 0;
+  kk_spmv<<<grid1(s->n, 128), 128, 0, c->stream>>>(s->n, mu, s->d_ia, s->d_ja, s->d_a, alpha, x, beta, yin, out, d);
+  HB_LAUNCH_END(c);
+}
+int k_zt_project(Ctx *c, const Sub *s, int mu, const double *x, double *T, int ldT) {
+  if (s->n == 0 || s->nu == 0) return 0;
+  const unsigned g = grid1(s->n, 1024);
+  int c0 = 0;
+  while (c0 < mu) {
+    const int left = mu - c0;
+    if (left >= 4) {
+      kk_zt<4><<<g, 256, 0, c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, x, T, ldT);
+      c0 += 4;
+    } else if (left >= 2) {
+      kk_zt<2><<<g, 256, 0, c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, x, T, ldT);
+      c0 += 2;
+    } else {
+      kk_zt<1><<<g, 256, 0, c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, x, T, ldT);
+      c0 += 1;
+    }
+    c->launches++;
+  }
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}
+int k_z_expand(Ctx *c, const Sub *s, int mu, const double *Y, int ldY, double *out) {
+  if (s->n == 0) return 0;
+  if (s->nu == 0) return k_fill(c, (int64_t)s->n * mu, 0.0, out);
+  const unsigned g = grid1(s->n);
+  int c0 = 0;
+  while (c0 < mu) {
+    const int left = mu - c0;
+    if (left >= 4) {
+      kk_zexp<4><<<g, 256, s->nu * 4 * sizeof(double), c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, Y, ldY, out);
+      c0 += 4;
+    } else if (left >= 2) {
+      kk_zexp<2><<<g, 256, s->nu * 2 * sizeof(double), c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, Y, ldY, out);
+      c0 += 2;
+    } else {
+      kk_zexp<1><<<g, 256, s->nu * sizeof(double), c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, Y, ldY, out);
+      c0 += 1;
+    }
+    c->launches++;
+  }
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}
+int k_pack(Ctx *c, const Sub *s, int mu, const double *x, double *send) {
+  if (s->h == 0) return 0;
+  kk_pack<<<grid1((int64_t)s->h * mu), 256, 0, c->stream>>>(s->h, s->n, mu, s->d_map, s->d_ebase, s->d_esize, x, send);
+  HB_LAUNCH_END(c);
+}
+int k_unpack(Ctx *c, const Sub *s, int mu, double *x) {
+  if (s->nuniq == 0) return 0;
+  kk_unpack<<<grid1((int64_t)s->nuniq * mu), 256, 0, c->stream>>>(s->nuniq, s->n, mu, s->d_uidx, s->d_useg, s->d_upos, s->d_ebase, s->d_esize, s->d_recv, x);
+  HB_LAUNCH_END(c);
+}
+int k_dot(Ctx *c, const Sub *s, int mu, const double *x, const double *y, double *res) {
+  if (s->n == 0) return 0;
+  unsigned g = grid1(s->n);
+  if (g > 1184) g = 1184;
+  kk_dot<<<g, 256, 0, c->stream>>>(s->n, mu, s->d_d, x, y, res);
+  HB_LAUNCH_END(c);
+}
+int k_coarse_solve(Ctx *c, int mu) {
+  if (c->Nc == 0) return 0;
+  kk_coarse<<<1, 256, 0, c->stream>>>(c->Nc, mu, c->Lnu, c->d_E, c->d_Einv, c->d_T, c->d_Y, c->d_R);
+  HB_LAUNCH_END(c);
+}
+int k_bc(Ctx *c, const Sub *s, int mu, const double *b, double *x) {
+  const int nbc = (int)s->bc.size();
+  if (nbc == 0) return 0;
+  kk_bc<<<grid1((int64_t)nbc * mu), 256, 0, c->stream>>>(nbc, s->n, mu, s->d_bc_idx, s->d_bc_val, b, x);
+  HB_LAUNCH_END(c);
+}
+
+}  // namespace hb

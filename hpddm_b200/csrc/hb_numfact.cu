@@ -1,0 +1,564 @@
+// GPU multifrontal numeric factorisation producing the *inverted-diagonal-block*
+// supernodal panels that the SpTRSV kernels stream (hb_solve.cu).
+//
+// Replaces Schwarz::callNumfact -> SUBDOMAIN<K>::numfact (reference:
+// include/HPDDM_schwarz.hpp:337-368; the arithmetic itself is third-party there:
+// include/HPDDM_SuiteSparse.hpp:264-371, include/HPDDM_MUMPS.hpp:228-291).
+// Setup phase only -- off the measured hot path; dense front kernels of large
+// fronts go through cuSOLVER/cuBLAS, small fronts through a batched CTA-per-front
+// kernel.
+//
+// Per front (pivots s1, border s2, frontal matrix F column-major, ld = s1+s2):
+//   SPD :  F11 = L L^T ; L21 = F21 L^-T ; S = F22 - L21 L21^T
+//          panel = [ W ; M ] , W = L^-1 , M = L21 W           (used by both sweeps)
+//   LU  :  F11 = L U (no pivoting) ; L21 = F21 U^-1 ; U12 = L^-1 F12 ; S = F22 - L21 U12
+//          panL = [ L^-1 ; L21 L^-1 ] , panU = [ U^-T ; (U^-1 U12)^T ]
+// so that  forward : y1 = W b1 ,  b2 -= M b1          (one row-major GEMV)
+//          backward: x1 = panU^T [ y1 ; -x2 ]         (one transposed GEMV)
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+
+#include "hb_internal.h"
+
+namespace hb {
+
+namespace {
+
+constexpr int SMALL = 160;  // fronts with s1+s2 <= SMALL are factored by the batched kernel
+
+struct FrontDev {
+  int64_t foff;  // element offset of F in the level buffer
+  int64_t poff;  // panel offset
+  int s1, s2;
+};
+
+__global__ void k_assemble(int64_t ne, const int *__restrict__ efront, const int *__restrict__ erow, const int *__restrict__ ecol,
+                           const double *__restrict__ eval, const int64_t *__restrict__ foff, const int *__restrict__ fs, double *F) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int f = efront[e];
+  atomicAdd(&F[foff[f] + erow[e] + (int64_t)ecol[e] * fs[f]], eval[e]);
+}
+
+struct EATask {
+  int child;
+  int j0;  // first column of the child's update matrix handled by this CTA
+};
+// extend-add: F_parent[rel[i], rel[j]] += U_child[i, j]
+__global__ void k_extend_add(const EATask *__restrict__ tasks, const Front *__restrict__ fronts, const int *__restrict__ rel,
+                             const int64_t *__restrict__ foff, const double *__restrict__ Fchild, double *Fpar, int lower_only) {
+  EATask t = tasks[blockIdx.x];
+  const Front c = fronts[t.child];
+  const Front p = fronts[c.parent];
+  const int lc = c.s1 + c.s2, lp = p.s1 + p.s2;
+  const double *U = Fchild + foff[t.child] + c.s1 + (int64_t)c.s1 * lc;
+  double *P = Fpar + foff[c.parent];
+  const int *r = rel + c.rptr;
+  const int j1 = min(t.j0 + 16, c.s2);
+  for (int j = t.j0; j < j1; ++j) {
+    const int64_t pj = (int64_t)r[j] * lp;
+    for (int i = (lower_only ? j : 0) + threadIdx.x; i < c.s2; i += blockDim.x) atomicAdd(&P[r[i] + pj], U[i + (int64_t)j * lc]);
+  }
+}
+
+// ------------------------------------------------------------------ small fronts
+// one CTA per front; F in global memory (L1/L2 resident for these sizes)
+__global__ void __launch_bounds__(256) k_factor_small(const int *__restrict__ list, const Front *__restrict__ fronts, const int64_t *__restrict__ foff,
+                                                        double *Fbuf, double *panL, double *panU, int symmetric, int *info) {
+  const int f = list[blockIdx.x];
+  const Front fr = fronts[f];
+  const int s1 = fr.s1, s2 = fr.s2, s = s1 + s2;
+  double *F = Fbuf + foff[f];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int bad;
+  if (tid == 0) bad = 0;
+  __syncthreads();
+  for (int k = 0; k < s1; ++k) {
+    const double piv = F[k + (int64_t)k * s];
+    if (symmetric ? !(piv > 0.0) : !(fabs(piv) > 0.0)) {
+      if (tid == 0) bad = 1;
+    }
+    __syncthreads();
+    if (bad) break;
+    if (symmetric) {
+      const double sq = sqrt(piv);
+      for (int i = k + tid; i < s; i += nt) F[i + (int64_t)k * s] = (i == k) ? sq : F[i + (int64_t)k * s] / sq;
+      __syncthreads();
+      const int m = s - k - 1;
+      for (int idx = tid; idx < m * m; idx += nt) {
+        const int j = k + 1 + idx / m, i = k + 1 + idx % m;
+        if (i >= j) F[i + (int64_t)j * s] -= F[i + (int64_t)k * s] * F[j + (int64_t)k * s];
+      }
+    } else {
+      for (int i = k + 1 + tid; i < s; i += nt) F[i + (int64_t)k * s] /= piv;
+      __syncthreads();
+      const int m = s - k - 1;
+      for (int idx = tid; idx < m * m; idx += nt) {
+        const int j = k + 1 + idx / m, i = k + 1 + idx % m;
+        F[i + (int64_t)j * s] -= F[i + (int64_t)k * s] * F[k + (int64_t)j * s];
+      }
+    }
+    __syncthreads();
+  }
+  if (bad) {
+    if (tid == 0) atomicExch(info, f + 1);
+    return;
+  }
+  // ---- W = (lower factor)^-1 written straight into the panel (row-major trapezoid)
+  double *P = panL + fr.poff;
+  const int ldp = hb_ldp(s1);
+  auto prow = [&](double *base, int r) -> double * {
+    const int k = r / RB;
+    return base + hb_blk_off(k) + (int64_t)(r - k * RB) * hb_wblk(s1, k);
+  };
+  // zero-fill pivot trapezoid (structural zeros above the diagonal + padding)
+  for (int64_t q = tid; q < hb_upd_off(s1); q += nt) P[q] = 0.0;
+  if (!symmetric) {
+    double *Q = panU + fr.poff;
+    for (int64_t q = tid; q < hb_upd_off(s1); q += nt) Q[q] = 0.0;
+  }
+  __syncthreads();
+  // column j of W by forward substitution, one thread per column
+  for (int j = tid; j < s1; j += nt) {
+    for (int i = j; i < s1; ++i) {
+      double acc = (i == j) ? 1.0 : 0.0;
+      for (int k = j; k < i; ++k) acc -= F[i + (int64_t)k * s] * prow(P, k)[j];
+      prow(P, i)[j] = symmetric ? acc / F[i + (int64_t)i * s] : acc;  // LU: unit lower
+    }
+  }
+  if (!symmetric) {
+    // V = U11^-1 (upper); store V^T: Q[r][c] = V[c][r], c <= r.  V^T = (U11^T)^-1, U11^T lower with Lt[i][k] = U[k][i]
+    double *Q = panU + fr.poff;
+    for (int j = tid; j < s1; j += nt) {
+      for (int i = j; i < s1; ++i) {
+        double acc = (i == j) ? 1.0 : 0.0;
+        for (int k = j; k < i; ++k) acc -= F[k + (int64_t)i * s] * prow(Q, k)[j];
+        prow(Q, i)[j] = acc / F[i + (int64_t)i * s];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- update rows: M = L21 * W
+  double *Pu = P + hb_upd_off(s1);
+  for (int idx = tid; idx < s2 * ldp; idx += nt) {
+    const int i = idx / ldp, c = idx % ldp;
+    double acc = 0.0;
+    if (c < s1)
+      for (int k = c; k < s1; ++k) acc += F[s1 + i + (int64_t)k * s] * prow(P, k)[c];
+    Pu[(int64_t)i * ldp + c] = acc;
+  }
+  if (!symmetric) {
+    // N12 = V * U12 ; panU update row i, col c = N12[c][i] = sum_{k>=c} V[c][k] U12[k][i], V[c][k] = Q[k][c]
+    double *Q = panU + fr.poff;
+    double *Qu = Q + hb_upd_off(s1);
+    for (int idx = tid; idx < s2 * ldp; idx += nt) {
+      const int i = idx / ldp, c = idx % ldp;
+      double acc = 0.0;
+      if (c < s1)
+        for (int k = c; k < s1; ++k) acc += prow(Q, k)[c] * F[k + (int64_t)(s1 + i) * s];
+      Qu[(int64_t)i * ldp + c] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ large fronts: F (col-major) -> panel (row-major trapezoid)
+// mode 0: lower part  panel[r][c] = F[r + c*ld]   (pivot rows: c<=r, unit_diag -> 1 on the diagonal)
+// mode 1: upper part transposed  panel[r][c] = F[c + r*ld]
+__global__ void k_to_panel(const double *__restrict__ F, int s1, int s2, int mode, int unit_diag, double *P) {
+  const int ld = s1 + s2, ldp = hb_ldp(s1);
+  const int r0 = blockIdx.x * 32;  // 32 panel rows per CTA
+  __shared__ double tile[32][33];
+  const int nrows = min(32, s1 + s2 - r0);
+  for (int c0 = 0; c0 < ldp; c0 += 32) {
+    if (mode == 0) {
+      // read F[r0+tx + (c0+ty)*ld] coalesced along rows (tx), transpose through smem
+      for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
+        const int r = r0 + threadIdx.x, c = c0 + ty;
+        tile[ty][threadIdx.x] = (r < s1 + s2 && c < s1) ? F[r + (int64_t)c * ld] : 0.0;
+      }
+    } else {
+      for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
+        const int r = r0 + ty, c = c0 + threadIdx.x;  // F[c + r*ld]: coalesced along c
+        tile[threadIdx.x][ty] = (r < s1 + s2 && c < s1) ? F[c + (int64_t)r * ld] : 0.0;
+      }
+    }
+    __syncthreads();
+    for (int ty = threadIdx.y; ty < nrows; ty += blockDim.y) {
+      const int r = r0 + ty, c = c0 + threadIdx.x;
+      double v = tile[threadIdx.x][ty];
+      if (r < s1) {
+        const int k = r / RB, w = hb_wblk(s1, k);
+        if (c < w) {
+          if (c > r) v = 0.0;
+          else if (c == r && unit_diag) v = 1.0;
+          P[hb_blk_off(k) + (int64_t)(r - k * RB) * w + c] = v;
+        }
+      } else if (c < ldp) {
+        P[hb_upd_off(s1) + (int64_t)(r - s1) * ldp + c] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+struct Libs {
+  cusolverDnHandle_t so = nullptr;
+  cublasHandle_t bl = nullptr;
+  cusolverDnParams_t params = nullptr;
+  double *work = nullptr;
+  size_t work_bytes = 0;
+  void *hwork = nullptr;
+  size_t hwork_bytes = 0;
+  int *dinfo = nullptr;
+  ~Libs() {
+    if (work) cudaFree(work);
+    if (hwork) free(hwork);
+    if (dinfo) cudaFree(dinfo);
+    if (params) cusolverDnDestroyParams(params);
+    if (so) cusolverDnDestroy(so);
+    if (bl) cublasDestroy(bl);
+  }
+  int ensure(size_t dev_bytes, size_t host_bytes) {
+    if (dev_bytes > work_bytes) {
+      if (work) cudaFree(work);
+      HB_CUDA(cudaMalloc(&work, dev_bytes));
+      work_bytes = dev_bytes;
+    }
+    if (host_bytes > hwork_bytes) {
+      if (hwork) free(hwork);
+      hwork = malloc(host_bytes);
+      hwork_bytes = host_bytes;
+    }
+    return 0;
+  }
+};
+
+#define HB_SOLVER(call)                                                      \
+  do {                                                                       \
+    cusolverStatus_t st__ = (call);                                          \
+    if (st__ != CUSOLVER_STATUS_SUCCESS) {                                   \
+      set_error("cuSOLVER status %d at %s:%d", (int)st__, __FILE__, __LINE__); \
+      return HPDDM_B200_ERR_CUDA;                                            \
+    }                                                                        \
+  } while (0)
+#define HB_BLAS(call)                                                      \
+  do {                                                                     \
+    cublasStatus_t st__ = (call);                                          \
+    if (st__ != CUBLAS_STATUS_SUCCESS) {                                   \
+      set_error("cuBLAS status %d at %s:%d", (int)st__, __FILE__, __LINE__); \
+      return HPDDM_B200_ERR_CUDA;                                          \
+    }                                                                      \
+  } while (0)
+
+static int factor_large(Libs &L, cudaStream_t st, double *F, int s1, int s2, bool symmetric, double *panL, double *panU) {
+  const int ld = s1 + s2;
+  const double one = 1.0, mone = -1.0;
+  double *F11 = F, *F21 = F + s1, *F12 = F + (int64_t)s1 * ld, *F22 = F + s1 + (int64_t)s1 * ld;
+  size_t wd = 0, wh = 0;
+  if (symmetric) {
+    int lwork = 0;
+    HB_SOLVER(cusolverDnDpotrf_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, s1, F11, ld, &lwork));
+    HB_CHECK(L.ensure((size_t)lwork * sizeof(double), 0));
+    HB_SOLVER(cusolverDnDpotrf(L.so, CUBLAS_FILL_MODE_LOWER, s1, F11, ld, L.work, lwork, L.dinfo));
+    if (s2 > 0) {
+      HB_BLAS(cublasDtrsm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, F11, ld, F21, ld));
+      HB_BLAS(cublasDsyrk(L.bl, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, s2, s1, &mone, F21, ld, &one, F22, ld));
+    }
+    HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, &wd, &wh));
+    HB_CHECK(L.ensure(wd, wh));
+    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 1));
+    if (s2 > 0) HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, F11, ld, F21, ld, F21, ld));
+    k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(F, s1, s2, 0, 0, panL);
+  } else {
+    int lwork = 0;
+    HB_SOLVER(cusolverDnDgetrf_bufferSize(L.so, s1, s1, F11, ld, &lwork));
+    HB_CHECK(L.ensure((size_t)lwork * sizeof(double), 0));
+    HB_SOLVER(cusolverDnDgetrf(L.so, s1, s1, F11, ld, L.work, nullptr, L.dinfo));  // devIpiv = NULL: no pivoting
+    if (s2 > 0) {
+      HB_BLAS(cublasDtrsm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, F11, ld, F21, ld));
+      HB_BLAS(cublasDtrsm(L.bl, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_UNIT, s1, s2, &one, F11, ld, F12, ld));
+      HB_BLAS(cublasDgemm(L.bl, CUBLAS_OP_N, CUBLAS_OP_N, s2, s2, s1, &mone, F21, ld, F12, ld, &one, F22, ld));
+    }
+    HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_UNIT, s1, CUDA_R_64F, F11, ld, &wd, &wh));
+    HB_CHECK(L.ensure(wd, wh));
+    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 1));
+    HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, &wd, &wh));
+    HB_CHECK(L.ensure(wd, wh));
+    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 1));
+    if (s2 > 0) {
+      HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_UNIT, s2, s1, &one, F11, ld, F21, ld, F21, ld));
+      HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s1, s2, &one, F11, ld, F12, ld, F12, ld));
+    }
+    k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(F, s1, s2, 0, 1, panL);
+    k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(F, s1, s2, 1, 0, panU);
+  }
+  return 0;
+}
+
+template <class T>
+static int upload(const std::vector<T> &v, T **d) {
+  *d = nullptr;
+  if (v.empty()) return 0;
+  HB_CUDA(cudaMalloc(d, v.size() * sizeof(T)));
+  HB_CUDA(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
+  Symbolic &S = s->sym;
+  DeviceFactor &D = s->fac;
+  cudaStream_t st = s->ctx->stream;
+  const int F = (int)S.fronts.size();
+  const int n = S.n;
+  // ---- host: matrix entries -> (front,row,col), grouped by level
+  std::vector<int64_t> lvl_cnt(S.nlevels + 1, 0);
+  auto loc = [&](int f, int p) {
+    const Front &fr = S.fronts[f];
+    if (p < fr.p0 + fr.s1) return p - fr.p0;
+    const int *b = S.rowidx.data() + fr.rptr;
+    return fr.s1 + (int)(std::lower_bound(b, b + fr.s2, p) - b);
+  };
+  std::vector<int> efront, erow, ecol;
+  std::vector<double> eval;
+  {
+    const int64_t nnz = A.ia[n];
+    std::vector<int> tf, tr, tc;
+    std::vector<double> tv;
+    tf.reserve(nnz);
+    tr.reserve(nnz);
+    tc.reserve(nnz);
+    tv.reserve(nnz);
+    for (int i = 0; i < n; ++i) {
+      const int pi = S.iperm[i];
+      for (int k = A.ia[i]; k < A.ia[i + 1]; ++k) {
+        const int pj = S.iperm[A.ja[k]];
+        if (symmetric && pi < pj) continue;
+        int f, r, c;
+        if (pi >= pj) {
+          f = S.front_of[pj];
+          r = loc(f, pi);
+          c = pj - S.fronts[f].p0;
+        } else {
+          f = S.front_of[pi];
+          r = pi - S.fronts[f].p0;
+          c = loc(f, pj);
+        }
+        tf.push_back(f);
+        tr.push_back(r);
+        tc.push_back(c);
+        tv.push_back(A.a[k]);
+        lvl_cnt[S.fronts[f].level + 1]++;
+      }
+    }
+    for (int l = 0; l < S.nlevels; ++l) lvl_cnt[l + 1] += lvl_cnt[l];
+    const size_t ne = tf.size();
+    efront.resize(ne);
+    erow.resize(ne);
+    ecol.resize(ne);
+    eval.resize(ne);
+    std::vector<int64_t> pos(lvl_cnt.begin(), lvl_cnt.end() - 1);
+    for (size_t e = 0; e < ne; ++e) {
+      int64_t q = pos[S.fronts[tf[e]].level]++;
+      efront[q] = tf[e];
+      erow[q] = tr[e];
+      ecol[q] = tc[e];
+      eval[q] = tv[e];
+    }
+  }
+  // ---- per-front F offsets (per level), uploaded once
+  std::vector<int64_t> foff(F, 0);
+  std::vector<int> fs(F, 0);
+  std::vector<int64_t> lvl_elems(S.nlevels, 0);
+  for (int l = 0; l < S.nlevels; ++l) {
+    int64_t off = 0;
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      int f = S.level_order[q];
+      const Front &fr = S.fronts[f];
+      foff[f] = off;
+      fs[f] = fr.s1 + fr.s2;
+      off += (int64_t)fs[f] * fs[f];
+    }
+    lvl_elems[l] = off;
+  }
+  int *d_efront = nullptr, *d_erow = nullptr, *d_ecol = nullptr, *d_fs = nullptr, *d_rel = nullptr, *d_list = nullptr;
+  double *d_eval = nullptr;
+  int64_t *d_foff = nullptr;
+  EATask *d_tasks = nullptr;
+  int *d_info = nullptr;
+  double *Fprev = nullptr, *Fcur = nullptr;
+  Libs L;
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaFree(d_efront);
+    cudaFree(d_erow);
+    cudaFree(d_ecol);
+    cudaFree(d_eval);
+    cudaFree(d_fs);
+    cudaFree(d_foff);
+    cudaFree(d_rel);
+    cudaFree(d_list);
+    cudaFree(d_tasks);
+    cudaFree(d_info);
+    cudaFree(Fprev);
+    cudaFree(Fcur);
+  };
+#define NF_CHECK(x)   \
+  do {                \
+    rc = (x);         \
+    if (rc < 0) {     \
+      cleanup();      \
+      return rc;      \
+    }                 \
+  } while (0)
+#define NF_CUDA(call)                                                                             \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+      cleanup();                                                                                  \
+      return e__ == cudaErrorMemoryAllocation ? HPDDM_B200_ERR_NOMEM : HPDDM_B200_ERR_CUDA;        \
+    }                                                                                             \
+  } while (0)
+  NF_CHECK(upload(efront, &d_efront));
+  NF_CHECK(upload(erow, &d_erow));
+  NF_CHECK(upload(ecol, &d_ecol));
+  NF_CHECK(upload(eval, &d_eval));
+  NF_CHECK(upload(fs, &d_fs));
+  NF_CHECK(upload(foff, &d_foff));
+  NF_CHECK(upload(S.rel, &d_rel));
+  NF_CUDA(cudaMalloc(&d_info, 4 * sizeof(int)));
+  NF_CUDA(cudaMemset(d_info, 0, 4 * sizeof(int)));
+  if (cusolverDnCreate(&L.so) != CUSOLVER_STATUS_SUCCESS || cublasCreate(&L.bl) != CUBLAS_STATUS_SUCCESS) {
+    set_error("cannot create cuSOLVER/cuBLAS handles");
+    cleanup();
+    return HPDDM_B200_ERR_CUDA;
+  }
+  cusolverDnSetStream(L.so, st);
+  cublasSetStream(L.bl, st);
+  NF_CUDA(cudaMalloc(&L.dinfo, 4 * sizeof(int)));
+  NF_CUDA(cudaMemset(L.dinfo, 0, 4 * sizeof(int)));
+  // ---- panel store
+  if (!D.panL) NF_CUDA(cudaMalloc(&D.panL, std::max<int64_t>(S.panel_elems, 16) * sizeof(double)));
+  if (!symmetric) {
+    if (!D.panU || D.panU == D.panL) NF_CUDA(cudaMalloc(&D.panU, std::max<int64_t>(S.panel_elems, 16) * sizeof(double)));
+  } else {
+    if (D.panU && D.panU != D.panL) cudaFree(D.panU);
+    D.panU = D.panL;
+  }
+  D.symmetric = symmetric;
+  std::vector<int> small_list;
+  std::vector<EATask> tasks;
+  for (int l = 0; l < S.nlevels; ++l) {
+    NF_CUDA(cudaMalloc(&Fcur, std::max<int64_t>(lvl_elems[l], 1) * sizeof(double)));
+    NF_CUDA(cudaMemsetAsync(Fcur, 0, lvl_elems[l] * sizeof(double), st));
+    const int64_t e0 = lvl_cnt[l], e1 = lvl_cnt[l + 1];
+    if (e1 > e0) {
+      k_assemble<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, st>>>(e1 - e0, d_efront + e0, d_erow + e0, d_ecol + e0, d_eval + e0, d_foff, d_fs, Fcur);
+      s->ctx->launches++;
+    }
+    if (l > 0) {
+      tasks.clear();
+      for (int q = S.level_ptr[l - 1]; q < S.level_ptr[l]; ++q) {
+        int c = S.level_order[q];
+        if (S.fronts[c].parent < 0) continue;
+        for (int j0 = 0; j0 < S.fronts[c].s2; j0 += 16) tasks.push_back({c, j0});
+      }
+      if (!tasks.empty()) {
+        cudaFree(d_tasks);
+        d_tasks = nullptr;
+        NF_CHECK(upload(tasks, &d_tasks));
+        k_extend_add<<<(unsigned)tasks.size(), 128, 0, st>>>(d_tasks, D.fronts, d_rel, d_foff, Fprev, Fcur, symmetric ? 1 : 0);
+        s->ctx->launches++;
+      }
+    }
+    small_list.clear();
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      int f = S.level_order[q];
+      if (fs[f] <= SMALL) small_list.push_back(f);
+    }
+    if (!small_list.empty()) {
+      cudaFree(d_list);
+      d_list = nullptr;
+      NF_CHECK(upload(small_list, &d_list));
+      k_factor_small<<<(unsigned)small_list.size(), 256, 0, st>>>(d_list, D.fronts, d_foff, Fcur, D.panL, D.panU, symmetric ? 1 : 0, d_info);
+      s->ctx->launches++;
+    }
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      int f = S.level_order[q];
+      if (fs[f] <= SMALL) continue;
+      const Front &fr = S.fronts[f];
+      NF_CHECK(factor_large(L, st, Fcur + foff[f], fr.s1, fr.s2, symmetric, D.panL + fr.poff, D.panU + fr.poff));
+      s->ctx->launches += 8;
+    }
+    // pivots / library status of this level
+    int hinfo[4] = {0, 0, 0, 0}, linfo[4] = {0, 0, 0, 0};
+    NF_CUDA(cudaMemcpyAsync(hinfo, d_info, sizeof(hinfo), cudaMemcpyDeviceToHost, st));
+    NF_CUDA(cudaMemcpyAsync(linfo, L.dinfo, sizeof(linfo), cudaMemcpyDeviceToHost, st));
+    NF_CUDA(cudaStreamSynchronize(st));
+    if (hinfo[0] != 0 || linfo[0] != 0 || linfo[1] != 0) {
+      set_error("numfact: %s pivot breakdown at level %d (front %d, potrf/getrf info %d, trtri info %d)", symmetric ? "Cholesky" : "LU", l, hinfo[0] - 1,
+                linfo[0], linfo[1]);
+      cleanup();
+      return HPDDM_B200_ERR_NUMERIC;
+    }
+    cudaFree(Fprev);
+    Fprev = Fcur;
+    Fcur = nullptr;
+  }
+  cleanup();
+  NF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+void free_factor(DeviceFactor &f) {
+  if (f.panU && f.panU != f.panL) cudaFree(f.panU);
+  cudaFree(f.panL);
+  cudaFree(f.fronts);
+  cudaFree(f.rowidx);
+  cudaFree(f.fwd);
+  cudaFree(f.bwd);
+  cudaFree(f.perm);
+  cudaFree(f.b);
+  cudaFree(f.y);
+  cudaFree(f.x);
+  f = DeviceFactor();
+}
+
+int numfact_device(Sub *s, const HostCSR &A) {
+  auto t0 = std::chrono::steady_clock::now();
+  free_factor(s->fac);
+  int leaf = 64;
+  if (const char *e = getenv("HPDDM_B200_LEAF")) leaf = std::max(1, atoi(e));
+  HB_CHECK(symbolic_analyze(A, s->gx, s->gy, s->gz, s->gdof, leaf, s->sym));
+  auto t1 = std::chrono::steady_clock::now();
+  s->t_symbolic = std::chrono::duration<double>(t1 - t0).count();
+  Symbolic &S = s->sym;
+  DeviceFactor &D = s->fac;
+  HB_CHECK(upload(S.fronts, &D.fronts));
+  HB_CHECK(upload(S.rowidx, &D.rowidx));
+  HB_CHECK(upload(S.fwd, &D.fwd));
+  HB_CHECK(upload(S.bwd, &D.bwd));
+  HB_CHECK(upload(S.perm, &D.perm));
+  HB_CUDA(cudaMalloc(&D.b, (size_t)S.n * sizeof(double)));
+  HB_CUDA(cudaMalloc(&D.y, (size_t)S.n * sizeof(double)));
+  HB_CUDA(cudaMalloc(&D.x, (size_t)S.n * sizeof(double)));
+  int rc = HPDDM_B200_ERR_NUMERIC;
+  const bool force_lu = getenv("HPDDM_B200_FORCE_LU") != nullptr;
+  if (A.symmetric && !force_lu) rc = numfact_try(s, A, true);
+  if (rc == HPDDM_B200_ERR_NUMERIC) rc = numfact_try(s, A, false);
+  if (rc < 0) {
+    free_factor(D);
+    return rc;
+  }
+  D.valid = true;
+  s->t_numfact = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+  return 0;
+}
+
+}  // namespace hb

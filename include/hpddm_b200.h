@@ -1,0 +1,190 @@
+/*
+ * hpddm_b200.h -- C ABI of libhpddm_b200.so: the B200-native (sm_100a)
+ * implementation of HPDDM's one-/two-level (O)RAS preconditioner-apply path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes,
+ * no C++/torch types.  The header-only host layer (hpddm_b200/host/HPDDM_B200.hpp)
+ * forwards the reference's C++ surface (HPDDM::Schwarz, Subdomain::exchange,
+ * CoarseOperator::callSolver, the SUBDOMAIN solver-plugin concept) to these
+ * entry points; a Python ctypes binding lives in hpddm_b200/capi.py.
+ *
+ * Every entry point names the reference interface it replaces (paths relative
+ * to the HPDDM tree, hpddm/hpddm @ ce8f7bf).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative code on error (matches
+ *    HPDDM_CALL, include/HPDDM_iterative.hpp:30-34, which only propagates
+ *    negatives); hpddm_b200_last_error() returns a message for the calling thread.
+ *  - vectors are column-major n_loc x mu, leading dimension n_loc (exactly what
+ *    Schwarz::apply receives, include/HPDDM_schwarz.hpp:527-528).
+ *  - a *context* owns one GPU, one stream and (optionally) one NCCL
+ *    communicator; it hosts one or more *subdomains* (HPDDM: one MPI rank =
+ *    one subdomain; several per context are allowed so that a decomposition can
+ *    be exercised on a single GPU).  Global subdomain ranks are contiguous per
+ *    context: context p of `nproc` hosts ranks [p*L, (p+1)*L), L = local count.
+ *  - collective calls (hpddm_b200_apply & co.) take arrays with one pointer per
+ *    LOCAL subdomain, in the order the subdomains were created.
+ *  - `where` says where the caller's vectors live: HPDDM_B200_HOST pointers are
+ *    staged through pinned buffers inside the call (this is what an unchanged
+ *    Krylov driver passes, include/HPDDM_GMRES.hpp:116); HPDDM_B200_DEVICE
+ *    pointers are used in place on the context's stream.
+ */
+#ifndef HPDDM_B200_H
+#define HPDDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hpddm_b200_ctx hpddm_b200_ctx;
+typedef struct hpddm_b200_sub hpddm_b200_sub;
+
+#define HPDDM_B200_HOST 0
+#define HPDDM_B200_DEVICE 1
+
+/* Prcndtnr of include/HPDDM_enum.hpp as selected by Schwarz::callNumfact
+ * (include/HPDDM_schwarz.hpp:343-363) */
+#define HPDDM_B200_PRCNDTNR_NO 0
+#define HPDDM_B200_PRCNDTNR_SY 1 /* ASM */
+#define HPDDM_B200_PRCNDTNR_GE 2 /* RAS */
+#define HPDDM_B200_PRCNDTNR_OS 3 /* SORAS */
+#define HPDDM_B200_PRCNDTNR_OG 4 /* ORAS */
+
+/* -hpddm_schwarz_coarse_correction (include/HPDDM_define.hpp:141-199,
+ * include/HPDDM_option_impl.hpp:84); NONE = option unset -> one-level branch of
+ * Schwarz::apply (schwarz.hpp:531) */
+#define HPDDM_B200_CORRECTION_NONE (-1)
+#define HPDDM_B200_CORRECTION_DEFLATED 0
+#define HPDDM_B200_CORRECTION_ADDITIVE 1
+#define HPDDM_B200_CORRECTION_BALANCED 2
+
+/* error codes */
+#define HPDDM_B200_ERR_ARG (-1)
+#define HPDDM_B200_ERR_CUDA (-2)
+#define HPDDM_B200_ERR_STATE (-3)
+#define HPDDM_B200_ERR_NUMERIC (-4) /* zero / negative pivot */
+#define HPDDM_B200_ERR_NCCL (-5)
+#define HPDDM_B200_ERR_NOMEM (-6)
+
+const char *hpddm_b200_last_error(void);
+const char *hpddm_b200_version(void);
+
+/* ---- context ------------------------------------------------------------- */
+/* One per process (or per GPU).  Replaces MPI_Init + Subdomain::communicator_
+ * ownership (include/HPDDM_subdomain.hpp:49-63). */
+int hpddm_b200_ctx_create(int device, hpddm_b200_ctx **ctx);
+int hpddm_b200_ctx_destroy(hpddm_b200_ctx *ctx);
+/* NCCL bootstrap (replaces the MPI communicator on the hot path only, SURVEY.md
+ * section 5): rank 0 of the job calls unique_id, broadcasts the 128 bytes with
+ * whatever it has (MPI_Bcast, torch.distributed, a file), every process then
+ * calls comm_init.  Not calling comm_init = single-process decomposition. */
+int hpddm_b200_nccl_unique_id(void *id128);
+int hpddm_b200_ctx_comm_init(hpddm_b200_ctx *ctx, const void *id128, int proc_rank, int nproc);
+int hpddm_b200_ctx_synchronize(hpddm_b200_ctx *ctx);
+/* raw cudaStream_t of the context (for callers that time with CUDA events) */
+void *hpddm_b200_ctx_stream(hpddm_b200_ctx *ctx);
+/* number of kernels this library launched on the context since creation */
+int64_t hpddm_b200_ctx_launch_count(hpddm_b200_ctx *ctx);
+/* device allocation helpers for callers without a CUDA runtime binding */
+int hpddm_b200_malloc(hpddm_b200_ctx *ctx, size_t bytes, void **dptr);
+int hpddm_b200_free(hpddm_b200_ctx *ctx, void *dptr);
+int hpddm_b200_memcpy(hpddm_b200_ctx *ctx, void *dst, const void *src, size_t bytes, int dst_where, int src_where);
+
+/* ---- subdomain setup ------------------------------------------------------ */
+/* HPDDM::Schwarz<...> A;  (examples/schwarz.cpp:90) */
+int hpddm_b200_sub_create(hpddm_b200_ctx *ctx, int global_rank, hpddm_b200_sub **sub);
+int hpddm_b200_sub_destroy(hpddm_b200_sub *sub);
+/* Subdomain::initialize(MatrixCSR*, ...) matrix part (include/HPDDM_subdomain.hpp:165-183).
+ * MatrixCSR layout (include/HPDDM_matrix.hpp:33-57,156-165): ia[n+1], ja[nnz], a[nnz];
+ * sym != 0 => lower triangle only; numbering 'C' or 'F'.  The arrays are copied. */
+int hpddm_b200_sub_set_matrix(hpddm_b200_sub *sub, int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering);
+/* Subdomain::initialize neighbour part, C-array overload (subdomain.hpp:238-259):
+ * `count` neighbours, global ranks `ranks[i]`, `sizes[i]` shared dofs each,
+ * indices concatenated in `idx` (C numbering).  Sorted by rank inside, empty
+ * lists dropped, as the reference does. */
+int hpddm_b200_sub_set_neighbors(hpddm_b200_sub *sub, int count, const int *ranks, const int *sizes, const int *idx);
+/* Schwarz::initialize(d) (include/HPDDM_schwarz.hpp:178): the partition of unity
+ * (after multiplicityScaling).  Copied to the device. */
+int hpddm_b200_sub_set_scaling(hpddm_b200_sub *sub, const double *d);
+/* Optional ordering hint: the dofs are a lexicographic nx x ny x nz grid with
+ * `dof` unknowns per node (x fastest) -> geometric nested dissection.  Without
+ * it an algebraic (BFS level-set) nested dissection is used.  New; nothing in
+ * the reference corresponds (orderings are chosen inside MUMPS/CHOLMOD). */
+int hpddm_b200_sub_set_grid_hint(hpddm_b200_sub *sub, int nx, int ny, int nz, int dof);
+/* Schwarz::multiplicityScaling (include/HPDDM_schwarz.hpp:381-404), collective:
+ * d[s] in/out (host), one array per local subdomain. */
+int hpddm_b200_multiplicity_scaling(hpddm_b200_ctx *ctx, double *const *d);
+/* Schwarz::callNumfact -> SUBDOMAIN::numfact (schwarz.hpp:337-368; e.g.
+ * include/HPDDM_SuiteSparse.hpp:264-371): GPU multifrontal LL^T / LU of the
+ * local matrix (or of the ORAS/SORAS matrix passed as ia/ja/a when
+ * prcndtnr = OG / OS; pass NULLs to factor the matrix given to set_matrix).
+ * Leaves the supernodal panels in HBM in the layout the SpTRSV consumes. */
+int hpddm_b200_sub_numfact(hpddm_b200_sub *sub, int prcndtnr, int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering);
+/* Preconditioner::setVectors (include/HPDDM_preconditioner.hpp:358-362): Z =
+ * ev_[0], one contiguous column-major n x nu block.  Copied to the device. */
+int hpddm_b200_sub_set_vectors(hpddm_b200_sub *sub, const double *Z, int nu);
+/* Schwarz::buildTwo (include/HPDDM_schwarz.hpp:440-495 -> preconditioner.hpp:124-257
+ * -> CoarseOperator::construction, coarse_operator_impl.hpp:220-272; Galerkin
+ * blocks of include/HPDDM_operator.hpp:395-528), collective: assembles
+ * E = Z^T A Z on the GPUs, replicates and factors it. */
+int hpddm_b200_build_coarse(hpddm_b200_ctx *ctx);
+/* Alternative to build_coarse: install a user-assembled dense coarse operator
+ * (N_c x N_c column-major, N_c = sum of all nu).  UserCoarseOperator analogue,
+ * include/HPDDM_operator.hpp:351-375. */
+int hpddm_b200_set_coarse(hpddm_b200_ctx *ctx, const double *E, int Nc);
+/* copy out the assembled coarse operator (host, N_c x N_c column-major);
+ * -hpddm_level_2_dump_matrix analogue (coarse_operator_impl.hpp:1031-1061) */
+int hpddm_b200_get_coarse(hpddm_b200_ctx *ctx, double *E, int *Nc);
+
+/* ---- the hot path (collective over the context's subdomains) --------------- */
+/* Schwarz::start<false>(b, x, mu) (include/HPDDM_schwarz.hpp:496-514): impose
+ * penalised rows on x, exchange(x), size the coarse work space for mu columns. */
+int hpddm_b200_start(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int where);
+/* Subdomain::end (include/HPDDM_subdomain.hpp:289) */
+int hpddm_b200_end(hpddm_b200_ctx *ctx);
+/* Schwarz::apply<false>(in, out, mu, work) (include/HPDDM_schwarz.hpp:527-612).
+ * `in` is never modified (a private work space is used). */
+int hpddm_b200_apply(hpddm_b200_ctx *ctx, const double *const *in, double *const *out, int mu, int correction, int where);
+/* Schwarz::deflation<false>(in, out, mu) (include/HPDDM_schwarz.hpp:1602-1622) */
+int hpddm_b200_deflation(hpddm_b200_ctx *ctx, const double *const *in, double *const *out, int mu, int where);
+/* Schwarz::exchange(x, mu) when scaled != 0 (schwarz.hpp:180-188), else
+ * Subdomain::exchange(x, mu) (include/HPDDM_subdomain.hpp:115-130); in place. */
+int hpddm_b200_exchange(hpddm_b200_ctx *ctx, double *const *x, int mu, int scaled, int where);
+/* Schwarz::GMV(in, out, mu) (include/HPDDM_schwarz.hpp:726-747) */
+int hpddm_b200_gmv(hpddm_b200_ctx *ctx, const double *const *in, double *const *out, int mu, int where);
+/* SUBDOMAIN::solve(b, x, n) (e.g. include/HPDDM_SuiteSparse.hpp:388-423):
+ * local triangular solves only, no communication. */
+int hpddm_b200_sub_solve(hpddm_b200_sub *sub, const double *b, double *x, int mu, int where);
+/* CoarseOperator::callSolver(rhs, mu) (include/HPDDM_coarse_operator_impl.hpp:1630-1732):
+ * rhs[s] = nu_s x mu (column-major, ld = nu_s) in, solution out. */
+int hpddm_b200_coarse_solve(hpddm_b200_ctx *ctx, double *const *rhs, int mu, int where);
+/* D-weighted dot products per column, summed over the context's subdomains and
+ * (when a communicator exists) all processes: sum_i d_i x_i y_i -- the
+ * reduction the Krylov layer performs (include/HPDDM_GMRES.hpp:59-68,
+ * include/HPDDM_iterative.hpp:455-468).  result[mu] on the host. */
+int hpddm_b200_dot(hpddm_b200_ctx *ctx, const double *const *x, const double *const *y, int mu, double *result, int where);
+
+/* ---- introspection (Subdomain::statistics analogue, subdomain.hpp:405-454) -- */
+typedef struct hpddm_b200_stats {
+  int64_t n;             /* dofs */
+  int64_t nnz_a;         /* stored nonzeros of the local matrix (full pattern) */
+  int64_t nnz_factor;    /* factor values stored per triangular factor (trapezoid panels) */
+  int64_t factor_bytes;  /* HBM bytes of all panels (L and, for LU, U) */
+  int64_t index_bytes;   /* supernodal row-index + work-item bytes read per solve */
+  int64_t fronts;        /* supernodes */
+  int64_t levels;        /* elimination-tree levels = kernel launches per sweep */
+  int64_t halo;          /* h = sum of neighbour map sizes */
+  int64_t nu;            /* local deflation vectors */
+  int symmetric;         /* 1: LL^T, one panel set; 0: LU, two panel sets */
+  double numfact_seconds;
+  double symbolic_seconds;
+} hpddm_b200_stats;
+int hpddm_b200_sub_stats(hpddm_b200_sub *sub, hpddm_b200_stats *st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPDDM_B200_H */

@@ -1,0 +1,52 @@
+"""CPU-side checks: the C-ABI library loads, exports every symbol include/hpddm_b200.h
+declares, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from hpddm_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hpddm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hpddm_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == capi.EXPORTS
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    for name in declared_symbols():
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.hpddm_b200_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    rc = capi.lib().hpddm_b200_ctx_create(0, C.byref(h))
+    assert rc < 0
+    assert b"no CPU fallback" in capi.lib().hpddm_b200_last_error()
+    with pytest.raises(capi.HpddmB200Error):
+        capi.check(rc)
+
+
+def test_product_does_not_import_oracle():
+    import subprocess
+    import sys
+    code = "import sys; import hpddm_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "hpddm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f

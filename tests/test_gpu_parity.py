@@ -1,0 +1,178 @@
+"""GPU parity tests: every hot-path entry point of libhpddm_b200.so, called through
+the C ABI (ctypes), against the CPU oracle on the same seeded inputs.
+
+Tolerance: FP64 relative 1e-10 (BASELINE.json north_star: <= 1e-10 on the
+preconditioned residual, identical Krylov iteration count).
+"""
+import numpy as np
+import pytest
+
+from oracle.generate import generate_world
+from oracle.krylov import OracleOperator, gmres
+from oracle.schwarz import ADDITIVE, BALANCED, DEFLATED, SchwarzWorld
+from hpddm_b200 import KrylovOperator
+from tests.helpers import build_gpu_decomposition, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def make_world(dim, size, nu=0, mu=2, **kw):
+    parts = generate_world(size, dim=dim, mu=mu, neumann=nu > 0, **kw)
+    w = SchwarzWorld(parts)
+    w.multiplicity_scaling()
+    w.numfact()
+    if nu > 0:
+        w.solve_gevp([p["MatNeumann"] for p in parts], nu=nu)
+        w.build_coarse()
+    return parts, w
+
+
+@pytest.fixture(scope="module")
+def poisson3d():
+    parts, w = make_world(3, 8, nu=4, mu=3, N=(14, 14, 14), overlap=1)
+    deco = build_gpu_decomposition(parts, w, two_level=True)
+    yield parts, w, deco
+    deco.close()
+
+
+def rhs(parts, w, seed=0):
+    rs = np.random.RandomState(seed)
+    x = [np.asfortranarray(rs.standard_normal(p["f"].shape)) for p in parts]
+    return x
+
+
+def test_local_solve(poisson3d):
+    parts, w, deco = poisson3d
+    for r, s in enumerate(deco.subs):
+        b = parts[r]["f"]
+        got = s.solve(b)
+        ref = w.solver[r].solve(b)
+        assert relerr([got], [ref]) < TOL
+        st = s.statistics()
+        assert st["symmetric"] == 1 and st["nnz_factor"] > 0
+
+
+def test_exchange_scaled_and_unscaled(poisson3d):
+    parts, w, deco = poisson3d
+    x = rhs(parts, w, 1)
+    ref = w.exchange([v.copy() for v in x])
+    assert relerr(deco.exchange(x, scaled=True), ref) < 1e-14
+    ref = w.subdomain_exchange([v.copy() for v in x])
+    assert relerr(deco.exchange(x, scaled=False), ref) < 1e-14
+
+
+def test_multiplicity_scaling_matches_oracle():
+    parts, w = make_world(3, 8, N=(10, 10, 10), overlap=2)
+    deco = build_gpu_decomposition(parts, None, own_scaling=True)
+    ds = deco.multiplicityScaling([p["d"] for p in parts])
+    for r in range(8):
+        assert np.abs(ds[r] - w.d[r]).max() < 1e-15
+    deco.close()
+
+
+def test_gmv(poisson3d):
+    parts, w, deco = poisson3d
+    x = rhs(parts, w, 2)
+    assert relerr(deco.GMV(x), w.GMV(x)) < 1e-13
+
+
+def test_coarse_operator_assembly(poisson3d):
+    parts, w, deco = poisson3d
+    E = deco.getCoarse()
+    assert E.shape == w.E.shape
+    assert np.abs(E - w.E).max() / np.abs(w.E).max() < 1e-12
+
+
+def test_coarse_solve(poisson3d):
+    parts, w, deco = poisson3d
+    rs = np.random.RandomState(3)
+    uc = [np.asfortranarray(rs.standard_normal((w.nu[r], 2))) for r in range(w.P)]
+    ref = w.call_solver([u.copy() for u in uc])
+    got = deco.callSolver(uc)
+    assert relerr(got, ref) < 1e-11
+
+
+def test_deflation(poisson3d):
+    parts, w, deco = poisson3d
+    x = rhs(parts, w, 4)
+    assert relerr(deco.deflation(x), w.deflation(x)) < TOL
+
+
+@pytest.mark.parametrize("correction", [None, DEFLATED, ADDITIVE, BALANCED])
+def test_apply(poisson3d, correction):
+    parts, w, deco = poisson3d
+    x = rhs(parts, w, 5)
+    ref = w.apply(x, correction)
+    got = deco.apply(x, correction)
+    assert relerr(got, ref) < TOL
+
+
+def test_start_and_dot(poisson3d):
+    parts, w, deco = poisson3d
+    b = rhs(parts, w, 6)
+    x0 = rhs(parts, w, 7)
+    ref = w.start(b, [v.copy() for v in x0])
+    got = deco.start(b, x0)
+    deco.end()
+    assert relerr(got, ref) < 1e-14
+    assert np.abs(deco.dot(b, x0) - w.dot(b, x0)).max() / np.abs(w.dot(b, x0)).max() < 1e-12
+
+
+@pytest.mark.parametrize("correction", [None, DEFLATED])
+def test_gmres_iteration_count_identical(poisson3d, correction):
+    """north_star: identical Krylov iteration count, preconditioned residual parity."""
+    parts, w, deco = poisson3d
+    b = w.exchange([p["f"].copy() for p in parts])
+    it_ref, x_ref, ap_ref = gmres(OracleOperator(w, correction), b)
+    it_gpu, x_gpu, ap_gpu = gmres(KrylovOperator(deco, correction), b)
+    assert it_gpu == it_ref and ap_gpu == ap_ref
+    assert relerr(x_gpu, x_ref) < 1e-8
+    res = w.compute_residual(x_gpu, b)
+    assert np.all(res[:, 1] / res[:, 0] < 1e-5)
+
+
+def test_config1_2d_quirk_matrix_lu_path():
+    """BASELINE config 1: examples/generate.cpp 2-D Poisson 100x100, 4 ranks, overlap 1, one-level RAS.
+    The generator's skewed stencil makes the local matrices non-symmetric -> LU panels."""
+    parts, w = make_world(2, 4, mu=0, Nx=100, Ny=100, overlap=1)
+    deco = build_gpu_decomposition(parts, w)
+    assert deco.subs[0].statistics()["symmetric"] == 0
+    x = [p["f"].copy() for p in parts]
+    assert relerr(deco.apply(x, None), w.apply(x, None)) < TOL
+    b = [p["f"].copy() for p in parts]
+    it_ref, _, _ = gmres(OracleOperator(w), b, restart=25, max_it=80)
+    it_gpu, xg, _ = gmres(KrylovOperator(deco), b, restart=25, max_it=80)
+    assert it_gpu == it_ref and it_gpu <= 45           # examples/schwarz.cpp:140
+    res = w.compute_residual(xg, b)
+    assert res[0, 1] / res[0, 0] < 1e-2                # examples/schwarz.cpp:143
+    deco.close()
+
+
+def test_algebraic_ordering_without_grid_hint():
+    parts, w = make_world(3, 2, mu=1, N=(12, 10, 9), overlap=1)
+    deco = build_gpu_decomposition(parts, w, grid_hint=False)
+    x = [p["f"].copy() for p in parts]
+    assert relerr(deco.apply(x, None), w.apply(x, None)) < TOL
+    deco.close()
+
+
+def test_symmetric_csr_input():
+    parts, w = make_world(3, 2, mu=1, N=(10, 10, 10), overlap=1, sym=True)
+    deco = build_gpu_decomposition(parts, w)
+    x = [p["f"].copy() for p in parts]
+    assert relerr(deco.apply(x, None), w.apply(x, None)) < TOL
+    assert relerr(deco.GMV(x), w.GMV(x)) < 1e-13
+    deco.close()
+
+
+def test_single_subdomain_direct_solve_residual():
+    """examples/schwarz.cpp:149-178 (1 rank): numfact + solve, ||Ax-b||/||b|| <= 1e-6."""
+    parts, w = make_world(3, 1, mu=2, N=(24, 24, 24), overlap=1)
+    deco = build_gpu_decomposition(parts, w)
+    b = parts[0]["f"]
+    x = deco.subs[0].solve(b)
+    A = w.A[0]
+    r = np.linalg.norm(A @ x - b, axis=0) / np.linalg.norm(b, axis=0)
+    assert r.max() < 1e-12
+    deco.close()
