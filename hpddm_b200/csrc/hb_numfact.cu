@@ -25,10 +25,12 @@
 #include "hb_internal.h"
 
 namespace hb {
+const char *get_error();
+static const char *get_error_msg() { return get_error(); }
 
 namespace {
 
-constexpr int SMALL = 160;  // fronts with s1+s2 <= SMALL are factored by the batched kernel
+static int SMALL = 160;   // fronts with s1+s2 <= SMALL are factored by the batched kernel
 
 struct FrontDev {
   int64_t foff;  // element offset of F in the level buffer
@@ -168,17 +170,20 @@ __global__ void __launch_bounds__(256) k_factor_small(const int *__restrict__ li
 // ------------------------------------------------------------------ large fronts: F (col-major) -> panel (row-major trapezoid)
 // mode 0: lower part  panel[r][c] = F[r + c*ld]   (pivot rows: c<=r, unit_diag -> 1 on the diagonal)
 // mode 1: upper part transposed  panel[r][c] = F[c + r*ld]
-__global__ void k_to_panel(const double *__restrict__ F, int s1, int s2, int mode, int unit_diag, double *P) {
+__global__ void k_to_panel(const double *__restrict__ Fpiv, int ldpiv, const double *__restrict__ F, int s1, int s2, int mode, double *P) {
+  // mode 0: pivot rows from Fpiv (lower triangular, ld = ldpiv), update rows from F21 = F + s1 (ld = s1+s2)
+  // mode 1: everything from the upper part of F, transposed (Fpiv unused)
   const int ld = s1 + s2, ldp = hb_ldp(s1);
   const int r0 = blockIdx.x * 32;  // 32 panel rows per CTA
   __shared__ double tile[32][33];
   const int nrows = min(32, s1 + s2 - r0);
   for (int c0 = 0; c0 < ldp; c0 += 32) {
     if (mode == 0) {
-      // read F[r0+tx + (c0+ty)*ld] coalesced along rows (tx), transpose through smem
       for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
         const int r = r0 + threadIdx.x, c = c0 + ty;
-        tile[ty][threadIdx.x] = (r < s1 + s2 && c < s1) ? F[r + (int64_t)c * ld] : 0.0;
+        double v = 0.0;
+        if (r < s1 + s2 && c < s1) v = (r < s1) ? Fpiv[r + (int64_t)c * ldpiv] : F[r + (int64_t)c * ld];
+        tile[ty][threadIdx.x] = v;
       }
     } else {
       for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
@@ -194,7 +199,6 @@ __global__ void k_to_panel(const double *__restrict__ F, int s1, int s2, int mod
         const int k = r / RB, w = hb_wblk(s1, k);
         if (c < w) {
           if (c > r) v = 0.0;
-          else if (c == r && unit_diag) v = 1.0;
           P[hb_blk_off(k) + (int64_t)(r - k * RB) * w + c] = v;
         }
       } else if (c < ldp) {
@@ -203,6 +207,14 @@ __global__ void k_to_panel(const double *__restrict__ F, int s1, int s2, int mod
     }
     __syncthreads();
   }
+}
+
+// S = unit-lower part of the packed LU factors in F11 (strict lower + ones), zero above
+__global__ void k_unit_lower(const double *__restrict__ F, int s1, int ld, double *S) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)s1 * s1) return;
+  const int r = (int)(t % s1), c = (int)(t / s1);
+  S[t] = r > c ? F[r + (int64_t)c * ld] : (r == c ? 1.0 : 0.0);
 }
 
 struct Libs {
@@ -214,7 +226,10 @@ struct Libs {
   void *hwork = nullptr;
   size_t hwork_bytes = 0;
   int *dinfo = nullptr;
+  double *scratch = nullptr;
+  size_t scratch_bytes = 0;
   ~Libs() {
+    if (scratch) cudaFree(scratch);
     if (work) cudaFree(work);
     if (hwork) free(hwork);
     if (dinfo) cudaFree(dinfo);
@@ -272,7 +287,7 @@ static int factor_large(Libs &L, cudaStream_t st, double *F, int s1, int s2, boo
     HB_CHECK(L.ensure(wd, wh));
     HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 1));
     if (s2 > 0) HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, F11, ld, F21, ld, F21, ld));
-    k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(F, s1, s2, 0, 0, panL);
+    k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(F, ld, F, s1, s2, 0, panL);
   } else {
     int lwork = 0;
     HB_SOLVER(cusolverDnDgetrf_bufferSize(L.so, s1, s1, F11, ld, &lwork));
@@ -283,18 +298,28 @@ static int factor_large(Libs &L, cudaStream_t st, double *F, int s1, int s2, boo
       HB_BLAS(cublasDtrsm(L.bl, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_UNIT, s1, s2, &one, F11, ld, F12, ld));
       HB_BLAS(cublasDgemm(L.bl, CUBLAS_OP_N, CUBLAS_OP_N, s2, s2, s1, &mone, F21, ld, F12, ld, &one, F22, ld));
     }
-    HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_UNIT, s1, CUDA_R_64F, F11, ld, &wd, &wh));
+    // L11 and U11 share F11: split the unit-lower factor into a scratch matrix so that both
+    // inversions are plain non-unit trtri calls
+    if ((size_t)s1 * s1 * sizeof(double) > L.scratch_bytes) {
+      if (L.scratch) cudaFree(L.scratch);
+      L.scratch = nullptr;
+      HB_CUDA(cudaMalloc(&L.scratch, (size_t)s1 * s1 * sizeof(double)));
+      L.scratch_bytes = (size_t)s1 * s1 * sizeof(double);
+    }
+    double *S = L.scratch;
+    k_unit_lower<<<(unsigned)(((int64_t)s1 * s1 + 255) / 256), 256, 0, st>>>(F11, s1, ld, S);
+    HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, S, s1, &wd, &wh));
     HB_CHECK(L.ensure(wd, wh));
-    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 1));
+    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, S, s1, L.work, wd, L.hwork, wh, L.dinfo + 1));
     HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, &wd, &wh));
     HB_CHECK(L.ensure(wd, wh));
-    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 1));
+    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 2));
     if (s2 > 0) {
-      HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_UNIT, s2, s1, &one, F11, ld, F21, ld, F21, ld));
+      HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, S, s1, F21, ld, F21, ld));
       HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s1, s2, &one, F11, ld, F12, ld, F12, ld));
     }
-    k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(F, s1, s2, 0, 1, panL);
-    k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(F, s1, s2, 1, 0, panU);
+    k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(S, s1, F, s1, s2, 0, panL);
+    k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(nullptr, 0, F, s1, s2, 1, panU);
   }
   return 0;
 }
@@ -499,7 +524,7 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
     NF_CUDA(cudaMemcpyAsync(hinfo, d_info, sizeof(hinfo), cudaMemcpyDeviceToHost, st));
     NF_CUDA(cudaMemcpyAsync(linfo, L.dinfo, sizeof(linfo), cudaMemcpyDeviceToHost, st));
     NF_CUDA(cudaStreamSynchronize(st));
-    if (hinfo[0] != 0 || linfo[0] != 0 || linfo[1] != 0) {
+    if (hinfo[0] != 0 || linfo[0] != 0 || linfo[1] != 0 || linfo[2] != 0) {
       set_error("numfact: %s pivot breakdown at level %d (front %d, potrf/getrf info %d, trtri info %d)", symmetric ? "Cholesky" : "LU", l, hinfo[0] - 1,
                 linfo[0], linfo[1]);
       cleanup();
@@ -534,6 +559,7 @@ int numfact_device(Sub *s, const HostCSR &A) {
   auto t0 = std::chrono::steady_clock::now();
   free_factor(s->fac);
   int leaf = 64;
+  if (const char *e = getenv("HPDDM_B200_SMALL")) SMALL = atoi(e);
   if (const char *e = getenv("HPDDM_B200_LEAF")) leaf = std::max(1, atoi(e));
   HB_CHECK(symbolic_analyze(A, s->gx, s->gy, s->gz, s->gdof, leaf, s->sym));
   auto t1 = std::chrono::steady_clock::now();
@@ -551,7 +577,10 @@ int numfact_device(Sub *s, const HostCSR &A) {
   int rc = HPDDM_B200_ERR_NUMERIC;
   const bool force_lu = getenv("HPDDM_B200_FORCE_LU") != nullptr;
   if (A.symmetric && !force_lu) rc = numfact_try(s, A, true);
-  if (rc == HPDDM_B200_ERR_NUMERIC) rc = numfact_try(s, A, false);
+  if (rc == HPDDM_B200_ERR_NUMERIC) {
+    if (A.symmetric && !force_lu) fprintf(stderr, "[hpddm_b200] subdomain %d: Cholesky failed (%s); retrying with LU\n", s->grank, get_error_msg());
+    rc = numfact_try(s, A, false);
+  }
   if (rc < 0) {
     free_factor(D);
     return rc;

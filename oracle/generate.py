@@ -1,256 +1,4 @@
-"""Problem generators (oracle side; test infrastructure only).
-
-``generate2d`` restates ``examples/generate.cpp:43-311`` of the reference
-(2-D cell-centred 5-point Poisson on [0,10]^2, xGrid x yGrid ranks, `overlap`
-extra cells on every interior side, ramp partition of unity, neighbour lists
-enumerated in global lexicographic order), *including* its quirk that the
-"row below/above" column offset is ``Nx/xGrid`` and not the local row length
-(``generate.cpp:202,219,233``) -- reproduced, not fixed.
-
-``generate3d`` is the 3-D generalisation used by BASELINE configs 2/3
-(7-point stencil, px x py x pz ranks) following the same conventions
-(SURVEY.md section 7 step 1); here the stencil offsets are the true local
-strides.
-
-Both return plain numpy/scipy objects, 'C' numbering.
-"""
-import numpy as np
-import scipy.sparse as sp
-
-
-def _split_grid_2d(size):
-    # generate.cpp:51-53
-    xg = int(np.sqrt(size))
-    while size % xg != 0:
-        xg -= 1
-    return xg, size // xg
-
-
-def _ramp(lo_art, hi_art, start, end, overlap):
-    """distance (in cells) to the artificial faces of one axis, +inf if none.
-    generate.cpp:96-186: d = layer_index / overlap on the first `overlap`
-    layers next to an artificial (interior) face."""
-    idx = np.arange(start, end)
-    dist = np.full(idx.shape, np.inf)
-    if lo_art:
-        dist = np.minimum(dist, idx - start)
-    if hi_art:
-        dist = np.minimum(dist, end - 1 - idx)
-    return dist
-
-
-def generate2d(rank, size, Nx=100, Ny=100, overlap=1, mu=0, sym=False, neumann=False, seed=1234):
-    """examples/generate.cpp:43-311.  Returns dict with keys
-    o (neighbour ranks, in the order the reference pushes them), mapping (list
-    of int32 arrays), ndof, Mat (csr; lower triangle with diagonal last in row if
-    sym), MatNeumann (csr or None), d, f (ndof x max(mu,1), F-order), box."""
-    xGrid, yGrid = _split_grid_2d(size)
-    y = rank // xGrid
-    x = rank - xGrid * y
-    iStart = max(x * Nx // xGrid - overlap, 0)
-    iEnd = min((x + 1) * Nx // xGrid + overlap, Nx)
-    jStart = max(y * Ny // yGrid - overlap, 0)
-    jEnd = min((y + 1) * Ny // yGrid + overlap, Ny)
-    w, h = iEnd - iStart, jEnd - jStart
-    ndof = w * h
-    dx = 10.0 / Nx
-    dy = 10.0 / Ny
-    # --- right-hand side (generate.cpp:69-92)
-    if mu == 0:
-        xsc, ysc = [6.5, 2.0, 7.0], [8.0, 7.0, 3.0]
-        rsc, asc = [0.3, 0.3, 0.4], [0.3, 0.2, -0.1]
-        ii, jj = np.meshgrid(np.arange(iStart, iEnd), np.arange(jStart, jEnd))
-        xx = dx * (ii + 0.5)
-        yy = dy * (jj + 0.5)
-        frs = np.ones_like(xx)
-        for n in range(3):
-            xd, yd = xx - xsc[n], yy - ysc[n]
-            m = np.sqrt(xd * xd + yd * yd) <= rsc[n]
-            frs = frs - np.where(m, asc[n] * np.cos(0.5 * np.pi * xd / rsc[n]) * np.cos(0.5 * np.pi * yd / rsc[n]), 0.0)
-        f = frs.reshape(-1, 1).copy(order="F")
-    else:
-        # the reference draws from std::random_device (not reproducible); the
-        # oracle uses a seeded stream instead
-        rs = np.random.RandomState(seed + rank)
-        f = np.asfortranarray(rs.uniform(0.0, 1.0, size=(mu, ndof)).T)
-    # --- partition of unity ramp (generate.cpp:94-186)
-    distx = _ramp(iStart != 0, iEnd != Nx, iStart, iEnd, overlap)
-    disty = _ramp(jStart != 0, jEnd != Ny, jStart, jEnd, overlap)
-    dist = np.minimum(distx[None, :], disty[:, None])
-    d = np.minimum(dist / overlap, 1.0).reshape(-1)
-    # --- neighbours + mappings, pushed in increasing-rank order
-    o, mapping = [], []
-    loc = np.arange(ndof).reshape(h, w)
-    for dyy in (-1, 0, 1):
-        for dxx in (-1, 0, 1):
-            if dxx == 0 and dyy == 0:
-                continue
-            nx_, ny_ = x + dxx, y + dyy
-            if not (0 <= nx_ < xGrid and 0 <= ny_ < yGrid):
-                continue
-            cols = slice(0, w) if dxx == 0 else (slice(0, 2 * overlap) if dxx < 0 else slice(w - 2 * overlap, w))
-            rows = slice(0, h) if dyy == 0 else (slice(0, 2 * overlap) if dyy < 0 else slice(h - 2 * overlap, h))
-            o.append(ny_ * xGrid + nx_)
-            mapping.append(loc[rows, cols].reshape(-1).astype(np.int32))
-    # --- matrix (generate.cpp:188-243), quirk: vertical offset = Nx / xGrid
-    off = Nx // xGrid
-    rows_, cols_, vals_ = [], [], []
-    rowsN, colsN, valsN = [], [], []
-    k = 0
-    for j in range(jStart, jEnd):
-        for i in range(iStart, iEnd):
-            ent = []
-            if j > jStart:
-                ent.append((k - off, -1 / (dy * dy), -1 / (dx * dx) if i == iStart else 0.0))
-            if i > iStart:
-                ent.append((k - 1, -1 / (dx * dx), -1 / (dy * dy) if j == jStart else 0.0))
-            ent.append((k, 2 / (dx * dx) + 2 / (dy * dy), 0.0))
-            if not sym:
-                if i < iEnd - 1:
-                    ent.append((k + 1, -1 / (dx * dx), -1 / (dy * dy) if j == jEnd - 1 else 0.0))
-                if j < jEnd - 1:
-                    ent.append((k + off, -1 / (dy * dy), -1 / (dx * dx) if i == iEnd - 1 else 0.0))
-            for c, v, _ in ent:
-                rows_.append(k)
-                cols_.append(c)
-                vals_.append(v)
-            if neumann:
-                # generate.cpp:245-297 (both branches produce the same full matrix)
-                entN = list(ent)
-                if sym:
-                    if i < iEnd - 1:
-                        entN.append((k + 1, -1 / (dx * dx), -1 / (dy * dy) if j == jEnd - 1 else 0.0))
-                    if j < jEnd - 1:
-                        entN.append((k + off, -1 / (dy * dy), -1 / (dx * dx) if i == iEnd - 1 else 0.0))
-                for c, v, extra in entN:
-                    rowsN.append(k)
-                    colsN.append(c)
-                    valsN.append(v + extra)
-            k += 1
-    Mat = _csr_keep_order(rows_, cols_, vals_, ndof)
-    MatN = _csr_keep_order(rowsN, colsN, valsN, ndof) if neumann else None
-    return dict(o=o, mapping=mapping, ndof=ndof, Mat=Mat, MatNeumann=MatN, d=d, f=f, sym=sym,
-                box=((iStart, iEnd), (jStart, jEnd)), grid=(xGrid, yGrid), dims=(w, h, 1))
-
-
-def _csr_keep_order(r, c, v, n):
-    """CSR with entries kept in insertion order (no sorting / duplicate merge);
-    out-of-range columns produced by the reference quirk cannot occur because
-    the reference guards with j>jStart / j<jEnd-1."""
-    r = np.asarray(r, dtype=np.int64)
-    ia = np.zeros(n + 1, dtype=np.int32)
-    np.add.at(ia, r + 1, 1)
-    ia = np.cumsum(ia).astype(np.int32)
-    A = sp.csr_matrix((np.asarray(v, dtype=np.float64), np.asarray(c, dtype=np.int32), ia), shape=(n, n))
-    return A
-
-
-def split_grid_3d(size):
-    """px*py*pz = size, as cubic as possible, px >= py >= pz (1,2,4,8 ->
-    1x1x1, 2x1x1, 2x2x1, 2x2x2: SURVEY.md section 8e)."""
-    best = None
-    for pz in range(1, size + 1):
-        if size % pz:
-            continue
-        for py in range(pz, size // pz + 1):
-            if (size // pz) % py:
-                continue
-            px = size // (pz * py)
-            if px < py:
-                continue
-            cost = px - pz
-            if best is None or cost < best[0]:
-                best = (cost, (px, py, pz))
-    return best[1]
-
-
-def generate3d(rank, size, N=(16, 16, 16), overlap=1, mu=1, grid=None, neumann=False, seed=1234, sym=False):
-    """3-D 7-point cell-centred Poisson on [0,10]^3, N = (Nx,Ny,Nz) cells,
-    grid = (px,py,pz) ranks (x fastest in rank numbering, as generate.cpp:55-56
-    does in 2-D).  Same conventions as generate2d; true local strides."""
-    Nx, Ny, Nz = N
-    px, py, pz = grid if grid is not None else split_grid_3d(size)
-    assert px * py * pz == size
-    z = rank // (px * py)
-    y = (rank - z * px * py) // px
-    x = rank - z * px * py - y * px
-    st = [max(x * Nx // px - overlap, 0), max(y * Ny // py - overlap, 0), max(z * Nz // pz - overlap, 0)]
-    en = [min((x + 1) * Nx // px + overlap, Nx), min((y + 1) * Ny // py + overlap, Ny), min((z + 1) * Nz // pz + overlap, Nz)]
-    w, h, t = en[0] - st[0], en[1] - st[1], en[2] - st[2]
-    ndof = w * h * t
-    hx, hy, hz = 10.0 / Nx, 10.0 / Ny, 10.0 / Nz
-    rs = np.random.RandomState(seed + rank)
-    f = np.asfortranarray(rs.uniform(0.0, 1.0, size=(max(mu, 1), ndof)).T)
-    dist = np.minimum(np.minimum(_ramp(st[0] != 0, en[0] != Nx, st[0], en[0], overlap)[None, None, :],
-                                 _ramp(st[1] != 0, en[1] != Ny, st[1], en[1], overlap)[None, :, None]),
-                      _ramp(st[2] != 0, en[2] != Nz, st[2], en[2], overlap)[:, None, None])
-    d = np.minimum(dist / overlap, 1.0).reshape(-1)
-    loc = np.arange(ndof).reshape(t, h, w)
-    o, mapping = [], []
-    dims = (w, h, t)
-    pos = (x, y, z)
-    pg = (px, py, pz)
-    for dz in (-1, 0, 1):
-        for dyy in (-1, 0, 1):
-            for dxx in (-1, 0, 1):
-                dd = (dxx, dyy, dz)
-                if dd == (0, 0, 0):
-                    continue
-                nb = [pos[a] + dd[a] for a in range(3)]
-                if not all(0 <= nb[a] < pg[a] for a in range(3)):
-                    continue
-                sl = []
-                for a in range(3):
-                    if dd[a] == 0:
-                        sl.append(slice(0, dims[a]))
-                    elif dd[a] < 0:
-                        sl.append(slice(0, 2 * overlap))
-                    else:
-                        sl.append(slice(dims[a] - 2 * overlap, dims[a]))
-                o.append(nb[2] * px * py + nb[1] * px + nb[0])
-                mapping.append(loc[sl[2], sl[1], sl[0]].reshape(-1).astype(np.int32))
-    # 7-point stencil, vectorised
-    kk = loc
-    cx, cy, cz = -1 / (hx * hx), -1 / (hy * hy), -1 / (hz * hz)
-    diag = 2 / (hx * hx) + 2 / (hy * hy) + 2 / (hz * hz)
-    R, C, V = [kk.reshape(-1)], [kk.reshape(-1)], [np.full(ndof, diag)]
-    VN = [np.full(ndof, diag)]
-    dN = np.zeros((t, h, w))
-    # Neumann (natural) condition on artificial faces: drop the missing
-    # neighbour from the diagonal as well
-    if st[0] != 0:
-        dN[:, :, 0] += cx
-    if en[0] != Nx:
-        dN[:, :, -1] += cx
-    if st[1] != 0:
-        dN[:, 0, :] += cy
-    if en[1] != Ny:
-        dN[:, -1, :] += cy
-    if st[2] != 0:
-        dN[0, :, :] += cz
-    if en[2] != Nz:
-        dN[-1, :, :] += cz
-    VN[0] = VN[0] + dN.reshape(-1)
-    for (a, b, c) in ((kk[:, :, 1:], kk[:, :, :-1], cx), (kk[:, 1:, :], kk[:, :-1, :], cy), (kk[1:, :, :], kk[:-1, :, :], cz)):
-        a, b = a.reshape(-1), b.reshape(-1)
-        R += [a, b]
-        C += [b, a]
-        V += [np.full(a.size, c), np.full(a.size, c)]
-        VN += [np.full(a.size, c), np.full(a.size, c)]
-    R, C = np.concatenate(R), np.concatenate(C)
-    Mat = sp.csr_matrix((np.concatenate(V), (R, C)), shape=(ndof, ndof))
-    Mat.sort_indices()
-    MatN = None
-    if neumann:
-        MatN = sp.csr_matrix((np.concatenate(VN), (R, C)), shape=(ndof, ndof))
-        MatN.sort_indices()
-    if sym:
-        Mat = sp.tril(Mat, format="csr")
-        Mat.sort_indices()
-    return dict(o=o, mapping=mapping, ndof=ndof, Mat=Mat, MatNeumann=MatN, d=d, f=f, sym=sym,
-                box=tuple(zip(st, en)), grid=(px, py, pz), dims=dims)
-
-
-def generate_world(size, dim=2, **kw):
-    gen = generate2d if dim == 2 else generate3d
-    return [gen(r, size, **kw) for r in range(size)]
+"""Inputs are produced by the driver-side generators (hpddm_b200/examples/generate.py, the
+mirror of the reference's examples/generate.cpp); re-exported here for the oracle's tests."""
+from hpddm_b200.examples.generate import *  # noqa: F401,F403
+from hpddm_b200.examples.generate import generate2d, generate3d, generate_world, split_grid_3d  # noqa: F401
