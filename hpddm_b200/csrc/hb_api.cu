@@ -77,13 +77,16 @@ static int nccl_load() {
   } while (0)
 constexpr int NCCL_INT32 = 2, NCCL_F64 = 8, NCCL_SUM = 0;
 
+// uploads are issued on the context's (non-blocking) stream and waited for: a plain cudaMemcpy
+// from pageable memory is neither ordered against that stream nor guaranteed to have landed
 template <class T>
-static int up(const std::vector<T> &v, T **d) {
+static int up(const std::vector<T> &v, T **d, cudaStream_t st) {
   if (*d) cudaFree(*d);
   *d = nullptr;
   if (v.empty()) return 0;
   HB_CUDA(cudaMalloc(d, v.size() * sizeof(T)));
-  HB_CUDA(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  HB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -459,9 +462,9 @@ int hpddm_b200_sub_set_matrix(hpddm_b200_sub *sub, int n, int nnz, const int *ia
   HB_CUDA(cudaSetDevice(s->ctx->device));
   HB_CHECK(to_host_csr(n, nnz, ia, ja, a, sym, numbering, s->A));
   s->n = n;
-  HB_CHECK(up(s->A.ia, &s->d_ia));
-  HB_CHECK(up(s->A.ja, &s->d_ja));
-  HB_CHECK(up(s->A.a, &s->d_a));
+  HB_CHECK(up(s->A.ia, &s->d_ia, s->ctx->stream));
+  HB_CHECK(up(s->A.ja, &s->d_ja, s->ctx->stream));
+  HB_CHECK(up(s->A.a, &s->d_a, s->ctx->stream));
   // Subdomain::boundaryCond (subdomain.hpp:310-336): a row is a boundary condition when its
   // diagonal is penalised (>= EPS*PEN) or when its part left of / on the diagonal is the identity
   s->bc.clear();
@@ -487,8 +490,8 @@ int hpddm_b200_sub_set_matrix(hpddm_b200_sub *sub, int n, int nnz, const int *ia
     bi.push_back(p.first);
     bv.push_back(p.second);
   }
-  HB_CHECK(up(bi, &s->d_bc_idx));
-  HB_CHECK(up(bv, &s->d_bc_val));
+  HB_CHECK(up(bi, &s->d_bc_idx, s->ctx->stream));
+  HB_CHECK(up(bv, &s->d_bc_val, s->ctx->stream));
   s->ctx->mu_cap = 0;  // work vectors depend on n
   return 0;
 }
@@ -526,9 +529,9 @@ int hpddm_b200_sub_set_neighbors(hpddm_b200_sub *sub, int count, const int *rank
       ebase[e] = s->nb_ptr[i];
       esize[e] = s->nb_ptr[i + 1] - s->nb_ptr[i];
     }
-  HB_CHECK(up(s->nb_idx, &s->d_map));
-  HB_CHECK(up(ebase, &s->d_ebase));
-  HB_CHECK(up(esize, &s->d_esize));
+  HB_CHECK(up(s->nb_idx, &s->d_map, s->ctx->stream));
+  HB_CHECK(up(ebase, &s->d_ebase, s->ctx->stream));
+  HB_CHECK(up(esize, &s->d_esize, s->ctx->stream));
   // unique targets, contributions in neighbour order
   std::vector<int> ord(s->h);
   std::iota(ord.begin(), ord.end(), 0);
@@ -544,9 +547,9 @@ int hpddm_b200_sub_set_neighbors(hpddm_b200_sub *sub, int count, const int *rank
   }
   if (!uidx.empty()) useg.push_back((int)upos.size());
   s->nuniq = (int)uidx.size();
-  HB_CHECK(up(uidx, &s->d_uidx));
-  HB_CHECK(up(useg, &s->d_useg));
-  HB_CHECK(up(upos, &s->d_upos));
+  HB_CHECK(up(uidx, &s->d_uidx, s->ctx->stream));
+  HB_CHECK(up(useg, &s->d_useg, s->ctx->stream));
+  HB_CHECK(up(upos, &s->d_upos, s->ctx->stream));
   s->ctx->mu_cap = 0;
   return 0;
 }
@@ -556,7 +559,7 @@ int hpddm_b200_sub_set_scaling(hpddm_b200_sub *sub, const double *d) {
   if (!s || !d) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(s->ctx->device));
   s->d_host.assign(d, d + s->n);
-  return up(s->d_host, &s->d_d);
+  return up(s->d_host, &s->d_d, s->ctx->stream);
 }
 
 int hpddm_b200_sub_set_grid_hint(hpddm_b200_sub *sub, int nx, int ny, int nz, int dof) {
@@ -630,7 +633,8 @@ int hpddm_b200_sub_set_vectors(hpddm_b200_sub *sub, const double *Z, int nu) {
   s->nu = nu;
   if (nu > 0) {
     HB_CUDA(cudaMalloc(&s->d_Z, (size_t)s->n * nu * sizeof(double)));
-    HB_CUDA(cudaMemcpy(s->d_Z, Z, (size_t)s->n * nu * sizeof(double), cudaMemcpyHostToDevice));
+    HB_CUDA(cudaMemcpyAsync(s->d_Z, Z, (size_t)s->n * nu * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+    HB_CUDA(cudaStreamSynchronize(s->ctx->stream));
   }
   return 0;
 }
@@ -703,8 +707,8 @@ static int install_coarse(Ctx *c, const std::vector<double> &E) {
   c->E_host = E;
   std::vector<double> Einv;
   HB_CHECK(invert_dense(N, E, Einv));
-  HB_CHECK(up(c->E_host, &c->d_E));
-  HB_CHECK(up(Einv, &c->d_Einv));
+  HB_CHECK(up(c->E_host, &c->d_E, c->stream));
+  HB_CHECK(up(Einv, &c->d_Einv, c->stream));
   if (c->d_R) cudaFree(c->d_R);
   HB_CUDA(cudaMalloc(&c->d_R, std::max(N, 1) * sizeof(double)));
   return 0;

@@ -324,12 +324,16 @@ static int factor_large(Libs &L, cudaStream_t st, double *F, int s1, int s2, boo
   return 0;
 }
 
+// NOTE: a plain cudaMemcpy from pageable memory may return before the DMA has landed and the
+// legacy default stream does not order against our non-blocking stream: every upload is
+// issued on the context's stream and waited for.
 template <class T>
-static int upload(const std::vector<T> &v, T **d) {
+static int upload(const std::vector<T> &v, T **d, cudaStream_t st) {
   *d = nullptr;
   if (v.empty()) return 0;
   HB_CUDA(cudaMalloc(d, v.size() * sizeof(T)));
-  HB_CUDA(cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMemcpyAsync(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+  HB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -448,13 +452,13 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
       return e__ == cudaErrorMemoryAllocation ? HPDDM_B200_ERR_NOMEM : HPDDM_B200_ERR_CUDA;        \
     }                                                                                             \
   } while (0)
-  NF_CHECK(upload(efront, &d_efront));
-  NF_CHECK(upload(erow, &d_erow));
-  NF_CHECK(upload(ecol, &d_ecol));
-  NF_CHECK(upload(eval, &d_eval));
-  NF_CHECK(upload(fs, &d_fs));
-  NF_CHECK(upload(foff, &d_foff));
-  NF_CHECK(upload(S.rel, &d_rel));
+  NF_CHECK(upload(efront, &d_efront, st));
+  NF_CHECK(upload(erow, &d_erow, st));
+  NF_CHECK(upload(ecol, &d_ecol, st));
+  NF_CHECK(upload(eval, &d_eval, st));
+  NF_CHECK(upload(fs, &d_fs, st));
+  NF_CHECK(upload(foff, &d_foff, st));
+  NF_CHECK(upload(S.rel, &d_rel, st));
   NF_CUDA(cudaMalloc(&d_info, 4 * sizeof(int)));
   NF_CUDA(cudaMemset(d_info, 0, 4 * sizeof(int)));
   if (cusolverDnCreate(&L.so) != CUSOLVER_STATUS_SUCCESS || cublasCreate(&L.bl) != CUBLAS_STATUS_SUCCESS) {
@@ -495,7 +499,7 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
       if (!tasks.empty()) {
         cudaFree(d_tasks);
         d_tasks = nullptr;
-        NF_CHECK(upload(tasks, &d_tasks));
+        NF_CHECK(upload(tasks, &d_tasks, st));
         k_extend_add<<<(unsigned)tasks.size(), 128, 0, st>>>(d_tasks, D.fronts, d_rel, d_foff, Fprev, Fcur, symmetric ? 1 : 0);
         s->ctx->launches++;
       }
@@ -508,7 +512,7 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
     if (!small_list.empty()) {
       cudaFree(d_list);
       d_list = nullptr;
-      NF_CHECK(upload(small_list, &d_list));
+      NF_CHECK(upload(small_list, &d_list, st));
       k_factor_small<<<(unsigned)small_list.size(), 256, 0, st>>>(d_list, D.fronts, d_foff, Fcur, D.panL, D.panU, symmetric ? 1 : 0, d_info);
       s->ctx->launches++;
     }
@@ -524,6 +528,25 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
     NF_CUDA(cudaMemcpyAsync(hinfo, d_info, sizeof(hinfo), cudaMemcpyDeviceToHost, st));
     NF_CUDA(cudaMemcpyAsync(linfo, L.dinfo, sizeof(linfo), cudaMemcpyDeviceToHost, st));
     NF_CUDA(cudaStreamSynchronize(st));
+    if (getenv("HPDDM_B200_DEBUG")) {
+      int nl = 0;
+      for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) nl += fs[S.level_order[q]] > SMALL;
+      fprintf(stderr, "[hpddm_b200] level %d: %d fronts (%d via cuSOLVER), F buffer %.3f GB, info small=%d lib=%d/%d/%d\n", l, S.level_ptr[l + 1] - S.level_ptr[l], nl,
+              lvl_elems[l] * 8e-9, hinfo[0], linfo[0], linfo[1], linfo[2]);
+      if (hinfo[0] != 0) {
+        const int f = hinfo[0] - 1;
+        const Front &fr = S.fronts[f];
+        fprintf(stderr, "[hpddm_b200]   failing front %d: p0 %d s1 %d s2 %d level %d parent %d children:", f, fr.p0, fr.s1, fr.s2, fr.level, fr.parent);
+        for (int c : S.children[f]) fprintf(stderr, " %d(s1 %d s2 %d lvl %d)", c, S.fronts[c].s1, S.fronts[c].s2, S.fronts[c].level);
+        fprintf(stderr, "\n");
+        std::vector<double> hf((size_t)fs[f] * fs[f]);
+        cudaMemcpyAsync(hf.data(), Fcur + foff[f], hf.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[hpddm_b200]   diag(F) after partial factorisation:");
+        for (int k = 0; k < fs[f] && k < 40; ++k) fprintf(stderr, " %.3g", hf[k + (size_t)k * fs[f]]);
+        fprintf(stderr, "\n");
+      }
+    }
     if (hinfo[0] != 0 || linfo[0] != 0 || linfo[1] != 0 || linfo[2] != 0) {
       set_error("numfact: %s pivot breakdown at level %d (front %d, potrf/getrf info %d, trtri info %d)", symmetric ? "Cholesky" : "LU", l, hinfo[0] - 1,
                 linfo[0], linfo[1]);
@@ -556,6 +579,7 @@ void free_factor(DeviceFactor &f) {
 }
 
 int numfact_device(Sub *s, const HostCSR &A) {
+  cudaStream_t st = s->ctx->stream;
   auto t0 = std::chrono::steady_clock::now();
   free_factor(s->fac);
   int leaf = 64;
@@ -566,11 +590,11 @@ int numfact_device(Sub *s, const HostCSR &A) {
   s->t_symbolic = std::chrono::duration<double>(t1 - t0).count();
   Symbolic &S = s->sym;
   DeviceFactor &D = s->fac;
-  HB_CHECK(upload(S.fronts, &D.fronts));
-  HB_CHECK(upload(S.rowidx, &D.rowidx));
-  HB_CHECK(upload(S.fwd, &D.fwd));
-  HB_CHECK(upload(S.bwd, &D.bwd));
-  HB_CHECK(upload(S.perm, &D.perm));
+  HB_CHECK(upload(S.fronts, &D.fronts, st));
+  HB_CHECK(upload(S.rowidx, &D.rowidx, st));
+  HB_CHECK(upload(S.fwd, &D.fwd, st));
+  HB_CHECK(upload(S.bwd, &D.bwd, st));
+  HB_CHECK(upload(S.perm, &D.perm, st));
   HB_CUDA(cudaMalloc(&D.b, (size_t)S.n * sizeof(double)));
   HB_CUDA(cudaMalloc(&D.y, (size_t)S.n * sizeof(double)));
   HB_CUDA(cudaMalloc(&D.x, (size_t)S.n * sizeof(double)));

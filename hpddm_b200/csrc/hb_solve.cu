@@ -32,8 +32,31 @@ __device__ __forceinline__ double2 ldg_stream(const double2 *p) {
   return r;
 }
 
-__global__ void __launch_bounds__(256) k_fwd(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
-                                             const int *__restrict__ rowidx, const double *__restrict__ pan, double *b, double *y) {
+// 8 row sums spread over the warp -> lane L (L % 4 == 0) ends up with the total of row
+// 4*bit4(L) + 2*bit3(L) + bit2(L): 9 shuffles instead of 40
+__device__ __forceinline__ double reduce8(double (&a)[8], int lane) {
+  const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double send = u16 ? a[i] : a[i + 4], keep = u16 ? a[i + 4] : a[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double send = u8 ? a[i] : a[i + 2], keep = u8 ? a[i + 2] : a[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const double send = u4 ? a[0] : a[1], keep = u4 ? a[1] : a[0];
+    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+  return a[0];
+}
+
+__global__ void __launch_bounds__(256, 3) k_fwd(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
+                                                const int *__restrict__ rowidx, const double *__restrict__ pan, double *b, double *y) {
   __shared__ __align__(16) double bs[8][FCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = (int64_t)blockIdx.x * 8 + warp;
@@ -65,83 +88,100 @@ __global__ void __launch_bounds__(256) k_fwd(const FwdItem *__restrict__ items, 
   __syncwarp();
   const int nv = (nc + 1) >> 1;
   const double2 *bs2 = reinterpret_cast<const double2 *>(mybs);
-  for (int r = 0; r < nrows; r += 4) {
-    const double2 *p0 = reinterpret_cast<const double2 *>(base + (int64_t)r * stride + c0);
-    const double2 *p1 = reinterpret_cast<const double2 *>(base + (int64_t)min(r + 1, nrows - 1) * stride + c0);
-    const double2 *p2 = reinterpret_cast<const double2 *>(base + (int64_t)min(r + 2, nrows - 1) * stride + c0);
-    const double2 *p3 = reinterpret_cast<const double2 *>(base + (int64_t)min(r + 3, nrows - 1) * stride + c0);
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 2
+  const int st2 = stride >> 1;  // row stride in double2
+  const int rsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  for (int r = 0; r < nrows; r += 8) {
+    const double2 *p = reinterpret_cast<const double2 *>(base + (int64_t)r * stride + c0);
+    const int nr = min(8, nrows - r);
+    double a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = 0.0;
     for (int j = lane; j < nv; j += 32) {
-      const double2 t0 = ldg_stream(p0 + j), t1 = ldg_stream(p1 + j), t2 = ldg_stream(p2 + j), t3 = ldg_stream(p3 + j);
+      double2 t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t[q] = (q < nr) ? ldg_stream(p + (int64_t)q * st2 + j) : make_double2(0.0, 0.0);
       const double2 bb = bs2[j];
-      a0 = fma(t0.x, bb.x, fma(t0.y, bb.y, a0));
-      a1 = fma(t1.x, bb.x, fma(t1.y, bb.y, a1));
-      a2 = fma(t2.x, bb.x, fma(t2.y, bb.y, a2));
-      a3 = fma(t3.x, bb.x, fma(t3.y, bb.y, a3));
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = fma(t[q].x, bb.x, fma(t[q].y, bb.y, a[q]));
     }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    a2 = warp_sum(a2);
-    a3 = warp_sum(a3);
-    if (lane < 4 && r + lane < nrows) {
-      const double v = lane == 0 ? a0 : (lane == 1 ? a1 : (lane == 2 ? a2 : a3));
-      if (pivot) atomicAdd(&y[f.p0 + RB * w.rblk + r + lane], v);
-      else atomicAdd(&b[rowidx[f.rptr + RB * (w.rblk - nb1) + r + lane]], -v);
+    const double v = reduce8(a, lane);
+    if ((lane & 3) == 0 && rsel < nr) {
+      if (pivot) atomicAdd(&y[f.p0 + RB * w.rblk + r + rsel], v);
+      else atomicAdd(&b[rowidx[f.rptr + RB * (w.rblk - nb1) + r + rsel]], -v);
     }
   }
 }
 
-__global__ void __launch_bounds__(256) k_bwd(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
-                                             const int *__restrict__ rowidx, const double *__restrict__ pan, const double *__restrict__ y, double *x) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t it = (int64_t)blockIdx.x * 8 + warp;
-  if (it >= nitems) return;
-  const BwdItem w = items[it];
-  const Front f = fronts[w.front];
+// NJ = number of 64-column slabs of the chunk this lane covers (1, 2 or 4); rows are
+// processed in groups of 8/NJ so that 8 128-bit loads are in flight per lane
+template <int NJ>
+__device__ __forceinline__ void bwd_item(const BwdItem &w, const Front &f, const int *__restrict__ rowidx, const double *__restrict__ pan,
+                                         const double *__restrict__ y, double *x, int lane) {
+  constexpr int G = 8 / NJ;
   const int s1 = f.s1, ldp = hb_ldp(s1);
   const double *P = pan + f.poff;
   const double *Pu = P + hb_upd_off(s1);
-  double2 acc[4];
+  double2 acc[NJ];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) acc[j] = make_double2(0.0, 0.0);
+  for (int j = 0; j < NJ; ++j) acc[j] = make_double2(0.0, 0.0);
   const int cl = w.c0 + 2 * lane;  // this lane's first column
   for (int rb = 0; rb < w.nr; rb += 32) {
     const int r = w.r0 + rb + lane;
     double u = 0.0;
     if (rb + lane < w.nr) u = (r < s1) ? y[f.p0 + r] : -x[rowidx[f.rptr + r - s1]];
     const int nq = min(32, w.nr - rb);
-#pragma unroll 4
-    for (int q = 0; q < nq; ++q) {
-      const double uq = __shfl_sync(0xffffffffu, u, q);
-      const int rr = w.r0 + rb + q;
-      const double *rowp;
-      int wlim;
-      if (rr < s1) {
-        const int k = rr / RB;
-        wlim = hb_wblk(s1, k);
-        rowp = P + hb_blk_off(k) + (int64_t)(rr - k * RB) * wlim;
-      } else {
-        wlim = ldp;
-        rowp = Pu + (int64_t)(rr - s1) * ldp;
-      }
+    for (int q = 0; q < nq; q += G) {
+      double2 t[G][NJ];
+      double uq[G];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = cl + 64 * j;
-        if (c < wlim) {
-          const double2 t = ldg_stream(reinterpret_cast<const double2 *>(rowp + c));
-          acc[j].x = fma(t.x, uq, acc[j].x);
-          acc[j].y = fma(t.y, uq, acc[j].y);
+      for (int g = 0; g < G; ++g) {
+        uq[g] = __shfl_sync(0xffffffffu, u, (q + g) & 31);
+        const int rr = w.r0 + rb + q + g;
+        const double *rowp;
+        int wlim;
+        if (rr < s1) {
+          const int k = rr / RB;
+          wlim = hb_wblk(s1, k);
+          rowp = P + hb_blk_off(k) + (int64_t)(rr - k * RB) * wlim;
+        } else {
+          wlim = ldp;
+          rowp = Pu + (int64_t)(rr - s1) * ldp;
+        }
+        if (q + g >= nq) wlim = 0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int c = cl + 64 * j;
+          t[g][j] = (c < wlim) ? ldg_stream(reinterpret_cast<const double2 *>(rowp + c)) : make_double2(0.0, 0.0);
         }
       }
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          acc[j].x = fma(t[g][j].x, uq[g], acc[j].x);
+          acc[j].y = fma(t[g][j].y, uq[g], acc[j].y);
+        }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     const int c = cl + 64 * j;
     if (c < s1) atomicAdd(&x[f.p0 + c], acc[j].x);
     if (c + 1 < s1) atomicAdd(&x[f.p0 + c + 1], acc[j].y);
   }
+}
+
+__global__ void __launch_bounds__(256, 3) k_bwd(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
+                                                const int *__restrict__ rowidx, const double *__restrict__ pan, const double *__restrict__ y, double *x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t it = (int64_t)blockIdx.x * 8 + warp;
+  if (it >= nitems) return;
+  const BwdItem w = items[it];
+  const Front f = fronts[w.front];
+  const int width = min(BCH, hb_ldp(f.s1) - w.c0);
+  if (width <= 64) bwd_item<1>(w, f, rowidx, pan, y, x, lane);
+  else if (width <= 128) bwd_item<2>(w, f, rowidx, pan, y, x, lane);
+  else bwd_item<4>(w, f, rowidx, pan, y, x, lane);
 }
 
 __global__ void k_perm_in(int n, const int *__restrict__ perm, const double *__restrict__ in, double *b, double *y, double *x) {
