@@ -231,9 +231,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--m", type=int, default=int(os.environ.get("HPDDM_B200_BENCH_M", 96)), help="cells per subdomain edge")
+    ap.add_argument("--cells", dest="m", type=int, default=int(os.environ.get("HPDDM_B200_BENCH_M", 96)), help="cells per subdomain edge")
     ap.add_argument("--nu", type=int, default=20)
-    ap.add_argument("--cpu-m", type=int, default=40)
+    ap.add_argument("--cpu-cells", dest="cpu_m", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":

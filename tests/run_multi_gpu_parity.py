@@ -1,0 +1,71 @@
+"""Multi-GPU parity driver (launch with torchrun, one rank per GPU):
+every rank hosts one subdomain, halo + coarse gather go over NCCL; each rank
+rebuilds the whole decomposition with the CPU oracle (small sizes) and checks its
+own slice of apply / deflation / GMV / GMRES.  Exit code != 0 on mismatch."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from hpddm_b200 import Decomposition, KrylovOperator
+    from hpddm_b200.examples.generate import generate_world, split_grid_3d
+    from oracle.krylov import OracleOperator, gmres
+    from oracle.schwarz import ADDITIVE, BALANCED, DEFLATED, SchwarzWorld
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    grid = split_grid_3d(world)
+    m = int(os.environ.get("PARITY_M", 10))
+    N = tuple(g * m for g in grid)
+    parts = generate_world(world, dim=3, N=N, overlap=1, mu=2, grid=grid, neumann=True)
+    w = SchwarzWorld(parts)
+    w.multiplicity_scaling()
+    w.numfact()
+    w.solve_gevp([p["MatNeumann"] for p in parts], nu=3)
+    w.build_coarse()
+    deco = Decomposition(local)
+    deco.comm_init_torch()
+    p = parts[rank]
+    s = deco.add(rank)
+    s.initialize(p["Mat"], p["o"], p["mapping"])
+    s.setGridHint(*p["dims"])
+    d = deco.multiplicityScaling([p["d"]])[0]
+    ok = np.abs(d - w.d[rank]).max() < 1e-15
+    s.callNumfact()
+    s.setVectors(w.Z[rank])
+    deco.buildTwo()
+    E = deco.getCoarse()
+    errs = {"E": np.abs(E - w.E).max() / np.abs(w.E).max()}
+    rs = np.random.RandomState(7)
+    x_all = [np.asfortranarray(rs.standard_normal(q["f"].shape)) for q in parts]
+    for name, corr in (("one-level", None), ("deflated", DEFLATED), ("additive", ADDITIVE), ("balanced", BALANCED)):
+        ref = w.apply(x_all, corr)[rank]
+        got = deco.apply([x_all[rank]], corr)[0]
+        errs[name] = np.abs(got - ref).max() / np.abs(ref).max()
+    ref = w.GMV(x_all)[rank]
+    errs["gmv"] = np.abs(deco.GMV([x_all[rank]])[0] - ref).max() / np.abs(ref).max()
+    ref = w.deflation(x_all)[rank]
+    errs["deflation"] = np.abs(deco.deflation([x_all[rank]])[0] - ref).max() / np.abs(ref).max()
+    b_all = w.exchange([q["f"].copy() for q in parts])
+    it_ref, x_ref, _ = gmres(OracleOperator(w, DEFLATED), b_all)
+    it_gpu, x_gpu, _ = gmres(KrylovOperator(deco, DEFLATED), [b_all[rank]])
+    errs["gmres_x"] = np.abs(x_gpu[0] - x_ref[rank]).max() / np.abs(x_ref[rank]).max()
+    bad = (not ok) or it_gpu != it_ref or any(v > 1e-10 for k, v in errs.items() if k != "gmres_x") or errs["gmres_x"] > 1e-7
+    print(f"rank {rank}/{world}: d_ok={ok} it_gpu={it_gpu} it_ref={it_ref} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()) + (" FAIL" if bad else " OK"), flush=True)
+    t = torch.tensor([1.0 if bad else 0.0], device="cuda")
+    dist.all_reduce(t)
+    deco.close()
+    dist.destroy_process_group()
+    sys.exit(1 if t.item() > 0 else 0)
+
+
+if __name__ == "__main__":
+    main()
