@@ -1,0 +1,66 @@
+"""Runs oracle/_ref/ref_driver (the UNMODIFIED reference headers + examples/generate.cpp,
+built by this directory's Makefile) and stores its per-rank dumps as tests/golden/*.npz.
+
+    python oracle/ref_build/make_goldens.py
+
+The goldens pin (a) the driver-side generator, (b) the oracle restatement and (c) the CUDA
+path against outputs of the reference itself (tests/test_golden_reference.py).
+"""
+import os
+import struct
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # BASELINE config 1 (examples/schwarz.cpp test line, Makefile:310 of the reference)
+    "config1_100x100_p4_ras": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_gmres_restart=25", "-hpddm_max_it", "80", "-Nx", "100", "-Ny", "100"]),
+    # small cases with every hot-path output
+    "small_40x40_p4_ras": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40"]),
+    "small_40x40_p4_twolevel_nu3": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40"]),
+    "small_48x30_p6_ov2_twolevel_nu2": dict(np=6, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "2", "-Nx", "48", "-Ny", "30", "-overlap", "2"]),
+    "small_36x36_p4_symcsr_twolevel_nu2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "2", "-Nx", "36", "-Ny", "36", "-symmetric_csr", "1"]),
+}
+
+
+def read_dump(path):
+    out = {}
+    with open(path, "rb") as f:
+        while True:
+            h = f.read(4)
+            if len(h) < 4:
+                break
+            (ln,) = struct.unpack("i", h)
+            name = f.read(ln).decode()
+            t = f.read(1).decode()
+            (cnt,) = struct.unpack("q", f.read(8))
+            out[name] = np.frombuffer(f.read(cnt * (8 if t == "d" else 4)), dtype=np.float64 if t == "d" else np.int32).copy()
+    return out
+
+
+def main():
+    if not os.path.exists(DRIVER):
+        sys.exit("oracle/_ref/ref_driver missing: run `make -C oracle/ref_build` where /root/reference exists")
+    os.makedirs(OUT, exist_ok=True)
+    for name, case in CASES.items():
+        with tempfile.TemporaryDirectory() as tmp:
+            env = dict(os.environ, HPDDM_SHIM_NP=str(case["np"]), HPDDM_REF_DUMP=os.path.join(tmp, "g"))
+            res = subprocess.run([DRIVER] + case["args"], env=env, cwd=tmp, capture_output=True, text=True, timeout=600)
+            line = [ln for ln in res.stdout.splitlines() if ln.startswith("ref_driver:")]
+            print(name, line)
+            blob = {"args": np.array(" ".join(case["args"])), "np": np.array(case["np"])}
+            for r in range(case["np"]):
+                for k, v in read_dump(os.path.join(tmp, f"g_{r}.bin")).items():
+                    blob[f"r{r}_{k}"] = v
+            np.savez_compressed(os.path.join(OUT, name + ".npz"), **blob)
+
+
+if __name__ == "__main__":
+    main()

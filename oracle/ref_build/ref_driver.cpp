@@ -1,0 +1,137 @@
+// Golden-vector generator: drives the UNMODIFIED reference headers (HPDDM::Schwarz, the
+// reference's examples/generate.cpp, IterativeMethod::solve) and dumps inputs/outputs of the
+// hot path per rank.  Built by oracle/ref_build/Makefile against the in-box MPI shim, the
+// dense LAPACK SUBDOMAIN/COARSEOPERATOR plugins (-DLAPACKSUB -DDLAPACK) and scipy's OpenBLAS.
+// Mirrors the control flow of the reference's examples/schwarz.cpp:40-147 (which cannot dump).
+// TEST INFRASTRUCTURE ONLY.
+#include "schwarz.hpp"  // the reference's examples/schwarz.hpp (K, symCoarse, generate())
+
+#include <cstdio>
+#include <string>
+
+static FILE *g_out = nullptr;
+static void dump(const char *name, char type, const void *data, long long count) {
+  int len = (int)strlen(name);
+  fwrite(&len, sizeof(int), 1, g_out);
+  fwrite(name, 1, len, g_out);
+  fwrite(&type, 1, 1, g_out);
+  fwrite(&count, sizeof(long long), 1, g_out);
+  fwrite(data, type == 'd' ? 8 : 4, count, g_out);
+}
+static void dumpd(const char *name, const double *d, long long n) { dump(name, 'd', d, n); }
+static void dumpi(const char *name, const int *d, long long n) { dump(name, 'i', d, n); }
+
+int main(int argc, char **argv) {
+  MPI_Init(&argc, &argv);
+  int rankWorld, sizeWorld;
+  MPI_Comm_size(MPI_COMM_WORLD, &sizeWorld);
+  MPI_Comm_rank(MPI_COMM_WORLD, &rankWorld);
+  HPDDM::Option &opt = *HPDDM::Option::get();
+  opt.parse(argc, argv, false,
+            {std::forward_as_tuple("overlap=<1>", "Number of grid points in the overlap.", HPDDM::Option::Arg::positive),
+             std::forward_as_tuple("Nx=<100>", "Number of grid points in the x-direction.", HPDDM::Option::Arg::positive),
+             std::forward_as_tuple("Ny=<100>", "Number of grid points in the y-direction.", HPDDM::Option::Arg::positive),
+             std::forward_as_tuple("generate_random_rhs=<0>", "Number of generated random right-hand sides.", HPDDM::Option::Arg::integer),
+             std::forward_as_tuple("symmetric_csr=(0|1)", "Assemble symmetric matrices.", HPDDM::Option::Arg::argument),
+             std::forward_as_tuple("nonuniform=(0|1)", "Use a different number of eigenpairs to compute on each subdomain.", HPDDM::Option::Arg::argument),
+             std::forward_as_tuple("deflation_vectors=<0>", "Number of analytic deflation vectors per subdomain (golden runs).", HPDDM::Option::Arg::integer),
+             std::forward_as_tuple("prefix=<string>", "Use a prefix.", HPDDM::Option::Arg::argument)});
+  std::string out = getenv("HPDDM_REF_DUMP") ? getenv("HPDDM_REF_DUMP") : "golden";
+  out += "_" + std::to_string(rankWorld) + ".bin";
+  g_out = fopen(out.c_str(), "wb");
+  std::vector<std::vector<int>> mapping;
+  mapping.reserve(8);
+  std::list<int> o;
+  HPDDM::MatrixCSR<K> *Mat, *MatNeumann = nullptr;
+  K *f, *sol;
+  HPDDM::underlying_type<K> *d = nullptr;
+  int ndof;
+  generate(rankWorld, sizeWorld, o, mapping, ndof, Mat, MatNeumann, d, f, sol);
+  const int mu = 1;
+  {
+    int hdr[4] = {ndof, Mat->nnz_, (int)Mat->sym_, sizeWorld};
+    dumpi("header", hdr, 4);
+    dumpi("ia", Mat->ia_, ndof + 1);
+    dumpi("ja", Mat->ja_, Mat->nnz_);
+    dumpd("a", Mat->a_, Mat->nnz_);
+    dumpd("d_ramp", d, ndof);
+    dumpd("f", f, ndof);
+    std::vector<int> ov(o.begin(), o.end());
+    dumpi("o", ov.data(), ov.size());
+    for (size_t i = 0; i < mapping.size(); ++i) dumpi(("mapping" + std::to_string(i)).c_str(), mapping[i].data(), mapping[i].size());
+  }
+  HPDDM::Schwarz<SUBDOMAIN, COARSEOPERATOR, symCoarse, K> A;
+  A.Subdomain::initialize(Mat, o, mapping);
+  decltype(mapping)().swap(mapping);
+  A.multiplicityScaling(d);
+  A.initialize(d);
+  dumpd("d", d, ndof);
+  const int nuOpt = (int)opt.app()["deflation_vectors"];
+  int nu = 0;
+  if (nuOpt > 0) {
+    // analytic deflation vectors (stand-in for the GenEO eigenvectors: Z is an INPUT of the hot path)
+    nu = nuOpt;
+    K **deflation = new K *[nu];
+    *deflation = new K[(size_t)nu * ndof];
+    for (int k = 0; k < nu; ++k) {
+      deflation[k] = *deflation + (size_t)k * ndof;
+      for (int i = 0; i < ndof; ++i) deflation[k][i] = k == 0 ? 1.0 : std::cos(3.141592653589793 * k * (i + 0.5) / ndof) + 0.1 * ((i * 7 + k) % 5);
+    }
+    dumpd("Z", *deflation, (long long)nu * ndof);
+    A.setVectors(deflation);
+    opt["geneo_nu"] = nu;
+    if (!opt.set("schwarz_coarse_correction")) opt["schwarz_coarse_correction"] = HPDDM_SCHWARZ_COARSE_CORRECTION_DEFLATED;
+    A.super::initialize(nu);
+    A.buildTwo(MPI_COMM_WORLD);
+  }
+  A.callNumfact();
+  // deterministic, consistent input vector
+  std::vector<K> v(ndof), w(ndof), work(ndof);
+  for (int i = 0; i < ndof; ++i) v[i] = std::sin(0.37 * i + 0.11 * rankWorld) + 0.5;
+  A.exchange<true>(v.data(), 1);
+  dumpd("v", v.data(), ndof);
+  {
+    std::vector<K> x(v);
+    bool alloc = A.setBuffer();
+    A.Subdomain::exchange(x.data(), 1);
+    dumpd("subdomain_exchange_v", x.data(), ndof);
+    A.GMV(v.data(), w.data(), 1);
+    A.clearBuffer(alloc);
+    dumpd("gmv_v", w.data(), ndof);
+  }
+  {
+    std::vector<K> x(ndof, K());
+    bool alloc = A.start(f, x.data(), 1);  // allocates halo buffers + uc_ like the Krylov drivers do
+    const double saved = nuOpt > 0 ? opt["schwarz_coarse_correction"] : -1.0;
+    if (nuOpt > 0) opt.remove("schwarz_coarse_correction");
+    A.apply(v.data(), w.data(), 1, work.data());
+    dumpd("apply_onelevel_v", w.data(), ndof);
+    if (nuOpt > 0) {
+      A.deflation<false>(v.data(), w.data(), 1);
+      dumpd("deflation_v", w.data(), ndof);
+      const char *names[3] = {"apply_deflated_v", "apply_additive_v", "apply_balanced_v"};
+      const double vals[3] = {HPDDM_SCHWARZ_COARSE_CORRECTION_DEFLATED, HPDDM_SCHWARZ_COARSE_CORRECTION_ADDITIVE, HPDDM_SCHWARZ_COARSE_CORRECTION_BALANCED};
+      for (int c = 0; c < 3; ++c) {
+        opt["schwarz_coarse_correction"] = vals[c];
+        A.apply(v.data(), w.data(), 1, work.data());
+        dumpd(names[c], w.data(), ndof);
+      }
+      opt["schwarz_coarse_correction"] = saved;
+    }
+    A.end(alloc);
+  }
+  int it = HPDDM::IterativeMethod::solve(A, f, sol, mu, A.getCommunicator());
+  HPDDM::underlying_type<K> storage[2];
+  A.computeResidual(sol, f, storage, mu);
+  dumpi("iterations", &it, 1);
+  dumpd("sol", sol, ndof);
+  dumpd("residual", storage, 2);
+  if (rankWorld == 0) printf("ref_driver: %d ranks, ndof %d, nu %d, it %d, residual %.3e / %.3e\n", sizeWorld, ndof, nu, it, storage[1], storage[0]);
+  fclose(g_out);
+  delete[] d;
+  delete MatNeumann;
+  delete[] sol;
+  delete[] f;
+  MPI_Finalize();
+  return 0;
+}

@@ -153,15 +153,21 @@ class SchwarzWorld:
 
     # ------------------------------------------------------ boundary conditions
     def boundary_conditions(self, r):
-        """Subdomain::boundaryCond(itions) (subdomain.hpp:310-336): rows that are
-        the identity scaled by a penalty >= EPS*PEN (none for the Poisson
-        generators, whose diagonals are O(1e2))."""
+        """Subdomain::boundaryCond(itions) (subdomain.hpp:310-336): row i is a boundary
+        condition when its diagonal is penalised (|a_ii| >= EPS*PEN) or when the part of the
+        row left of / on the diagonal is the identity; value = a_ii.  None for the Poisson
+        generators (diagonals O(1e2), non-trivial rows)."""
         A = self.A[r]
         out = {}
         dg = A.diagonal()
-        cand = np.nonzero(np.abs(dg) >= HPDDM_EPS * HPDDM_PEN)[0]
-        for i in cand:
+        for i in np.nonzero(np.abs(dg) >= HPDDM_EPS * HPDDM_PEN)[0]:
             out[int(i)] = dg[i]
+        for i in np.nonzero(np.abs(dg - 1.0) <= HPDDM_EPS)[0]:
+            lo, hi = A.indptr[i], A.indptr[i + 1]
+            cols, vals = A.indices[lo:hi], A.data[lo:hi]
+            left = cols < i
+            if not np.any(np.abs(vals[left]) > HPDDM_EPS):
+                out[int(i)] = dg[i]
         return out
 
     def start(self, b, x):
@@ -237,7 +243,7 @@ class SchwarzWorld:
         self.set_vectors(Z)
         return Z
 
-    def build_coarse(self):
+    def build_coarse(self, lapack_tr_quirk=False):
         """Galerkin coarse operator E = Z^H A Z, block (i,j):
         E_ii = Z_i^H D_i A_i D_i Z_i ; E_ij = Z_i^H D_i R_ij (A_j D_j Z_j)
         (operator.hpp:395-403 applyFromNeighbor, 440-503 C = A*D with columns
@@ -262,7 +268,14 @@ class SchwarzWorld:
                 E[off[i]:off[i + 1], off[j]:off[j + 1]] = self.Z[i].T @ tmp
         self.E = E
         self.off = off
-        self.Elu = sla.lu_factor(E)
+        # Plugin quirk, reproduced only on request: the reference's dense LAPACK coarse solver
+        # (LapackTR, HPDDM_LAPACK.hpp:349-356 via numfact<numbering_, true> at :426) fills its dense
+        # array transposed when the coarse pattern is not full, and then calls getrs("N"): it solves
+        # E^T y = rhs.  Invisible for symmetric E (every SPD configuration), visible with the
+        # non-symmetric matrices of the 2-D generator on > 4 ranks.  The sparse coarse solvers
+        # (MUMPS / SuiteSparse) and this repo's CUDA path solve E y = rhs.
+        full = all(len(self.map[i]) == self.P - 1 for i in range(self.P))
+        self.Elu = sla.lu_factor(E.T if (lapack_tr_quirk and not full) else E)
         return E
 
     def call_solver(self, uc):

@@ -1,0 +1,44 @@
+"""Loader for tests/golden/*.npz (outputs of the unmodified reference, see
+oracle/ref_build/make_goldens.py)."""
+import glob
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def cases():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def arg_value(args, key, default):
+    toks = args.replace("=", " ").split()
+    for i, t in enumerate(toks):
+        if t.lstrip("-") == key.lstrip("-") and i + 1 < len(toks):
+            return toks[i + 1]
+    return default
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    P = int(z["np"])
+    args = str(z["args"])
+    parts, ref = [], []
+    for r in range(P):
+        g = {k[len(f"r{r}_"):]: z[k] for k in z.files if k.startswith(f"r{r}_")}
+        n, nnz, sym, _ = [int(v) for v in g["header"]]
+        Mat = sp.csr_matrix((g["a"], g["ja"], g["ia"]), shape=(n, n))
+        mapping = [g[f"mapping{i}"] for i in range(len(g["o"]))]
+        parts.append(dict(o=[int(v) for v in g["o"]], mapping=mapping, ndof=n, Mat=Mat, sym=bool(sym), d=g["d_ramp"].copy(),
+                          f=np.asfortranarray(g["f"].reshape(-1, 1))))
+        ref.append(g)
+    meta = dict(P=P, args=args, Nx=int(arg_value(args, "Nx", 100)), Ny=int(arg_value(args, "Ny", 100)), overlap=int(arg_value(args, "overlap", 1)),
+                sym=arg_value(args, "symmetric_csr", "0") == "1", nu=int(arg_value(args, "deflation_vectors", 0)),
+                restart=int(arg_value(args, "hpddm_gmres_restart", 40)), max_it=int(arg_value(args, "hpddm_max_it", 100)))
+    return parts, ref, meta
+
+
+def col(v):
+    return np.asfortranarray(np.asarray(v, dtype=np.float64).reshape(-1, 1))

@@ -1,0 +1,68 @@
+"""CPU: the driver-side generator and the oracle restatement against outputs of the
+UNMODIFIED reference (HPDDM headers + examples/generate.cpp compiled against the in-box MPI
+shim with the dense LAPACK plugins: oracle/ref_build/).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from hpddm_b200.examples.generate import generate2d
+from oracle.krylov import OracleOperator, gmres
+from oracle.schwarz import ADDITIVE, BALANCED, DEFLATED, SchwarzWorld
+from tests.golden_util import cases, col, load
+
+TOL = 1e-10
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a).reshape(-1) - np.asarray(b).reshape(-1)).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name", cases())
+def test_generator_is_bit_identical_to_examples_generate_cpp(name):
+    parts, ref, meta = load(name)
+    for r in range(meta["P"]):
+        mine = generate2d(r, meta["P"], Nx=meta["Nx"], Ny=meta["Ny"], overlap=meta["overlap"], mu=0, sym=meta["sym"])
+        g = ref[r]
+        assert mine["ndof"] == int(g["header"][0])
+        assert np.array_equal(mine["Mat"].indptr, g["ia"]) and np.array_equal(mine["Mat"].indices, g["ja"])
+        assert np.array_equal(mine["Mat"].data, g["a"])          # bit-exact values, same entry order
+        assert np.array_equal(mine["d"], g["d_ramp"])
+        assert mine["o"] == [int(v) for v in g["o"]]
+        for a, b in zip(mine["mapping"], parts[r]["mapping"]):
+            assert np.array_equal(a, b)
+        assert rel(mine["f"], g["f"]) < 1e-15
+
+
+@pytest.mark.parametrize("name", cases())
+def test_oracle_reproduces_the_reference(name):
+    parts, ref, meta = load(name)
+    P = meta["P"]
+    w = SchwarzWorld(parts)
+    w.multiplicity_scaling()
+    for r in range(P):
+        assert np.abs(w.d[r] - ref[r]["d"]).max() < 1e-15
+    w.numfact()
+    v = [col(ref[r]["v"]) for r in range(P)]
+    got = w.subdomain_exchange([x.copy() for x in v])
+    assert max(rel(got[r], ref[r]["subdomain_exchange_v"]) for r in range(P)) < 1e-14
+    got = w.GMV(v)
+    assert max(rel(got[r], ref[r]["gmv_v"]) for r in range(P)) < 1e-13
+    got = w.apply(v, None)
+    assert max(rel(got[r], ref[r]["apply_onelevel_v"]) for r in range(P)) < TOL
+    corr = None
+    if meta["nu"] > 0:
+        w.set_vectors([ref[r]["Z"].reshape(meta["nu"], -1).T for r in range(P)])
+        # lapack_tr_quirk: see SchwarzWorld.build_coarse -- the goldens were produced with the dense LAPACK coarse plugin
+        w.build_coarse(lapack_tr_quirk=True)
+        got = w.deflation(v)
+        assert max(rel(got[r], ref[r]["deflation_v"]) for r in range(P)) < TOL
+        for c, key in ((DEFLATED, "apply_deflated_v"), (ADDITIVE, "apply_additive_v"), (BALANCED, "apply_balanced_v")):
+            got = w.apply(v, c)
+            assert max(rel(got[r], ref[r][key]) for r in range(P)) < TOL, key
+        corr = DEFLATED
+    b = [parts[r]["f"].copy() for r in range(P)]
+    it, x, _ = gmres(OracleOperator(w, corr), b, restart=meta["restart"], max_it=meta["max_it"])
+    assert it == int(ref[0]["iterations"][0])                      # identical Krylov iteration count
+    assert max(rel(x[r], ref[r]["sol"]) for r in range(P)) < 1e-7
+    res = w.compute_residual(x, b)
+    assert abs(res[0, 0] - ref[0]["residual"][0]) < 1e-10 * ref[0]["residual"][0]
+    assert abs(res[0, 1] - ref[0]["residual"][1]) < 1e-3 * ref[0]["residual"][1]
