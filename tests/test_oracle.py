@@ -61,3 +61,25 @@ def test_two_level_reduces_iterations_3d():
     lhs = np.concatenate([w.Z[r].T @ (w.d[r][:, None] * Aq[r]) for r in range(w.P)])
     rhs = np.concatenate([w.Z[r].T @ (w.d[r][:, None] * v[r]) for r in range(w.P)])
     assert np.abs(lhs - rhs).max() < 1e-9 * np.abs(rhs).max()
+
+
+def test_cpu_benchmark_arm_matches_the_oracle():
+    """oracle/cpu_ras.cpp (the CPU arm timed by bench.py) computes the same deflated apply."""
+    import bench
+    from hpddm_b200.examples.generate import generate3d
+    L = bench._cpu_lib()
+    m, nu = 14, 6
+    part = generate3d(0, 1, N=(m, m, m), overlap=1, mu=1, grid=(1, 1, 1))
+    Z = bench.cosine_modes(part["dims"], nu)
+    h = L.cpu_ras_create(m, nu, Z.ctypes.data, 2)
+    x = part["f"][:, 0].copy()
+    y = np.empty_like(x)
+    L.cpu_ras_apply(h, x.ctypes.data, y.ctypes.data)
+    L.cpu_ras_destroy(h)
+    w = SchwarzWorld([part])
+    w.multiplicity_scaling()
+    w.numfact()
+    w.set_vectors([Z])
+    w.build_coarse()
+    ref = w.apply([x.reshape(-1, 1)], DEFLATED)[0][:, 0]
+    assert np.abs(ref - y).max() / np.abs(ref).max() < 1e-12
