@@ -208,7 +208,8 @@ def cpu_baseline(args, m=None, steps=None, budget_s=150.0):
     CSR SpMV), all host threads, ONE subdomain of the same workload.  The subdomain edge is reduced
     (and reported) if the CPU factorisation would not fit the time budget."""
     L = _cpu_lib()
-    threads = os.cpu_count() or 1
+    # scipy's OpenBLAS is built for at most 128 threads *including callers*: stay well below
+    threads = max(1, min(os.cpu_count() or 1, 64))
     m = m or args.m
     # probe: factorisation time scales ~ m^6
     probe = min(m, 48)

@@ -764,9 +764,11 @@ int hpddm_b200_build_coarse(hpddm_b200_ctx *ctx) {
   double *d_rows = nullptr;  // Lnu x N, column-major
   HB_CUDA(cudaMalloc(&d_rows, std::max<size_t>((size_t)Lnu * N, 1) * sizeof(double)));
   HB_CUDA(cudaMemsetAsync(d_rows, 0, (size_t)Lnu * N * sizeof(double), c->stream));
-  // column block of global subdomain j: X = R_j^T D_j Z_j restricted to every subdomain
-  // (halo of a vector that is non-zero on j only), W = A_i X, block = Z_i^T D_i W.
-  // Equals E_ij = Z_i^H D_i R_ij (A_j D_j Z_j), include/HPDDM_operator.hpp:395-403,505-528.
+  // column block of global subdomain j, exactly the reference's formula
+  //   E_ij = Z_i^H D_i R_ij (A_j D_j Z_j)      (include/HPDDM_operator.hpp:395-403,505-528):
+  // W = A_j (D_j Z_j) is formed on j with j's OWN matrix (applyToNeighbor), its values on the
+  // shared dofs travel to the neighbours (an unscaled halo of a vector that is zero everywhere
+  // but on j), every subdomain i then projects Z_i^T (D_i W|_i) (applyFromNeighbor).
   std::vector<double *> X(L);
   for (int j = 0; j < P; ++j) {
     const int nuj = nu_all[j];
@@ -776,14 +778,16 @@ int hpddm_b200_build_coarse(hpddm_b200_ctx *ctx) {
     for (int i = 0; i < L; ++i) {
       Sub *s = c->subs[i];
       X[i] = s->d_work;
-      if (s->grank == j) HB_CHECK(k_scale(c, s->n, nuj, s->d_d, s->d_Z, s->d_work));
-      else HB_CUDA(cudaMemsetAsync(s->d_work, 0, (size_t)s->n * nuj * sizeof(double), c->stream));
+      if (s->grank == j) {
+        HB_CHECK(k_scale(c, s->n, nuj, s->d_d, s->d_Z, s->d_tmp));
+        HB_CHECK(k_spmv(c, s, nuj, 1.0, s->d_tmp, 0.0, nullptr, s->d_work, nullptr));
+      } else
+        HB_CUDA(cudaMemsetAsync(s->d_work, 0, (size_t)s->n * nuj * sizeof(double), c->stream));
     }
     HB_CHECK(halo(c, X.data(), nuj));
     for (int i = 0; i < L; ++i) {
       Sub *s = c->subs[i];
-      HB_CHECK(k_spmv(c, s, nuj, 1.0, s->d_work, 0.0, nullptr, s->d_tmp, nullptr));
-      HB_CHECK(k_zt_project(c, s, nuj, s->d_tmp, d_rows + s->coff + (size_t)gcol * Lnu, Lnu));
+      HB_CHECK(k_zt_project(c, s, nuj, s->d_work, d_rows + s->coff + (size_t)gcol * Lnu, Lnu));
     }
   }
   std::vector<double> E((size_t)N * N, 0.0);
