@@ -209,7 +209,8 @@ def cpu_baseline(args, m=None, steps=None, budget_s=150.0):
     (and reported) if the CPU factorisation would not fit the time budget."""
     L = _cpu_lib()
     # scipy's OpenBLAS is built for at most 128 threads *including callers*: stay well below
-    threads = max(1, min(os.cpu_count() or 1, 64))
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, min(avail, 64))
     m = m or args.m
     # probe: factorisation time scales ~ m^6
     probe = min(m, 48)
@@ -237,7 +238,7 @@ def cpu_baseline(args, m=None, steps=None, budget_s=150.0):
     nnz = L.cpu_ras_nnz_factor(h)
     tf = L.cpu_ras_factor_seconds(h)
     L.cpu_ras_destroy(h)
-    return {"value": 1.0 / dt, "unit": "subdomain-applies/s", "cores": threads, "kind": "port", "ms_per_apply": dt * 1e3,
+    return {"value": 1.0 / dt, "unit": "subdomain-applies/s", "cores": threads, "host_cpus": os.cpu_count(), "affinity_cpus": avail, "kind": "port", "ms_per_apply": dt * 1e3,
             "effective_gbs": (2 * 8 * nnz + 8 * n * (2 * args.nu + 12 + 7 * 1.5)) / dt / 1e9,
             "sample": f"oracle/cpu_ras.cpp (supernodal Cholesky + BLAS-2 supernodal solves, OpenMP x {threads} threads), one subdomain of {m}^3 cells"
                       f"{'' if m == args.m else f' (reduced from {args.m}^3 to fit the CPU time budget)'}, nu={args.nu}, {k} applies, nnz(L)={nnz:.3g}, CPU analysis+numfact {tf:.1f}s (setup {t_create:.1f}s)"}
