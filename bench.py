@@ -185,6 +185,18 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def usable_cpus():
+    """CPUs this process may really use: affinity mask capped by the cgroup CPU quota (cpu.max)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def _cpu_lib():
     import ctypes as C
     path = os.path.join(ROOT, "oracle", "_build", "libcpu_ras.so")
@@ -209,7 +221,7 @@ def cpu_baseline(args, m=None, steps=None, budget_s=150.0):
     (and reported) if the CPU factorisation would not fit the time budget."""
     L = _cpu_lib()
     # scipy's OpenBLAS is built for at most 128 threads *including callers*: stay well below
-    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    avail = usable_cpus()
     threads = max(1, min(avail, 64))
     m = m or args.m
     # probe: factorisation time scales ~ m^6
