@@ -117,12 +117,13 @@ def run_b200(args):
     deco.buildTwo()
     st = s.statistics()
     nnz_a = st["nnz_a"]
-    by = algorithmic_bytes(st, nnz_a, args.nu)
+    by = algorithmic_bytes(st, nnz_a, args.nu, args.mu)
     stream = torch.cuda.ExternalStream(deco.stream, device=local)
-    x_dev = torch.rand(n, dtype=torch.float64, device="cuda")
+    mu = args.mu
+    x_dev = torch.rand(n * mu, dtype=torch.float64, device="cuda")
     y_dev = torch.empty_like(x_dev)
-    x_pin = torch.rand(n, dtype=torch.float64).pin_memory()
-    y_pin = torch.empty(n, dtype=torch.float64).pin_memory()
+    x_pin = torch.rand(n * mu, dtype=torch.float64).pin_memory()
+    y_pin = torch.empty(n * mu, dtype=torch.float64).pin_memory()
     torch.cuda.synchronize()
 
     def barrier():
@@ -150,12 +151,12 @@ def run_b200(args):
     sampler = ClockSampler(local)
     sampler.start()
     l0 = deco.launches
-    ms_dev = timed(lambda: deco.apply_device([x_dev], [y_dev], 1, "deflated"), args.steps, args.warmup)
+    ms_dev = timed(lambda: deco.apply_device([x_dev], [y_dev], mu, "deflated"), args.steps, args.warmup)
     launches = (deco.launches - l0) // (args.steps + args.warmup) * args.steps
     # dominant kernel alone: the local triangular solves (forward + backward sweeps)
     from hpddm_b200 import capi
-    ms_trsv = timed(lambda: capi.check(capi.lib().hpddm_b200_sub_solve(s.h, x_dev.data_ptr(), y_dev.data_ptr(), 1, capi.DEVICE)), args.steps, args.warmup)
-    ms_e2e = timed(lambda: deco.apply_host_inplace([x_pin], [y_pin], 1, "deflated"), args.steps, args.warmup)
+    ms_trsv = timed(lambda: capi.check(capi.lib().hpddm_b200_sub_solve(s.h, x_dev.data_ptr(), y_dev.data_ptr(), mu, capi.DEVICE)), args.steps, args.warmup)
+    ms_e2e = timed(lambda: deco.apply_host_inplace([x_pin], [y_pin], mu, "deflated"), args.steps, args.warmup)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     peak, peak_src = peaks()
@@ -164,11 +165,11 @@ def run_b200(args):
         "metric": METRIC, "value": world * args.steps / (ms_dev * 1e-3), "unit": "subdomain-applies/s", "applies_per_s": args.steps / (ms_dev * 1e-3),
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config3 slice: 3-D Poisson {N[0]}x{N[1]}x{N[2]}, {world} subdomain(s) of {m}^3 cells + overlap 1 (n_loc={n}), two-level RAS deflated, nu={args.nu}, mu=1",
+        "config": {"workload": f"config3 slice: 3-D Poisson {N[0]}x{N[1]}x{N[2]}, {world} subdomain(s) of {m}^3 cells + overlap 1 (n_loc={n}), two-level RAS deflated, nu={args.nu}, mu={args.mu}",
                    "parallelism": f"{grid[0]}x{grid[1]}x{grid[2]} subdomains, 1/GPU", "l2": "inputs (factor panels) larger than L2, no flush needed",
                    "nnz_factor": st["nnz_factor"], "factor_gb": st["factor_bytes"] / 1e9, "levels": st["levels"], "fronts": st["fronts"],
                    "numfact_s": round(t_fact, 3), "symbolic_s": round(st["symbolic_seconds"], 3)},
-        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "subdomain-applies/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n,
+        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "subdomain-applies/s", "h2d_bytes_per_step": 8 * n * mu, "d2h_bytes_per_step": 8 * n * mu,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "supernodal SpTRSV sweeps (k_fwd + k_bwd, all levels)", "bound": "hbm", "achieved": trsv_gbs, "peak": peak, "peak_source": peak_src,
@@ -278,6 +279,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", dest="m", type=int, default=int(os.environ.get("HPDDM_B200_BENCH_M", 128)), help="cells per subdomain edge")
     ap.add_argument("--nu", type=int, default=20)
+    ap.add_argument("--rhs", dest="mu", type=int, default=1, help="right-hand sides per apply (block methods)")
     ap.add_argument("--cpu-cells", dest="cpu_m", type=int, default=0, help="subdomain edge of the CPU sample (0 = same as --cells)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

@@ -269,7 +269,12 @@ static int deflation_core(Ctx *c, const std::vector<const double *> &in, const s
 }
 
 static int solve_cols(Sub *s, const double *b, double *x, int mu, const double *scale, bool acc) {
-  for (int col = 0; col < mu; ++col) HB_CHECK(sptrsv_solve(s, b + (size_t)col * s->n, x + (size_t)col * s->n, scale, acc));
+  int col = 0;
+  while (col < mu) {  // panels are streamed once per group of 4 / 2 / 1 right-hand sides
+    const int g = (mu - col >= 4) ? 4 : ((mu - col >= 2) ? 2 : 1);
+    HB_CHECK(sptrsv_solve(s, b + (size_t)col * s->n, x + (size_t)col * s->n, g, scale, acc));
+    col += g;
+  }
   return 0;
 }
 

@@ -117,7 +117,9 @@ struct DeviceFactor {
   FwdItem *fwd = nullptr;
   BwdItem *bwd = nullptr;
   int *perm = nullptr;   // perm[new] = old
-  double *b = nullptr, *y = nullptr, *x = nullptr;  // permuted work vectors (n each)
+  double *b = nullptr, *y = nullptr, *x = nullptr;  // permuted work vectors (n * 4 each: up to 4 RHS per pass)
+  cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};  // captured sweep launches for mu = 1, 2, 4
+  int sweep_launches = 0;                                  // kernels inside one captured graph
 };
 
 struct Ctx;
@@ -190,9 +192,9 @@ struct Ctx {
 // ---------------------------------------------------------------- kernels (launchers)
 int numfact_device(Sub *s, const HostCSR &A);
 void free_factor(DeviceFactor &f);
-// x = A^{-1} b for one column, natural ordering in/out, device pointers.
+// x = A^{-1} b for mu in {1,2,4} columns (column stride n), natural ordering in/out, device pointers.
 // scale: optional d (natural order) applied on output (out = d .* x); accumulate: out += instead of =
-int sptrsv_solve(Sub *s, const double *b, double *x, const double *scale, bool accumulate);
+int sptrsv_solve(Sub *s, const double *b, double *x, int mu, const double *scale, bool accumulate);
 
 int k_scale(Ctx *c, int n, int mu, const double *d, const double *in, double *out);      // out = d.*in
 int k_axpy(Ctx *c, int64_t n, double a, const double *x, double *y);                     // y += a x

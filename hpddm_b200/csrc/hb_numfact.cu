@@ -565,6 +565,8 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
 }  // namespace
 
 void free_factor(DeviceFactor &f) {
+  for (cudaGraphExec_t &g : f.graph)
+    if (g) cudaGraphExecDestroy(g);
   if (f.panU && f.panU != f.panL) cudaFree(f.panU);
   cudaFree(f.panL);
   cudaFree(f.fronts);
@@ -595,9 +597,11 @@ int numfact_device(Sub *s, const HostCSR &A) {
   HB_CHECK(upload(S.fwd, &D.fwd, st));
   HB_CHECK(upload(S.bwd, &D.bwd, st));
   HB_CHECK(upload(S.perm, &D.perm, st));
-  HB_CUDA(cudaMalloc(&D.b, (size_t)S.n * sizeof(double)));
-  HB_CUDA(cudaMalloc(&D.y, (size_t)S.n * sizeof(double)));
-  HB_CUDA(cudaMalloc(&D.x, (size_t)S.n * sizeof(double)));
+  HB_CUDA(cudaMalloc(&D.b, (size_t)S.n * 4 * sizeof(double)));
+  HB_CUDA(cudaMalloc(&D.y, (size_t)S.n * 4 * sizeof(double)));
+  HB_CUDA(cudaMalloc(&D.x, (size_t)S.n * 4 * sizeof(double)));
+  D.sweep_launches = 0;
+  for (int l = 0; l < S.nlevels; ++l) D.sweep_launches += (S.fwd_ptr[l + 1] > S.fwd_ptr[l]) + (S.bwd_ptr[l + 1] > S.bwd_ptr[l]);
   int rc = HPDDM_B200_ERR_NUMERIC;
   const bool force_lu = getenv("HPDDM_B200_FORCE_LU") != nullptr;
   if (A.symmetric && !force_lu) rc = numfact_try(s, A, true);

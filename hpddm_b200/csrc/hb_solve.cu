@@ -12,7 +12,7 @@
 //     x[piv(f)]   += P_f^T * [ y[piv(f)] ; -x[struct(f)] ]
 // Each panel value is read exactly once per sweep with 128-bit coalesced loads;
 // a warp owns one work item (<= 32 rows x 512 columns forward, <= 128 rows x 256
-// columns backward), reduces with shuffles and publishes with FP64 atomics
+// columns backward; 1, 2 or 4 right-hand sides per pass over the panels), reduces with shuffles and publishes with FP64 atomics
 // (RED.ADD.F64).  Pure HBM streaming: 0.25 flop/byte.
 #include "hb_internal.h"
 
@@ -55,8 +55,13 @@ __device__ __forceinline__ double reduce8(double (&a)[8], int lane) {
   return a[0];
 }
 
+// Forward sweep work item, MU right-hand sides at once (panel values are read once for all MU).
+// R = 8 / MU rows and JU = MU column slabs are in flight together (8 x 128-bit panel loads per
+// lane), the R * MU = 8 partial sums go through one reduce8.
+template <int MU>
 __global__ void __launch_bounds__(256, 3) k_fwd(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
-                                                const int *__restrict__ rowidx, const double *__restrict__ pan, double *b, double *y) {
+                                                const int *__restrict__ rowidx, const double *__restrict__ pan, double *b, double *y, int n) {
+  constexpr int R = 8 / MU, JU = MU, CW = FCH / MU;
   __shared__ __align__(16) double bs[8][FCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = (int64_t)blockIdx.x * 8 + warp;
@@ -80,62 +85,83 @@ __global__ void __launch_bounds__(256, 3) k_fwd(const FwdItem *__restrict__ item
     nrows = min(RB, f.s2 - RB * k2);
     cmax = s1;
   }
-  const int c0 = w.c0, c1 = min(cmax, c0 + FCH);
-  const int nc = c1 - c0;
+  const int c1 = min(cmax, w.c0 + FCH);
   double *mybs = bs[warp];
-  for (int c = lane; c < nc; c += 32) mybs[c] = b[f.p0 + c0 + c];
-  if ((nc & 1) && lane == 0) mybs[nc] = 0.0;  // panels are zero-padded to even widths
-  __syncwarp();
-  const int nv = (nc + 1) >> 1;
   const double2 *bs2 = reinterpret_cast<const double2 *>(mybs);
   const int st2 = stride >> 1;  // row stride in double2
   const int rsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  for (int r = 0; r < nrows; r += 8) {
-    const double2 *p = reinterpret_cast<const double2 *>(base + (int64_t)r * stride + c0);
-    const int nr = min(8, nrows - r);
-    double a[8];
+  for (int cs = w.c0; cs < c1; cs += CW) {
+    const int nc = min(CW, c1 - cs);
+    __syncwarp();
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = 0.0;
-    for (int j = lane; j < nv; j += 32) {
-      double2 t[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) t[q] = (q < nr) ? ldg_stream(p + (int64_t)q * st2 + j) : make_double2(0.0, 0.0);
-      const double2 bb = bs2[j];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) a[q] = fma(t[q].x, bb.x, fma(t[q].y, bb.y, a[q]));
+    for (int m = 0; m < MU; ++m) {
+      for (int c = lane; c < nc; c += 32) mybs[m * CW + c] = b[(int64_t)m * n + f.p0 + cs + c];
+      if ((nc & 1) && lane == 0) mybs[m * CW + nc] = 0.0;  // panels are zero-padded to even widths
     }
-    const double v = reduce8(a, lane);
-    if ((lane & 3) == 0 && rsel < nr) {
-      if (pivot) atomicAdd(&y[f.p0 + RB * w.rblk + r + rsel], v);
-      else atomicAdd(&b[rowidx[f.rptr + RB * (w.rblk - nb1) + r + rsel]], -v);
+    __syncwarp();
+    const int nv = (nc + 1) >> 1;
+    for (int r = 0; r < nrows; r += R) {
+      const double2 *p = reinterpret_cast<const double2 *>(base + (int64_t)r * stride + cs);
+      const int nr = min(R, nrows - r);
+      double a[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = 0.0;
+      for (int j0 = lane; j0 < nv; j0 += 32 * JU) {
+        double2 t[R][JU];
+#pragma unroll
+        for (int u = 0; u < JU; ++u)
+#pragma unroll
+          for (int q = 0; q < R; ++q) t[q][u] = (q < nr && j0 + 32 * u < nv) ? ldg_stream(p + (int64_t)q * st2 + j0 + 32 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < JU; ++u) {
+          if (j0 + 32 * u < nv) {
+#pragma unroll
+            for (int m = 0; m < MU; ++m) {
+              const double2 bb = bs2[m * (CW / 2) + j0 + 32 * u];
+#pragma unroll
+              for (int q = 0; q < R; ++q) a[q * MU + m] = fma(t[q][u].x, bb.x, fma(t[q][u].y, bb.y, a[q * MU + m]));
+            }
+          }
+        }
+      }
+      const double v = reduce8(a, lane);
+      const int q = rsel / MU, m = rsel % MU;
+      if ((lane & 3) == 0 && q < nr) {
+        if (pivot) atomicAdd(&y[(int64_t)m * n + f.p0 + RB * w.rblk + r + q], v);
+        else atomicAdd(&b[(int64_t)m * n + rowidx[f.rptr + RB * (w.rblk - nb1) + r + q]], -v);
+      }
     }
   }
 }
 
-// NJ = number of 64-column slabs of the chunk this lane covers (1, 2 or 4); rows are
-// processed in groups of 8/NJ so that 8 128-bit loads are in flight per lane
-template <int NJ>
-__device__ __forceinline__ void bwd_item(const BwdItem &w, const Front &f, const int *__restrict__ rowidx, const double *__restrict__ pan,
-                                         const double *__restrict__ y, double *x, int lane) {
+// Backward sweep work item.  NJ = 64-column slabs covered per pass (NJ * MU <= 4 accumulator
+// pairs per lane); rows are processed in groups of 8 / NJ so that 8 128-bit loads are in flight.
+template <int NJ, int MU>
+__device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int cbase, const int *__restrict__ rowidx, const double *__restrict__ pan,
+                                         const double *__restrict__ y, double *x, int n, int lane) {
   constexpr int G = 8 / NJ;
   const int s1 = f.s1, ldp = hb_ldp(s1);
   const double *P = pan + f.poff;
   const double *Pu = P + hb_upd_off(s1);
-  double2 acc[NJ];
+  double2 acc[NJ][MU];
 #pragma unroll
-  for (int j = 0; j < NJ; ++j) acc[j] = make_double2(0.0, 0.0);
-  const int cl = w.c0 + 2 * lane;  // this lane's first column
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int m = 0; m < MU; ++m) acc[j][m] = make_double2(0.0, 0.0);
+  const int cl = cbase + 2 * lane;  // this lane's first column
   for (int rb = 0; rb < w.nr; rb += 32) {
     const int r = w.r0 + rb + lane;
-    double u = 0.0;
-    if (rb + lane < w.nr) u = (r < s1) ? y[f.p0 + r] : -x[rowidx[f.rptr + r - s1]];
+    double u[MU];
+#pragma unroll
+    for (int m = 0; m < MU; ++m) {
+      u[m] = 0.0;
+      if (rb + lane < w.nr) u[m] = (r < s1) ? y[(int64_t)m * n + f.p0 + r] : -x[(int64_t)m * n + rowidx[f.rptr + r - s1]];
+    }
     const int nq = min(32, w.nr - rb);
     for (int q = 0; q < nq; q += G) {
       double2 t[G][NJ];
-      double uq[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        uq[g] = __shfl_sync(0xffffffffu, u, (q + g) & 31);
         const int rr = w.r0 + rb + q + g;
         const double *rowp;
         int wlim;
@@ -157,79 +183,125 @@ __device__ __forceinline__ void bwd_item(const BwdItem &w, const Front &f, const
 #pragma unroll
       for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          acc[j].x = fma(t[g][j].x, uq[g], acc[j].x);
-          acc[j].y = fma(t[g][j].y, uq[g], acc[j].y);
+        for (int m = 0; m < MU; ++m) {
+          const double uq = __shfl_sync(0xffffffffu, u[m], (q + g) & 31);
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            acc[j][m].x = fma(t[g][j].x, uq, acc[j][m].x);
+            acc[j][m].y = fma(t[g][j].y, uq, acc[j][m].y);
+          }
         }
     }
   }
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
     const int c = cl + 64 * j;
-    if (c < s1) atomicAdd(&x[f.p0 + c], acc[j].x);
-    if (c + 1 < s1) atomicAdd(&x[f.p0 + c + 1], acc[j].y);
+#pragma unroll
+    for (int m = 0; m < MU; ++m) {
+      if (c < s1) atomicAdd(&x[(int64_t)m * n + f.p0 + c], acc[j][m].x);
+      if (c + 1 < s1) atomicAdd(&x[(int64_t)m * n + f.p0 + c + 1], acc[j][m].y);
+    }
   }
 }
 
-__global__ void __launch_bounds__(256, 3) k_bwd(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
-                                                const int *__restrict__ rowidx, const double *__restrict__ pan, const double *__restrict__ y, double *x) {
+template <int MU>
+__global__ void __launch_bounds__(256, MU == 4 ? 2 : 3) k_bwd(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
+                                                const int *__restrict__ rowidx, const double *__restrict__ pan, const double *__restrict__ y, double *x, int n) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = (int64_t)blockIdx.x * 8 + warp;
   if (it >= nitems) return;
   const BwdItem w = items[it];
   const Front f = fronts[w.front];
   const int width = min(BCH, hb_ldp(f.s1) - w.c0);
-  if (width <= 64) bwd_item<1>(w, f, rowidx, pan, y, x, lane);
-  else if (width <= 128) bwd_item<2>(w, f, rowidx, pan, y, x, lane);
-  else bwd_item<4>(w, f, rowidx, pan, y, x, lane);
+  constexpr int NJMAX = 4 / MU;  // 4, 2, 1
+  for (int cb = 0; cb < width; cb += 64 * NJMAX) {
+    const int left = width - cb;
+    if (NJMAX >= 4 && left > 128) bwd_pass<(NJMAX >= 4 ? 4 : NJMAX), MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
+    else if (NJMAX >= 2 && left > 64) bwd_pass<(NJMAX >= 2 ? 2 : NJMAX), MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
+    else bwd_pass<1, MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
+  }
 }
 
-__global__ void k_perm_in(int n, const int *__restrict__ perm, const double *__restrict__ in, double *b, double *y, double *x) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    b[i] = in[perm[i]];
-    y[i] = 0.0;
-    x[i] = 0.0;
+__global__ void k_perm_in(int n, int mu, const int *__restrict__ perm, const double *__restrict__ in, double *b, double *y, double *x) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < (int64_t)n * mu) {
+    const int i = (int)(t % n);
+    const int64_t c = t / n;
+    b[t] = in[c * n + perm[i]];
+    y[t] = 0.0;
+    x[t] = 0.0;
   }
 }
-__global__ void k_perm_out(int n, const int *__restrict__ perm, const double *__restrict__ x, const double *__restrict__ d, double *out, int accumulate) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
+__global__ void k_perm_out(int n, int mu, const int *__restrict__ perm, const double *__restrict__ x, const double *__restrict__ d, double *out, int accumulate) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < (int64_t)n * mu) {
+    const int i = (int)(t % n);
+    const int64_t c = t / n;
     const int p = perm[i];
-    double v = x[i];
+    double v = x[t];
     if (d) v *= d[p];
-    out[p] = accumulate ? out[p] + v : v;
+    out[c * n + p] = accumulate ? out[c * n + p] + v : v;
   }
+}
+
+template <int MU>
+static int launch_levels(Sub *s, cudaStream_t st) {
+  DeviceFactor &D = s->fac;
+  const Symbolic &S = s->sym;
+  const int n = S.n;
+  for (int l = 0; l < S.nlevels; ++l) {
+    const int64_t i0 = S.fwd_ptr[l], ni = S.fwd_ptr[l + 1] - i0;
+    if (ni <= 0) continue;
+    k_fwd<MU><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+  }
+  for (int l = S.nlevels - 1; l >= 0; --l) {
+    const int64_t i0 = S.bwd_ptr[l], ni = S.bwd_ptr[l + 1] - i0;
+    if (ni <= 0) continue;
+    k_bwd<MU><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n);
+  }
+  HB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace
 
-int sptrsv_solve(Sub *s, const double *b, double *x, const double *scale, bool accumulate) {
+// x = A^{-1} b for mu in {1, 2, 4} columns at once (natural ordering in/out, device pointers,
+// column stride n).  The 2 * nlevels sweep launches are replayed from a CUDA graph captured on
+// first use (their arguments never change); only the two permutation kernels see the caller's
+// pointers.
+int sptrsv_solve(Sub *s, const double *b, double *x, int mu, const double *scale, bool accumulate) {
   DeviceFactor &D = s->fac;
   if (!D.valid) {
     set_error("solve: no factorisation (call numfact first)");
     return HPDDM_B200_ERR_STATE;
   }
+  if (mu != 1 && mu != 2 && mu != 4) {
+    set_error("sptrsv_solve: mu must be 1, 2 or 4");
+    return HPDDM_B200_ERR_ARG;
+  }
   const Symbolic &S = s->sym;
   cudaStream_t st = s->ctx->stream;
   const int n = S.n;
   if (n == 0) return 0;
-  k_perm_in<<<(n + 255) / 256, 256, 0, st>>>(n, D.perm, b, D.b, D.y, D.x);
-  s->ctx->launches++;
-  for (int l = 0; l < S.nlevels; ++l) {
-    const int64_t i0 = S.fwd_ptr[l], ni = S.fwd_ptr[l + 1] - i0;
-    if (ni <= 0) continue;
-    k_fwd<<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y);
-    s->ctx->launches++;
+  const int gi = mu == 1 ? 0 : (mu == 2 ? 1 : 2);
+  static const bool use_graph = getenv("HPDDM_B200_NO_GRAPH") == nullptr;
+  k_perm_in<<<(unsigned)(((int64_t)n * mu + 255) / 256), 256, 0, st>>>(n, mu, D.perm, b, D.b, D.y, D.x);
+  if (use_graph && !D.graph[gi]) {
+    cudaGraph_t g = nullptr;
+    HB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = mu == 1 ? launch_levels<1>(s, st) : (mu == 2 ? launch_levels<2>(s, st) : launch_levels<4>(s, st));
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc < 0 || e != cudaSuccess) {
+      set_error("CUDA graph capture of the SpTRSV sweeps failed (%s)", cudaGetErrorString(e));
+      return HPDDM_B200_ERR_CUDA;
+    }
+    HB_CUDA(cudaGraphInstantiate(&D.graph[gi], g, 0));
+    cudaGraphDestroy(g);
   }
-  for (int l = S.nlevels - 1; l >= 0; --l) {
-    const int64_t i0 = S.bwd_ptr[l], ni = S.bwd_ptr[l + 1] - i0;
-    if (ni <= 0) continue;
-    k_bwd<<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x);
-    s->ctx->launches++;
-  }
-  k_perm_out<<<(n + 255) / 256, 256, 0, st>>>(n, D.perm, D.x, scale, x, accumulate ? 1 : 0);
-  s->ctx->launches++;
+  if (use_graph) HB_CUDA(cudaGraphLaunch(D.graph[gi], st));
+  else HB_CHECK((mu == 1 ? launch_levels<1>(s, st) : (mu == 2 ? launch_levels<2>(s, st) : launch_levels<4>(s, st))));
+  k_perm_out<<<(unsigned)(((int64_t)n * mu + 255) / 256), 256, 0, st>>>(n, mu, D.perm, D.x, scale, x, accumulate ? 1 : 0);
+  s->ctx->launches += 2 + D.sweep_launches;
   HB_CUDA(cudaGetLastError());
   return 0;
 }

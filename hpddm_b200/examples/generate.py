@@ -255,3 +255,112 @@ def generate3d(rank, size, N=(16, 16, 16), overlap=1, mu=1, grid=None, neumann=F
 def generate_world(size, dim=2, **kw):
     gen = generate2d if dim == 2 else generate3d
     return [gen(r, size, **kw) for r in range(size)]
+
+
+# ----------------------------------------------------------------------------- 3-D linear elasticity (BASELINE config 4)
+def _hex8_stiffness(h, E=1.0, nu=0.3):
+    """24x24 stiffness of a trilinear (Q1) hexahedron of size hx x hy x hz, isotropic material,
+    2x2x2 Gauss quadrature; dofs ordered node-major (node = i + 2j + 4k), component fastest."""
+    lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+    mu = E / (2 * (1 + nu))
+    C = np.zeros((6, 6))
+    C[:3, :3] = lam
+    C[np.arange(3), np.arange(3)] += 2 * mu
+    C[np.arange(3, 6), np.arange(3, 6)] = mu
+    g = 1 / np.sqrt(3.0)
+    K = np.zeros((24, 24))
+    corners = np.array([[i, j, k] for k in (0, 1) for j in (0, 1) for i in (0, 1)], dtype=float) * 2 - 1
+    for xi in (-g, g):
+        for eta in (-g, g):
+            for zeta in (-g, g):
+                p = np.array([xi, eta, zeta])
+                dN = np.zeros((8, 3))
+                for a in range(8):
+                    s = corners[a]
+                    for c in range(3):
+                        o = [q for q in range(3) if q != c]
+                        dN[a, c] = 0.125 * s[c] * (1 + s[o[0]] * p[o[0]]) * (1 + s[o[1]] * p[o[1]]) * 2.0 / h[c]
+                B = np.zeros((6, 24))
+                for a in range(8):
+                    B[0, 3 * a] = dN[a, 0]
+                    B[1, 3 * a + 1] = dN[a, 1]
+                    B[2, 3 * a + 2] = dN[a, 2]
+                    B[3, 3 * a] = dN[a, 1]
+                    B[3, 3 * a + 1] = dN[a, 0]
+                    B[4, 3 * a + 1] = dN[a, 2]
+                    B[4, 3 * a + 2] = dN[a, 1]
+                    B[5, 3 * a] = dN[a, 2]
+                    B[5, 3 * a + 2] = dN[a, 0]
+                K += B.T @ C @ B * (h[0] * h[1] * h[2] / 8.0)
+    return K
+
+
+def _assemble_elasticity(lo, hi, Nn, h, Ke, penalty):
+    """stiffness of the elements inside the node box [lo, hi) (local node numbering, x fastest,
+    3 interleaved dofs per node); nodes on the global face x = 0 are clamped by penalisation
+    (HPDDM's convention: diagonal = 1e30, picked up by Subdomain::boundaryConditions)."""
+    w, hh, t = [hi[a] - lo[a] for a in range(3)]
+    nid = np.arange(w * hh * t).reshape(t, hh, w)
+    conn = np.stack([nid[k:t - 1 + k, j:hh - 1 + j, i:w - 1 + i].reshape(-1) for k in (0, 1) for j in (0, 1) for i in (0, 1)], axis=1)
+    dofs = (3 * conn[:, :, None] + np.arange(3)[None, None, :]).reshape(conn.shape[0], 24)
+    R = np.repeat(dofs, 24, axis=1).reshape(-1)
+    C = np.tile(dofs, (1, 24)).reshape(-1)
+    V = np.tile(Ke.reshape(-1), conn.shape[0])
+    n = 3 * w * hh * t
+    A = sp.csr_matrix((V, (R, C)), shape=(n, n))
+    if penalty and lo[0] == 0:
+        clamp = (3 * nid[:, :, 0].reshape(-1)[:, None] + np.arange(3)[None, :]).reshape(-1)
+        A = A.tolil()
+        for i in clamp:
+            A[i, i] = penalty
+        A = A.tocsr()
+    A.sort_indices()
+    return A
+
+
+def generate_elasticity3d(rank, size, Nn=(9, 9, 7), overlap=1, mu=4, grid=None, neumann=False, seed=4321, penalty=1e30):
+    """Q1 hexahedral linear elasticity (E = 1, nu_P = 0.3) on [0,10]^3 with Nn nodes per direction and 3
+    dofs per node (config 4 of BASELINE.json, element model of the reference's examples/petsc/ex56.c);
+    same decomposition conventions as generate3d, on nodes.  The local matrix is the global matrix
+    restricted to the subdomain's dofs (assembled globally: test sizes only)."""
+    px, py, pz = grid if grid is not None else split_grid_3d(size)
+    z = rank // (px * py)
+    y = (rank - z * px * py) // px
+    x = rank - z * px * py - y * px
+    pos, pg = (x, y, z), (px, py, pz)
+    st = [max(pos[a] * Nn[a] // pg[a] - overlap, 0) for a in range(3)]
+    en = [min((pos[a] + 1) * Nn[a] // pg[a] + overlap, Nn[a]) for a in range(3)]
+    dims = tuple(en[a] - st[a] for a in range(3))
+    h = [10.0 / (Nn[a] - 1) for a in range(3)]
+    Ke = _hex8_stiffness(h)
+    Aglob = _assemble_elasticity([0, 0, 0], list(Nn), Nn, h, Ke, penalty)
+    gid = np.arange(Nn[0] * Nn[1] * Nn[2]).reshape(Nn[2], Nn[1], Nn[0])
+    nodes = gid[st[2]:en[2], st[1]:en[1], st[0]:en[0]].reshape(-1)
+    dofs = (3 * nodes[:, None] + np.arange(3)[None, :]).reshape(-1)
+    Mat = sp.csr_matrix(Aglob[dofs][:, dofs])
+    Mat.sort_indices()
+    ndof = dofs.size
+    dist = np.minimum(np.minimum(_ramp(st[0] != 0, en[0] != Nn[0], st[0], en[0], overlap)[None, None, :],
+                                 _ramp(st[1] != 0, en[1] != Nn[1], st[1], en[1], overlap)[None, :, None]),
+                      _ramp(st[2] != 0, en[2] != Nn[2], st[2], en[2], overlap)[:, None, None])
+    d = np.repeat(np.minimum(dist / overlap, 1.0).reshape(-1), 3)
+    loc = np.arange(dims[0] * dims[1] * dims[2]).reshape(dims[2], dims[1], dims[0])
+    o, mapping = [], []
+    for dz in (-1, 0, 1):
+        for dyy in (-1, 0, 1):
+            for dxx in (-1, 0, 1):
+                dd = (dxx, dyy, dz)
+                if dd == (0, 0, 0):
+                    continue
+                nb = [pos[a] + dd[a] for a in range(3)]
+                if not all(0 <= nb[a] < pg[a] for a in range(3)):
+                    continue
+                sl = [slice(0, dims[a]) if dd[a] == 0 else (slice(0, 2 * overlap) if dd[a] < 0 else slice(dims[a] - 2 * overlap, dims[a])) for a in range(3)]
+                ln = loc[sl[2], sl[1], sl[0]].reshape(-1)
+                o.append(nb[2] * px * py + nb[1] * px + nb[0])
+                mapping.append((3 * ln[:, None] + np.arange(3)[None, :]).reshape(-1).astype(np.int32))
+    rs = np.random.RandomState(seed + rank)
+    f = np.asfortranarray(rs.uniform(0.0, 1.0, size=(max(mu, 1), ndof)).T)
+    MatN = _assemble_elasticity(st, en, Nn, h, Ke, penalty) if neumann else None
+    return dict(o=o, mapping=mapping, ndof=ndof, Mat=Mat, MatNeumann=MatN, d=d, f=f, sym=False, box=tuple(zip(st, en)), grid=(px, py, pz),
+                dims=(dims[0], dims[1], dims[2], 3))

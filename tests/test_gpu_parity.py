@@ -176,3 +176,42 @@ def test_single_subdomain_direct_solve_residual():
     r = np.linalg.norm(A @ x - b, axis=0) / np.linalg.norm(b, axis=0)
     assert r.max() < 1e-12
     deco.close()
+
+
+def test_config4_elasticity_block_rhs_penalised_dirichlet():
+    """BASELINE config 4 in small: Q1 linear elasticity, 3 dofs/node, 2x2x1 subdomains, GenEO nu=6,
+    block of 4 right-hand sides (one pass over the panels), clamped face by 1e30 penalisation ->
+    Subdomain::boundaryConditions path of Schwarz::start."""
+    from hpddm_b200.examples.generate import generate_elasticity3d
+    parts = [generate_elasticity3d(r, 4, Nn=(9, 9, 6), overlap=1, mu=4, grid=(2, 2, 1), neumann=True) for r in range(4)]
+    w = SchwarzWorld(parts)
+    w.multiplicity_scaling()
+    w.numfact()
+    w.solve_gevp([p["MatNeumann"] for p in parts], nu=6)
+    w.build_coarse()
+    deco = build_gpu_decomposition(parts, w, two_level=True)
+    assert deco.subs[0].statistics()["symmetric"] == 1
+    x = rhs(parts, w, 11)
+    for corr in (None, DEFLATED, BALANCED):
+        assert relerr(deco.apply(x, corr), w.apply(x, corr)) < TOL
+    b = [p["f"].copy() for p in parts]
+    x0 = rhs(parts, w, 12)
+    assert relerr(deco.start(b, x0), w.start(b, [v.copy() for v in x0])) < 1e-13
+    deco.end()
+    b = w.exchange([p["f"].copy() for p in parts])
+    it_ref, x_ref, _ = gmres(OracleOperator(w, DEFLATED), b)
+    it_gpu, x_gpu, _ = gmres(KrylovOperator(deco, DEFLATED), b)
+    assert it_gpu == it_ref
+    assert relerr(x_gpu, x_ref) < 1e-7
+    deco.close()
+
+
+@pytest.mark.parametrize("mu", [1, 2, 4, 7])
+def test_block_solve_matches_column_by_column(poisson3d, mu):
+    parts, w, deco = poisson3d
+    rs = np.random.RandomState(20 + mu)
+    for r, s in enumerate(deco.subs[:2]):
+        b = np.asfortranarray(rs.standard_normal((w.n[r], mu)))
+        got = s.solve(b)
+        ref = w.solver[r].solve(b)
+        assert relerr([got], [ref]) < TOL
