@@ -117,8 +117,24 @@ public:
 };
 
 /* ------------------------------------------------------------------ 2. Schwarz mirror */
+namespace b200 {
+/* stand-alone stand-in for HPDDM::OptionsPrefix<K> (include/HPDDM_option.hpp:389-460) */
 template <class K>
-class B200Schwarz {
+class NoPrefix {
+  std::string prefix_;
+
+public:
+  typedef K scalar_type;
+  void        setPrefix(const std::string &p) { prefix_ = p; }
+  std::string prefix() const { return prefix_; }
+  std::string prefix(const std::string &opt) const { return prefix_ + opt; }
+};
+}  // namespace b200
+
+/* Base: inside the reference pass HPDDM::OptionsPrefix<K> (what Subdomain<K> derives from,
+ * include/HPDDM_subdomain.hpp:47) so that the recycling Krylov methods find storage()/k()/allocate(). */
+template <class K, class Base = b200::NoPrefix<K>>
+class B200Schwarz : public Base {
   static_assert(std::is_same<K, double>::value, "hpddm_b200: only K = double is implemented");
 
 public:
@@ -132,7 +148,6 @@ private:
   MatrixCSR<K>   *a_;
   const double   *d_;
   int             dof_, rank_, size_, nu_, correction_;
-  std::string     prefix_;
   std::vector<std::pair<unsigned short, std::vector<int>>> map_;
 
 public:
@@ -156,9 +171,6 @@ public:
       b200::check(hpddm_b200_ctx_comm_init(ctx_, id, rank, size), "hpddm_b200_ctx_comm_init");
     }
   }
-  void setPrefix(const std::string &p) { prefix_ = p; }
-  std::string prefix() const { return prefix_; }
-  std::string prefix(const std::string &opt) const { return prefix_ + opt; }
   /* Subdomain::initialize(a, o, r) (include/HPDDM_subdomain.hpp:165-236) */
   template <class Neighbor, class Mapping>
   void initialize(MatrixCSR<K> *const &a, const Neighbor &o, const Mapping &r)

@@ -50,3 +50,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_host_cpp_header_compiles_and_links():
+    """hpddm_b200/host/HPDDM_B200.hpp: every member of B200Sub / B200Schwarz instantiates and the
+    symbols resolve against libhpddm_b200.so (no reference tree needed)."""
+    import subprocess
+    import tempfile
+    src = os.path.join(ROOT, "tests", "native", "test_host_header.cpp")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "t")
+        subprocess.check_call(["g++", "-std=c++11", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "hpddm_b200", "host"), src,
+                               "-L", os.path.join(ROOT, "hpddm_b200", "lib"), "-lhpddm_b200", "-Wl,-rpath," + os.path.join(ROOT, "hpddm_b200", "lib"), "-o", exe])
+        subprocess.check_call([exe])
