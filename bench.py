@@ -177,6 +177,15 @@ def run_b200(args):
                      "apply_gbs": by["apply"] / (ms_dev / args.steps * 1e-3) / 1e9},
         "clocks": sampler.summary(),
     }
+    if args.krylov:
+        from hpddm_b200 import KrylovOperator
+        sys.path.insert(0, ROOT)
+        bvec = [np.asfortranarray(part["f"][:, :1])]
+        bvec = deco.exchange(bvec, scaled=True)
+        t0 = time.time()
+        it_dev, _, res = deco.solve(bvec, correction="deflated")
+        t_dev = time.time() - t0
+        out["krylov"] = {"device_resident_gmres_s": t_dev, "iterations": it_dev, "rel_residual": float(res[0])}
     if args.cpu_baseline and rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_baseline(args, m=args.cpu_m or None, steps=5, budget_s=60.0)
     if rank == 0:
@@ -282,6 +291,7 @@ def main():
     ap.add_argument("--rhs", dest="mu", type=int, default=1, help="right-hand sides per apply (block methods)")
     ap.add_argument("--cpu-cells", dest="cpu_m", type=int, default=0, help="subdomain edge of the CPU sample (0 = same as --cells)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--krylov", action="store_true", help="also time a full GMRES solve: device-resident driver vs host-driven loop over the C ABI")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -79,6 +79,11 @@ constexpr int NCCL_INT32 = 2, NCCL_F64 = 8, NCCL_SUM = 0;
 
 // uploads are issued on the context's (non-blocking) stream and waited for: a plain cudaMemcpy
 // from pageable memory is neither ordered against that stream nor guaranteed to have landed
+int nccl_allreduce_sum(Ctx *c, double *buf, int count) {
+  if (c->nproc > 1) HB_NCCL(g_nccl.AllReduce(buf, buf, count, NCCL_F64, NCCL_SUM, c->nccl, c->stream));
+  return 0;
+}
+
 template <class T>
 static int up(const std::vector<T> &v, T **d, cudaStream_t st) {
   if (*d) cudaFree(*d);
@@ -153,7 +158,7 @@ static int build_links(Ctx *c) {
 
 // halo sum  x_s[map] += neighbours' values  (Subdomain::exchange, subdomain.hpp:115-130),
 // all mu columns and all neighbours in one round.  x[] = device pointers per local subdomain.
-static int halo(Ctx *c, double *const *x, int mu) {
+int halo(Ctx *c, double *const *x, int mu) {
   bool any = false;
   for (Sub *s : c->subs) any = any || s->h > 0;
   if (!any) return 0;
@@ -205,7 +210,7 @@ static int halo(Ctx *c, double *const *x, int mu) {
   return 0;
 }
 
-static int check_ready(Ctx *c, int mu) {
+int check_ready(Ctx *c, int mu) {
   if (!c || mu < 1) {
     set_error("bad context / mu");
     return HPDDM_B200_ERR_ARG;
@@ -222,7 +227,7 @@ static int check_ready(Ctx *c, int mu) {
 }
 
 // stage user vectors: returns device pointers to use for reading
-static int stage_in(Ctx *c, const double *const *in, int mu, int where, std::vector<const double *> &dev) {
+int stage_in(Ctx *c, const double *const *in, int mu, int where, std::vector<const double *> &dev) {
   dev.resize(c->subs.size());
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
@@ -234,11 +239,11 @@ static int stage_in(Ctx *c, const double *const *in, int mu, int where, std::vec
   }
   return 0;
 }
-static void out_ptrs(Ctx *c, double *const *out, int where, std::vector<double *> &dev) {
+void out_ptrs(Ctx *c, double *const *out, int where, std::vector<double *> &dev) {
   dev.resize(c->subs.size());
   for (size_t i = 0; i < c->subs.size(); ++i) dev[i] = where == HPDDM_B200_HOST ? c->subs[i]->d_out : out[i];
 }
-static int stage_out(Ctx *c, double *const *out, int mu, int where) {
+int stage_out(Ctx *c, double *const *out, int mu, int where) {
   if (where != HPDDM_B200_HOST) return 0;
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
@@ -278,10 +283,91 @@ static int solve_cols(Sub *s, const double *b, double *x, int mu, const double *
   return 0;
 }
 
-static int gmv_core(Ctx *c, const std::vector<const double *> &in, const std::vector<double *> &out, int mu) {
+int gmv_core(Ctx *c, const std::vector<const double *> &in, const std::vector<double *> &out, int mu) {
   for (size_t i = 0; i < c->subs.size(); ++i) HB_CHECK(k_spmv(c, c->subs[i], mu, 1.0, in[i], 0.0, nullptr, out[i], c->subs[i]->d_d));
   return halo(c, out.data(), mu);
 }
+
+// Schwarz::apply on device pointers (schwarz.hpp:527-612); `ind` is never modified
+int apply_core(Ctx *c, const std::vector<const double *> &ind, const std::vector<double *> &outd, int mu, int correction) {
+  const size_t L = c->subs.size();
+  const bool two_level = c->Nc > 0 && c->d_Einv && correction != HPDDM_B200_CORRECTION_NONE;
+  if (!two_level) {  // schwarz.hpp:531-547
+    bool scaled_exchange = true;
+    for (size_t i = 0; i < L; ++i) {
+      Sub *s = c->subs[i];
+      const size_t len = (size_t)s->n * mu;
+      switch (s->prcndtnr) {
+      case HPDDM_B200_PRCNDTNR_NO:
+        HB_CHECK(k_copy(c, len, ind[i], outd[i]));
+        break;
+      case HPDDM_B200_PRCNDTNR_GE:
+      case HPDDM_B200_PRCNDTNR_OG:
+        HB_CHECK(solve_cols(s, ind[i], outd[i], mu, s->d_d, false));  // out = D A^-1 in (D fused into the solve epilogue)
+        break;
+      case HPDDM_B200_PRCNDTNR_OS:
+        HB_CHECK(k_scale(c, s->n, mu, s->d_d, ind[i], s->d_tmp));
+        HB_CHECK(solve_cols(s, s->d_tmp, outd[i], mu, s->d_d, false));
+        scaled_exchange = false;
+        break;
+      default:  // SY
+        HB_CHECK(solve_cols(s, ind[i], outd[i], mu, nullptr, false));
+        scaled_exchange = false;
+      }
+    }
+    (void)scaled_exchange;  // scaling already applied where the reference applies it
+    bool all_no = true;
+    for (Sub *s : c->subs) all_no = all_no && s->prcndtnr == HPDDM_B200_PRCNDTNR_NO;
+    if (!all_no) HB_CHECK(halo(c, outd.data(), mu));
+    return 0;
+  }
+  std::vector<double *> work(L), tmp(L);
+  std::vector<const double *> cwork(L), ctmp(L);
+  for (size_t i = 0; i < L; ++i) {
+    work[i] = c->subs[i]->d_work;
+    tmp[i] = c->subs[i]->d_tmp;
+    cwork[i] = work[i];
+    ctmp[i] = tmp[i];
+  }
+  if (correction == HPDDM_B200_CORRECTION_ADDITIVE) {  // schwarz.hpp:552-571
+    HB_CHECK(deflation_core(c, ind, outd, mu));
+    for (size_t i = 0; i < L; ++i) {
+      Sub *s = c->subs[i];
+      HB_CHECK(solve_cols(s, ind[i], outd[i], mu, nullptr, true));             // out += A^-1 in
+      HB_CHECK(k_scale(c, s->n, mu, s->d_d, outd[i], outd[i]));                // exchange(out): D ...
+    }
+    HB_CHECK(halo(c, outd.data(), mu));                                          // ... then halo sum
+    return 0;
+  }
+  // DEFLATED / BALANCED (schwarz.hpp:572-608)
+  HB_CHECK(deflation_core(c, ind, outd, mu));                                    // out = Q in          (573)
+  for (size_t i = 0; i < L; ++i) {
+    Sub *s = c->subs[i];
+    HB_CHECK(k_spmv(c, s, mu, -1.0, outd[i], 1.0, ind[i], work[i], s->d_d));     // work = D (in - A out) (581-586 + diag of 588)
+  }
+  HB_CHECK(halo(c, work.data(), mu));                                            // exchange(work)      (588)
+  for (size_t i = 0; i < L; ++i) {
+    Sub *s = c->subs[i];
+    if (s->prcndtnr == HPDDM_B200_PRCNDTNR_OS) HB_CHECK(k_scale(c, s->n, mu, s->d_d, work[i], work[i]));  // (589)
+    HB_CHECK(solve_cols(s, work[i], work[i], mu, s->d_d, false));                // work = D A^-1 work  (590 + diag of 591)
+  }
+  HB_CHECK(halo(c, work.data(), mu));                                            // exchange(work)      (591)
+  if (correction == HPDDM_B200_CORRECTION_BALANCED) {                            // (593-606)
+    HB_CHECK(gmv_core(c, cwork, tmp, mu));
+    std::vector<double *> t2(L, nullptr);
+    // allocate a transient buffer per subdomain (rare path)
+    for (size_t i = 0; i < L; ++i) HB_CUDA(cudaMalloc(&t2[i], std::max<size_t>((size_t)c->subs[i]->n * mu, 1) * sizeof(double)));
+    int rc = deflation_core(c, ctmp, t2, mu);
+    if (rc == 0)
+      for (size_t i = 0; i < L && rc == 0; ++i) rc = k_axpy(c, (int64_t)c->subs[i]->n * mu, -1.0, t2[i], work[i]);
+    cudaStreamSynchronize(c->stream);
+    for (size_t i = 0; i < L; ++i) cudaFree(t2[i]);
+    HB_CHECK(rc);
+  }
+  for (size_t i = 0; i < L; ++i) HB_CHECK(k_axpy(c, (int64_t)c->subs[i]->n * mu, 1.0, work[i], outd[i]));  // out += work (607)
+  return 0;
+}
+
 
 }  // namespace hb
 
@@ -886,85 +972,11 @@ int hpddm_b200_deflation(hpddm_b200_ctx *ctx, const double *const *in, double *c
 int hpddm_b200_apply(hpddm_b200_ctx *ctx, const double *const *in, double *const *out, int mu, int correction, int where) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CHECK(check_ready(c, mu));
-  const size_t L = c->subs.size();
   std::vector<const double *> ind;
   std::vector<double *> outd;
   HB_CHECK(stage_in(c, in, mu, where, ind));
   out_ptrs(c, out, where, outd);
-  const bool two_level = c->Nc > 0 && c->d_Einv && correction != HPDDM_B200_CORRECTION_NONE;
-  if (!two_level) {  // schwarz.hpp:531-547
-    bool scaled_exchange = true;
-    for (size_t i = 0; i < L; ++i) {
-      Sub *s = c->subs[i];
-      const size_t len = (size_t)s->n * mu;
-      switch (s->prcndtnr) {
-      case HPDDM_B200_PRCNDTNR_NO:
-        HB_CHECK(k_copy(c, len, ind[i], outd[i]));
-        break;
-      case HPDDM_B200_PRCNDTNR_GE:
-      case HPDDM_B200_PRCNDTNR_OG:
-        HB_CHECK(solve_cols(s, ind[i], outd[i], mu, s->d_d, false));  // out = D A^-1 in (D fused into the solve epilogue)
-        break;
-      case HPDDM_B200_PRCNDTNR_OS:
-        HB_CHECK(k_scale(c, s->n, mu, s->d_d, ind[i], s->d_tmp));
-        HB_CHECK(solve_cols(s, s->d_tmp, outd[i], mu, s->d_d, false));
-        scaled_exchange = false;
-        break;
-      default:  // SY
-        HB_CHECK(solve_cols(s, ind[i], outd[i], mu, nullptr, false));
-        scaled_exchange = false;
-      }
-    }
-    (void)scaled_exchange;  // scaling already applied where the reference applies it
-    bool all_no = true;
-    for (Sub *s : c->subs) all_no = all_no && s->prcndtnr == HPDDM_B200_PRCNDTNR_NO;
-    if (!all_no) HB_CHECK(halo(c, outd.data(), mu));
-    return stage_out(c, out, mu, where);
-  }
-  std::vector<double *> work(L), tmp(L);
-  std::vector<const double *> cwork(L), ctmp(L);
-  for (size_t i = 0; i < L; ++i) {
-    work[i] = c->subs[i]->d_work;
-    tmp[i] = c->subs[i]->d_tmp;
-    cwork[i] = work[i];
-    ctmp[i] = tmp[i];
-  }
-  if (correction == HPDDM_B200_CORRECTION_ADDITIVE) {  // schwarz.hpp:552-571
-    HB_CHECK(deflation_core(c, ind, outd, mu));
-    for (size_t i = 0; i < L; ++i) {
-      Sub *s = c->subs[i];
-      HB_CHECK(solve_cols(s, ind[i], outd[i], mu, nullptr, true));             // out += A^-1 in
-      HB_CHECK(k_scale(c, s->n, mu, s->d_d, outd[i], outd[i]));                // exchange(out): D ...
-    }
-    HB_CHECK(halo(c, outd.data(), mu));                                          // ... then halo sum
-    return stage_out(c, out, mu, where);
-  }
-  // DEFLATED / BALANCED (schwarz.hpp:572-608)
-  HB_CHECK(deflation_core(c, ind, outd, mu));                                    // out = Q in          (573)
-  for (size_t i = 0; i < L; ++i) {
-    Sub *s = c->subs[i];
-    HB_CHECK(k_spmv(c, s, mu, -1.0, outd[i], 1.0, ind[i], work[i], s->d_d));     // work = D (in - A out) (581-586 + diag of 588)
-  }
-  HB_CHECK(halo(c, work.data(), mu));                                            // exchange(work)      (588)
-  for (size_t i = 0; i < L; ++i) {
-    Sub *s = c->subs[i];
-    if (s->prcndtnr == HPDDM_B200_PRCNDTNR_OS) HB_CHECK(k_scale(c, s->n, mu, s->d_d, work[i], work[i]));  // (589)
-    HB_CHECK(solve_cols(s, work[i], work[i], mu, s->d_d, false));                // work = D A^-1 work  (590 + diag of 591)
-  }
-  HB_CHECK(halo(c, work.data(), mu));                                            // exchange(work)      (591)
-  if (correction == HPDDM_B200_CORRECTION_BALANCED) {                            // (593-606)
-    HB_CHECK(gmv_core(c, cwork, tmp, mu));
-    std::vector<double *> t2(L, nullptr);
-    // allocate a transient buffer per subdomain (rare path)
-    for (size_t i = 0; i < L; ++i) HB_CUDA(cudaMalloc(&t2[i], std::max<size_t>((size_t)c->subs[i]->n * mu, 1) * sizeof(double)));
-    int rc = deflation_core(c, ctmp, t2, mu);
-    if (rc == 0)
-      for (size_t i = 0; i < L && rc == 0; ++i) rc = k_axpy(c, (int64_t)c->subs[i]->n * mu, -1.0, t2[i], work[i]);
-    cudaStreamSynchronize(c->stream);
-    for (size_t i = 0; i < L; ++i) cudaFree(t2[i]);
-    HB_CHECK(rc);
-  }
-  for (size_t i = 0; i < L; ++i) HB_CHECK(k_axpy(c, (int64_t)c->subs[i]->n * mu, 1.0, work[i], outd[i]));  // out += work (607)
+  HB_CHECK(hb::apply_core(c, ind, outd, mu, correction));
   return stage_out(c, out, mu, where);
 }
 

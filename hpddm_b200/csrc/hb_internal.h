@@ -212,4 +212,18 @@ int k_dot(Ctx *c, const Sub *s, int mu, const double *x, const double *y, double
 int k_coarse_solve(Ctx *c, int mu);  // d_Y = E^{-1} d_T with one refinement step
 int k_bc(Ctx *c, const Sub *s, int mu, const double *b, double *x);
 
+// orchestration helpers shared by hb_api.cu and hb_krylov.cu (device pointers, one per local subdomain)
+int check_ready(Ctx *c, int mu);
+int halo(Ctx *c, double *const *x, int mu);
+int apply_core(Ctx *c, const std::vector<const double *> &in, const std::vector<double *> &out, int mu, int correction);
+int gmv_core(Ctx *c, const std::vector<const double *> &in, const std::vector<double *> &out, int mu);
+int stage_in(Ctx *c, const double *const *in, int mu, int where, std::vector<const double *> &dev);
+void out_ptrs(Ctx *c, double *const *out, int where, std::vector<double *> &dev);
+int stage_out(Ctx *c, double *const *out, int mu, int where);
+int nccl_allreduce_sum(Ctx *c, double *buf, int count);
+// Krylov helper kernels (hb_kernels.cu)
+int k_vdots(Ctx *c, const Sub *s, int k, const double *V, const double *w, double *T);      // T[j] += sum_i d_i V[i,j] w[i]
+int k_vupdate(Ctx *c, const Sub *s, int k, const double *V, const double *h, double sign, double *w);  // w += sign * V h
+int k_scal_copy(Ctx *c, int64_t n, double a, const double *x, double *y);                  // y = a x
+
 }  // namespace hb

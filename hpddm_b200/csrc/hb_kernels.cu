@@ -193,6 +193,22 @@ __global__ void kk_bc(int nbc, int n, int mu, const int *__restrict__ idx, const
   x[idx[q] + (int64_t)c * n] = b[idx[q] + (int64_t)c * n] / val[q];
 }
 
+// w[i] += sign * sum_j V[i + j*n] h[j]   (Gram-Schmidt update / Krylov linear combination)
+__global__ void __launch_bounds__(256) kk_vupdate(int n, int k, const double *__restrict__ V, const double *__restrict__ h, double sign, double *w) {
+  extern __shared__ double hs[];
+  for (int t = threadIdx.x; t < k; t += blockDim.x) hs[t] = h[t];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+  for (int j = 0; j < k; ++j) acc = fma(V[i + (int64_t)j * n], hs[j], acc);
+  w[i] += sign * acc;
+}
+__global__ void kk_scal_copy(int64_t n, double a, const double *__restrict__ x, double *y) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n) y[t] = a * x[t];
+}
+
 inline unsigned grid1(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
 }  // namespace
@@ -290,6 +306,21 @@ int k_dot(Ctx *c, const Sub *s, int mu, const double *x, const double *y, double
 int k_coarse_solve(Ctx *c, int mu) {
   if (c->Nc == 0) return 0;
   kk_coarse<<<1, 256, 0, c->stream>>>(c->Nc, mu, c->Lnu, c->d_E, c->d_Einv, c->d_T, c->d_Y, c->d_R);
+  HB_LAUNCH_END(c);
+}
+int k_vdots(Ctx *c, const Sub *s, int k, const double *V, const double *w, double *T) {
+  if (s->n == 0 || k == 0) return 0;
+  kk_zt<1><<<grid1(s->n, 1024), 256, 0, c->stream>>>(s->n, k, 0, V, s->d_d, w, T, k);
+  HB_LAUNCH_END(c);
+}
+int k_vupdate(Ctx *c, const Sub *s, int k, const double *V, const double *h, double sign, double *w) {
+  if (s->n == 0 || k == 0) return 0;
+  kk_vupdate<<<grid1(s->n), 256, k * sizeof(double), c->stream>>>(s->n, k, V, h, sign, w);
+  HB_LAUNCH_END(c);
+}
+int k_scal_copy(Ctx *c, int64_t n, double a, const double *x, double *y) {
+  if (n == 0) return 0;
+  kk_scal_copy<<<grid1(n), 256, 0, c->stream>>>(n, a, x, y);
   HB_LAUNCH_END(c);
 }
 int k_bc(Ctx *c, const Sub *s, int mu, const double *b, double *x) {

@@ -230,6 +230,18 @@ class Decomposition:
         capi.check(capi.lib().hpddm_b200_dot(self.ctx, capi.ptr_array(x), capi.ptr_array(y), mu, capi.ptr(res), capi.HOST))
         return res
 
+    # IterativeMethod::solve (include/HPDDM_iterative.hpp:1013-1111) with the Krylov basis resident in HBM
+    def solve(self, b, x0=None, correction="__default__", restart=40, max_it=100, tol=1e-6):
+        corr = self.correction if correction == "__default__" else correction
+        b = [_f(v) for v in b]
+        x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v).copy(order="F") for v in x0]
+        mu = b[0].shape[1]
+        it = C.c_int(0)
+        res = np.zeros(mu)
+        capi.check(capi.lib().hpddm_b200_solve(self.ctx, capi.ptr_array(b), capi.ptr_array(x), mu, capi.CORRECTION[corr], int(restart), int(max_it), float(tol),
+                                               capi.HOST, C.byref(it), capi.ptr(res)))
+        return it.value, x, res
+
     # --- hot path, device-resident vectors (raw addresses / torch tensors)
     def apply_device(self, ins, outs, mu, correction="__default__"):
         corr = self.correction if correction == "__default__" else correction

@@ -167,6 +167,15 @@ int hpddm_b200_coarse_solve(hpddm_b200_ctx *ctx, double *const *rhs, int mu, int
  * include/HPDDM_iterative.hpp:455-468).  result[mu] on the host. */
 int hpddm_b200_dot(hpddm_b200_ctx *ctx, const double *const *x, const double *const *y, int mu, double *result, int where);
 
+/* ---- device-resident Krylov driver ("next" row of SURVEY.md section 8f) ------------------------------ */
+/* IterativeMethod::solve -> GMRES (include/HPDDM_iterative.hpp:1013-1111, include/HPDDM_GMRES.hpp:31-158) with the
+ * reference defaults: right preconditioning, classical Gram-Schmidt, D-weighted inner products, convergence when
+ * |s_i| / ||b||_D <= tol.  The Krylov basis stays in HBM; x holds the initial guess on entry, the solution on exit;
+ * rel_residual[mu] (optional) receives the last preconditioned residual estimates.  Returns the iteration count in
+ * *iterations (the value IterativeMethod::solve returns). */
+int hpddm_b200_solve(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int correction, int restart, int max_it, double tol, int where,
+                     int *iterations, double *rel_residual);
+
 /* ---- introspection (Subdomain::statistics analogue, subdomain.hpp:405-454) -- */
 typedef struct hpddm_b200_stats {
   int64_t n;             /* dofs */

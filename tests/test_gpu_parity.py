@@ -215,3 +215,23 @@ def test_block_solve_matches_column_by_column(poisson3d, mu):
         got = s.solve(b)
         ref = w.solver[r].solve(b)
         assert relerr([got], [ref]) < TOL
+
+
+@pytest.mark.parametrize("correction", [None, DEFLATED])
+def test_device_resident_gmres_matches_reference_algorithm(poisson3d, correction):
+    """hpddm_b200_solve (Krylov basis in HBM) = same iteration count / solution as the restated
+    IterativeMethod::GMRES driving the oracle and as the host-driven loop over the C ABI."""
+    parts, w, deco = poisson3d
+    b = w.exchange([p["f"].copy() for p in parts])
+    it_ref, x_ref, _ = gmres(OracleOperator(w, correction), b)
+    it_dev, x_dev, res = deco.solve(b, correction=correction)
+    assert it_dev == it_ref
+    assert relerr(x_dev, x_ref) < 1e-8
+    assert np.all(res <= 1e-6)
+    r = w.compute_residual(x_dev, b)
+    assert np.all(r[:, 1] / r[:, 0] < 1e-5)
+    # restart path
+    it_ref2, x_ref2, _ = gmres(OracleOperator(w, correction), b, restart=3, max_it=60, tol=1e-8)
+    it_dev2, x_dev2, _ = deco.solve(b, correction=correction, restart=3, max_it=60, tol=1e-8)
+    assert it_dev2 == it_ref2
+    assert relerr(x_dev2, x_ref2) < 1e-8
