@@ -160,6 +160,11 @@ def run_b200(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     peak, peak_src = peaks()
+    traffic = None
+    try:  # DRAM bytes of one solve measured by ncu for this configuration (profiles/), if captured
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["cells"].get(str(m), {}).get("dram_bytes") if args.mu == 1 else None
+    except Exception:
+        pass
     trsv_gbs = by["trsv"] / (ms_trsv / args.steps * 1e-3) / 1e9
     out = {
         "metric": METRIC, "value": world * args.steps / (ms_dev * 1e-3), "unit": "subdomain-applies/s", "applies_per_s": args.steps / (ms_dev * 1e-3),
@@ -173,7 +178,7 @@ def run_b200(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "supernodal SpTRSV sweeps (k_fwd + k_bwd, all levels)", "bound": "hbm", "achieved": trsv_gbs, "peak": peak, "peak_source": peak_src,
-                     "unit": "GB/s", "frac": trsv_gbs / peak, "traffic": None, "algorithmic_bytes_per_launch_set": by["trsv"], "ms": ms_trsv / args.steps,
+                     "unit": "GB/s", "frac": trsv_gbs / peak, "traffic": traffic, "algorithmic_bytes_per_launch_set": by["trsv"], "ms": ms_trsv / args.steps,
                      "apply_gbs": by["apply"] / (ms_dev / args.steps * 1e-3) / 1e9},
         "clocks": sampler.summary(),
     }

@@ -235,3 +235,30 @@ def test_device_resident_gmres_matches_reference_algorithm(poisson3d, correction
     it_dev2, x_dev2, _ = deco.solve(b, correction=correction, restart=3, max_it=60, tol=1e-8)
     assert it_dev2 == it_ref2
     assert relerr(x_dev2, x_ref2) < 1e-8
+
+
+@pytest.mark.parametrize("method", ["asm", "oras", "soras"])
+def test_one_level_variants_asm_oras_soras(method):
+    """The other branches of Schwarz::apply (schwarz.hpp:538-546): ASM (SY), ORAS (OG, factorises a
+    user-supplied Robin-like matrix), SORAS (OS: D-scaled in and out, unscaled exchange)."""
+    import scipy.sparse as sp
+    from oracle.schwarz import OG, OS, SY
+    parts, w = make_world(3, 4, mu=2, N=(12, 12, 6), overlap=2)
+    robin = None
+    if method in ("oras", "soras"):
+        # optimised transmission conditions modelled by an extra diagonal term on the overlap
+        robin = [sp.csr_matrix(w.A[r] + sp.diags(0.5 * abs(w.A[r].diagonal()).max() * (w.d[r] < 1.0))) for r in range(w.P)]
+    w.type = {"asm": SY, "oras": OG, "soras": OS}[method]
+    w.numfact(robin)
+    from hpddm_b200 import Decomposition
+    deco = Decomposition(0)
+    for r, p in enumerate(parts):
+        s = deco.add(r)
+        s.initialize(p["Mat"], p["o"], p["mapping"])
+        s.setGridHint(*p["dims"])
+        s.setScaling(w.d[r])
+    for r, s in enumerate(deco.subs):
+        s.callNumfact(A=None if robin is None else robin[r], method=method)
+    x = rhs(parts, w, 31)
+    assert relerr(deco.apply(x, None), w.apply(x, None)) < TOL
+    deco.close()
