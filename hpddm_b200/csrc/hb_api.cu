@@ -122,7 +122,7 @@ static int ensure_capacity(Ctx *c, int mu) {
   for (double **p : {&c->d_T, &c->d_Y}) {
     if (*p) cudaFree(*p);
     *p = nullptr;
-    HB_CUDA(cudaMalloc(p, std::max<size_t>((size_t)std::max(c->Nc, 1) * mu, 1) * sizeof(double)));
+    HB_CUDA(cudaMalloc(p, std::max<size_t>((size_t)std::max(c->Lnu * c->nproc, 1) * mu, 1) * sizeof(double)));
   }
   if (c->d_res) cudaFree(c->d_res);
   HB_CUDA(cudaMalloc(&c->d_res, std::max(mu, 64) * sizeof(double)));
@@ -262,7 +262,7 @@ static int deflation_core(Ctx *c, const std::vector<const double *> &in, const s
     set_error("deflation: no coarse operator (call build_coarse / set_coarse)");
     return HPDDM_B200_ERR_STATE;
   }
-  HB_CUDA(cudaMemsetAsync(c->d_T, 0, (size_t)c->Nc * mu * sizeof(double), c->stream));
+  HB_CUDA(cudaMemsetAsync(c->d_T, 0, (size_t)c->Lnu * c->nproc * mu * sizeof(double), c->stream));
   for (size_t i = 0; i < c->subs.size(); ++i) HB_CHECK(k_zt_project(c, c->subs[i], mu, in[i], coarse_block(c, c->d_T, c->subs[i], mu), c->Lnu));
   if (c->nproc > 1) {
     // CoarseOperator::callSolver gather (coarse_operator_impl.hpp:1708) -> all-gather + replicated solve
@@ -413,7 +413,7 @@ int hpddm_b200_ctx_destroy(hpddm_b200_ctx *ctx) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (Sub *s : c->subs) sub_free(s);
-  for (void *p : {(void *)c->d_E, (void *)c->d_Einv, (void *)c->d_T, (void *)c->d_Y, (void *)c->d_R, (void *)c->d_res})
+  for (void *p : {(void *)c->d_E, (void *)c->d_Einv, (void *)c->d_T, (void *)c->d_Y, (void *)c->d_R, (void *)c->d_res, (void *)c->d_rowproc, (void *)c->d_rowloc})
     if (p) cudaFree(p);
   if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
   cudaStreamDestroy(c->stream);
@@ -730,33 +730,44 @@ int hpddm_b200_sub_set_vectors(hpddm_b200_sub *sub, const double *Z, int nu) {
   return 0;
 }
 
-// coarse numbering: [proc][local subdomain][vector]; requires the same number of
-// local subdomains and of local coarse rows on every process (uniform nu).
+// coarse numbering: [proc][local subdomain][vector].  Processes may own different numbers of coarse
+// rows (non-uniform nu, e.g. -nonuniform / geneo_threshold in the reference): the communication
+// layout pads every process block to Lmax = max_p Lnu_p rows so that one ncclAllGather moves it.
 static int coarse_layout(Ctx *c) {
   int Lnu = 0;
   for (Sub *s : c->subs) {
     s->coff = Lnu;
     Lnu += s->nu;
   }
-  c->Lnu = Lnu;
+  std::vector<int> all(c->nproc, Lnu);
   if (c->nproc > 1) {
     int *dbuf = nullptr;
     HB_CUDA(cudaMalloc(&dbuf, c->nproc * sizeof(int)));
     HB_CUDA(cudaMemcpyAsync(dbuf + c->proc_rank, &Lnu, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     HB_NCCL(g_nccl.AllGather(dbuf + c->proc_rank, dbuf, 1, NCCL_INT32, c->nccl, c->stream));
-    std::vector<int> all(c->nproc);
     HB_CUDA(cudaMemcpyAsync(all.data(), dbuf, c->nproc * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(dbuf);
-    for (int v : all)
-      if (v != Lnu) {
-        set_error("coarse space: %d local vectors here, %d on another process (non-uniform nu across processes is not supported yet)", Lnu, v);
-        return HPDDM_B200_ERR_STATE;
-      }
   }
-  c->Nc = Lnu * c->nproc;
-  c->loc_off = Lnu * c->proc_rank;
-  c->mu_cap = 0;  // coarse work space depends on Nc
+  c->Lnu_p = all;
+  c->coarse_off.assign(c->nproc + 1, 0);
+  int Lmax = 0;
+  for (int p = 0; p < c->nproc; ++p) {
+    c->coarse_off[p + 1] = c->coarse_off[p] + all[p];
+    Lmax = std::max(Lmax, all[p]);
+  }
+  c->Lnu = Lmax;
+  c->Nc = c->coarse_off[c->nproc];
+  c->loc_off = c->coarse_off[c->proc_rank];
+  std::vector<int> rowproc(c->Nc), rowloc(c->Nc);
+  for (int p = 0; p < c->nproc; ++p)
+    for (int r = 0; r < all[p]; ++r) {
+      rowproc[c->coarse_off[p] + r] = p;
+      rowloc[c->coarse_off[p] + r] = r;
+    }
+  HB_CHECK(up(rowproc, &c->d_rowproc, c->stream));
+  HB_CHECK(up(rowloc, &c->d_rowloc, c->stream));
+  c->mu_cap = 0;  // coarse work space depends on the layout
   return 0;
 }
 
@@ -864,7 +875,7 @@ int hpddm_b200_build_coarse(hpddm_b200_ctx *ctx) {
   for (int j = 0; j < P; ++j) {
     const int nuj = nu_all[j];
     if (nuj == 0) continue;
-    int gcol = (j / L) * Lnu;
+    int gcol = c->coarse_off[j / L];
     for (int t = (j / L) * L; t < j; ++t) gcol += nu_all[t];
     for (int i = 0; i < L; ++i) {
       Sub *s = c->subs[i];
@@ -884,17 +895,17 @@ int hpddm_b200_build_coarse(hpddm_b200_ctx *ctx) {
   std::vector<double> E((size_t)N * N, 0.0);
   if (c->nproc > 1) {
     double *d_all = nullptr;
-    HB_CUDA(cudaMalloc(&d_all, (size_t)N * N * sizeof(double)));
+    HB_CUDA(cudaMalloc(&d_all, std::max<size_t>((size_t)Lnu * c->nproc * N, 1) * sizeof(double)));
     HB_NCCL(g_nccl.AllGather(d_rows, d_all, (size_t)Lnu * N, NCCL_F64, c->nccl, c->stream));
-    std::vector<double> tmp((size_t)N * N);
+    std::vector<double> tmp((size_t)Lnu * c->nproc * N);
     HB_CUDA(cudaMemcpyAsync(tmp.data(), d_all, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_all);
     for (int p = 0; p < c->nproc; ++p)
       for (int col = 0; col < N; ++col)
-        for (int r = 0; r < Lnu; ++r) E[(size_t)p * Lnu + r + (size_t)col * N] = tmp[(size_t)p * Lnu * N + (size_t)col * Lnu + r];
+        for (int r = 0; r < c->Lnu_p[p]; ++r) E[(size_t)c->coarse_off[p] + r + (size_t)col * N] = tmp[(size_t)p * Lnu * N + (size_t)col * Lnu + r];
   } else {
-    HB_CUDA(cudaMemcpyAsync(E.data(), d_rows, E.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(E.data(), d_rows, E.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));  // single process: Lmax == N
     HB_CUDA(cudaStreamSynchronize(c->stream));
   }
   cudaFree(d_rows);
@@ -1009,7 +1020,7 @@ int hpddm_b200_coarse_solve(hpddm_b200_ctx *ctx, double *const *rhs, int mu, int
   }
   const cudaMemcpyKind kin = where == HPDDM_B200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const cudaMemcpyKind kout = where == HPDDM_B200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-  HB_CUDA(cudaMemsetAsync(c->d_T, 0, (size_t)c->Nc * mu * sizeof(double), c->stream));
+  HB_CUDA(cudaMemsetAsync(c->d_T, 0, (size_t)c->Lnu * c->nproc * mu * sizeof(double), c->stream));
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     if (s->nu == 0) continue;

@@ -178,7 +178,9 @@ struct Ctx {
   double *d_E = nullptr, *d_Einv = nullptr;  // Nc x Nc column-major
   double *d_T = nullptr, *d_Y = nullptr;     // Nc x mu_cap, layout [proc][col][row-in-proc]
   double *d_R = nullptr;                     // Nc residual of the coarse refinement step
-  int Lnu = 0;                               // coarse rows owned by each process (uniform)
+  int Lnu = 0;                               // Lmax: coarse rows per process block in the (padded) communication layout
+  std::vector<int> Lnu_p;                    // actual coarse rows of every process
+  int *d_rowproc = nullptr, *d_rowloc = nullptr;  // coarse row -> (process, row inside its block)
   int loc_off = 0;                           // first coarse row of this process
   double *d_res = nullptr;                   // small device scratch (dots)
   std::vector<double> E_host;

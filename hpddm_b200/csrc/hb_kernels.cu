@@ -160,10 +160,10 @@ __global__ void __launch_bounds__(256) kk_dot(int n, int mu, const double *__res
 
 // Replicated coarse solve (one CTA): Y = Einv T ; R = T - E Y ; Y += Einv R.
 // Coarse vectors use the communication layout [proc][col][row-in-proc]:
-//   v(r, c) = buf[(r / Lnu) * Lnu * mu + c * Lnu + r % Lnu]
-__global__ void __launch_bounds__(256) kk_coarse(int Nc, int mu, int Lnu, const double *__restrict__ E, const double *__restrict__ Einv,
-                                                 const double *__restrict__ T, double *Y, double *R) {
-  auto at = [&](int r, int c) -> int64_t { return (int64_t)(r / Lnu) * Lnu * mu + (int64_t)c * Lnu + r % Lnu; };
+//   v(r, c) = buf[rowproc[r] * Lmax * mu + c * Lmax + rowloc[r]]   (process blocks padded to Lmax rows)
+__global__ void __launch_bounds__(256) kk_coarse(int Nc, int mu, int Lnu, const int *__restrict__ rowproc, const int *__restrict__ rowloc,
+                                                 const double *__restrict__ E, const double *__restrict__ Einv, const double *__restrict__ T, double *Y, double *R) {
+  auto at = [&](int r, int c) -> int64_t { return (int64_t)rowproc[r] * Lnu * mu + (int64_t)c * Lnu + rowloc[r]; };
   for (int c = 0; c < mu; ++c) {
     for (int r = threadIdx.x; r < Nc; r += blockDim.x) {
       double acc = 0.0;
@@ -305,7 +305,7 @@ int k_dot(Ctx *c, const Sub *s, int mu, const double *x, const double *y, double
 }
 int k_coarse_solve(Ctx *c, int mu) {
   if (c->Nc == 0) return 0;
-  kk_coarse<<<1, 256, 0, c->stream>>>(c->Nc, mu, c->Lnu, c->d_E, c->d_Einv, c->d_T, c->d_Y, c->d_R);
+  kk_coarse<<<1, 256, 0, c->stream>>>(c->Nc, mu, c->Lnu, c->d_rowproc, c->d_rowloc, c->d_E, c->d_Einv, c->d_T, c->d_Y, c->d_R);
   HB_LAUNCH_END(c);
 }
 int k_vdots(Ctx *c, const Sub *s, int k, const double *V, const double *w, double *T) {

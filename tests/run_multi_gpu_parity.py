@@ -30,6 +30,8 @@ def main():
     w.multiplicity_scaling()
     w.numfact()
     w.solve_gevp([p["MatNeumann"] for p in parts], nu=3)
+    if os.environ.get("PARITY_NONUNIFORM"):   # different number of deflation vectors per rank (reference: -nonuniform)
+        w.set_vectors([z[:, :1 + (r % 3)] for r, z in enumerate(w.Z)])
     w.build_coarse()
     deco = Decomposition(local)
     deco.comm_init_torch()

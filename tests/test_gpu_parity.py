@@ -262,3 +262,17 @@ def test_one_level_variants_asm_oras_soras(method):
     x = rhs(parts, w, 31)
     assert relerr(deco.apply(x, None), w.apply(x, None)) < TOL
     deco.close()
+
+
+def test_nonuniform_number_of_deflation_vectors():
+    """-nonuniform of the reference's test matrix (Makefile:312-347): a different nu on every subdomain."""
+    parts, w = make_world(3, 4, nu=4, mu=2, N=(12, 12, 6), overlap=1)
+    w.set_vectors([z[:, :1 + r] for r, z in enumerate(w.Z)])   # nu = 1, 2, 3, 4
+    w.build_coarse()
+    deco = build_gpu_decomposition(parts, w, two_level=True)
+    assert deco.getCoarse().shape == (10, 10)
+    assert np.abs(deco.getCoarse() - w.E).max() / np.abs(w.E).max() < 1e-12
+    x = rhs(parts, w, 41)
+    for corr in (DEFLATED, ADDITIVE, BALANCED):
+        assert relerr(deco.apply(x, corr), w.apply(x, corr)) < TOL
+    deco.close()
