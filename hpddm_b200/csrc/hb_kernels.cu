@@ -38,27 +38,38 @@ __global__ void kk_fill(int64_t n, double v, double *y) {
 }
 
 // out[i,c] = (d ? d[i] : 1) * (beta * yin[i,c] + alpha * sum_k a[k] x[ja[k],c])
-__global__ void kk_spmv(int n, int mu, const int *__restrict__ ia, const int *__restrict__ ja, const double *__restrict__ a, double alpha,
-                        const double *__restrict__ x, double beta, const double *__restrict__ yin, double *out, const double *__restrict__ d) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// CSR "vector" kernel: LPR lanes cooperate on a row (coalesced a/ja reads), LPR chosen from the mean row length
+template <int LPR>
+__global__ void __launch_bounds__(256) kk_spmv(int n, int mu, const int *__restrict__ ia, const int *__restrict__ ja, const double *__restrict__ a, double alpha,
+                                               const double *__restrict__ x, double beta, const double *__restrict__ yin, double *out, const double *__restrict__ d) {
+  const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int i = (int)(gt / LPR), sub = (int)(gt % LPR);
+  if (i >= n) return;  // LPR divides the warp size: a whole row group leaves together
   const int k0 = ia[i], k1 = ia[i + 1];
   const double di = d ? d[i] : 1.0;
   for (int c = 0; c < mu; ++c) {
     const double *xc = x + (int64_t)c * n;
     double acc = 0.0;
-    for (int k = k0; k < k1; ++k) acc = fma(a[k], xc[ja[k]], acc);
-    double v = alpha * acc;
-    if (beta != 0.0) v += beta * yin[i + (int64_t)c * n];
-    out[i + (int64_t)c * n] = di * v;
+    for (int k = k0 + sub; k < k1; k += LPR) acc = fma(a[k], xc[ja[k]], acc);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LPR);
+    if (sub == 0) {
+      double v = alpha * acc;
+      if (beta != 0.0) v += beta * yin[i + (int64_t)c * n];
+      out[i + (int64_t)c * n] = di * v;
+    }
   }
 }
 
-// T[k + ldT*c] += sum_i Z[i + k*n] * d[i] * x[i + c*n] ; 1024 rows per CTA, Z read once per column group
+// T[k + ldT*c] += sum_i Z[i + k*n] * d[i] * x[i + c*n] ; 1024 rows per CTA, Z read once per column group.
+// Vectors are processed in chunks of KC: KC * 4 independent 8-byte loads per thread are in flight, the
+// KC * MB partial sums are reduced once per chunk (shuffles + one shared-memory pass) and published with
+// one atomic per (CTA, vector, column).
 template <int MB>
 __global__ void __launch_bounds__(256) kk_zt(int n, int nu, int c0, const double *__restrict__ Z, const double *__restrict__ d, const double *__restrict__ x,
                                              double *T, int ldT) {
-  __shared__ double red[8][MB];
+  constexpr int KC = 8 / MB >= 2 ? 8 / MB : 2;  // 8, 4, 2
+  __shared__ double red[8][KC * MB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int base = blockIdx.x * 1024;
   double w[4][MB];
@@ -68,29 +79,40 @@ __global__ void __launch_bounds__(256) kk_zt(int n, int nu, int c0, const double
 #pragma unroll
     for (int m = 0; m < MB; ++m) w[q][m] = (i < n) ? d[i] * x[i + (int64_t)(c0 + m) * n] : 0.0;
   }
-  for (int k = 0; k < nu; ++k) {
-    const double *zk = Z + (int64_t)k * n;
-    double acc[MB];
+  for (int k0 = 0; k0 < nu; k0 += KC) {
+    double z[KC][4];
 #pragma unroll
-    for (int m = 0; m < MB; ++m) acc[m] = 0.0;
+    for (int kk = 0; kk < KC; ++kk)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int i = base + tid + 256 * q;
-      const double z = (i < n) ? zk[i] : 0.0;
+      for (int q = 0; q < 4; ++q) {
+        const int i = base + tid + 256 * q;
+        z[kk][q] = (k0 + kk < nu && i < n) ? Z[i + (int64_t)(k0 + kk) * n] : 0.0;
+      }
+    double acc[KC][MB];
 #pragma unroll
-      for (int m = 0; m < MB; ++m) acc[m] = fma(z, w[q][m], acc[m]);
-    }
+    for (int kk = 0; kk < KC; ++kk)
 #pragma unroll
-    for (int m = 0; m < MB; ++m) {
-      acc[m] = warp_sum(acc[m]);
-      if (lane == 0) red[warp][m] = acc[m];
+      for (int m = 0; m < MB; ++m) {
+        double a = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a = fma(z[kk][q], w[q][m], a);
+        acc[kk][m] = warp_sum(a);
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int kk = 0; kk < KC; ++kk)
+#pragma unroll
+        for (int m = 0; m < MB; ++m) red[warp][kk * MB + m] = acc[kk][m];
     }
     __syncthreads();
-    if (tid < MB) {
-      double s = 0.0;
+    if (tid < KC * MB) {
+      const int kk = tid / MB, m = tid % MB;
+      if (k0 + kk < nu) {
+        double sum = 0.0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) s += red[q][tid];
-      atomicAdd(&T[k + (int64_t)ldT * (c0 + tid)], s);
+        for (int q = 0; q < 8; ++q) sum += red[q][tid];
+        atomicAdd(&T[k0 + kk + (int64_t)ldT * (c0 + m)], sum);
+      }
     }
     __syncthreads();
   }
@@ -240,7 +262,13 @@ int k_fill(Ctx *c, int64_t n, double v, double *y) {
 }
 int k_spmv(Ctx *c, const Sub *s, int mu, double alpha, const double *x, double beta, const double *yin, double *out, const double *d) {
   if (s->n == 0) return 0;
-  kk_spmv<<<grid1(s->n, 128), 128, 0, c->stream>>>(s->n, mu, s->d_ia, s->d_ja, s->d_a, alpha, x, beta, yin, out, d);
+  const double avg = (double)s->A.ia[s->n] / s->n;
+#define HB_SPMV(L) kk_spmv<L><<<grid1((int64_t)s->n * L), 256, 0, c->stream>>>(s->n, mu, s->d_ia, s->d_ja, s->d_a, alpha, x, beta, yin, out, d)
+  if (avg <= 12) HB_SPMV(4);
+  else if (avg <= 40) HB_SPMV(8);
+  else if (avg <= 96) HB_SPMV(16);
+  else HB_SPMV(32);
+#undef HB_SPMV
   HB_LAUNCH_END(c);
 }
 int k_zt_project(Ctx *c, const Sub *s, int mu, const double *x, double *T, int ldT) {
