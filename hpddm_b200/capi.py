@@ -54,6 +54,8 @@ _SIGS = {
     "hpddm_b200_multiplicity_scaling": (C.c_int, [_P, _P]),
     "hpddm_b200_sub_numfact": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_char]),
     "hpddm_b200_sub_set_vectors": (C.c_int, [_P, _P, C.c_int]),
+    "hpddm_b200_sub_solve_gevp": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_char, C.c_int, C.c_double, C.c_int, _P]),
+    "hpddm_b200_sub_get_vectors": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),
     "hpddm_b200_build_coarse": (C.c_int, [_P]),
     "hpddm_b200_set_coarse": (C.c_int, [_P, _P, C.c_int]),
     "hpddm_b200_get_coarse": (C.c_int, [_P, _P, C.POINTER(C.c_int)]),

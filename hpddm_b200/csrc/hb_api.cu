@@ -273,7 +273,7 @@ static int deflation_core(Ctx *c, const std::vector<const double *> &in, const s
   return halo(c, out.data(), mu);
 }
 
-static int solve_cols(Sub *s, const double *b, double *x, int mu, const double *scale, bool acc) {
+int solve_cols(Sub *s, const double *b, double *x, int mu, const double *scale, bool acc) {
   int col = 0;
   while (col < mu) {  // panels are streamed once per group of 4 / 2 / 1 right-hand sides
     const int g = (mu - col >= 4) ? 4 : ((mu - col >= 2) ? 2 : 1);
@@ -293,7 +293,6 @@ int apply_core(Ctx *c, const std::vector<const double *> &ind, const std::vector
   const size_t L = c->subs.size();
   const bool two_level = c->Nc > 0 && c->d_Einv && correction != HPDDM_B200_CORRECTION_NONE;
   if (!two_level) {  // schwarz.hpp:531-547
-    bool scaled_exchange = true;
     for (size_t i = 0; i < L; ++i) {
       Sub *s = c->subs[i];
       const size_t len = (size_t)s->n * mu;
@@ -308,14 +307,12 @@ int apply_core(Ctx *c, const std::vector<const double *> &ind, const std::vector
       case HPDDM_B200_PRCNDTNR_OS:
         HB_CHECK(k_scale(c, s->n, mu, s->d_d, ind[i], s->d_tmp));
         HB_CHECK(solve_cols(s, s->d_tmp, outd[i], mu, s->d_d, false));
-        scaled_exchange = false;
         break;
       default:  // SY
         HB_CHECK(solve_cols(s, ind[i], outd[i], mu, nullptr, false));
-        scaled_exchange = false;
       }
     }
-    (void)scaled_exchange;  // scaling already applied where the reference applies it
+    // the D-scaling is already applied where the reference applies it (fused into the solve epilogue for GE/OG/OS)
     bool all_no = true;
     for (Sub *s : c->subs) all_no = all_no && s->prcndtnr == HPDDM_B200_PRCNDTNR_NO;
     if (!all_no) HB_CHECK(halo(c, outd.data(), mu));
@@ -495,7 +492,8 @@ int hpddm_b200_sub_destroy(hpddm_b200_sub *sub) {
 }
 
 // MatrixCSR -> full-pattern, C-numbered, column-sorted host CSR
-static int to_host_csr(int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering, HostCSR &H) {
+extern "C++" {
+int hb::to_host_csr(int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering, HostCSR &H) {
   if (n < 0 || nnz < 0 || (n > 0 && (!ia || !ja || !a))) {
     set_error("set_matrix: bad arguments");
     return HPDDM_B200_ERR_ARG;
@@ -546,6 +544,7 @@ static int to_host_csr(int n, int nnz, const int *ia, const int *ja, const doubl
   H.symmetric = symm;
   return 0;
 }
+}  // extern "C++"
 
 int hpddm_b200_sub_set_matrix(hpddm_b200_sub *sub, int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering) {
   Sub *s = reinterpret_cast<Sub *>(sub);

@@ -214,6 +214,13 @@ int k_dot(Ctx *c, const Sub *s, int mu, const double *x, const double *y, double
 int k_coarse_solve(Ctx *c, int mu);  // d_Y = E^{-1} d_T with one refinement step
 int k_bc(Ctx *c, const Sub *s, int mu, const double *b, double *x);
 
+int k_zt_raw(Ctx *c, int n, int nu, const double *Z, const double *d, int mu, const double *x, double *T, int ldT);
+int k_zexp_raw(Ctx *c, int n, int nu, const double *Z, const double *d, int mu, const double *Y, int ldY, double *out);
+int k_spmv_raw(Ctx *c, int n, int64_t nnz, const int *ia, const int *ja, const double *a, int mu, double alpha, const double *x, double beta, const double *yin,
+               double *out, const double *d);
+int k_flush_tiny(Ctx *c, int64_t n, double tiny, double *v);
+int to_host_csr(int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering, HostCSR &H);
+int solve_cols(Sub *s, const double *b, double *x, int mu, const double *scale, bool acc);
 // orchestration helpers shared by hb_api.cu and hb_krylov.cu (device pointers, one per local subdomain)
 int check_ready(Ctx *c, int mu);
 int halo(Ctx *c, double *const *x, int mu);

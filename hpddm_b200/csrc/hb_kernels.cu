@@ -208,6 +208,12 @@ __global__ void __launch_bounds__(256) kk_coarse(int Nc, int mu, int Lnu, const 
   }
 }
 
+// v[i] = 0 where |v[i]| < tiny (Schwarz::solveGEVP post-processing, schwarz.hpp:713)
+__global__ void kk_flush_tiny(int64_t n, double tiny, double *v) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < n && fabs(v[t]) < tiny) v[t] = 0.0;
+}
+
 __global__ void kk_bc(int nbc, int n, int mu, const int *__restrict__ idx, const double *__restrict__ val, const double *__restrict__ b, double *x) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nbc * mu) return;
@@ -262,8 +268,13 @@ int k_fill(Ctx *c, int64_t n, double v, double *y) {
 }
 int k_spmv(Ctx *c, const Sub *s, int mu, double alpha, const double *x, double beta, const double *yin, double *out, const double *d) {
   if (s->n == 0) return 0;
-  const double avg = (double)s->A.ia[s->n] / s->n;
-#define HB_SPMV(L) kk_spmv<L><<<grid1((int64_t)s->n * L), 256, 0, c->stream>>>(s->n, mu, s->d_ia, s->d_ja, s->d_a, alpha, x, beta, yin, out, d)
+  return k_spmv_raw(c, s->n, s->A.ia[s->n], s->d_ia, s->d_ja, s->d_a, mu, alpha, x, beta, yin, out, d);
+}
+int k_spmv_raw(Ctx *c, int n, int64_t nnz, const int *ia, const int *ja, const double *a, int mu, double alpha, const double *x, double beta, const double *yin,
+               double *out, const double *d) {
+  if (n == 0) return 0;
+  const double avg = (double)nnz / n;
+#define HB_SPMV(L) kk_spmv<L><<<grid1((int64_t)n * L), 256, 0, c->stream>>>(n, mu, ia, ja, a, alpha, x, beta, yin, out, d)
   if (avg <= 12) HB_SPMV(4);
   else if (avg <= 40) HB_SPMV(8);
   else if (avg <= 96) HB_SPMV(16);
@@ -271,20 +282,22 @@ int k_spmv(Ctx *c, const Sub *s, int mu, double alpha, const double *x, double b
 #undef HB_SPMV
   HB_LAUNCH_END(c);
 }
-int k_zt_project(Ctx *c, const Sub *s, int mu, const double *x, double *T, int ldT) {
-  if (s->n == 0 || s->nu == 0) return 0;
-  const unsigned g = grid1(s->n, 1024);
+int k_zt_project(Ctx *c, const Sub *s, int mu, const double *x, double *T, int ldT) { return k_zt_raw(c, s->n, s->nu, s->d_Z, s->d_d, mu, x, T, ldT); }
+// T[k + ldT*col] += sum_i Z[i,k] d[i] x[i,col]  on raw arrays (Z: n x nu column-major)
+int k_zt_raw(Ctx *c, int n, int nu, const double *Z, const double *d, int mu, const double *x, double *T, int ldT) {
+  if (n == 0 || nu == 0) return 0;
+  const unsigned g = grid1(n, 1024);
   int c0 = 0;
   while (c0 < mu) {
     const int left = mu - c0;
     if (left >= 4) {
-      kk_zt<4><<<g, 256, 0, c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, x, T, ldT);
+      kk_zt<4><<<g, 256, 0, c->stream>>>(n, nu, c0, Z, d, x, T, ldT);
       c0 += 4;
     } else if (left >= 2) {
-      kk_zt<2><<<g, 256, 0, c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, x, T, ldT);
+      kk_zt<2><<<g, 256, 0, c->stream>>>(n, nu, c0, Z, d, x, T, ldT);
       c0 += 2;
     } else {
-      kk_zt<1><<<g, 256, 0, c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, x, T, ldT);
+      kk_zt<1><<<g, 256, 0, c->stream>>>(n, nu, c0, Z, d, x, T, ldT);
       c0 += 1;
     }
     c->launches++;
@@ -295,18 +308,23 @@ int k_zt_project(Ctx *c, const Sub *s, int mu, const double *x, double *T, int l
 int k_z_expand(Ctx *c, const Sub *s, int mu, const double *Y, int ldY, double *out) {
   if (s->n == 0) return 0;
   if (s->nu == 0) return k_fill(c, (int64_t)s->n * mu, 0.0, out);
-  const unsigned g = grid1(s->n);
+  return k_zexp_raw(c, s->n, s->nu, s->d_Z, s->d_d, mu, Y, ldY, out);
+}
+// out[i,col] = d[i] * sum_k Z[i,k] Y[k,col]  on raw arrays
+int k_zexp_raw(Ctx *c, int n, int nu, const double *Z, const double *d, int mu, const double *Y, int ldY, double *out) {
+  if (n == 0 || nu == 0) return 0;
+  const unsigned g = grid1(n);
   int c0 = 0;
   while (c0 < mu) {
     const int left = mu - c0;
     if (left >= 4) {
-      kk_zexp<4><<<g, 256, s->nu * 4 * sizeof(double), c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, Y, ldY, out);
+      kk_zexp<4><<<g, 256, nu * 4 * sizeof(double), c->stream>>>(n, nu, c0, Z, d, Y, ldY, out);
       c0 += 4;
     } else if (left >= 2) {
-      kk_zexp<2><<<g, 256, s->nu * 2 * sizeof(double), c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, Y, ldY, out);
+      kk_zexp<2><<<g, 256, nu * 2 * sizeof(double), c->stream>>>(n, nu, c0, Z, d, Y, ldY, out);
       c0 += 2;
     } else {
-      kk_zexp<1><<<g, 256, s->nu * sizeof(double), c->stream>>>(s->n, s->nu, c0, s->d_Z, s->d_d, Y, ldY, out);
+      kk_zexp<1><<<g, 256, nu * sizeof(double), c->stream>>>(n, nu, c0, Z, d, Y, ldY, out);
       c0 += 1;
     }
     c->launches++;
@@ -349,6 +367,11 @@ int k_vupdate(Ctx *c, const Sub *s, int k, const double *V, const double *h, dou
 int k_scal_copy(Ctx *c, int64_t n, double a, const double *x, double *y) {
   if (n == 0) return 0;
   kk_scal_copy<<<grid1(n), 256, 0, c->stream>>>(n, a, x, y);
+  HB_LAUNCH_END(c);
+}
+int k_flush_tiny(Ctx *c, int64_t n, double tiny, double *v) {
+  if (n == 0) return 0;
+  kk_flush_tiny<<<grid1(n), 256, 0, c->stream>>>(n, tiny, v);
   HB_LAUNCH_END(c);
 }
 int k_bc(Ctx *c, const Sub *s, int mu, const double *b, double *x) {

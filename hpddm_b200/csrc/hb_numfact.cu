@@ -32,12 +32,6 @@ namespace {
 
 static int SMALL = 160;   // fronts with s1+s2 <= SMALL are factored by the batched kernel
 
-struct FrontDev {
-  int64_t foff;  // element offset of F in the level buffer
-  int64_t poff;  // panel offset
-  int s1, s2;
-};
-
 __global__ void k_assemble(int64_t ne, const int *__restrict__ efront, const int *__restrict__ erow, const int *__restrict__ ecol,
                            const double *__restrict__ eval, const int64_t *__restrict__ foff, const int *__restrict__ fs, double *F) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

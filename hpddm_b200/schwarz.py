@@ -91,6 +91,25 @@ class Schwarz:
         assert Z.shape[0] == self.n
         capi.check(capi.lib().hpddm_b200_sub_set_vectors(self.h, capi.ptr(Z), int(Z.shape[1])))
 
+    # Schwarz::solveGEVP<EIGENSOLVER>(MatNeumann)  (include/HPDDM_schwarz.hpp:665-715), on the GPU
+    def solveGEVP(self, MatNeumann, nu=20, tol=1e-6, max_it=100, sym=False):
+        A = sp.csr_matrix(MatNeumann)
+        ia = np.ascontiguousarray(A.indptr, dtype=np.int32)
+        ja = np.ascontiguousarray(A.indices, dtype=np.int32)
+        a = np.ascontiguousarray(A.data, dtype=np.float64)
+        lam = np.zeros(nu)
+        it = capi.check(capi.lib().hpddm_b200_sub_solve_gevp(self.h, A.shape[0], int(a.size), capi.ptr(ia), capi.ptr(ja), capi.ptr(a), int(bool(sym)), b"C",
+                                                               int(nu), float(tol), int(max_it), capi.ptr(lam)))
+        return lam, it
+
+    def getVectors(self):
+        nu = C.c_int(0)
+        capi.check(capi.lib().hpddm_b200_sub_get_vectors(self.h, None, C.byref(nu)))
+        Z = np.zeros((self.n, nu.value), order="F")
+        if nu.value:
+            capi.check(capi.lib().hpddm_b200_sub_get_vectors(self.h, capi.ptr(Z), C.byref(nu)))
+        return Z
+
     # SUBDOMAIN::solve(b, x, n)  (e.g. include/HPDDM_SuiteSparse.hpp:388-423)
     def solve(self, b):
         b = _f(b)

@@ -126,6 +126,15 @@ int hpddm_b200_sub_numfact(hpddm_b200_sub *sub, int prcndtnr, int n, int nnz, co
 /* Preconditioner::setVectors (include/HPDDM_preconditioner.hpp:358-362): Z =
  * ev_[0], one contiguous column-major n x nu block.  Copied to the device. */
 int hpddm_b200_sub_set_vectors(hpddm_b200_sub *sub, const double *Z, int nu);
+/* Schwarz::solveGEVP<EIGENSOLVER>(A_Neumann) (include/HPDDM_schwarz.hpp:665-715 + scaleIntoOverlap 622-657; the reference's
+ * EIGENSOLVER is ARPACK in shift-invert mode, include/HPDDM_ARPACK.hpp:84-178): the nu smallest eigenpairs of
+ * A_Neu x = lambda (D A_Neu D restricted to the overlap) x, computed on the GPU (block subspace iteration on A_Neu^-1 B with the
+ * block SpTRSV) and installed as the deflation vectors.  tol <= 0 -> 1e-6 (eigensolver_tol), max_it <= 0 -> 100.
+ * eigenvalues[nu] optional.  Returns the number of iterations (> 0) or a negative error code.  Needs set_neighbors + set_scaling. */
+int hpddm_b200_sub_solve_gevp(hpddm_b200_sub *sub, int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering, int nu, double tol,
+                              int max_it, double *eigenvalues);
+/* Preconditioner::getVectors (include/HPDDM_preconditioner.hpp): copy Z (n x nu, column-major) back to the host; Z may be NULL to query nu */
+int hpddm_b200_sub_get_vectors(hpddm_b200_sub *sub, double *Z, int *nu);
 /* Schwarz::buildTwo (include/HPDDM_schwarz.hpp:440-495 -> preconditioner.hpp:124-257
  * -> CoarseOperator::construction, coarse_operator_impl.hpp:220-272; Galerkin
  * blocks of include/HPDDM_operator.hpp:395-528), collective: assembles

@@ -276,3 +276,67 @@ def test_nonuniform_number_of_deflation_vectors():
     for corr in (DEFLATED, ADDITIVE, BALANCED):
         assert relerr(deco.apply(x, corr), w.apply(x, corr)) < TOL
     deco.close()
+
+
+def test_error_paths_return_negative_codes_not_crashes():
+    """HPDDM_CALL only propagates negative returns (include/HPDDM_iterative.hpp:30-34): every misuse
+    must come back as an error code + message, never as a crash or a silent fallback."""
+    import scipy.sparse as sp
+    from hpddm_b200 import Decomposition, capi
+    deco = Decomposition(0)
+    s = deco.add(0)
+    A = sp.diags([[-1.0] * 9, [2.0] * 10, [-1.0] * 9], [-1, 0, 1], format="csr")
+    s.initialize(A, [], [])
+    s.setScaling(np.ones(10))
+    x = [np.ones((10, 1), order="F")]
+    with pytest.raises(capi.HpddmB200Error, match="no factorisation"):
+        deco.apply(x, None)                                   # apply before callNumfact
+    s.callNumfact()
+    assert relerr(deco.apply(x, None), [np.linalg.solve(A.toarray(), x[0])]) < 1e-13
+    with pytest.raises(capi.HpddmB200Error, match="no coarse operator"):
+        deco.deflation(x)                                     # deflation without buildTwo
+    assert relerr(deco.apply(x, "deflated"), deco.apply(x, None)) == 0.0   # correction set but no coarse space: one-level branch (schwarz.hpp:531)
+    # singular matrix: numfact reports a pivot breakdown
+    s2 = deco.add(1)
+    Z = sp.csr_matrix(np.zeros((4, 4)) + np.eye(4) * 0.0 + np.diag([1.0, 0.0, 1.0, 1.0]))
+    s2.initialize(Z + sp.csr_matrix(([0.0], ([1], [1])), shape=(4, 4)), [], [])
+    with pytest.raises(capi.HpddmB200Error, match="pivot"):
+        s2.callNumfact()
+    # neighbour that does not exist in a single-process context
+    deco2 = Decomposition(0)
+    t = deco2.add(0)
+    t.initialize(A, [3], [np.array([0, 1], dtype=np.int32)])
+    t.setScaling(np.ones(10))
+    with pytest.raises(capi.HpddmB200Error, match="does not exist"):
+        deco2.exchange(x)
+    deco.close()
+    deco2.close()
+
+
+def test_geneo_eigensolve_on_gpu_spans_the_reference_subspace():
+    """Schwarz::solveGEVP on the GPU: same eigenvalues and deflation subspace as the dense generalised
+    eigensolve of the oracle (ARPACK's tolerance in the reference is 1e-6), same GMRES iteration count."""
+    import scipy.linalg as sla
+    parts, w = make_world(3, 8, nu=5, mu=1, N=(12, 12, 12), overlap=1)
+    deco = build_gpu_decomposition(parts, w, two_level=False)
+    for r, s in enumerate(deco.subs):
+        lam, it = s.solveGEVP(parts[r]["MatNeumann"], nu=5)
+        assert 0 < it < 100
+        Zg = s.getVectors()
+        A = parts[r]["MatNeumann"].toarray()
+        B = w.scale_into_overlap(parts[r]["MatNeumann"], r).toarray()
+        th = sla.eigh(B, A, eigvals_only=True)[::-1][:5]
+        assert np.abs(lam - 1.0 / th).max() / np.abs(1.0 / th).max() < 1e-6
+        # principal angles between the two 5-dimensional subspaces
+        Qg, _ = np.linalg.qr(Zg)
+        Qo, _ = np.linalg.qr(w.Z[r])
+        sv = np.linalg.svd(Qg.T @ Qo, compute_uv=False)
+        assert np.sqrt(max(0.0, 1 - sv.min() ** 2)) < 1e-3
+    deco.buildTwo()
+    b = w.exchange([p["f"].copy() for p in parts])
+    it_ref, _, _ = gmres(OracleOperator(w, DEFLATED), b)
+    it_gpu, x, _ = deco.solve(b, correction=DEFLATED)
+    assert it_gpu == it_ref
+    res = w.compute_residual(x, b)
+    assert np.all(res[:, 1] / res[:, 0] < 1e-5)
+    deco.close()
