@@ -317,17 +317,17 @@ def test_geneo_eigensolve_on_gpu_spans_the_reference_subspace():
     """Schwarz::solveGEVP on the GPU: same eigenvalues and deflation subspace as the dense generalised
     eigensolve of the oracle (ARPACK's tolerance in the reference is 1e-6), same GMRES iteration count."""
     import scipy.linalg as sla
-    parts, w = make_world(3, 8, nu=5, mu=1, N=(12, 12, 12), overlap=1)
+    parts, w = make_world(3, 8, nu=4, mu=1, N=(12, 12, 12), overlap=1)
     deco = build_gpu_decomposition(parts, w, two_level=False)
     for r, s in enumerate(deco.subs):
-        lam, it = s.solveGEVP(parts[r]["MatNeumann"], nu=5)
+        lam, it = s.solveGEVP(parts[r]["MatNeumann"], nu=4)
         assert 0 < it < 100
         Zg = s.getVectors()
         A = parts[r]["MatNeumann"].toarray()
         B = w.scale_into_overlap(parts[r]["MatNeumann"], r).toarray()
-        th = sla.eigh(B, A, eigvals_only=True)[::-1][:5]
+        th = sla.eigh(B, A, eigvals_only=True)[::-1][:4]
         assert np.abs(lam - 1.0 / th).max() / np.abs(1.0 / th).max() < 1e-6
-        # principal angles between the two 5-dimensional subspaces
+        # principal angles between the two subspaces (nu = 4 = 1 + a 3-fold degenerate cluster of the cubic subdomain: a closed cluster)
         Qg, _ = np.linalg.qr(Zg)
         Qo, _ = np.linalg.qr(w.Z[r])
         sv = np.linalg.svd(Qg.T @ Qo, compute_uv=False)
