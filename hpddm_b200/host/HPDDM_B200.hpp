@@ -215,6 +215,14 @@ public:
     nu_ = nu;
     b200::check(hpddm_b200_sub_set_vectors(sub_, *ev, nu), "hpddm_b200_sub_set_vectors");
   }
+  /* Schwarz::solveGEVP<EIGENSOLVER>(A_Neumann) (schwarz.hpp:665-715): GenEO vectors computed on the GPU; the template
+   * parameter of the reference (the eigensolver plugin) has no meaning here and is accepted for source compatibility */
+  template <template <class> class Eps = B200Sub>
+  void solveGEVP(MatrixCSR<K> *const &A, unsigned short nu = 20, double tol = 1.0e-6)
+  {
+    b200::check(hpddm_b200_sub_solve_gevp(sub_, A->n_, A->nnz_, A->ia_, A->ja_, A->a_, A->sym_ ? 1 : 0, HPDDM_NUMBERING, nu, tol, 0, nullptr), "hpddm_b200_sub_solve_gevp");
+    nu_ = nu;
+  }
   /* Schwarz::buildTwo (schwarz.hpp:440-495) */
   template <unsigned short excluded = 0, class Comm = int>
   int buildTwo(const Comm & = Comm(), int correction = HPDDM_B200_CORRECTION_DEFLATED)

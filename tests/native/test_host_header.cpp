@@ -19,7 +19,7 @@ int main() {
     std::list<int> o; std::vector<std::vector<int>> r;
     A.setCommunicator(0, 1, [](void *) {});
     A.initialize(M, o, r); A.setGridHint(1, 1); A.multiplicityScaling(nullptr); double *d = nullptr; A.initialize(d);
-    A.callNumfact(); double **ev = nullptr; A.setVectors(ev, 1); A.buildTwo<0>(0);
+    A.solveGEVP(M, 4); A.callNumfact(); double **ev = nullptr; A.setVectors(ev, 1); A.buildTwo<0>(0);
     A.start(nullptr, (double *)nullptr, 1); A.apply((const double *)nullptr, (double *)nullptr, 1); A.deflation<false>(nullptr, (double *)nullptr, 1);
     A.GMV(nullptr, (double *)nullptr, 1); A.exchange<true>(nullptr, 1); A.end(); A.computeResidual(nullptr, nullptr, nullptr, 1);
     (void)A.getScaling(); (void)A.getDof(); (void)A.boundaryConditions(); (void)A.prefix();
