@@ -58,8 +58,9 @@ __device__ __forceinline__ double reduce8(double (&a)[8], int lane) {
 // Forward sweep work item, MU right-hand sides at once (panel values are read once for all MU).
 // R = 8 / MU rows and JU = MU column slabs are in flight together (8 x 128-bit panel loads per
 // lane), the R * MU = 8 partial sums go through one reduce8.
+// (MU = 1 is held to 64 registers -> 4 CTAs / SM: measured +2 % at m = 128 over the 80-register build, profiles/README.md)
 template <int MU>
-__global__ void __launch_bounds__(256, 3) k_fwd(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
+__global__ void __launch_bounds__(256, MU == 1 ? 4 : 3) k_fwd(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
                                                 const int *__restrict__ rowidx, const double *__restrict__ pan, double *b, double *y, int n) {
   constexpr int R = 8 / MU, JU = MU, CW = FCH / MU;
   __shared__ __align__(16) double bs[8][FCH];
@@ -129,96 +130,6 @@ __global__ void __launch_bounds__(256, 3) k_fwd(const FwdItem *__restrict__ item
       if ((lane & 3) == 0 && q < nr) {
         if (pivot) atomicAdd(&y[(int64_t)m * n + f.p0 + RB * w.rblk + r + q], v);
         else atomicAdd(&b[(int64_t)m * n + rowidx[f.rptr + RB * (w.rblk - nb1) + r + q]], -v);
-      }
-    }
-  }
-}
-
-// ---- experimental forward variants for MU = 1 (selected with HPDDM_B200_FWD_VAR; see profiles/README.md)
-// VAR 1: same code as k_fwd<1> limited to 64 registers (4 CTAs / SM)
-// VAR 2: all 32 rows of the block keep their accumulator for the whole column chunk: one pipeline drain per item
-template <int VAR>
-__global__ void __launch_bounds__(256, VAR == 1 ? 4 : 2) k_fwd_x(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
-                                                                 const int *__restrict__ rowidx, const double *__restrict__ pan, double *b, double *y, int n) {
-  __shared__ __align__(16) double bs[8][FCH];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t it = (int64_t)blockIdx.x * 8 + warp;
-  if (it >= nitems) return;
-  const FwdItem w = items[it];
-  const Front f = fronts[w.front];
-  const int s1 = f.s1, nb1 = (s1 + RB - 1) / RB;
-  const double *base;
-  int nrows, stride, cmax;
-  const bool pivot = w.rblk < nb1;
-  if (pivot) {
-    const int k = w.rblk;
-    stride = hb_wblk(s1, k);
-    base = pan + f.poff + hb_blk_off(k);
-    nrows = min(RB, s1 - RB * k);
-    cmax = min(s1, RB * (k + 1));
-  } else {
-    const int k2 = w.rblk - nb1;
-    stride = hb_ldp(s1);
-    base = pan + f.poff + hb_upd_off(s1) + (int64_t)k2 * RB * stride;
-    nrows = min(RB, f.s2 - RB * k2);
-    cmax = s1;
-  }
-  const int c1 = min(cmax, w.c0 + FCH);
-  const int nc = c1 - w.c0;
-  double *mybs = bs[warp];
-  for (int c = lane; c < nc; c += 32) mybs[c] = b[f.p0 + w.c0 + c];
-  if ((nc & 1) && lane == 0) mybs[nc] = 0.0;
-  __syncwarp();
-  const int nv = (nc + 1) >> 1;
-  const double2 *bs2 = reinterpret_cast<const double2 *>(mybs);
-  const int st2 = stride >> 1;
-  const int rsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  const double2 *p = reinterpret_cast<const double2 *>(base + w.c0);
-  if (VAR == 1) {
-    for (int r = 0; r < nrows; r += 8) {
-      const int nr = min(8, nrows - r);
-      double a[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) a[q] = 0.0;
-      for (int j = lane; j < nv; j += 32) {
-        double2 t[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) t[q] = (q < nr) ? ldg_stream(p + (int64_t)(r + q) * st2 + j) : make_double2(0.0, 0.0);
-        const double2 bb = bs2[j];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) a[q] = fma(t[q].x, bb.x, fma(t[q].y, bb.y, a[q]));
-      }
-      const double v = reduce8(a, lane);
-      if ((lane & 3) == 0 && rsel < nr) {
-        if (pivot) atomicAdd(&y[f.p0 + RB * w.rblk + r + rsel], v);
-        else atomicAdd(&b[rowidx[f.rptr + RB * (w.rblk - nb1) + r + rsel]], -v);
-      }
-    }
-  } else {
-    double a[32];
-#pragma unroll
-    for (int q = 0; q < 32; ++q) a[q] = 0.0;
-    for (int j = lane; j < nv; j += 32) {
-      const double2 bb = bs2[j];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        double2 t[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) t[q] = (8 * g + q < nrows) ? ldg_stream(p + (int64_t)(8 * g + q) * st2 + j) : make_double2(0.0, 0.0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) a[8 * g + q] = fma(t[q].x, bb.x, fma(t[q].y, bb.y, a[8 * g + q]));
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      double aa[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) aa[q] = a[8 * g + q];
-      const double v = reduce8(aa, lane);
-      const int r = 8 * g + rsel;
-      if ((lane & 3) == 0 && r < nrows) {
-        if (pivot) atomicAdd(&y[f.p0 + RB * w.rblk + r], v);
-        else atomicAdd(&b[rowidx[f.rptr + RB * (w.rblk - nb1) + r]], -v);
       }
     }
   }
@@ -342,10 +253,7 @@ static int launch_levels(Sub *s, cudaStream_t st) {
   for (int l = 0; l < S.nlevels; ++l) {
     const int64_t i0 = S.fwd_ptr[l], ni = S.fwd_ptr[l + 1] - i0;
     if (ni <= 0) continue;
-    static const int fwd_var = getenv("HPDDM_B200_FWD_VAR") ? atoi(getenv("HPDDM_B200_FWD_VAR")) : 0;
-    if (MU == 1 && fwd_var == 1) k_fwd_x<1><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
-    else if (MU == 1 && fwd_var == 2) k_fwd_x<2><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
-    else k_fwd<MU><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+    k_fwd<MU><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
   }
   for (int l = S.nlevels - 1; l >= 0; --l) {
     const int64_t i0 = S.bwd_ptr[l], ni = S.bwd_ptr[l + 1] - i0;
