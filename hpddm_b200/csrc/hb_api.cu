@@ -79,6 +79,10 @@ constexpr int NCCL_INT32 = 2, NCCL_F64 = 8, NCCL_SUM = 0;
 
 // uploads are issued on the context's (non-blocking) stream and waited for: a plain cudaMemcpy
 // from pageable memory is neither ordered against that stream nor guaranteed to have landed
+int nccl_allgather_bytes(Ctx *c, const void *send, void *recv, size_t bytes_per_rank) {
+  if (c->nproc > 1) HB_NCCL(g_nccl.AllGather(send, recv, bytes_per_rank, 0 /* ncclChar */, c->nccl, c->stream));
+  return 0;
+}
 int nccl_allreduce_sum(Ctx *c, double *buf, int count) {
   if (c->nproc > 1) HB_NCCL(g_nccl.AllReduce(buf, buf, count, NCCL_F64, NCCL_SUM, c->nccl, c->stream));
   return 0;
@@ -158,10 +162,15 @@ static int build_links(Ctx *c) {
 
 // halo sum  x_s[map] += neighbours' values  (Subdomain::exchange, subdomain.hpp:115-130),
 // all mu columns and all neighbours in one round.  x[] = device pointers per local subdomain.
-int halo(Ctx *c, double *const *x, int mu) {
+int halo(Ctx *c, double *const *x, int mu, bool allow_p2p) {
   bool any = false;
   for (Sub *s : c->subs) any = any || s->h > 0;
   if (!any) return 0;
+  if (allow_p2p) {
+    const int done = p2p_halo(c, x, mu);  // one subdomain per process: NVLink peer-memory path (hb_p2p.cu)
+    if (done < 0) return done;
+    if (done == 1) return 0;
+  }
   int li = 0;
   for (Sub *s : c->subs) HB_CHECK(k_pack(c, s, mu, x[li++], s->d_send));
   // local neighbours: device copy out of the peer's send segment
@@ -250,7 +259,7 @@ int stage_out(Ctx *c, double *const *out, int mu, int where) {
     HB_CUDA(cudaMemcpyAsync(out[i], s->d_out, (size_t)s->n * mu * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
   HB_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return p2p_check(c);
 }
 
 // coarse vectors: layout [proc][col][row-in-proc] (see kk_coarse)
@@ -409,6 +418,7 @@ int hpddm_b200_ctx_destroy(hpddm_b200_ctx *ctx) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  p2p_free(c);
   for (Sub *s : c->subs) sub_free(s);
   for (void *p : {(void *)c->d_E, (void *)c->d_Einv, (void *)c->d_T, (void *)c->d_Y, (void *)c->d_R, (void *)c->d_res, (void *)c->d_rowproc, (void *)c->d_rowloc})
     if (p) cudaFree(p);
@@ -673,7 +683,7 @@ int hpddm_b200_multiplicity_scaling(hpddm_b200_ctx *ctx, double *const *d) {
     HB_CUDA(cudaMemcpyAsync(s->d_work, d[i], (size_t)s->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     src[i] = s->d_work;
   }
-  HB_CHECK(halo(c, src.data(), 1));
+  HB_CHECK(halo(c, src.data(), 1, false));  // the send / recv staging buffers themselves are read back below: NCCL path
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     std::vector<double> recv(s->h), send(s->h);

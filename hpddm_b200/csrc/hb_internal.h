@@ -123,6 +123,7 @@ struct DeviceFactor {
 };
 
 struct Ctx;
+struct P2P;
 
 struct Sub {
   Ctx *ctx = nullptr;
@@ -189,6 +190,7 @@ struct Ctx {
   size_t pin_bytes = 0;
   int mu_cap = 0;
   bool started = false;
+  P2P *p2p = nullptr;  // NVLink peer-memory halo state (hb_p2p.cu)
 };
 
 // ---------------------------------------------------------------- kernels (launchers)
@@ -223,13 +225,17 @@ int to_host_csr(int n, int nnz, const int *ia, const int *ja, const double *a, i
 int solve_cols(Sub *s, const double *b, double *x, int mu, const double *scale, bool acc);
 // orchestration helpers shared by hb_api.cu and hb_krylov.cu (device pointers, one per local subdomain)
 int check_ready(Ctx *c, int mu);
-int halo(Ctx *c, double *const *x, int mu);
+int halo(Ctx *c, double *const *x, int mu, bool allow_p2p = true);
 int apply_core(Ctx *c, const std::vector<const double *> &in, const std::vector<double *> &out, int mu, int correction);
 int gmv_core(Ctx *c, const std::vector<const double *> &in, const std::vector<double *> &out, int mu);
 int stage_in(Ctx *c, const double *const *in, int mu, int where, std::vector<const double *> &dev);
 void out_ptrs(Ctx *c, double *const *out, int where, std::vector<double *> &dev);
 int stage_out(Ctx *c, double *const *out, int mu, int where);
 int nccl_allreduce_sum(Ctx *c, double *buf, int count);
+int nccl_allgather_bytes(Ctx *c, const void *send, void *recv, size_t bytes_per_rank);
+int p2p_halo(Ctx *c, double *const *x, int mu);  // 1 = done over peer memory, 0 = use NCCL
+int p2p_check(Ctx *c);
+void p2p_free(Ctx *c);
 // Krylov helper kernels (hb_kernels.cu)
 int k_vdots(Ctx *c, const Sub *s, int k, const double *V, const double *w, double *T);      // T[j] += sum_i d_i V[i,j] w[i]
 int k_vupdate(Ctx *c, const Sub *s, int k, const double *V, const double *h, double sign, double *w);  // w += sign * V h
