@@ -65,6 +65,7 @@ struct FwdItem {
   int front;
   int rblk;  // row block index: < nb1 -> pivot block, else update block (rblk - nb1)
   int c0;    // first column
+  int cw;    // columns of this item (<= FCH; smaller on levels that would otherwise under-fill the GPU)
 };
 // backward-sweep work item (one warp): BCH columns x up to BROWS rows
 struct BwdItem {

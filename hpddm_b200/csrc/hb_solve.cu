@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256, MU == 1 ? 4 : 3) k_fwd(const FwdItem *__r
     nrows = min(RB, f.s2 - RB * k2);
     cmax = s1;
   }
-  const int c1 = min(cmax, w.c0 + FCH);
+  const int c1 = min(cmax, w.c0 + w.cw);
   double *mybs = bs[warp];
   const double2 *bs2 = reinterpret_cast<const double2 *>(mybs);
   const int st2 = stride >> 1;  // row stride in double2

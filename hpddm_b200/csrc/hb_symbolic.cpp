@@ -329,23 +329,47 @@ int symbolic_analyze(const HostCSR &A, int nx, int ny, int nz, int dof, int leaf
   }
   S.panel_elems = off;
   S.nnz_factor = nnzf;
-  // ---- work items
+  // ---- work items.  Default granularity: forward 32 rows x FCH columns, backward BROWS rows x BCH columns per warp.
+  // Levels whose panels would yield fewer items than the GPU has warp slots (the few huge fronts near the
+  // root of small problems) get proportionally finer items so that all SMs stream.
+  const int64_t target_items = 148 * 4 * 8;  // SMs x resident CTAs x warps
   S.fwd_ptr.assign(S.nlevels + 1, 0);
   S.bwd_ptr.assign(S.nlevels + 1, 0);
   for (int l = 0; l < S.nlevels; ++l) {
+    auto count = [&](int fch, int brows, int64_t &nf, int64_t &nbw) {
+      nf = nbw = 0;
+      for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+        const Front &fr = S.fronts[S.level_order[q]];
+        const int nb1 = (fr.s1 + RB - 1) / RB, nb2 = (fr.s2 + RB - 1) / RB;
+        for (int k = 0; k < nb1; ++k) nf += (std::min(fr.s1, RB * (k + 1)) + fch - 1) / fch;
+        nf += (int64_t)nb2 * ((fr.s1 + fch - 1) / fch);
+        for (int c0 = 0; c0 < fr.s1; c0 += BCH) nbw += (fr.s1 + fr.s2 - (c0 / RB) * RB + brows - 1) / brows;
+      }
+    };
+    int fch = FCH, brows = BROWS;
+    int64_t nf, nbw;
+    count(fch, brows, nf, nbw);
+    while (nf < target_items && fch > 128) {
+      fch /= 2;
+      count(fch, brows, nf, nbw);
+    }
+    while (nbw < target_items && brows > 32) {
+      brows /= 2;
+      count(fch, brows, nf, nbw);
+    }
     for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
       int f = S.level_order[q];
       const Front &fr = S.fronts[f];
       const int nb1 = (fr.s1 + RB - 1) / RB, nb2 = (fr.s2 + RB - 1) / RB;
       for (int k = 0; k < nb1; ++k) {
         int w = std::min(fr.s1, RB * (k + 1));
-        for (int c0 = 0; c0 < w; c0 += FCH) S.fwd.push_back({f, k, c0});
+        for (int c0 = 0; c0 < w; c0 += fch) S.fwd.push_back({f, k, c0, fch});
       }
       for (int k = 0; k < nb2; ++k)
-        for (int c0 = 0; c0 < fr.s1; c0 += FCH) S.fwd.push_back({f, nb1 + k, c0});
+        for (int c0 = 0; c0 < fr.s1; c0 += fch) S.fwd.push_back({f, nb1 + k, c0, fch});
       for (int c0 = 0; c0 < fr.s1; c0 += BCH) {
         int rstart = (c0 / RB) * RB;  // rows above hold structural zeros in this chunk
-        for (int r0 = rstart; r0 < fr.s1 + fr.s2; r0 += BROWS) S.bwd.push_back({f, c0, r0, std::min(BROWS, fr.s1 + fr.s2 - r0)});
+        for (int r0 = rstart; r0 < fr.s1 + fr.s2; r0 += brows) S.bwd.push_back({f, c0, r0, std::min(brows, fr.s1 + fr.s2 - r0)});
       }
     }
     S.fwd_ptr[l + 1] = (int64_t)S.fwd.size();
