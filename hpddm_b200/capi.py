@@ -1,4 +1,5 @@
-"""ctypes binding of the C ABI declared in include/hpddm_b200.h.
+"""ctypes binding of the C ABI declared in include/hpddm_b200.h (K = double) and
+include/hpddm_b200z.h (K = complex double; same entry points with the hpddm_b200z_ prefix).
 
 This is the *only* way Python code reaches the product: through the same
 extern "C" entry points a C++/MPI host program binds.  There is no CPU
@@ -71,6 +72,9 @@ _SIGS = {
     "hpddm_b200_sub_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "hpddm_b200_solve": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
 }
+# the complex instantiation exports the same set under the hpddm_b200z_ prefix, with identical
+# argument shapes (scalars travel behind pointers)
+_SIGS.update({k.replace("hpddm_b200_", "hpddm_b200z_", 1): v for k, v in list(_SIGS.items())})
 EXPORTS = sorted(_SIGS)
 
 
@@ -90,10 +94,37 @@ def lib():
     return _lib
 
 
-def check(rc):
+def check(rc, prefix="hpddm_b200"):
     if rc < 0:
-        raise HpddmB200Error(f"libhpddm_b200 error {rc}: {lib().hpddm_b200_last_error().decode()}")
+        raise HpddmB200Error(f"libhpddm_b200 error {rc}: {getattr(lib(), prefix + '_last_error')().decode()}")
     return rc
+
+
+class Api:
+    """The entry points of one scalar type: api.apply(...) -> hpddm_b200[z]_apply(...)."""
+
+    def __init__(self, prefix, dtype):
+        self.prefix = prefix
+        self.dtype = np.dtype(dtype)
+
+    def __getattr__(self, name):
+        return getattr(lib(), f"{self.prefix}_{name}")
+
+    def check(self, rc):
+        return check(rc, self.prefix)
+
+
+REAL = Api("hpddm_b200", np.float64)
+COMPLEX = Api("hpddm_b200z", np.complex128)
+
+
+def api(dtype=np.float64):
+    dtype = np.dtype(dtype)
+    if dtype == np.float64:
+        return REAL
+    if dtype == np.complex128:
+        return COMPLEX
+    raise HpddmB200Error(f"unsupported scalar type {dtype}: the library is built for float64 and complex128")
 
 
 def ptr(a):

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <complex>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -111,25 +112,25 @@ static Sub *local_sub(Ctx *c, int grank) {
 static int ensure_capacity(Ctx *c, int mu) {
   if (mu <= c->mu_cap) return 0;
   for (Sub *s : c->subs) {
-    for (double **p : {&s->d_in, &s->d_out, &s->d_work, &s->d_tmp}) {
+    for (K **p : {&s->d_in, &s->d_out, &s->d_work, &s->d_tmp}) {
       if (*p) cudaFree(*p);
       *p = nullptr;
-      HB_CUDA(cudaMalloc(p, std::max<size_t>((size_t)s->n * mu, 1) * sizeof(double)));
+      HB_CUDA(cudaMalloc(p, std::max<size_t>((size_t)s->n * mu, 1) * sizeof(K)));
     }
-    for (double **p : {&s->d_send, &s->d_recv}) {
+    for (K **p : {&s->d_send, &s->d_recv}) {
       if (*p) cudaFree(*p);
       *p = nullptr;
-      HB_CUDA(cudaMalloc(p, std::max<size_t>((size_t)s->h * mu, 1) * sizeof(double)));
+      HB_CUDA(cudaMalloc(p, std::max<size_t>((size_t)s->h * mu, 1) * sizeof(K)));
     }
     s->mu_cap = mu;
   }
-  for (double **p : {&c->d_T, &c->d_Y}) {
+  for (K **p : {&c->d_T, &c->d_Y}) {
     if (*p) cudaFree(*p);
     *p = nullptr;
-    HB_CUDA(cudaMalloc(p, std::max<size_t>((size_t)std::max(c->Lnu * c->nproc, 1) * mu, 1) * sizeof(double)));
+    HB_CUDA(cudaMalloc(p, std::max<size_t>((size_t)std::max(c->Lnu * c->nproc, 1) * mu, 1) * sizeof(K)));
   }
   if (c->d_res) cudaFree(c->d_res);
-  HB_CUDA(cudaMalloc(&c->d_res, std::max(mu, 64) * sizeof(double)));
+  HB_CUDA(cudaMalloc(&c->d_res, std::max(mu, 64) * sizeof(K)));
   c->mu_cap = mu;
   return 0;
 }
@@ -162,7 +163,7 @@ static int build_links(Ctx *c) {
 
 // halo sum  x_s[map] += neighbours' values  (Subdomain::exchange, subdomain.hpp:115-130),
 // all mu columns and all neighbours in one round.  x[] = device pointers per local subdomain.
-int halo(Ctx *c, double *const *x, int mu, bool allow_p2p) {
+int halo(Ctx *c, K *const *x, int mu, bool allow_p2p) {
   bool any = false;
   for (Sub *s : c->subs) any = any || s->h > 0;
   if (!any) return 0;
@@ -180,7 +181,7 @@ int halo(Ctx *c, double *const *x, int mu, bool allow_p2p) {
       const size_t cnt = (size_t)(s->nb_ptr[i + 1] - s->nb_ptr[i]) * mu;
       if (s->peer_seg[i] >= 0) {
         Sub *o = local_sub(c, s->nb_rank[i]);
-        HB_CUDA(cudaMemcpyAsync(s->d_recv + (size_t)s->nb_ptr[i] * mu, o->d_send + (size_t)o->nb_ptr[s->peer_seg[i]] * mu, cnt * sizeof(double),
+        HB_CUDA(cudaMemcpyAsync(s->d_recv + (size_t)s->nb_ptr[i] * mu, o->d_send + (size_t)o->nb_ptr[s->peer_seg[i]] * mu, cnt * sizeof(K),
                                 cudaMemcpyDeviceToDevice, c->stream));
       } else
         remote = true;
@@ -206,11 +207,11 @@ int halo(Ctx *c, double *const *x, int mu, bool allow_p2p) {
     HB_NCCL(g_nccl.GroupStart());
     for (const Msg &m : recvs) {
       const size_t cnt = (size_t)(m.s->nb_ptr[m.i + 1] - m.s->nb_ptr[m.i]) * mu;
-      HB_NCCL(g_nccl.Recv(m.s->d_recv + (size_t)m.s->nb_ptr[m.i] * mu, cnt, NCCL_F64, owner_of(c, m.src), c->nccl, c->stream));
+      HB_NCCL(g_nccl.Recv(m.s->d_recv + (size_t)m.s->nb_ptr[m.i] * mu, cnt * KD, NCCL_F64, owner_of(c, m.src), c->nccl, c->stream));
     }
     for (const Msg &m : sends) {
       const size_t cnt = (size_t)(m.s->nb_ptr[m.i + 1] - m.s->nb_ptr[m.i]) * mu;
-      HB_NCCL(g_nccl.Send(m.s->d_send + (size_t)m.s->nb_ptr[m.i] * mu, cnt, NCCL_F64, owner_of(c, m.dst), c->nccl, c->stream));
+      HB_NCCL(g_nccl.Send(m.s->d_send + (size_t)m.s->nb_ptr[m.i] * mu, cnt * KD, NCCL_F64, owner_of(c, m.dst), c->nccl, c->stream));
     }
     HB_NCCL(g_nccl.GroupEnd());
   }
@@ -236,53 +237,53 @@ int check_ready(Ctx *c, int mu) {
 }
 
 // stage user vectors: returns device pointers to use for reading
-int stage_in(Ctx *c, const double *const *in, int mu, int where, std::vector<const double *> &dev) {
+int stage_in(Ctx *c, const K *const *in, int mu, int where, std::vector<const K *> &dev) {
   dev.resize(c->subs.size());
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     if (where == HPDDM_B200_HOST) {
-      HB_CUDA(cudaMemcpyAsync(s->d_in, in[i], (size_t)s->n * mu * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(s->d_in, in[i], (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
       dev[i] = s->d_in;
     } else
       dev[i] = in[i];
   }
   return 0;
 }
-void out_ptrs(Ctx *c, double *const *out, int where, std::vector<double *> &dev) {
+void out_ptrs(Ctx *c, K *const *out, int where, std::vector<K *> &dev) {
   dev.resize(c->subs.size());
   for (size_t i = 0; i < c->subs.size(); ++i) dev[i] = where == HPDDM_B200_HOST ? c->subs[i]->d_out : out[i];
 }
-int stage_out(Ctx *c, double *const *out, int mu, int where) {
+int stage_out(Ctx *c, K *const *out, int mu, int where) {
   if (where != HPDDM_B200_HOST) return 0;
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
-    HB_CUDA(cudaMemcpyAsync(out[i], s->d_out, (size_t)s->n * mu * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(out[i], s->d_out, (size_t)s->n * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
   }
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return p2p_check(c);
 }
 
 // coarse vectors: layout [proc][col][row-in-proc] (see kk_coarse)
-static double *coarse_block(Ctx *c, double *buf, const Sub *s, int mu) { return buf + (size_t)c->proc_rank * c->Lnu * mu + s->coff; }
+static K *coarse_block(Ctx *c, K *buf, const Sub *s, int mu) { return buf + (size_t)c->proc_rank * c->Lnu * mu + s->coff; }
 
 // out = exchange(Z E^-1 Z^T D in)   (Schwarz::deflation, schwarz.hpp:1602-1622), device pointers
-static int deflation_core(Ctx *c, const std::vector<const double *> &in, const std::vector<double *> &out, int mu) {
+static int deflation_core(Ctx *c, const std::vector<const K *> &in, const std::vector<K *> &out, int mu) {
   if (c->Nc == 0 || !c->d_Einv) {
     set_error("deflation: no coarse operator (call build_coarse / set_coarse)");
     return HPDDM_B200_ERR_STATE;
   }
-  HB_CUDA(cudaMemsetAsync(c->d_T, 0, (size_t)c->Lnu * c->nproc * mu * sizeof(double), c->stream));
+  HB_CUDA(cudaMemsetAsync(c->d_T, 0, (size_t)c->Lnu * c->nproc * mu * sizeof(K), c->stream));
   for (size_t i = 0; i < c->subs.size(); ++i) HB_CHECK(k_zt_project(c, c->subs[i], mu, in[i], coarse_block(c, c->d_T, c->subs[i], mu), c->Lnu));
   if (c->nproc > 1) {
     // CoarseOperator::callSolver gather (coarse_operator_impl.hpp:1708) -> all-gather + replicated solve
-    HB_NCCL(g_nccl.AllGather(c->d_T + (size_t)c->proc_rank * c->Lnu * mu, c->d_T, (size_t)c->Lnu * mu, NCCL_F64, c->nccl, c->stream));
+    HB_NCCL(g_nccl.AllGather(c->d_T + (size_t)c->proc_rank * c->Lnu * mu, c->d_T, (size_t)c->Lnu * mu * KD, NCCL_F64, c->nccl, c->stream));
   }
   HB_CHECK(k_coarse_solve(c, mu));
   for (size_t i = 0; i < c->subs.size(); ++i) HB_CHECK(k_z_expand(c, c->subs[i], mu, coarse_block(c, c->d_Y, c->subs[i], mu), c->Lnu, out[i]));
   return halo(c, out.data(), mu);
 }
 
-int solve_cols(Sub *s, const double *b, double *x, int mu, const double *scale, bool acc) {
+int solve_cols(Sub *s, const K *b, K *x, int mu, const double *scale, bool acc) {
   int col = 0;
   while (col < mu) {  // panels are streamed once per group of 4 / 2 / 1 right-hand sides
     const int g = (mu - col >= 4) ? 4 : ((mu - col >= 2) ? 2 : 1);
@@ -292,13 +293,13 @@ int solve_cols(Sub *s, const double *b, double *x, int mu, const double *scale, 
   return 0;
 }
 
-int gmv_core(Ctx *c, const std::vector<const double *> &in, const std::vector<double *> &out, int mu) {
+int gmv_core(Ctx *c, const std::vector<const K *> &in, const std::vector<K *> &out, int mu) {
   for (size_t i = 0; i < c->subs.size(); ++i) HB_CHECK(k_spmv(c, c->subs[i], mu, 1.0, in[i], 0.0, nullptr, out[i], c->subs[i]->d_d));
   return halo(c, out.data(), mu);
 }
 
 // Schwarz::apply on device pointers (schwarz.hpp:527-612); `ind` is never modified
-int apply_core(Ctx *c, const std::vector<const double *> &ind, const std::vector<double *> &outd, int mu, int correction) {
+int apply_core(Ctx *c, const std::vector<const K *> &ind, const std::vector<K *> &outd, int mu, int correction) {
   const size_t L = c->subs.size();
   const bool two_level = c->Nc > 0 && c->d_Einv && correction != HPDDM_B200_CORRECTION_NONE;
   if (!two_level) {  // schwarz.hpp:531-547
@@ -327,8 +328,8 @@ int apply_core(Ctx *c, const std::vector<const double *> &ind, const std::vector
     if (!all_no) HB_CHECK(halo(c, outd.data(), mu));
     return 0;
   }
-  std::vector<double *> work(L), tmp(L);
-  std::vector<const double *> cwork(L), ctmp(L);
+  std::vector<K *> work(L), tmp(L);
+  std::vector<const K *> cwork(L), ctmp(L);
   for (size_t i = 0; i < L; ++i) {
     work[i] = c->subs[i]->d_work;
     tmp[i] = c->subs[i]->d_tmp;
@@ -360,9 +361,9 @@ int apply_core(Ctx *c, const std::vector<const double *> &ind, const std::vector
   HB_CHECK(halo(c, work.data(), mu));                                            // exchange(work)      (591)
   if (correction == HPDDM_B200_CORRECTION_BALANCED) {                            // (593-606)
     HB_CHECK(gmv_core(c, cwork, tmp, mu));
-    std::vector<double *> t2(L, nullptr);
+    std::vector<K *> t2(L, nullptr);
     // allocate a transient buffer per subdomain (rare path)
-    for (size_t i = 0; i < L; ++i) HB_CUDA(cudaMalloc(&t2[i], std::max<size_t>((size_t)c->subs[i]->n * mu, 1) * sizeof(double)));
+    for (size_t i = 0; i < L; ++i) HB_CUDA(cudaMalloc(&t2[i], std::max<size_t>((size_t)c->subs[i]->n * mu, 1) * sizeof(K)));
     int rc = deflation_core(c, ctmp, t2, mu);
     if (rc == 0)
       for (size_t i = 0; i < L && rc == 0; ++i) rc = k_axpy(c, (int64_t)c->subs[i]->n * mu, -1.0, t2[i], work[i]);
@@ -381,10 +382,10 @@ using namespace hb;
 
 extern "C" {
 
-const char *hpddm_b200_last_error(void) { return hb::get_error(); }
-const char *hpddm_b200_version(void) { return "hpddm_b200 0.1 (sm_100a)"; }
+const char *HB_API(last_error)(void) { return hb::get_error(); }
+const char *HB_API(version)(void) { return HB_PREFIX " 0.2 (sm_100a, " "scalar = " HB_SCALAR_NAME ")"; }
 
-int hpddm_b200_ctx_create(int device, hpddm_b200_ctx **ctx) {
+int HB_API(ctx_create)(int device, hb_ctx_t **ctx) {
   if (!ctx) return HPDDM_B200_ERR_ARG;
   int cnt = 0;
   cudaError_t e = cudaGetDeviceCount(&cnt);
@@ -400,7 +401,7 @@ int hpddm_b200_ctx_create(int device, hpddm_b200_ctx **ctx) {
   Ctx *c = new Ctx;
   c->device = device;
   HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  *ctx = reinterpret_cast<hpddm_b200_ctx *>(c);
+  *ctx = reinterpret_cast<hb_ctx_t *>(c);
   return 0;
 }
 
@@ -413,7 +414,7 @@ static void sub_free(Sub *s) {
   delete s;
 }
 
-int hpddm_b200_ctx_destroy(hpddm_b200_ctx *ctx) {
+int HB_API(ctx_destroy)(hb_ctx_t *ctx) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c) return 0;
   cudaSetDevice(c->device);
@@ -428,7 +429,7 @@ int hpddm_b200_ctx_destroy(hpddm_b200_ctx *ctx) {
   return 0;
 }
 
-int hpddm_b200_nccl_unique_id(void *id128) {
+int HB_API(nccl_unique_id)(void *id128) {
   HB_CHECK(nccl_load());
   NcclId id;
   HB_NCCL(g_nccl.GetUniqueId(&id));
@@ -436,7 +437,7 @@ int hpddm_b200_nccl_unique_id(void *id128) {
   return 0;
 }
 
-int hpddm_b200_ctx_comm_init(hpddm_b200_ctx *ctx, const void *id128, int proc_rank, int nproc) {
+int HB_API(ctx_comm_init)(hb_ctx_t *ctx, const void *id128, int proc_rank, int nproc) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c || !id128 || nproc < 1 || proc_rank < 0 || proc_rank >= nproc) return HPDDM_B200_ERR_ARG;
   HB_CHECK(nccl_load());
@@ -449,27 +450,27 @@ int hpddm_b200_ctx_comm_init(hpddm_b200_ctx *ctx, const void *id128, int proc_ra
   return 0;
 }
 
-int hpddm_b200_ctx_synchronize(hpddm_b200_ctx *ctx) {
+int HB_API(ctx_synchronize)(hb_ctx_t *ctx) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
-void *hpddm_b200_ctx_stream(hpddm_b200_ctx *ctx) { return reinterpret_cast<Ctx *>(ctx)->stream; }
-int64_t hpddm_b200_ctx_launch_count(hpddm_b200_ctx *ctx) { return reinterpret_cast<Ctx *>(ctx)->launches; }
+void *HB_API(ctx_stream)(hb_ctx_t *ctx) { return reinterpret_cast<Ctx *>(ctx)->stream; }
+int64_t HB_API(ctx_launch_count)(hb_ctx_t *ctx) { return reinterpret_cast<Ctx *>(ctx)->launches; }
 
-int hpddm_b200_malloc(hpddm_b200_ctx *ctx, size_t bytes, void **dptr) {
+int HB_API(malloc)(hb_ctx_t *ctx, size_t bytes, void **dptr) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CUDA(cudaSetDevice(c->device));
   HB_CUDA(cudaMalloc(dptr, std::max<size_t>(bytes, 1)));
   return 0;
 }
-int hpddm_b200_free(hpddm_b200_ctx *ctx, void *dptr) {
+int HB_API(free)(hb_ctx_t *ctx, void *dptr) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CUDA(cudaSetDevice(c->device));
   HB_CUDA(cudaFree(dptr));
   return 0;
 }
-int hpddm_b200_memcpy(hpddm_b200_ctx *ctx, void *dst, const void *src, size_t bytes, int dst_where, int src_where) {
+int HB_API(memcpy)(hb_ctx_t *ctx, void *dst, const void *src, size_t bytes, int dst_where, int src_where) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CUDA(cudaSetDevice(c->device));
   cudaMemcpyKind k = dst_where == HPDDM_B200_DEVICE ? (src_where == HPDDM_B200_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
@@ -480,17 +481,17 @@ int hpddm_b200_memcpy(hpddm_b200_ctx *ctx, void *dst, const void *src, size_t by
 }
 
 // ------------------------------------------------------------------ subdomain setup
-int hpddm_b200_sub_create(hpddm_b200_ctx *ctx, int global_rank, hpddm_b200_sub **sub) {
+int HB_API(sub_create)(hb_ctx_t *ctx, int global_rank, hb_sub_t **sub) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c || !sub || global_rank < 0) return HPDDM_B200_ERR_ARG;
   Sub *s = new Sub;
   s->ctx = c;
   s->grank = global_rank;
   c->subs.push_back(s);
-  *sub = reinterpret_cast<hpddm_b200_sub *>(s);
+  *sub = reinterpret_cast<hb_sub_t *>(s);
   return 0;
 }
-int hpddm_b200_sub_destroy(hpddm_b200_sub *sub) {
+int HB_API(sub_destroy)(hb_sub_t *sub) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s) return 0;
   Ctx *c = s->ctx;
@@ -503,13 +504,13 @@ int hpddm_b200_sub_destroy(hpddm_b200_sub *sub) {
 
 // MatrixCSR -> full-pattern, C-numbered, column-sorted host CSR
 extern "C++" {
-int hb::to_host_csr(int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering, HostCSR &H) {
+int hb::to_host_csr(int n, int nnz, const int *ia, const int *ja, const K *a, int sym, char numbering, HostCSR &H) {
   if (n < 0 || nnz < 0 || (n > 0 && (!ia || !ja || !a))) {
     set_error("set_matrix: bad arguments");
     return HPDDM_B200_ERR_ARG;
   }
   const int sh = (numbering == 'F') ? 1 : 0;
-  std::vector<std::vector<std::pair<int, double>>> rows(n);
+  std::vector<std::vector<std::pair<int, K>>> rows(n);
   for (int i = 0; i < n; ++i)
     for (int k = ia[i] - sh; k < ia[i + 1] - sh; ++k) {
       const int j = ja[k] - sh;
@@ -526,7 +527,7 @@ int hb::to_host_csr(int n, int nnz, const int *ia, const int *ja, const double *
   H.a.clear();
   for (int i = 0; i < n; ++i) {
     auto &r = rows[i];
-    std::sort(r.begin(), r.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) { return x.first < y.first; });
+    std::stable_sort(r.begin(), r.end(), [](const std::pair<int, K> &x, const std::pair<int, K> &y) { return x.first < y.first; });
     for (size_t q = 0; q < r.size(); ++q) {
       if (!H.ja.empty() && (int)H.ja.size() > H.ia[i] && H.ja.back() == r[q].first) H.a.back() += r[q].second;  // merge duplicates
       else {
@@ -536,17 +537,17 @@ int hb::to_host_csr(int n, int nnz, const int *ia, const int *ja, const double *
     }
     H.ia[i + 1] = (int)H.ja.size();
   }
-  // numerical symmetry
-  bool symm = true;
+  // numerical symmetry (LL^T candidate); complex matrices always take the LU path
+  bool symm = !IS_COMPLEX;
   double amax = 0.0;
-  for (double v : H.a) amax = std::max(amax, std::fabs(v));
+  for (const K &v : H.a) amax = std::max(amax, hb_abs(v));
   for (int i = 0; i < n && symm; ++i)
     for (int k = H.ia[i]; k < H.ia[i + 1]; ++k) {
       const int j = H.ja[k];
       if (j == i) continue;
       const int *b = H.ja.data() + H.ia[j], *e = H.ja.data() + H.ia[j + 1];
       const int *p = std::lower_bound(b, e, i);
-      if (p == e || *p != i || std::fabs(H.a[p - H.ja.data()] - H.a[k]) > 1e-14 * amax) {
+      if (p == e || *p != i || hb_abs(H.a[p - H.ja.data()] - H.a[k]) > 1e-14 * amax) {
         symm = false;
         break;
       }
@@ -556,7 +557,7 @@ int hb::to_host_csr(int n, int nnz, const int *ia, const int *ja, const double *
 }
 }  // extern "C++"
 
-int hpddm_b200_sub_set_matrix(hpddm_b200_sub *sub, int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering) {
+int HB_API(sub_set_matrix)(hb_sub_t *sub, int n, int nnz, const int *ia, const int *ja, const K *a, int sym, char numbering) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(s->ctx->device));
@@ -569,23 +570,23 @@ int hpddm_b200_sub_set_matrix(hpddm_b200_sub *sub, int n, int nnz, const int *ia
   // diagonal is penalised (>= EPS*PEN) or when its part left of / on the diagonal is the identity
   s->bc.clear();
   for (int i = 0; i < n; ++i) {
-    double diag = 0.0;
+    K diag = mk(0.0);
     bool has_diag = false, identity = true;
     for (int k = s->A.ia[i]; k < s->A.ia[i + 1] && s->A.ja[k] <= i; ++k) {
       if (s->A.ja[k] == i) {
         diag = s->A.a[k];
         has_diag = true;
-        if (std::fabs(diag - 1.0) > 1e-12) identity = false;
-      } else if (std::fabs(s->A.a[k]) > 1e-12)
+        if (hb_abs(diag - mk(1.0)) > 1e-12) identity = false;
+      } else if (hb_abs(s->A.a[k]) > 1e-12)
         identity = false;
     }
     if (!has_diag) continue;
-    if (std::fabs(diag) >= 1e-12 * 1e30 || identity) {
-      if (std::fabs(diag) > 1e-12) s->bc.push_back({i, diag});
+    if (hb_abs(diag) >= 1e-12 * 1e30 || identity) {
+      if (hb_abs(diag) > 1e-12) s->bc.push_back({i, diag});
     }
   }
   std::vector<int> bi;
-  std::vector<double> bv;
+  std::vector<K> bv;
   for (auto &p : s->bc) {
     bi.push_back(p.first);
     bv.push_back(p.second);
@@ -596,7 +597,7 @@ int hpddm_b200_sub_set_matrix(hpddm_b200_sub *sub, int n, int nnz, const int *ia
   return 0;
 }
 
-int hpddm_b200_sub_set_neighbors(hpddm_b200_sub *sub, int count, const int *ranks, const int *sizes, const int *idx) {
+int HB_API(sub_set_neighbors)(hb_sub_t *sub, int count, const int *ranks, const int *sizes, const int *idx) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s || count < 0) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(s->ctx->device));
@@ -654,7 +655,7 @@ int hpddm_b200_sub_set_neighbors(hpddm_b200_sub *sub, int count, const int *rank
   return 0;
 }
 
-int hpddm_b200_sub_set_scaling(hpddm_b200_sub *sub, const double *d) {
+int HB_API(sub_set_scaling)(hb_sub_t *sub, const double *d) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s || !d) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(s->ctx->device));
@@ -662,7 +663,7 @@ int hpddm_b200_sub_set_scaling(hpddm_b200_sub *sub, const double *d) {
   return up(s->d_host, &s->d_d, s->ctx->stream);
 }
 
-int hpddm_b200_sub_set_grid_hint(hpddm_b200_sub *sub, int nx, int ny, int nz, int dof) {
+int HB_API(sub_set_grid_hint)(hb_sub_t *sub, int nx, int ny, int nz, int dof) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s || nx < 0 || ny < 0 || nz < 0 || dof < 1) return HPDDM_B200_ERR_ARG;
   s->gx = nx;
@@ -672,37 +673,40 @@ int hpddm_b200_sub_set_grid_hint(hpddm_b200_sub *sub, int nx, int ny, int nz, in
   return 0;
 }
 
-int hpddm_b200_multiplicity_scaling(hpddm_b200_ctx *ctx, double *const *d) {
+int HB_API(multiplicity_scaling)(hb_ctx_t *ctx, double *const *d) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CHECK(check_ready(c, 1));
   // gather d on the overlap and swap with the neighbours (schwarz.hpp:384-390)
   // pack d, swap send/recv buffers with the neighbours; the halo add lands in a scratch copy of d
-  std::vector<double *> src(c->subs.size());
+  std::vector<K *> src(c->subs.size());
+  std::vector<std::vector<K>> dk(c->subs.size());
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
-    HB_CUDA(cudaMemcpyAsync(s->d_work, d[i], (size_t)s->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    dk[i].resize(s->n);
+    for (int j = 0; j < s->n; ++j) dk[i][j] = mk(d[i][j]);
+    HB_CUDA(cudaMemcpyAsync(s->d_work, dk[i].data(), (size_t)s->n * sizeof(K), cudaMemcpyHostToDevice, c->stream));
     src[i] = s->d_work;
   }
   HB_CHECK(halo(c, src.data(), 1, false));  // the send / recv staging buffers themselves are read back below: NCCL path
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
-    std::vector<double> recv(s->h), send(s->h);
+    std::vector<K> recv(s->h), send(s->h);
     if (s->h) {
-      HB_CUDA(cudaMemcpyAsync(recv.data(), s->d_recv, s->h * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      HB_CUDA(cudaMemcpyAsync(send.data(), s->d_send, s->h * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      HB_CUDA(cudaMemcpyAsync(recv.data(), s->d_recv, s->h * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+      HB_CUDA(cudaMemcpyAsync(send.data(), s->d_send, s->h * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
     }
     HB_CUDA(cudaStreamSynchronize(c->stream));
     std::fill(d[i], d[i] + s->n, 1.0);  // schwarz.hpp:391
     for (int e = 0; e < s->h; ++e) {    // schwarz.hpp:392-401, neighbour order
       const int j = s->nb_idx[e];
-      if (std::fabs(send[e]) < 1e-12) d[i][j] = 0.0;
-      else d[i][j] /= 1.0 + d[i][j] * recv[e] / send[e];
+      if (std::fabs(hb_real(send[e])) < 1e-12) d[i][j] = 0.0;
+      else d[i][j] /= 1.0 + d[i][j] * hb_real(recv[e]) / hb_real(send[e]);
     }
   }
   return 0;
 }
 
-int hpddm_b200_sub_numfact(hpddm_b200_sub *sub, int prcndtnr, int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering) {
+int HB_API(sub_numfact)(hb_sub_t *sub, int prcndtnr, int n, int nnz, const int *ia, const int *ja, const K *a, int sym, char numbering) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(s->ctx->device));
@@ -724,7 +728,7 @@ int hpddm_b200_sub_numfact(hpddm_b200_sub *sub, int prcndtnr, int n, int nnz, co
   return numfact_device(s, s->A);
 }
 
-int hpddm_b200_sub_set_vectors(hpddm_b200_sub *sub, const double *Z, int nu) {
+int HB_API(sub_set_vectors)(hb_sub_t *sub, const K *Z, int nu) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s || nu < 0 || (nu > 0 && !Z)) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(s->ctx->device));
@@ -732,8 +736,8 @@ int hpddm_b200_sub_set_vectors(hpddm_b200_sub *sub, const double *Z, int nu) {
   s->d_Z = nullptr;
   s->nu = nu;
   if (nu > 0) {
-    HB_CUDA(cudaMalloc(&s->d_Z, (size_t)s->n * nu * sizeof(double)));
-    HB_CUDA(cudaMemcpyAsync(s->d_Z, Z, (size_t)s->n * nu * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
+    HB_CUDA(cudaMalloc(&s->d_Z, (size_t)s->n * nu * sizeof(K)));
+    HB_CUDA(cudaMemcpyAsync(s->d_Z, Z, (size_t)s->n * nu * sizeof(K), cudaMemcpyHostToDevice, s->ctx->stream));
     HB_CUDA(cudaStreamSynchronize(s->ctx->stream));
   }
   return 0;
@@ -781,51 +785,60 @@ static int coarse_layout(Ctx *c) {
 }
 
 // dense inverse in extended precision (Gauss-Jordan, partial pivoting)
-static int invert_dense(int N, const std::vector<double> &E, std::vector<double> &Einv) {
-  std::vector<long double> M((size_t)N * 2 * N);
+static int invert_dense(int N, const std::vector<K> &E, std::vector<K> &Einv) {
+#ifdef HB_COMPLEX
+  typedef std::complex<long double> XK;
+  auto in = [](const K &v) { return XK(v.re, v.im); };
+  auto outk = [](const XK &v) { return mk((double)v.real(), (double)v.imag()); };
+#else
+  typedef long double XK;
+  auto in = [](const K &v) { return (XK)v; };
+  auto outk = [](const XK &v) { return (double)v; };
+#endif
+  std::vector<XK> M((size_t)N * 2 * N);
   for (int i = 0; i < N; ++i)
     for (int j = 0; j < N; ++j) {
-      M[(size_t)i * 2 * N + j] = E[i + (size_t)j * N];
-      M[(size_t)i * 2 * N + N + j] = (i == j) ? 1.0L : 0.0L;
+      M[(size_t)i * 2 * N + j] = in(E[i + (size_t)j * N]);
+      M[(size_t)i * 2 * N + N + j] = (i == j) ? XK(1.0L) : XK(0.0L);
     }
   for (int k = 0; k < N; ++k) {
     int p = k;
     for (int i = k + 1; i < N; ++i)
-      if (fabsl(M[(size_t)i * 2 * N + k]) > fabsl(M[(size_t)p * 2 * N + k])) p = i;
-    if (fabsl(M[(size_t)p * 2 * N + k]) == 0.0L) {
+      if (std::abs(M[(size_t)i * 2 * N + k]) > std::abs(M[(size_t)p * 2 * N + k])) p = i;
+    if (std::abs(M[(size_t)p * 2 * N + k]) == 0.0L) {
       set_error("coarse operator is singular (column %d)", k);
       return HPDDM_B200_ERR_NUMERIC;
     }
     if (p != k)
       for (int j = 0; j < 2 * N; ++j) std::swap(M[(size_t)k * 2 * N + j], M[(size_t)p * 2 * N + j]);
-    const long double piv = M[(size_t)k * 2 * N + k];
+    const XK piv = M[(size_t)k * 2 * N + k];
     for (int j = 0; j < 2 * N; ++j) M[(size_t)k * 2 * N + j] /= piv;
     for (int i = 0; i < N; ++i) {
       if (i == k) continue;
-      const long double f = M[(size_t)i * 2 * N + k];
-      if (f == 0.0L) continue;
+      const XK f = M[(size_t)i * 2 * N + k];
+      if (f == XK(0.0L)) continue;
       for (int j = 0; j < 2 * N; ++j) M[(size_t)i * 2 * N + j] -= f * M[(size_t)k * 2 * N + j];
     }
   }
   Einv.resize((size_t)N * N);
   for (int i = 0; i < N; ++i)
-    for (int j = 0; j < N; ++j) Einv[i + (size_t)j * N] = (double)M[(size_t)i * 2 * N + N + j];
+    for (int j = 0; j < N; ++j) Einv[i + (size_t)j * N] = outk(M[(size_t)i * 2 * N + N + j]);
   return 0;
 }
 
-static int install_coarse(Ctx *c, const std::vector<double> &E) {
+static int install_coarse(Ctx *c, const std::vector<K> &E) {
   const int N = c->Nc;
   c->E_host = E;
-  std::vector<double> Einv;
+  std::vector<K> Einv;
   HB_CHECK(invert_dense(N, E, Einv));
   HB_CHECK(up(c->E_host, &c->d_E, c->stream));
   HB_CHECK(up(Einv, &c->d_Einv, c->stream));
   if (c->d_R) cudaFree(c->d_R);
-  HB_CUDA(cudaMalloc(&c->d_R, std::max(N, 1) * sizeof(double)));
+  HB_CUDA(cudaMalloc(&c->d_R, std::max(N, 1) * sizeof(K)));
   return 0;
 }
 
-int hpddm_b200_set_coarse(hpddm_b200_ctx *ctx, const double *E, int Nc) {
+int HB_API(set_coarse)(hb_ctx_t *ctx, const K *E, int Nc) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c || !E) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(c->device));
@@ -834,18 +847,18 @@ int hpddm_b200_set_coarse(hpddm_b200_ctx *ctx, const double *E, int Nc) {
     set_error("set_coarse: N_c = %d but the deflation vectors sum to %d", Nc, c->Nc);
     return HPDDM_B200_ERR_ARG;
   }
-  return install_coarse(c, std::vector<double>(E, E + (size_t)Nc * Nc));
+  return install_coarse(c, std::vector<K>(E, E + (size_t)Nc * Nc));
 }
 
-int hpddm_b200_get_coarse(hpddm_b200_ctx *ctx, double *E, int *Nc) {
+int HB_API(get_coarse)(hb_ctx_t *ctx, K *E, int *Nc) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c || !Nc) return HPDDM_B200_ERR_ARG;
   *Nc = c->Nc;
-  if (E && !c->E_host.empty()) memcpy(E, c->E_host.data(), c->E_host.size() * sizeof(double));
+  if (E && !c->E_host.empty()) memcpy(E, c->E_host.data(), c->E_host.size() * sizeof(K));
   return 0;
 }
 
-int hpddm_b200_build_coarse(hpddm_b200_ctx *ctx) {
+int HB_API(build_coarse)(hb_ctx_t *ctx) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(c->device));
@@ -872,15 +885,15 @@ int hpddm_b200_build_coarse(hpddm_b200_ctx *ctx) {
   }
   for (int v : nu_all) numax = std::max(numax, v);
   HB_CHECK(ensure_capacity(c, numax));
-  double *d_rows = nullptr;  // Lnu x N, column-major
-  HB_CUDA(cudaMalloc(&d_rows, std::max<size_t>((size_t)Lnu * N, 1) * sizeof(double)));
-  HB_CUDA(cudaMemsetAsync(d_rows, 0, (size_t)Lnu * N * sizeof(double), c->stream));
+  K *d_rows = nullptr;  // Lnu x N, column-major
+  HB_CUDA(cudaMalloc(&d_rows, std::max<size_t>((size_t)Lnu * N, 1) * sizeof(K)));
+  HB_CUDA(cudaMemsetAsync(d_rows, 0, (size_t)Lnu * N * sizeof(K), c->stream));
   // column block of global subdomain j, exactly the reference's formula
   //   E_ij = Z_i^H D_i R_ij (A_j D_j Z_j)      (include/HPDDM_operator.hpp:395-403,505-528):
   // W = A_j (D_j Z_j) is formed on j with j's OWN matrix (applyToNeighbor), its values on the
   // shared dofs travel to the neighbours (an unscaled halo of a vector that is zero everywhere
   // but on j), every subdomain i then projects Z_i^T (D_i W|_i) (applyFromNeighbor).
-  std::vector<double *> X(L);
+  std::vector<K *> X(L);
   for (int j = 0; j < P; ++j) {
     const int nuj = nu_all[j];
     if (nuj == 0) continue;
@@ -893,7 +906,7 @@ int hpddm_b200_build_coarse(hpddm_b200_ctx *ctx) {
         HB_CHECK(k_scale(c, s->n, nuj, s->d_d, s->d_Z, s->d_tmp));
         HB_CHECK(k_spmv(c, s, nuj, 1.0, s->d_tmp, 0.0, nullptr, s->d_work, nullptr));
       } else
-        HB_CUDA(cudaMemsetAsync(s->d_work, 0, (size_t)s->n * nuj * sizeof(double), c->stream));
+        HB_CUDA(cudaMemsetAsync(s->d_work, 0, (size_t)s->n * nuj * sizeof(K), c->stream));
     }
     HB_CHECK(halo(c, X.data(), nuj));
     for (int i = 0; i < L; ++i) {
@@ -901,20 +914,20 @@ int hpddm_b200_build_coarse(hpddm_b200_ctx *ctx) {
       HB_CHECK(k_zt_project(c, s, nuj, s->d_work, d_rows + s->coff + (size_t)gcol * Lnu, Lnu));
     }
   }
-  std::vector<double> E((size_t)N * N, 0.0);
+  std::vector<K> E((size_t)N * N, mk(0.0));
   if (c->nproc > 1) {
-    double *d_all = nullptr;
-    HB_CUDA(cudaMalloc(&d_all, std::max<size_t>((size_t)Lnu * c->nproc * N, 1) * sizeof(double)));
-    HB_NCCL(g_nccl.AllGather(d_rows, d_all, (size_t)Lnu * N, NCCL_F64, c->nccl, c->stream));
-    std::vector<double> tmp((size_t)Lnu * c->nproc * N);
-    HB_CUDA(cudaMemcpyAsync(tmp.data(), d_all, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    K *d_all = nullptr;
+    HB_CUDA(cudaMalloc(&d_all, std::max<size_t>((size_t)Lnu * c->nproc * N, 1) * sizeof(K)));
+    HB_NCCL(g_nccl.AllGather(d_rows, d_all, (size_t)Lnu * N * KD, NCCL_F64, c->nccl, c->stream));
+    std::vector<K> tmp((size_t)Lnu * c->nproc * N);
+    HB_CUDA(cudaMemcpyAsync(tmp.data(), d_all, tmp.size() * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_all);
     for (int p = 0; p < c->nproc; ++p)
       for (int col = 0; col < N; ++col)
         for (int r = 0; r < c->Lnu_p[p]; ++r) E[(size_t)c->coarse_off[p] + r + (size_t)col * N] = tmp[(size_t)p * Lnu * N + (size_t)col * Lnu + r];
   } else {
-    HB_CUDA(cudaMemcpyAsync(E.data(), d_rows, E.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));  // single process: Lmax == N
+    HB_CUDA(cudaMemcpyAsync(E.data(), d_rows, E.size() * sizeof(K), cudaMemcpyDeviceToHost, c->stream));  // single process: Lmax == N
     HB_CUDA(cudaStreamSynchronize(c->stream));
   }
   cudaFree(d_rows);
@@ -922,16 +935,16 @@ int hpddm_b200_build_coarse(hpddm_b200_ctx *ctx) {
 }
 
 // ------------------------------------------------------------------ hot path
-int hpddm_b200_start(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int where) {
+int HB_API(start)(hb_ctx_t *ctx, const K *const *b, K *const *x, int mu, int where) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CHECK(check_ready(c, mu));
-  std::vector<const double *> bd;
-  std::vector<double *> xd(c->subs.size());
+  std::vector<const K *> bd;
+  std::vector<K *> xd(c->subs.size());
   HB_CHECK(stage_in(c, b, mu, where, bd));
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     if (where == HPDDM_B200_HOST) {
-      HB_CUDA(cudaMemcpyAsync(s->d_out, x[i], (size_t)s->n * mu * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(s->d_out, x[i], (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
       xd[i] = s->d_out;
     } else
       xd[i] = x[i];
@@ -943,21 +956,21 @@ int hpddm_b200_start(hpddm_b200_ctx *ctx, const double *const *b, double *const 
   return stage_out(c, x, mu, where);
 }
 
-int hpddm_b200_end(hpddm_b200_ctx *ctx) {
+int HB_API(end)(hb_ctx_t *ctx) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c) return HPDDM_B200_ERR_ARG;
   c->started = false;
   return 0;
 }
 
-int hpddm_b200_exchange(hpddm_b200_ctx *ctx, double *const *x, int mu, int scaled, int where) {
+int HB_API(exchange)(hb_ctx_t *ctx, K *const *x, int mu, int scaled, int where) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CHECK(check_ready(c, mu));
-  std::vector<double *> xd(c->subs.size());
+  std::vector<K *> xd(c->subs.size());
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     if (where == HPDDM_B200_HOST) {
-      HB_CUDA(cudaMemcpyAsync(s->d_out, x[i], (size_t)s->n * mu * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(s->d_out, x[i], (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
       xd[i] = s->d_out;
     } else
       xd[i] = x[i];
@@ -967,60 +980,60 @@ int hpddm_b200_exchange(hpddm_b200_ctx *ctx, double *const *x, int mu, int scale
   return stage_out(c, x, mu, where);
 }
 
-int hpddm_b200_gmv(hpddm_b200_ctx *ctx, const double *const *in, double *const *out, int mu, int where) {
+int HB_API(gmv)(hb_ctx_t *ctx, const K *const *in, K *const *out, int mu, int where) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CHECK(check_ready(c, mu));
-  std::vector<const double *> ind;
-  std::vector<double *> outd;
+  std::vector<const K *> ind;
+  std::vector<K *> outd;
   HB_CHECK(stage_in(c, in, mu, where, ind));
   out_ptrs(c, out, where, outd);
   HB_CHECK(gmv_core(c, ind, outd, mu));
   return stage_out(c, out, mu, where);
 }
 
-int hpddm_b200_deflation(hpddm_b200_ctx *ctx, const double *const *in, double *const *out, int mu, int where) {
+int HB_API(deflation)(hb_ctx_t *ctx, const K *const *in, K *const *out, int mu, int where) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CHECK(check_ready(c, mu));
-  std::vector<const double *> ind;
-  std::vector<double *> outd;
+  std::vector<const K *> ind;
+  std::vector<K *> outd;
   HB_CHECK(stage_in(c, in, mu, where, ind));
   out_ptrs(c, out, where, outd);
   HB_CHECK(deflation_core(c, ind, outd, mu));
   return stage_out(c, out, mu, where);
 }
 
-int hpddm_b200_apply(hpddm_b200_ctx *ctx, const double *const *in, double *const *out, int mu, int correction, int where) {
+int HB_API(apply)(hb_ctx_t *ctx, const K *const *in, K *const *out, int mu, int correction, int where) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CHECK(check_ready(c, mu));
-  std::vector<const double *> ind;
-  std::vector<double *> outd;
+  std::vector<const K *> ind;
+  std::vector<K *> outd;
   HB_CHECK(stage_in(c, in, mu, where, ind));
   out_ptrs(c, out, where, outd);
   HB_CHECK(hb::apply_core(c, ind, outd, mu, correction));
   return stage_out(c, out, mu, where);
 }
 
-int hpddm_b200_sub_solve(hpddm_b200_sub *sub, const double *b, double *x, int mu, int where) {
+int HB_API(sub_solve)(hb_sub_t *sub, const K *b, K *x, int mu, int where) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s || mu < 1) return HPDDM_B200_ERR_ARG;
   Ctx *c = s->ctx;
   HB_CHECK(check_ready(c, mu));
-  const double *bd = b;
-  double *xd = x;
+  const K *bd = b;
+  K *xd = x;
   if (where == HPDDM_B200_HOST) {
-    HB_CUDA(cudaMemcpyAsync(s->d_in, b, (size_t)s->n * mu * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaMemcpyAsync(s->d_in, b, (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
     bd = s->d_in;
     xd = s->d_out;
   }
   HB_CHECK(solve_cols(s, bd, xd, mu, nullptr, false));
   if (where == HPDDM_B200_HOST) {
-    HB_CUDA(cudaMemcpyAsync(x, s->d_out, (size_t)s->n * mu * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaMemcpyAsync(x, s->d_out, (size_t)s->n * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
   }
   return 0;
 }
 
-int hpddm_b200_coarse_solve(hpddm_b200_ctx *ctx, double *const *rhs, int mu, int where) {
+int HB_API(coarse_solve)(hb_ctx_t *ctx, K *const *rhs, int mu, int where) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CHECK(check_ready(c, mu));
   if (c->Nc == 0 || !c->d_Einv) {
@@ -1029,52 +1042,52 @@ int hpddm_b200_coarse_solve(hpddm_b200_ctx *ctx, double *const *rhs, int mu, int
   }
   const cudaMemcpyKind kin = where == HPDDM_B200_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const cudaMemcpyKind kout = where == HPDDM_B200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-  HB_CUDA(cudaMemsetAsync(c->d_T, 0, (size_t)c->Lnu * c->nproc * mu * sizeof(double), c->stream));
+  HB_CUDA(cudaMemsetAsync(c->d_T, 0, (size_t)c->Lnu * c->nproc * mu * sizeof(K), c->stream));
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     if (s->nu == 0) continue;
-    HB_CUDA(cudaMemcpy2DAsync(coarse_block(c, c->d_T, s, mu), c->Lnu * sizeof(double), rhs[i], s->nu * sizeof(double), s->nu * sizeof(double), mu, kin, c->stream));
+    HB_CUDA(cudaMemcpy2DAsync(coarse_block(c, c->d_T, s, mu), c->Lnu * sizeof(K), rhs[i], s->nu * sizeof(K), s->nu * sizeof(K), mu, kin, c->stream));
   }
-  if (c->nproc > 1) HB_NCCL(g_nccl.AllGather(c->d_T + (size_t)c->proc_rank * c->Lnu * mu, c->d_T, (size_t)c->Lnu * mu, NCCL_F64, c->nccl, c->stream));
+  if (c->nproc > 1) HB_NCCL(g_nccl.AllGather(c->d_T + (size_t)c->proc_rank * c->Lnu * mu, c->d_T, (size_t)c->Lnu * mu * KD, NCCL_F64, c->nccl, c->stream));
   HB_CHECK(k_coarse_solve(c, mu));
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     if (s->nu == 0) continue;
-    HB_CUDA(cudaMemcpy2DAsync(rhs[i], s->nu * sizeof(double), coarse_block(c, c->d_Y, s, mu), c->Lnu * sizeof(double), s->nu * sizeof(double), mu, kout, c->stream));
+    HB_CUDA(cudaMemcpy2DAsync(rhs[i], s->nu * sizeof(K), coarse_block(c, c->d_Y, s, mu), c->Lnu * sizeof(K), s->nu * sizeof(K), mu, kout, c->stream));
   }
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
-int hpddm_b200_dot(hpddm_b200_ctx *ctx, const double *const *x, const double *const *y, int mu, double *result, int where) {
+int HB_API(dot)(hb_ctx_t *ctx, const K *const *x, const K *const *y, int mu, K *result, int where) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CHECK(check_ready(c, mu));
-  HB_CUDA(cudaMemsetAsync(c->d_res, 0, mu * sizeof(double), c->stream));
+  HB_CUDA(cudaMemsetAsync(c->d_res, 0, mu * sizeof(K), c->stream));
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
-    const double *xd = x[i], *yd = y[i];
+    const K *xd = x[i], *yd = y[i];
     if (where == HPDDM_B200_HOST) {
-      HB_CUDA(cudaMemcpyAsync(s->d_in, x[i], (size_t)s->n * mu * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-      HB_CUDA(cudaMemcpyAsync(s->d_tmp, y[i], (size_t)s->n * mu * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(s->d_in, x[i], (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaMemcpyAsync(s->d_tmp, y[i], (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
       xd = s->d_in;
       yd = s->d_tmp;
     }
     HB_CHECK(k_dot(c, s, mu, xd, yd, c->d_res));
   }
-  if (c->nproc > 1) HB_NCCL(g_nccl.AllReduce(c->d_res, c->d_res, mu, NCCL_F64, NCCL_SUM, c->nccl, c->stream));
-  HB_CUDA(cudaMemcpyAsync(result, c->d_res, mu * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (c->nproc > 1) HB_NCCL(g_nccl.AllReduce(c->d_res, c->d_res, mu * KD, NCCL_F64, NCCL_SUM, c->nccl, c->stream));
+  HB_CUDA(cudaMemcpyAsync(result, c->d_res, mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
-int hpddm_b200_sub_stats(hpddm_b200_sub *sub, hpddm_b200_stats *st) {
+int HB_API(sub_stats)(hb_sub_t *sub, hpddm_b200_stats *st) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s || !st) return HPDDM_B200_ERR_ARG;
   memset(st, 0, sizeof(*st));
   st->n = s->n;
   st->nnz_a = s->A.n ? s->A.ia[s->A.n] : 0;
   st->nnz_factor = s->sym.nnz_factor;
-  st->factor_bytes = s->sym.panel_elems * (int64_t)sizeof(double) * (s->fac.symmetric ? 1 : 2);
+  st->factor_bytes = s->sym.panel_elems * (int64_t)sizeof(K) * (s->fac.symmetric ? 1 : 2);
   st->index_bytes = (int64_t)s->sym.rowidx.size() * 4 + (int64_t)s->sym.fwd.size() * sizeof(FwdItem) + (int64_t)s->sym.bwd.size() * sizeof(BwdItem) +
                     (int64_t)s->sym.fronts.size() * sizeof(Front);
   st->fronts = (int64_t)s->sym.fronts.size();

@@ -17,6 +17,15 @@
 
 #include "hb_internal.h"
 
+#ifdef HB_COMPLEX
+// Complex scalars (BASELINE.json config 5: Helmholtz + DtN coarse space): the reference has no in-tree pencil for that case
+// either -- the driver supplies its coarse vectors through set_vectors.
+using namespace hb;
+extern "C" int HB_API(sub_solve_gevp)(hb_sub_t *, int, int, const int *, const int *, const K *, int, char, int, double, int, double *) {
+  set_error("solve_gevp: the GPU GenEO eigensolver is implemented for real scalars only; pass the coarse vectors with " HB_PREFIX "_sub_set_vectors");
+  return HPDDM_B200_ERR_STATE;
+}
+#else
 namespace hb {
 
 namespace {
@@ -123,7 +132,7 @@ int rayleigh_ritz(int k, std::vector<double> GA, std::vector<double> GB, std::ve
 
 using namespace hb;
 
-extern "C" int hpddm_b200_sub_solve_gevp(hpddm_b200_sub *sub, int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering, int nu,
+extern "C" int HB_API(sub_solve_gevp)(hb_sub_t *sub, int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering, int nu,
                                          double tol, int max_it, double *eigenvalues) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s || nu < 1 || n != s->n) {
@@ -279,13 +288,15 @@ extern "C" int hpddm_b200_sub_solve_gevp(hpddm_b200_sub *sub, int n, int nnz, co
 #undef GVC
 }
 
-extern "C" int hpddm_b200_sub_get_vectors(hpddm_b200_sub *sub, double *Z, int *nu) {
+#endif  // HB_COMPLEX
+
+extern "C" int HB_API(sub_get_vectors)(hb_sub_t *sub, K *Z, int *nu) {
   Sub *s = reinterpret_cast<Sub *>(sub);
   if (!s || !nu) return HPDDM_B200_ERR_ARG;
   *nu = s->nu;
   if (Z && s->nu > 0) {
     HB_CUDA(cudaSetDevice(s->ctx->device));
-    HB_CUDA(cudaMemcpyAsync(Z, s->d_Z, (size_t)s->n * s->nu * sizeof(double), cudaMemcpyDeviceToHost, s->ctx->stream));
+    HB_CUDA(cudaMemcpyAsync(Z, s->d_Z, (size_t)s->n * s->nu * sizeof(K), cudaMemcpyDeviceToHost, s->ctx->stream));
     HB_CUDA(cudaStreamSynchronize(s->ctx->stream));
   }
   return 0;

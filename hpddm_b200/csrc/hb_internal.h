@@ -6,7 +6,22 @@
 #include <string>
 #include <vector>
 
+#include "hb_scalar.h"
 #include "../../include/hpddm_b200.h"
+#ifdef HB_COMPLEX
+#define HPDDM_B200_Z_T hbz::cplx
+#include "../../include/hpddm_b200z.h"
+#endif
+
+#ifdef HB_COMPLEX
+typedef hpddm_b200z_ctx hb_ctx_t;
+typedef hpddm_b200z_sub hb_sub_t;
+#define HB_SCALAR_NAME "complex double"
+#else
+typedef hpddm_b200_ctx hb_ctx_t;
+typedef hpddm_b200_sub hb_sub_t;
+#define HB_SCALAR_NAME "double"
+#endif
 
 namespace hb {
 
@@ -74,8 +89,8 @@ struct BwdItem {
   int r0;  // first row (panel row index in [0, s1+s2))
   int nr;  // rows
 };
-constexpr int FCH = 512;    // forward column chunk
-constexpr int BCH = 256;    // backward column chunk (8 accumulators per lane)
+constexpr int FCH = 256 * VE;  // forward column chunk (4 KB of right-hand side per warp): 512 real / 256 complex
+constexpr int BCH = 128 * VE;  // backward column chunk (4 x 128-bit accumulators per lane): 256 real / 128 complex
 constexpr int BROWS = 128;  // backward rows per item
 
 struct Symbolic {
@@ -100,8 +115,8 @@ struct Symbolic {
 struct HostCSR {
   int n = 0;
   std::vector<int> ia, ja;  // full pattern, C numbering
-  std::vector<double> a;
-  bool symmetric = false;   // numerically symmetric
+  std::vector<K> a;
+  bool symmetric = false;   // numerically symmetric (real scalars only: LL^T candidate)
 };
 
 // builds ordering + supernodal structure.  grid hint: nx*ny*nz*dof == n or nx==0
@@ -111,14 +126,14 @@ int symbolic_analyze(const HostCSR &A, int nx, int ny, int nz, int dof, int leaf
 struct DeviceFactor {
   bool valid = false;
   bool symmetric = true;
-  double *panL = nullptr;  // forward panels
-  double *panU = nullptr;  // backward panels (== panL when symmetric)
+  K *panL = nullptr;  // forward panels
+  K *panU = nullptr;  // backward panels (== panL when symmetric)
   Front *fronts = nullptr;
   int *rowidx = nullptr;
   FwdItem *fwd = nullptr;
   BwdItem *bwd = nullptr;
   int *perm = nullptr;   // perm[new] = old
-  double *b = nullptr, *y = nullptr, *x = nullptr;  // permuted work vectors (n * 4 each: up to 4 RHS per pass)
+  K *b = nullptr, *y = nullptr, *x = nullptr;  // permuted work vectors (n * 4 each: up to 4 RHS per pass)
   cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};  // captured sweep launches for mu = 1, 2, 4
   int sweep_launches = 0;                                  // kernels inside one captured graph
 };
@@ -139,18 +154,18 @@ struct Sub {
   std::vector<double> d_host;
   // device
   int *d_ia = nullptr, *d_ja = nullptr;
-  double *d_a = nullptr;
-  double *d_d = nullptr;
+  K *d_a = nullptr;
+  double *d_d = nullptr;    // partition of unity: real (underlying_type<K>)
   int *d_map = nullptr;     // concatenated neighbour indices (h)
   int *d_ebase = nullptr, *d_esize = nullptr;  // per entry: start / size of its neighbour segment
   std::vector<int> peer_seg;  // for a local neighbour: its segment index that points back to us
   int h = 0;
-  double *d_send = nullptr, *d_recv = nullptr;  // h * mu_cap each
+  K *d_send = nullptr, *d_recv = nullptr;  // h * mu_cap each
   int *d_uidx = nullptr, *d_useg = nullptr, *d_upos = nullptr;  // deterministic unpack (CSR by unique target)
   int nuniq = 0;
-  std::vector<std::pair<int, double>> bc;  // penalised rows
+  std::vector<std::pair<int, K>> bc;  // penalised rows
   int *d_bc_idx = nullptr;
-  double *d_bc_val = nullptr;
+  K *d_bc_val = nullptr;
   // factor
   Symbolic sym;
   DeviceFactor fac;
@@ -158,10 +173,10 @@ struct Sub {
   double t_symbolic = 0, t_numfact = 0;
   // deflation
   int nu = 0;
-  double *d_Z = nullptr;
+  K *d_Z = nullptr;
   int coff = 0;             // offset of this subdomain in the coarse vector
   // work vectors (n * mu_cap)
-  double *d_in = nullptr, *d_out = nullptr, *d_work = nullptr, *d_tmp = nullptr;
+  K *d_in = nullptr, *d_out = nullptr, *d_work = nullptr, *d_tmp = nullptr;
   int mu_cap = 0;
 };
 
@@ -177,17 +192,17 @@ struct Ctx {
   int Nc = 0;
   std::vector<int> coarse_off;  // per global rank, size P+1
   std::vector<int> nu_all;
-  double *d_E = nullptr, *d_Einv = nullptr;  // Nc x Nc column-major
-  double *d_T = nullptr, *d_Y = nullptr;     // Nc x mu_cap, layout [proc][col][row-in-proc]
-  double *d_R = nullptr;                     // Nc residual of the coarse refinement step
+  K *d_E = nullptr, *d_Einv = nullptr;  // Nc x Nc column-major
+  K *d_T = nullptr, *d_Y = nullptr;     // Nc x mu_cap, layout [proc][col][row-in-proc]
+  K *d_R = nullptr;                     // Nc residual of the coarse refinement step
   int Lnu = 0;                               // Lmax: coarse rows per process block in the (padded) communication layout
   std::vector<int> Lnu_p;                    // actual coarse rows of every process
   int *d_rowproc = nullptr, *d_rowloc = nullptr;  // coarse row -> (process, row inside its block)
   int loc_off = 0;                           // first coarse row of this process
-  double *d_res = nullptr;                   // small device scratch (dots)
-  std::vector<double> E_host;
+  K *d_res = nullptr;                   // small device scratch (dots)
+  std::vector<K> E_host;
   // pinned staging
-  double *pin = nullptr;
+  K *pin = nullptr;
   size_t pin_bytes = 0;
   int mu_cap = 0;
   bool started = false;
@@ -195,51 +210,52 @@ struct Ctx {
 };
 
 // ---------------------------------------------------------------- kernels (launchers)
+// K = scalar type of this build (hb_scalar.h); `d` / `scale` (partition of unity) are always real
 int numfact_device(Sub *s, const HostCSR &A);
 void free_factor(DeviceFactor &f);
 // x = A^{-1} b for mu in {1,2,4} columns (column stride n), natural ordering in/out, device pointers.
 // scale: optional d (natural order) applied on output (out = d .* x); accumulate: out += instead of =
-int sptrsv_solve(Sub *s, const double *b, double *x, int mu, const double *scale, bool accumulate);
+int sptrsv_solve(Sub *s, const K *b, K *x, int mu, const double *scale, bool accumulate);
 
-int k_scale(Ctx *c, int n, int mu, const double *d, const double *in, double *out);      // out = d.*in
-int k_axpy(Ctx *c, int64_t n, double a, const double *x, double *y);                     // y += a x
-int k_copy(Ctx *c, int64_t n, const double *x, double *y);
-int k_fill(Ctx *c, int64_t n, double v, double *y);
+int k_scale(Ctx *c, int n, int mu, const double *d, const K *in, K *out);      // out = d.*in
+int k_axpy(Ctx *c, int64_t n, double a, const K *x, K *y);                     // y += a x
+int k_copy(Ctx *c, int64_t n, const K *x, K *y);
+int k_fill(Ctx *c, int64_t n, K v, K *y);
 // y = beta*yin + alpha * A x, optionally scaled by d: out = d .* (...)
-int k_spmv(Ctx *c, const Sub *s, int mu, double alpha, const double *x, double beta, const double *yin, double *out, const double *d);
-// T[k + nu*col] = sum_i Z[i,k] d[i] x[i,col]
-int k_zt_project(Ctx *c, const Sub *s, int mu, const double *x, double *T, int ldT);
+int k_spmv(Ctx *c, const Sub *s, int mu, double alpha, const K *x, double beta, const K *yin, K *out, const double *d);
+// T[k + nu*col] = sum_i conj(Z[i,k]) d[i] x[i,col]
+int k_zt_project(Ctx *c, const Sub *s, int mu, const K *x, K *T, int ldT);
 // out[i,col] = d[i] * sum_k Z[i,k] Y[k,col]
-int k_z_expand(Ctx *c, const Sub *s, int mu, const double *Y, int ldY, double *out);
-int k_pack(Ctx *c, const Sub *s, int mu, const double *x, double *send);
-int k_unpack(Ctx *c, const Sub *s, int mu, double *x);  // x[map] += d_recv, deterministic order
-int k_dot(Ctx *c, const Sub *s, int mu, const double *x, const double *y, double *res);
+int k_z_expand(Ctx *c, const Sub *s, int mu, const K *Y, int ldY, K *out);
+int k_pack(Ctx *c, const Sub *s, int mu, const K *x, K *send);
+int k_unpack(Ctx *c, const Sub *s, int mu, K *x);  // x[map] += d_recv, deterministic order
+int k_dot(Ctx *c, const Sub *s, int mu, const K *x, const K *y, K *res);  // res[col] += sum_i d_i conj(x_i) y_i
 int k_coarse_solve(Ctx *c, int mu);  // d_Y = E^{-1} d_T with one refinement step
-int k_bc(Ctx *c, const Sub *s, int mu, const double *b, double *x);
+int k_bc(Ctx *c, const Sub *s, int mu, const K *b, K *x);
 
-int k_zt_raw(Ctx *c, int n, int nu, const double *Z, const double *d, int mu, const double *x, double *T, int ldT);
-int k_zexp_raw(Ctx *c, int n, int nu, const double *Z, const double *d, int mu, const double *Y, int ldY, double *out);
-int k_spmv_raw(Ctx *c, int n, int64_t nnz, const int *ia, const int *ja, const double *a, int mu, double alpha, const double *x, double beta, const double *yin,
-               double *out, const double *d);
-int k_flush_tiny(Ctx *c, int64_t n, double tiny, double *v);
-int to_host_csr(int n, int nnz, const int *ia, const int *ja, const double *a, int sym, char numbering, HostCSR &H);
-int solve_cols(Sub *s, const double *b, double *x, int mu, const double *scale, bool acc);
+int k_zt_raw(Ctx *c, int n, int nu, const K *Z, const double *d, int mu, const K *x, K *T, int ldT);
+int k_zexp_raw(Ctx *c, int n, int nu, const K *Z, const double *d, int mu, const K *Y, int ldY, K *out);
+int k_spmv_raw(Ctx *c, int n, int64_t nnz, const int *ia, const int *ja, const K *a, int mu, double alpha, const K *x, double beta, const K *yin, K *out,
+               const double *d);
+int k_flush_tiny(Ctx *c, int64_t n, double tiny, K *v);
+int to_host_csr(int n, int nnz, const int *ia, const int *ja, const K *a, int sym, char numbering, HostCSR &H);
+int solve_cols(Sub *s, const K *b, K *x, int mu, const double *scale, bool acc);
 // orchestration helpers shared by hb_api.cu and hb_krylov.cu (device pointers, one per local subdomain)
 int check_ready(Ctx *c, int mu);
-int halo(Ctx *c, double *const *x, int mu, bool allow_p2p = true);
-int apply_core(Ctx *c, const std::vector<const double *> &in, const std::vector<double *> &out, int mu, int correction);
-int gmv_core(Ctx *c, const std::vector<const double *> &in, const std::vector<double *> &out, int mu);
-int stage_in(Ctx *c, const double *const *in, int mu, int where, std::vector<const double *> &dev);
-void out_ptrs(Ctx *c, double *const *out, int where, std::vector<double *> &dev);
-int stage_out(Ctx *c, double *const *out, int mu, int where);
-int nccl_allreduce_sum(Ctx *c, double *buf, int count);
+int halo(Ctx *c, K *const *x, int mu, bool allow_p2p = true);
+int apply_core(Ctx *c, const std::vector<const K *> &in, const std::vector<K *> &out, int mu, int correction);
+int gmv_core(Ctx *c, const std::vector<const K *> &in, const std::vector<K *> &out, int mu);
+int stage_in(Ctx *c, const K *const *in, int mu, int where, std::vector<const K *> &dev);
+void out_ptrs(Ctx *c, K *const *out, int where, std::vector<K *> &dev);
+int stage_out(Ctx *c, K *const *out, int mu, int where);
+int nccl_allreduce_sum(Ctx *c, double *buf, int count);  // count doubles (a K is KD doubles)
 int nccl_allgather_bytes(Ctx *c, const void *send, void *recv, size_t bytes_per_rank);
-int p2p_halo(Ctx *c, double *const *x, int mu);  // 1 = done over peer memory, 0 = use NCCL
+int p2p_halo(Ctx *c, K *const *x, int mu);  // 1 = done over peer memory, 0 = use NCCL
 int p2p_check(Ctx *c);
 void p2p_free(Ctx *c);
 // Krylov helper kernels (hb_kernels.cu)
-int k_vdots(Ctx *c, const Sub *s, int k, const double *V, const double *w, double *T);      // T[j] += sum_i d_i V[i,j] w[i]
-int k_vupdate(Ctx *c, const Sub *s, int k, const double *V, const double *h, double sign, double *w);  // w += sign * V h
-int k_scal_copy(Ctx *c, int64_t n, double a, const double *x, double *y);                  // y = a x
+int k_vdots(Ctx *c, const Sub *s, int k, const K *V, const K *w, K *T);               // T[j] += sum_i d_i conj(V[i,j]) w[i]
+int k_vupdate(Ctx *c, const Sub *s, int k, const K *V, const K *h, double sign, K *w);  // w += sign * V h
+int k_scal_copy(Ctx *c, int64_t n, double a, const K *x, K *y);                       // y = a x
 
 }  // namespace hb

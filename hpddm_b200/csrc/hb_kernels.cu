@@ -14,25 +14,25 @@ namespace hb {
 
 namespace {
 
-__device__ __forceinline__ double warp_sum(double v) {
+__device__ __forceinline__ K warp_sum(K v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = 16; o > 0; o >>= 1) v += hb_shfl_xor(v, o);
   return v;
 }
 
-__global__ void kk_scale(int n, int mu, const double *__restrict__ d, const double *__restrict__ in, double *out) {
+__global__ void kk_scale(int n, int mu, const double *__restrict__ d, const K *__restrict__ in, K *out) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t < (int64_t)n * mu) out[t] = d[t % n] * in[t];
 }
-__global__ void kk_axpy(int64_t n, double a, const double *__restrict__ x, double *y) {
+__global__ void kk_axpy(int64_t n, double a, const K *__restrict__ x, K *y) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t < n) y[t] += a * x[t];
+  if (t < n) y[t] = hb_fma(a, x[t], y[t]);
 }
-__global__ void kk_copy(int64_t n, const double *__restrict__ x, double *y) {
+__global__ void kk_copy(int64_t n, const K *__restrict__ x, K *y) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t < n) y[t] = x[t];
 }
-__global__ void kk_fill(int64_t n, double v, double *y) {
+__global__ void kk_fill(int64_t n, K v, K *y) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t < n) y[t] = v;
 }
@@ -40,62 +40,63 @@ __global__ void kk_fill(int64_t n, double v, double *y) {
 // out[i,c] = (d ? d[i] : 1) * (beta * yin[i,c] + alpha * sum_k a[k] x[ja[k],c])
 // CSR "vector" kernel: LPR lanes cooperate on a row (coalesced a/ja reads), LPR chosen from the mean row length
 template <int LPR>
-__global__ void __launch_bounds__(256) kk_spmv(int n, int mu, const int *__restrict__ ia, const int *__restrict__ ja, const double *__restrict__ a, double alpha,
-                                               const double *__restrict__ x, double beta, const double *__restrict__ yin, double *out, const double *__restrict__ d) {
+__global__ void __launch_bounds__(256) kk_spmv(int n, int mu, const int *__restrict__ ia, const int *__restrict__ ja, const K *__restrict__ a, double alpha,
+                                               const K *__restrict__ x, double beta, const K *__restrict__ yin, K *out, const double *__restrict__ d) {
   const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int i = (int)(gt / LPR), sub = (int)(gt % LPR);
   if (i >= n) return;  // LPR divides the warp size: a whole row group leaves together
   const int k0 = ia[i], k1 = ia[i + 1];
   const double di = d ? d[i] : 1.0;
   for (int c = 0; c < mu; ++c) {
-    const double *xc = x + (int64_t)c * n;
-    double acc = 0.0;
-    for (int k = k0 + sub; k < k1; k += LPR) acc = fma(a[k], xc[ja[k]], acc);
+    const K *xc = x + (int64_t)c * n;
+    K acc = mk(0.0);
+    for (int k = k0 + sub; k < k1; k += LPR) acc = hb_fma(a[k], xc[ja[k]], acc);
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LPR);
+    for (int o = LPR / 2; o > 0; o >>= 1) acc += hb_shfl_down(acc, o, LPR);
     if (sub == 0) {
-      double v = alpha * acc;
+      K v = alpha * acc;
       if (beta != 0.0) v += beta * yin[i + (int64_t)c * n];
       out[i + (int64_t)c * n] = di * v;
     }
   }
 }
 
-// T[k + ldT*c] += sum_i Z[i + k*n] * d[i] * x[i + c*n] ; 1024 rows per CTA, Z read once per column group.
+// T[k + ldT*c] += sum_i conj(Z[i + k*n]) * d[i] * x[i + c*n]  (Z^H: Wrapper<K>::transc, schwarz.hpp:1616) ; 1024 rows per CTA, Z read once per column group.
 // Vectors are processed in chunks of KC: KC * 4 independent 8-byte loads per thread are in flight, the
 // KC * MB partial sums are reduced once per chunk (shuffles + one shared-memory pass) and published with
 // one atomic per (CTA, vector, column).
 template <int MB>
-__global__ void __launch_bounds__(256) kk_zt(int n, int nu, int c0, const double *__restrict__ Z, const double *__restrict__ d, const double *__restrict__ x,
-                                             double *T, int ldT) {
-  constexpr int KC = 8 / MB >= 2 ? 8 / MB : 2;  // 8, 4, 2
-  __shared__ double red[8][KC * MB];
+__global__ void __launch_bounds__(256) kk_zt(int n, int nu, int c0, const K *__restrict__ Z, const double *__restrict__ d, const K *__restrict__ x,
+                                             K *T, int ldT) {
+  constexpr int KCR = 8 / MB >= 2 ? 8 / MB : 2;     // 8, 4, 2 vectors per chunk for real scalars
+  constexpr int KC = KCR / KD >= 1 ? KCR / KD : 1;  // complex: half as many (same bytes in flight)
+  __shared__ K red[8][KC * MB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int base = blockIdx.x * 1024;
-  double w[4][MB];
+  K w[4][MB];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int i = base + tid + 256 * q;
 #pragma unroll
-    for (int m = 0; m < MB; ++m) w[q][m] = (i < n) ? d[i] * x[i + (int64_t)(c0 + m) * n] : 0.0;
+    for (int m = 0; m < MB; ++m) w[q][m] = (i < n) ? d[i] * x[i + (int64_t)(c0 + m) * n] : mk(0.0);
   }
   for (int k0 = 0; k0 < nu; k0 += KC) {
-    double z[KC][4];
+    K z[KC][4];
 #pragma unroll
     for (int kk = 0; kk < KC; ++kk)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int i = base + tid + 256 * q;
-        z[kk][q] = (k0 + kk < nu && i < n) ? Z[i + (int64_t)(k0 + kk) * n] : 0.0;
+        z[kk][q] = (k0 + kk < nu && i < n) ? hb_conj(Z[i + (int64_t)(k0 + kk) * n]) : mk(0.0);
       }
-    double acc[KC][MB];
+    K acc[KC][MB];
 #pragma unroll
     for (int kk = 0; kk < KC; ++kk)
 #pragma unroll
       for (int m = 0; m < MB; ++m) {
-        double a = 0.0;
+        K a = mk(0.0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) a = fma(z[kk][q], w[q][m], a);
+        for (int q = 0; q < 4; ++q) a = hb_fma(z[kk][q], w[q][m], a);
         acc[kk][m] = warp_sum(a);
       }
     if (lane == 0) {
@@ -108,10 +109,10 @@ __global__ void __launch_bounds__(256) kk_zt(int n, int nu, int c0, const double
     if (tid < KC * MB) {
       const int kk = tid / MB, m = tid % MB;
       if (k0 + kk < nu) {
-        double sum = 0.0;
+        K sum = mk(0.0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) sum += red[q][tid];
-        atomicAdd(&T[k0 + kk + (int64_t)ldT * (c0 + m)], sum);
+        hb_atomic_add(&T[k0 + kk + (int64_t)ldT * (c0 + m)], sum);
       }
     }
     __syncthreads();
@@ -120,20 +121,21 @@ __global__ void __launch_bounds__(256) kk_zt(int n, int nu, int c0, const double
 
 // out[i + c*n] = d[i] * sum_k Z[i + k*n] * Y[k + ldY*c]
 template <int MB>
-__global__ void __launch_bounds__(256) kk_zexp(int n, int nu, int c0, const double *__restrict__ Z, const double *__restrict__ d, const double *__restrict__ Y,
-                                               int ldY, double *out) {
-  extern __shared__ double ys[];  // nu * MB
+__global__ void __launch_bounds__(256) kk_zexp(int n, int nu, int c0, const K *__restrict__ Z, const double *__restrict__ d, const K *__restrict__ Y,
+                                               int ldY, K *out) {
+  extern __shared__ __align__(16) unsigned char ys_raw[];
+  K *ys = reinterpret_cast<K *>(ys_raw);  // nu * MB
   for (int t = threadIdx.x; t < nu * MB; t += blockDim.x) ys[t] = Y[(t % nu) + (int64_t)ldY * (c0 + t / nu)];
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double acc[MB];
+  K acc[MB];
 #pragma unroll
-  for (int m = 0; m < MB; ++m) acc[m] = 0.0;
+  for (int m = 0; m < MB; ++m) acc[m] = mk(0.0);
   for (int k = 0; k < nu; ++k) {
-    const double z = Z[i + (int64_t)k * n];
+    const K z = Z[i + (int64_t)k * n];
 #pragma unroll
-    for (int m = 0; m < MB; ++m) acc[m] = fma(z, ys[k + nu * m], acc[m]);
+    for (int m = 0; m < MB; ++m) acc[m] = hb_fma(z, ys[k + nu * m], acc[m]);
   }
   const double di = d[i];
 #pragma unroll
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(256) kk_zexp(int n, int nu, int c0, const doub
 
 // send[ebase*mu + c*esize + (e - ebase)] = x[map[e] + c*n]
 __global__ void kk_pack(int h, int n, int mu, const int *__restrict__ map, const int *__restrict__ ebase, const int *__restrict__ esize,
-                        const double *__restrict__ x, double *send) {
+                        const K *__restrict__ x, K *send) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= (int64_t)h * mu) return;
   const int e = (int)(t % h), c = (int)(t / h);
@@ -150,11 +152,11 @@ __global__ void kk_pack(int h, int n, int mu, const int *__restrict__ map, const
 }
 // deterministic unpack-add: one thread per unique target dof, contributions summed in neighbour order
 __global__ void kk_unpack(int nuniq, int n, int mu, const int *__restrict__ uidx, const int *__restrict__ useg, const int *__restrict__ upos,
-                          const int *__restrict__ ebase, const int *__restrict__ esize, const double *__restrict__ recv, double *x) {
+                          const int *__restrict__ ebase, const int *__restrict__ esize, const K *__restrict__ recv, K *x) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= (int64_t)nuniq * mu) return;
   const int u = (int)(t % nuniq), c = (int)(t / nuniq);
-  double acc = x[uidx[u] + (int64_t)c * n];
+  K acc = x[uidx[u] + (int64_t)c * n];
   for (int q = useg[u]; q < useg[u + 1]; ++q) {
     const int e = upos[q];
     acc += recv[(int64_t)ebase[e] * mu + (int64_t)c * esize[e] + (e - ebase[e])];
@@ -162,19 +164,21 @@ __global__ void kk_unpack(int nuniq, int n, int mu, const int *__restrict__ uidx
   x[uidx[u] + (int64_t)c * n] = acc;
 }
 
-__global__ void __launch_bounds__(256) kk_dot(int n, int mu, const double *__restrict__ d, const double *__restrict__ x, const double *__restrict__ y, double *res) {
-  __shared__ double red[8];
+// res[c] += sum_i d[i] conj(x[i,c]) y[i,c]   (iterative.hpp:503)
+__global__ void __launch_bounds__(256) kk_dot(int n, int mu, const double *__restrict__ d, const K *__restrict__ x, const K *__restrict__ y, K *res) {
+  __shared__ K red[8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int c = 0; c < mu; ++c) {
-    double acc = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x) acc = fma(d[i] * x[i + (int64_t)c * n], y[i + (int64_t)c * n], acc);
+    K acc = mk(0.0);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      acc = hb_fma(d[i] * hb_conj(x[i + (int64_t)c * n]), y[i + (int64_t)c * n], acc);
     acc = warp_sum(acc);
     if (lane == 0) red[warp] = acc;
     __syncthreads();
     if (tid == 0) {
-      double s = 0.0;
+      K s = mk(0.0);
       for (int q = 0; q < 8; ++q) s += red[q];
-      atomicAdd(&res[c], s);
+      hb_atomic_add(&res[c], s);
     }
     __syncthreads();
   }
@@ -184,24 +188,24 @@ __global__ void __launch_bounds__(256) kk_dot(int n, int mu, const double *__res
 // Coarse vectors use the communication layout [proc][col][row-in-proc]:
 //   v(r, c) = buf[rowproc[r] * Lmax * mu + c * Lmax + rowloc[r]]   (process blocks padded to Lmax rows)
 __global__ void __launch_bounds__(256) kk_coarse(int Nc, int mu, int Lnu, const int *__restrict__ rowproc, const int *__restrict__ rowloc,
-                                                 const double *__restrict__ E, const double *__restrict__ Einv, const double *__restrict__ T, double *Y, double *R) {
+                                                 const K *__restrict__ E, const K *__restrict__ Einv, const K *__restrict__ T, K *Y, K *R) {
   auto at = [&](int r, int c) -> int64_t { return (int64_t)rowproc[r] * Lnu * mu + (int64_t)c * Lnu + rowloc[r]; };
   for (int c = 0; c < mu; ++c) {
     for (int r = threadIdx.x; r < Nc; r += blockDim.x) {
-      double acc = 0.0;
-      for (int k = 0; k < Nc; ++k) acc = fma(Einv[r + (int64_t)k * Nc], T[at(k, c)], acc);
+      K acc = mk(0.0);
+      for (int k = 0; k < Nc; ++k) acc = hb_fma(Einv[r + (int64_t)k * Nc], T[at(k, c)], acc);
       Y[at(r, c)] = acc;
     }
     __syncthreads();
     for (int r = threadIdx.x; r < Nc; r += blockDim.x) {
-      double acc = T[at(r, c)];
-      for (int k = 0; k < Nc; ++k) acc = fma(-E[r + (int64_t)k * Nc], Y[at(k, c)], acc);
+      K acc = T[at(r, c)];
+      for (int k = 0; k < Nc; ++k) acc = hb_fma(-E[r + (int64_t)k * Nc], Y[at(k, c)], acc);
       R[r] = acc;
     }
     __syncthreads();
     for (int r = threadIdx.x; r < Nc; r += blockDim.x) {
-      double acc = 0.0;
-      for (int k = 0; k < Nc; ++k) acc = fma(Einv[r + (int64_t)k * Nc], R[k], acc);
+      K acc = mk(0.0);
+      for (int k = 0; k < Nc; ++k) acc = hb_fma(Einv[r + (int64_t)k * Nc], R[k], acc);
       Y[at(r, c)] += acc;
     }
     __syncthreads();
@@ -209,12 +213,12 @@ __global__ void __launch_bounds__(256) kk_coarse(int Nc, int mu, int Lnu, const 
 }
 
 // v[i] = 0 where |v[i]| < tiny (Schwarz::solveGEVP post-processing, schwarz.hpp:713)
-__global__ void kk_flush_tiny(int64_t n, double tiny, double *v) {
+__global__ void kk_flush_tiny(int64_t n, double tiny, K *v) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t < n && fabs(v[t]) < tiny) v[t] = 0.0;
+  if (t < n && hb_abs(v[t]) < tiny) v[t] = mk(0.0);
 }
 
-__global__ void kk_bc(int nbc, int n, int mu, const int *__restrict__ idx, const double *__restrict__ val, const double *__restrict__ b, double *x) {
+__global__ void kk_bc(int nbc, int n, int mu, const int *__restrict__ idx, const K *__restrict__ val, const K *__restrict__ b, K *x) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nbc * mu) return;
   const int q = t % nbc, c = t / nbc;
@@ -222,17 +226,18 @@ __global__ void kk_bc(int nbc, int n, int mu, const int *__restrict__ idx, const
 }
 
 // w[i] += sign * sum_j V[i + j*n] h[j]   (Gram-Schmidt update / Krylov linear combination)
-__global__ void __launch_bounds__(256) kk_vupdate(int n, int k, const double *__restrict__ V, const double *__restrict__ h, double sign, double *w) {
-  extern __shared__ double hs[];
+__global__ void __launch_bounds__(256) kk_vupdate(int n, int k, const K *__restrict__ V, const K *__restrict__ h, double sign, K *w) {
+  extern __shared__ __align__(16) unsigned char hs_raw[];
+  K *hs = reinterpret_cast<K *>(hs_raw);
   for (int t = threadIdx.x; t < k; t += blockDim.x) hs[t] = h[t];
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double acc = 0.0;
-  for (int j = 0; j < k; ++j) acc = fma(V[i + (int64_t)j * n], hs[j], acc);
-  w[i] += sign * acc;
+  K acc = mk(0.0);
+  for (int j = 0; j < k; ++j) acc = hb_fma(V[i + (int64_t)j * n], hs[j], acc);
+  w[i] = hb_fma(sign, acc, w[i]);
 }
-__global__ void kk_scal_copy(int64_t n, double a, const double *__restrict__ x, double *y) {
+__global__ void kk_scal_copy(int64_t n, double a, const K *__restrict__ x, K *y) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t < n) y[t] = a * x[t];
 }
@@ -246,32 +251,32 @@ inline unsigned grid1(int64_t n, int bs = 256) { return (unsigned)((n + bs - 1) 
   HB_CUDA(cudaGetLastError()); \
   return 0
 
-int k_scale(Ctx *c, int n, int mu, const double *d, const double *in, double *out) {
+int k_scale(Ctx *c, int n, int mu, const double *d, const K *in, K *out) {
   if ((int64_t)n * mu == 0) return 0;
   kk_scale<<<grid1((int64_t)n * mu), 256, 0, c->stream>>>(n, mu, d, in, out);
   HB_LAUNCH_END(c);
 }
-int k_axpy(Ctx *c, int64_t n, double a, const double *x, double *y) {
+int k_axpy(Ctx *c, int64_t n, double a, const K *x, K *y) {
   if (n == 0) return 0;
   kk_axpy<<<grid1(n), 256, 0, c->stream>>>(n, a, x, y);
   HB_LAUNCH_END(c);
 }
-int k_copy(Ctx *c, int64_t n, const double *x, double *y) {
+int k_copy(Ctx *c, int64_t n, const K *x, K *y) {
   if (n == 0 || x == y) return 0;
   kk_copy<<<grid1(n), 256, 0, c->stream>>>(n, x, y);
   HB_LAUNCH_END(c);
 }
-int k_fill(Ctx *c, int64_t n, double v, double *y) {
+int k_fill(Ctx *c, int64_t n, K v, K *y) {
   if (n == 0) return 0;
   kk_fill<<<grid1(n), 256, 0, c->stream>>>(n, v, y);
   HB_LAUNCH_END(c);
 }
-int k_spmv(Ctx *c, const Sub *s, int mu, double alpha, const double *x, double beta, const double *yin, double *out, const double *d) {
+int k_spmv(Ctx *c, const Sub *s, int mu, double alpha, const K *x, double beta, const K *yin, K *out, const double *d) {
   if (s->n == 0) return 0;
   return k_spmv_raw(c, s->n, s->A.ia[s->n], s->d_ia, s->d_ja, s->d_a, mu, alpha, x, beta, yin, out, d);
 }
-int k_spmv_raw(Ctx *c, int n, int64_t nnz, const int *ia, const int *ja, const double *a, int mu, double alpha, const double *x, double beta, const double *yin,
-               double *out, const double *d) {
+int k_spmv_raw(Ctx *c, int n, int64_t nnz, const int *ia, const int *ja, const K *a, int mu, double alpha, const K *x, double beta, const K *yin, K *out,
+               const double *d) {
   if (n == 0) return 0;
   const double avg = (double)nnz / n;
 #define HB_SPMV(L) kk_spmv<L><<<grid1((int64_t)n * L), 256, 0, c->stream>>>(n, mu, ia, ja, a, alpha, x, beta, yin, out, d)
@@ -283,9 +288,9 @@ int k_spmv_raw(Ctx *c, int n, int64_t nnz, const int *ia, const int *ja, const d
 #undef HB_SPMV
   HB_LAUNCH_END(c);
 }
-int k_zt_project(Ctx *c, const Sub *s, int mu, const double *x, double *T, int ldT) { return k_zt_raw(c, s->n, s->nu, s->d_Z, s->d_d, mu, x, T, ldT); }
+int k_zt_project(Ctx *c, const Sub *s, int mu, const K *x, K *T, int ldT) { return k_zt_raw(c, s->n, s->nu, s->d_Z, s->d_d, mu, x, T, ldT); }
 // T[k + ldT*col] += sum_i Z[i,k] d[i] x[i,col]  on raw arrays (Z: n x nu column-major)
-int k_zt_raw(Ctx *c, int n, int nu, const double *Z, const double *d, int mu, const double *x, double *T, int ldT) {
+int k_zt_raw(Ctx *c, int n, int nu, const K *Z, const double *d, int mu, const K *x, K *T, int ldT) {
   if (n == 0 || nu == 0) return 0;
   const unsigned g = grid1(n, 1024);
   int c0 = 0;
@@ -306,26 +311,26 @@ int k_zt_raw(Ctx *c, int n, int nu, const double *Z, const double *d, int mu, co
   HB_CUDA(cudaGetLastError());
   return 0;
 }
-int k_z_expand(Ctx *c, const Sub *s, int mu, const double *Y, int ldY, double *out) {
+int k_z_expand(Ctx *c, const Sub *s, int mu, const K *Y, int ldY, K *out) {
   if (s->n == 0) return 0;
-  if (s->nu == 0) return k_fill(c, (int64_t)s->n * mu, 0.0, out);
+  if (s->nu == 0) return k_fill(c, (int64_t)s->n * mu, mk(0.0), out);
   return k_zexp_raw(c, s->n, s->nu, s->d_Z, s->d_d, mu, Y, ldY, out);
 }
 // out[i,col] = d[i] * sum_k Z[i,k] Y[k,col]  on raw arrays
-int k_zexp_raw(Ctx *c, int n, int nu, const double *Z, const double *d, int mu, const double *Y, int ldY, double *out) {
+int k_zexp_raw(Ctx *c, int n, int nu, const K *Z, const double *d, int mu, const K *Y, int ldY, K *out) {
   if (n == 0 || nu == 0) return 0;
   const unsigned g = grid1(n);
   int c0 = 0;
   while (c0 < mu) {
     const int left = mu - c0;
     if (left >= 4) {
-      kk_zexp<4><<<g, 256, nu * 4 * sizeof(double), c->stream>>>(n, nu, c0, Z, d, Y, ldY, out);
+      kk_zexp<4><<<g, 256, nu * 4 * sizeof(K), c->stream>>>(n, nu, c0, Z, d, Y, ldY, out);
       c0 += 4;
     } else if (left >= 2) {
-      kk_zexp<2><<<g, 256, nu * 2 * sizeof(double), c->stream>>>(n, nu, c0, Z, d, Y, ldY, out);
+      kk_zexp<2><<<g, 256, nu * 2 * sizeof(K), c->stream>>>(n, nu, c0, Z, d, Y, ldY, out);
       c0 += 2;
     } else {
-      kk_zexp<1><<<g, 256, nu * sizeof(double), c->stream>>>(n, nu, c0, Z, d, Y, ldY, out);
+      kk_zexp<1><<<g, 256, nu * sizeof(K), c->stream>>>(n, nu, c0, Z, d, Y, ldY, out);
       c0 += 1;
     }
     c->launches++;
@@ -333,17 +338,17 @@ int k_zexp_raw(Ctx *c, int n, int nu, const double *Z, const double *d, int mu, 
   HB_CUDA(cudaGetLastError());
   return 0;
 }
-int k_pack(Ctx *c, const Sub *s, int mu, const double *x, double *send) {
+int k_pack(Ctx *c, const Sub *s, int mu, const K *x, K *send) {
   if (s->h == 0) return 0;
   kk_pack<<<grid1((int64_t)s->h * mu), 256, 0, c->stream>>>(s->h, s->n, mu, s->d_map, s->d_ebase, s->d_esize, x, send);
   HB_LAUNCH_END(c);
 }
-int k_unpack(Ctx *c, const Sub *s, int mu, double *x) {
+int k_unpack(Ctx *c, const Sub *s, int mu, K *x) {
   if (s->nuniq == 0) return 0;
   kk_unpack<<<grid1((int64_t)s->nuniq * mu), 256, 0, c->stream>>>(s->nuniq, s->n, mu, s->d_uidx, s->d_useg, s->d_upos, s->d_ebase, s->d_esize, s->d_recv, x);
   HB_LAUNCH_END(c);
 }
-int k_dot(Ctx *c, const Sub *s, int mu, const double *x, const double *y, double *res) {
+int k_dot(Ctx *c, const Sub *s, int mu, const K *x, const K *y, K *res) {
   if (s->n == 0) return 0;
   unsigned g = grid1(s->n);
   if (g > 1184) g = 1184;
@@ -355,27 +360,27 @@ int k_coarse_solve(Ctx *c, int mu) {
   kk_coarse<<<1, 256, 0, c->stream>>>(c->Nc, mu, c->Lnu, c->d_rowproc, c->d_rowloc, c->d_E, c->d_Einv, c->d_T, c->d_Y, c->d_R);
   HB_LAUNCH_END(c);
 }
-int k_vdots(Ctx *c, const Sub *s, int k, const double *V, const double *w, double *T) {
+int k_vdots(Ctx *c, const Sub *s, int k, const K *V, const K *w, K *T) {
   if (s->n == 0 || k == 0) return 0;
   kk_zt<1><<<grid1(s->n, 1024), 256, 0, c->stream>>>(s->n, k, 0, V, s->d_d, w, T, k);
   HB_LAUNCH_END(c);
 }
-int k_vupdate(Ctx *c, const Sub *s, int k, const double *V, const double *h, double sign, double *w) {
+int k_vupdate(Ctx *c, const Sub *s, int k, const K *V, const K *h, double sign, K *w) {
   if (s->n == 0 || k == 0) return 0;
-  kk_vupdate<<<grid1(s->n), 256, k * sizeof(double), c->stream>>>(s->n, k, V, h, sign, w);
+  kk_vupdate<<<grid1(s->n), 256, k * sizeof(K), c->stream>>>(s->n, k, V, h, sign, w);
   HB_LAUNCH_END(c);
 }
-int k_scal_copy(Ctx *c, int64_t n, double a, const double *x, double *y) {
+int k_scal_copy(Ctx *c, int64_t n, double a, const K *x, K *y) {
   if (n == 0) return 0;
   kk_scal_copy<<<grid1(n), 256, 0, c->stream>>>(n, a, x, y);
   HB_LAUNCH_END(c);
 }
-int k_flush_tiny(Ctx *c, int64_t n, double tiny, double *v) {
+int k_flush_tiny(Ctx *c, int64_t n, double tiny, K *v) {
   if (n == 0) return 0;
   kk_flush_tiny<<<grid1(n), 256, 0, c->stream>>>(n, tiny, v);
   HB_LAUNCH_END(c);
 }
-int k_bc(Ctx *c, const Sub *s, int mu, const double *b, double *x) {
+int k_bc(Ctx *c, const Sub *s, int mu, const K *b, K *x) {
   const int nbc = (int)s->bc.size();
   if (nbc == 0) return 0;
   kk_bc<<<grid1((int64_t)nbc * mu), 256, 0, c->stream>>>(nbc, s->n, mu, s->d_bc_idx, s->d_bc_val, b, x);

@@ -33,11 +33,11 @@ namespace {
 static int SMALL = 160;   // fronts with s1+s2 <= SMALL are factored by the batched kernel
 
 __global__ void k_assemble(int64_t ne, const int *__restrict__ efront, const int *__restrict__ erow, const int *__restrict__ ecol,
-                           const double *__restrict__ eval, const int64_t *__restrict__ foff, const int *__restrict__ fs, double *F) {
+                           const K *__restrict__ eval, const int64_t *__restrict__ foff, const int *__restrict__ fs, K *F) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= ne) return;
   int f = efront[e];
-  atomicAdd(&F[foff[f] + erow[e] + (int64_t)ecol[e] * fs[f]], eval[e]);
+  hb_atomic_add(&F[foff[f] + erow[e] + (int64_t)ecol[e] * fs[f]], eval[e]);
 }
 
 struct EATask {
@@ -46,43 +46,43 @@ struct EATask {
 };
 // extend-add: F_parent[rel[i], rel[j]] += U_child[i, j]
 __global__ void k_extend_add(const EATask *__restrict__ tasks, const Front *__restrict__ fronts, const int *__restrict__ rel,
-                             const int64_t *__restrict__ foff, const double *__restrict__ Fchild, double *Fpar, int lower_only) {
+                             const int64_t *__restrict__ foff, const K *__restrict__ Fchild, K *Fpar, int lower_only) {
   EATask t = tasks[blockIdx.x];
   const Front c = fronts[t.child];
   const Front p = fronts[c.parent];
   const int lc = c.s1 + c.s2, lp = p.s1 + p.s2;
-  const double *U = Fchild + foff[t.child] + c.s1 + (int64_t)c.s1 * lc;
-  double *P = Fpar + foff[c.parent];
+  const K *U = Fchild + foff[t.child] + c.s1 + (int64_t)c.s1 * lc;
+  K *P = Fpar + foff[c.parent];
   const int *r = rel + c.rptr;
   const int j1 = min(t.j0 + 16, c.s2);
   for (int j = t.j0; j < j1; ++j) {
     const int64_t pj = (int64_t)r[j] * lp;
-    for (int i = (lower_only ? j : 0) + threadIdx.x; i < c.s2; i += blockDim.x) atomicAdd(&P[r[i] + pj], U[i + (int64_t)j * lc]);
+    for (int i = (lower_only ? j : 0) + threadIdx.x; i < c.s2; i += blockDim.x) hb_atomic_add(&P[r[i] + pj], U[i + (int64_t)j * lc]);
   }
 }
 
 // ------------------------------------------------------------------ small fronts
 // one CTA per front; F in global memory (L1/L2 resident for these sizes)
 __global__ void __launch_bounds__(256) k_factor_small(const int *__restrict__ list, const Front *__restrict__ fronts, const int64_t *__restrict__ foff,
-                                                        double *Fbuf, double *panL, double *panU, int symmetric, int *info) {
+                                                        K *Fbuf, K *panL, K *panU, int symmetric, int *info) {
   const int f = list[blockIdx.x];
   const Front fr = fronts[f];
   const int s1 = fr.s1, s2 = fr.s2, s = s1 + s2;
-  double *F = Fbuf + foff[f];
+  K *F = Fbuf + foff[f];
   const int tid = threadIdx.x, nt = blockDim.x;
   __shared__ int bad;
   if (tid == 0) bad = 0;
   __syncthreads();
   for (int k = 0; k < s1; ++k) {
-    const double piv = F[k + (int64_t)k * s];
-    if (symmetric ? !(piv > 0.0) : !(fabs(piv) > 0.0)) {
+    const K piv = F[k + (int64_t)k * s];
+    if (symmetric ? !(hb_real(piv) > 0.0) : !(hb_abs(piv) > 0.0)) {
       if (tid == 0) bad = 1;
     }
     __syncthreads();
     if (bad) break;
-    if (symmetric) {
-      const double sq = sqrt(piv);
-      for (int i = k + tid; i < s; i += nt) F[i + (int64_t)k * s] = (i == k) ? sq : F[i + (int64_t)k * s] / sq;
+    if (symmetric) {  // real scalars only (numfact_device never selects LL^T for complex)
+      const double sq = sqrt(hb_real(piv));
+      for (int i = k + tid; i < s; i += nt) F[i + (int64_t)k * s] = (i == k) ? mk(sq) : F[i + (int64_t)k * s] / sq;
       __syncthreads();
       const int m = s - k - 1;
       for (int idx = tid; idx < m * m; idx += nt) {
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_factor_small(const int *__restrict__ li
         if (i >= j) F[i + (int64_t)j * s] -= F[i + (int64_t)k * s] * F[j + (int64_t)k * s];
       }
     } else {
-      for (int i = k + 1 + tid; i < s; i += nt) F[i + (int64_t)k * s] /= piv;
+      for (int i = k + 1 + tid; i < s; i += nt) F[i + (int64_t)k * s] = F[i + (int64_t)k * s] / piv;
       __syncthreads();
       const int m = s - k - 1;
       for (int idx = tid; idx < m * m; idx += nt) {
@@ -105,33 +105,33 @@ __global__ void __launch_bounds__(256) k_factor_small(const int *__restrict__ li
     return;
   }
   // ---- W = (lower factor)^-1 written straight into the panel (row-major trapezoid)
-  double *P = panL + fr.poff;
+  K *P = panL + fr.poff;
   const int ldp = hb_ldp(s1);
-  auto prow = [&](double *base, int r) -> double * {
+  auto prow = [&](K *base, int r) -> K * {
     const int k = r / RB;
     return base + hb_blk_off(k) + (int64_t)(r - k * RB) * hb_wblk(s1, k);
   };
   // zero-fill pivot trapezoid (structural zeros above the diagonal + padding)
-  for (int64_t q = tid; q < hb_upd_off(s1); q += nt) P[q] = 0.0;
+  for (int64_t q = tid; q < hb_upd_off(s1); q += nt) P[q] = mk(0.0);
   if (!symmetric) {
-    double *Q = panU + fr.poff;
-    for (int64_t q = tid; q < hb_upd_off(s1); q += nt) Q[q] = 0.0;
+    K *Q = panU + fr.poff;
+    for (int64_t q = tid; q < hb_upd_off(s1); q += nt) Q[q] = mk(0.0);
   }
   __syncthreads();
   // column j of W by forward substitution, one thread per column
   for (int j = tid; j < s1; j += nt) {
     for (int i = j; i < s1; ++i) {
-      double acc = (i == j) ? 1.0 : 0.0;
+      K acc = mk((i == j) ? 1.0 : 0.0);
       for (int k = j; k < i; ++k) acc -= F[i + (int64_t)k * s] * prow(P, k)[j];
       prow(P, i)[j] = symmetric ? acc / F[i + (int64_t)i * s] : acc;  // LU: unit lower
     }
   }
   if (!symmetric) {
     // V = U11^-1 (upper); store V^T: Q[r][c] = V[c][r], c <= r.  V^T = (U11^T)^-1, U11^T lower with Lt[i][k] = U[k][i]
-    double *Q = panU + fr.poff;
+    K *Q = panU + fr.poff;
     for (int j = tid; j < s1; j += nt) {
       for (int i = j; i < s1; ++i) {
-        double acc = (i == j) ? 1.0 : 0.0;
+        K acc = mk((i == j) ? 1.0 : 0.0);
         for (int k = j; k < i; ++k) acc -= F[k + (int64_t)i * s] * prow(Q, k)[j];
         prow(Q, i)[j] = acc / F[i + (int64_t)i * s];
       }
@@ -139,21 +139,21 @@ __global__ void __launch_bounds__(256) k_factor_small(const int *__restrict__ li
   }
   __syncthreads();
   // ---- update rows: M = L21 * W
-  double *Pu = P + hb_upd_off(s1);
+  K *Pu = P + hb_upd_off(s1);
   for (int idx = tid; idx < s2 * ldp; idx += nt) {
     const int i = idx / ldp, c = idx % ldp;
-    double acc = 0.0;
+    K acc = mk(0.0);
     if (c < s1)
       for (int k = c; k < s1; ++k) acc += F[s1 + i + (int64_t)k * s] * prow(P, k)[c];
     Pu[(int64_t)i * ldp + c] = acc;
   }
   if (!symmetric) {
     // N12 = V * U12 ; panU update row i, col c = N12[c][i] = sum_{k>=c} V[c][k] U12[k][i], V[c][k] = Q[k][c]
-    double *Q = panU + fr.poff;
-    double *Qu = Q + hb_upd_off(s1);
+    K *Q = panU + fr.poff;
+    K *Qu = Q + hb_upd_off(s1);
     for (int idx = tid; idx < s2 * ldp; idx += nt) {
       const int i = idx / ldp, c = idx % ldp;
-      double acc = 0.0;
+      K acc = mk(0.0);
       if (c < s1)
         for (int k = c; k < s1; ++k) acc += prow(Q, k)[c] * F[k + (int64_t)(s1 + i) * s];
       Qu[(int64_t)i * ldp + c] = acc;
@@ -164,35 +164,35 @@ __global__ void __launch_bounds__(256) k_factor_small(const int *__restrict__ li
 // ------------------------------------------------------------------ large fronts: F (col-major) -> panel (row-major trapezoid)
 // mode 0: lower part  panel[r][c] = F[r + c*ld]   (pivot rows: c<=r, unit_diag -> 1 on the diagonal)
 // mode 1: upper part transposed  panel[r][c] = F[c + r*ld]
-__global__ void k_to_panel(const double *__restrict__ Fpiv, int ldpiv, const double *__restrict__ F, int s1, int s2, int mode, double *P) {
+__global__ void k_to_panel(const K *__restrict__ Fpiv, int ldpiv, const K *__restrict__ F, int s1, int s2, int mode, K *P) {
   // mode 0: pivot rows from Fpiv (lower triangular, ld = ldpiv), update rows from F21 = F + s1 (ld = s1+s2)
   // mode 1: everything from the upper part of F, transposed (Fpiv unused)
   const int ld = s1 + s2, ldp = hb_ldp(s1);
   const int r0 = blockIdx.x * 32;  // 32 panel rows per CTA
-  __shared__ double tile[32][33];
+  __shared__ K tile[32][33];
   const int nrows = min(32, s1 + s2 - r0);
   for (int c0 = 0; c0 < ldp; c0 += 32) {
     if (mode == 0) {
       for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
         const int r = r0 + threadIdx.x, c = c0 + ty;
-        double v = 0.0;
+        K v = mk(0.0);
         if (r < s1 + s2 && c < s1) v = (r < s1) ? Fpiv[r + (int64_t)c * ldpiv] : F[r + (int64_t)c * ld];
         tile[ty][threadIdx.x] = v;
       }
     } else {
       for (int ty = threadIdx.y; ty < 32; ty += blockDim.y) {
         const int r = r0 + ty, c = c0 + threadIdx.x;  // F[c + r*ld]: coalesced along c
-        tile[threadIdx.x][ty] = (r < s1 + s2 && c < s1) ? F[c + (int64_t)r * ld] : 0.0;
+        tile[threadIdx.x][ty] = (r < s1 + s2 && c < s1) ? F[c + (int64_t)r * ld] : mk(0.0);
       }
     }
     __syncthreads();
     for (int ty = threadIdx.y; ty < nrows; ty += blockDim.y) {
       const int r = r0 + ty, c = c0 + threadIdx.x;
-      double v = tile[threadIdx.x][ty];
+      K v = tile[threadIdx.x][ty];
       if (r < s1) {
         const int k = r / RB, w = hb_wblk(s1, k);
         if (c < w) {
-          if (c > r) v = 0.0;
+          if (c > r) v = mk(0.0);
           P[hb_blk_off(k) + (int64_t)(r - k * RB) * w + c] = v;
         }
       } else if (c < ldp) {
@@ -204,23 +204,23 @@ __global__ void k_to_panel(const double *__restrict__ Fpiv, int ldpiv, const dou
 }
 
 // S = unit-lower part of the packed LU factors in F11 (strict lower + ones), zero above
-__global__ void k_unit_lower(const double *__restrict__ F, int s1, int ld, double *S) {
+__global__ void k_unit_lower(const K *__restrict__ F, int s1, int ld, K *S) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= (int64_t)s1 * s1) return;
   const int r = (int)(t % s1), c = (int)(t / s1);
-  S[t] = r > c ? F[r + (int64_t)c * ld] : (r == c ? 1.0 : 0.0);
+  S[t] = r > c ? F[r + (int64_t)c * ld] : mk(r == c ? 1.0 : 0.0);
 }
 
 struct Libs {
   cusolverDnHandle_t so = nullptr;
   cublasHandle_t bl = nullptr;
   cusolverDnParams_t params = nullptr;
-  double *work = nullptr;
+  void *work = nullptr;
   size_t work_bytes = 0;
   void *hwork = nullptr;
   size_t hwork_bytes = 0;
   int *dinfo = nullptr;
-  double *scratch = nullptr;
+  K *scratch = nullptr;
   size_t scratch_bytes = 0;
   ~Libs() {
     if (scratch) cudaFree(scratch);
@@ -263,16 +263,33 @@ struct Libs {
     }                                                                      \
   } while (0)
 
-static int factor_large(Libs &L, cudaStream_t st, double *F, int s1, int s2, bool symmetric, double *panL, double *panU) {
+// cuSOLVER / cuBLAS entry points of this build's scalar type
+#ifdef HB_COMPLEX
+typedef cuDoubleComplex CK;
+#define HB_CUDA_K CUDA_C_64F
+#define HB_LIB(d, z) z
+#else
+typedef double CK;
+#define HB_CUDA_K CUDA_R_64F
+#define HB_LIB(d, z) d
+#endif
+static inline CK *ck(K *p) { return reinterpret_cast<CK *>(p); }
+static inline const CK *ck(const K *p) { return reinterpret_cast<const CK *>(p); }
+
+static int factor_large(Libs &L, cudaStream_t st, K *F, int s1, int s2, bool symmetric, K *panL, K *panU) {
   const int ld = s1 + s2;
-  const double one = 1.0, mone = -1.0;
-  double *F11 = F, *F21 = F + s1, *F12 = F + (int64_t)s1 * ld, *F22 = F + s1 + (int64_t)s1 * ld;
+  const K one = mk(1.0), mone = mk(-1.0);
+  K *F11 = F, *F21 = F + s1, *F12 = F + (int64_t)s1 * ld, *F22 = F + s1 + (int64_t)s1 * ld;
   size_t wd = 0, wh = 0;
   if (symmetric) {
+#ifdef HB_COMPLEX
+    set_error("numfact: LL^T is not available for complex scalars");
+    return HPDDM_B200_ERR_STATE;
+#else
     int lwork = 0;
     HB_SOLVER(cusolverDnDpotrf_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, s1, F11, ld, &lwork));
     HB_CHECK(L.ensure((size_t)lwork * sizeof(double), 0));
-    HB_SOLVER(cusolverDnDpotrf(L.so, CUBLAS_FILL_MODE_LOWER, s1, F11, ld, L.work, lwork, L.dinfo));
+    HB_SOLVER(cusolverDnDpotrf(L.so, CUBLAS_FILL_MODE_LOWER, s1, F11, ld, (double *)L.work, lwork, L.dinfo));
     if (s2 > 0) {
       HB_BLAS(cublasDtrsm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, F11, ld, F21, ld));
       HB_BLAS(cublasDsyrk(L.bl, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, s2, s1, &mone, F21, ld, &one, F22, ld));
@@ -282,35 +299,36 @@ static int factor_large(Libs &L, cudaStream_t st, double *F, int s1, int s2, boo
     HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 1));
     if (s2 > 0) HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, F11, ld, F21, ld, F21, ld));
     k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(F, ld, F, s1, s2, 0, panL);
+#endif
   } else {
     int lwork = 0;
-    HB_SOLVER(cusolverDnDgetrf_bufferSize(L.so, s1, s1, F11, ld, &lwork));
-    HB_CHECK(L.ensure((size_t)lwork * sizeof(double), 0));
-    HB_SOLVER(cusolverDnDgetrf(L.so, s1, s1, F11, ld, L.work, nullptr, L.dinfo));  // devIpiv = NULL: no pivoting
+    HB_SOLVER(HB_LIB(cusolverDnDgetrf_bufferSize, cusolverDnZgetrf_bufferSize)(L.so, s1, s1, ck(F11), ld, &lwork));
+    HB_CHECK(L.ensure((size_t)lwork * sizeof(K), 0));
+    HB_SOLVER(HB_LIB(cusolverDnDgetrf, cusolverDnZgetrf)(L.so, s1, s1, ck(F11), ld, (CK *)L.work, nullptr, L.dinfo));  // devIpiv = NULL: no pivoting
     if (s2 > 0) {
-      HB_BLAS(cublasDtrsm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, F11, ld, F21, ld));
-      HB_BLAS(cublasDtrsm(L.bl, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_UNIT, s1, s2, &one, F11, ld, F12, ld));
-      HB_BLAS(cublasDgemm(L.bl, CUBLAS_OP_N, CUBLAS_OP_N, s2, s2, s1, &mone, F21, ld, F12, ld, &one, F22, ld));
+      HB_BLAS(HB_LIB(cublasDtrsm, cublasZtrsm)(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, ck(&one), ck(F11), ld, ck(F21), ld));
+      HB_BLAS(HB_LIB(cublasDtrsm, cublasZtrsm)(L.bl, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_UNIT, s1, s2, ck(&one), ck(F11), ld, ck(F12), ld));
+      HB_BLAS(HB_LIB(cublasDgemm, cublasZgemm)(L.bl, CUBLAS_OP_N, CUBLAS_OP_N, s2, s2, s1, ck(&mone), ck(F21), ld, ck(F12), ld, ck(&one), ck(F22), ld));
     }
     // L11 and U11 share F11: split the unit-lower factor into a scratch matrix so that both
     // inversions are plain non-unit trtri calls
-    if ((size_t)s1 * s1 * sizeof(double) > L.scratch_bytes) {
+    if ((size_t)s1 * s1 * sizeof(K) > L.scratch_bytes) {
       if (L.scratch) cudaFree(L.scratch);
       L.scratch = nullptr;
-      HB_CUDA(cudaMalloc(&L.scratch, (size_t)s1 * s1 * sizeof(double)));
-      L.scratch_bytes = (size_t)s1 * s1 * sizeof(double);
+      HB_CUDA(cudaMalloc(&L.scratch, (size_t)s1 * s1 * sizeof(K)));
+      L.scratch_bytes = (size_t)s1 * s1 * sizeof(K);
     }
-    double *S = L.scratch;
+    K *S = L.scratch;
     k_unit_lower<<<(unsigned)(((int64_t)s1 * s1 + 255) / 256), 256, 0, st>>>(F11, s1, ld, S);
-    HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, S, s1, &wd, &wh));
+    HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, HB_CUDA_K, S, s1, &wd, &wh));
     HB_CHECK(L.ensure(wd, wh));
-    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, S, s1, L.work, wd, L.hwork, wh, L.dinfo + 1));
-    HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, &wd, &wh));
+    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, HB_CUDA_K, S, s1, L.work, wd, L.hwork, wh, L.dinfo + 1));
+    HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, HB_CUDA_K, F11, ld, &wd, &wh));
     HB_CHECK(L.ensure(wd, wh));
-    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 2));
+    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, HB_CUDA_K, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 2));
     if (s2 > 0) {
-      HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, S, s1, F21, ld, F21, ld));
-      HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s1, s2, &one, F11, ld, F12, ld, F12, ld));
+      HB_BLAS(HB_LIB(cublasDtrmm, cublasZtrmm)(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, ck(&one), ck(S), s1, ck(F21), ld, ck(F21), ld));
+      HB_BLAS(HB_LIB(cublasDtrmm, cublasZtrmm)(L.bl, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s1, s2, ck(&one), ck(F11), ld, ck(F12), ld, ck(F12), ld));
     }
     k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(S, s1, F, s1, s2, 0, panL);
     k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(nullptr, 0, F, s1, s2, 1, panU);
@@ -346,11 +364,11 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
     return fr.s1 + (int)(std::lower_bound(b, b + fr.s2, p) - b);
   };
   std::vector<int> efront, erow, ecol;
-  std::vector<double> eval;
+  std::vector<K> eval;
   {
     const int64_t nnz = A.ia[n];
     std::vector<int> tf, tr, tc;
-    std::vector<double> tv;
+    std::vector<K> tv;
     tf.reserve(nnz);
     tr.reserve(nnz);
     tc.reserve(nnz);
@@ -408,11 +426,11 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
     lvl_elems[l] = off;
   }
   int *d_efront = nullptr, *d_erow = nullptr, *d_ecol = nullptr, *d_fs = nullptr, *d_rel = nullptr, *d_list = nullptr;
-  double *d_eval = nullptr;
+  K *d_eval = nullptr;
   int64_t *d_foff = nullptr;
   EATask *d_tasks = nullptr;
   int *d_info = nullptr;
-  double *Fprev = nullptr, *Fcur = nullptr;
+  K *Fprev = nullptr, *Fcur = nullptr;
   Libs L;
   int rc = 0;
   auto cleanup = [&]() {
@@ -465,9 +483,9 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
   NF_CUDA(cudaMalloc(&L.dinfo, 4 * sizeof(int)));
   NF_CUDA(cudaMemset(L.dinfo, 0, 4 * sizeof(int)));
   // ---- panel store
-  if (!D.panL) NF_CUDA(cudaMalloc(&D.panL, std::max<int64_t>(S.panel_elems, 16) * sizeof(double)));
+  if (!D.panL) NF_CUDA(cudaMalloc(&D.panL, std::max<int64_t>(S.panel_elems, 16) * sizeof(K)));
   if (!symmetric) {
-    if (!D.panU || D.panU == D.panL) NF_CUDA(cudaMalloc(&D.panU, std::max<int64_t>(S.panel_elems, 16) * sizeof(double)));
+    if (!D.panU || D.panU == D.panL) NF_CUDA(cudaMalloc(&D.panU, std::max<int64_t>(S.panel_elems, 16) * sizeof(K)));
   } else {
     if (D.panU && D.panU != D.panL) cudaFree(D.panU);
     D.panU = D.panL;
@@ -476,8 +494,8 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
   std::vector<int> small_list;
   std::vector<EATask> tasks;
   for (int l = 0; l < S.nlevels; ++l) {
-    NF_CUDA(cudaMalloc(&Fcur, std::max<int64_t>(lvl_elems[l], 1) * sizeof(double)));
-    NF_CUDA(cudaMemsetAsync(Fcur, 0, lvl_elems[l] * sizeof(double), st));
+    NF_CUDA(cudaMalloc(&Fcur, std::max<int64_t>(lvl_elems[l], 1) * sizeof(K)));
+    NF_CUDA(cudaMemsetAsync(Fcur, 0, lvl_elems[l] * sizeof(K), st));
     const int64_t e0 = lvl_cnt[l], e1 = lvl_cnt[l + 1];
     if (e1 > e0) {
       k_assemble<<<(unsigned)((e1 - e0 + 255) / 256), 256, 0, st>>>(e1 - e0, d_efront + e0, d_erow + e0, d_ecol + e0, d_eval + e0, d_foff, d_fs, Fcur);
@@ -526,18 +544,18 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
       int nl = 0;
       for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) nl += fs[S.level_order[q]] > SMALL;
       fprintf(stderr, "[hpddm_b200] level %d: %d fronts (%d via cuSOLVER), F buffer %.3f GB, info small=%d lib=%d/%d/%d\n", l, S.level_ptr[l + 1] - S.level_ptr[l], nl,
-              lvl_elems[l] * 8e-9, hinfo[0], linfo[0], linfo[1], linfo[2]);
+              lvl_elems[l] * sizeof(K) * 1e-9, hinfo[0], linfo[0], linfo[1], linfo[2]);
       if (hinfo[0] != 0) {
         const int f = hinfo[0] - 1;
         const Front &fr = S.fronts[f];
         fprintf(stderr, "[hpddm_b200]   failing front %d: p0 %d s1 %d s2 %d level %d parent %d children:", f, fr.p0, fr.s1, fr.s2, fr.level, fr.parent);
         for (int c : S.children[f]) fprintf(stderr, " %d(s1 %d s2 %d lvl %d)", c, S.fronts[c].s1, S.fronts[c].s2, S.fronts[c].level);
         fprintf(stderr, "\n");
-        std::vector<double> hf((size_t)fs[f] * fs[f]);
-        cudaMemcpyAsync(hf.data(), Fcur + foff[f], hf.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+        std::vector<K> hf((size_t)fs[f] * fs[f]);
+        cudaMemcpyAsync(hf.data(), Fcur + foff[f], hf.size() * sizeof(K), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         fprintf(stderr, "[hpddm_b200]   diag(F) after partial factorisation:");
-        for (int k = 0; k < fs[f] && k < 40; ++k) fprintf(stderr, " %.3g", hf[k + (size_t)k * fs[f]]);
+        for (int k = 0; k < fs[f] && k < 40; ++k) fprintf(stderr, " %.3g", hb_real(hf[k + (size_t)k * fs[f]]));
         fprintf(stderr, "\n");
       }
     }
@@ -591,9 +609,9 @@ int numfact_device(Sub *s, const HostCSR &A) {
   HB_CHECK(upload(S.fwd, &D.fwd, st));
   HB_CHECK(upload(S.bwd, &D.bwd, st));
   HB_CHECK(upload(S.perm, &D.perm, st));
-  HB_CUDA(cudaMalloc(&D.b, (size_t)S.n * 4 * sizeof(double)));
-  HB_CUDA(cudaMalloc(&D.y, (size_t)S.n * 4 * sizeof(double)));
-  HB_CUDA(cudaMalloc(&D.x, (size_t)S.n * 4 * sizeof(double)));
+  HB_CUDA(cudaMalloc(&D.b, (size_t)S.n * 4 * sizeof(K)));
+  HB_CUDA(cudaMalloc(&D.y, (size_t)S.n * 4 * sizeof(K)));
+  HB_CUDA(cudaMalloc(&D.x, (size_t)S.n * 4 * sizeof(K)));
   D.sweep_launches = 0;
   for (int l = 0; l < S.nlevels; ++l) D.sweep_launches += (S.fwd_ptr[l + 1] > S.fwd_ptr[l]) + (S.bwd_ptr[l + 1] > S.bwd_ptr[l]);
   int rc = HPDDM_B200_ERR_NUMERIC;

@@ -18,10 +18,10 @@ struct P2P {
   bool tried = false, on = false;
   int mu_cap = 0;
   unsigned long long round = 0;
-  double *recv2 = nullptr;              // 2 * h * mu_cap
+  K *recv2 = nullptr;                   // 2 * h * mu_cap
   unsigned long long *flags = nullptr;  // one per neighbour, written remotely
   int *d_enb = nullptr;                 // neighbour index of every map entry
-  double **d_peer_base = nullptr;       // per neighbour: base of ITS receive buffer (mapped here)
+  K **d_peer_base = nullptr;       // per neighbour: base of ITS receive buffer (mapped here)
   long long *d_peer_stride = nullptr;   // per neighbour: h_peer * mu_cap (slot stride)
   long long *d_peer_off = nullptr;      // per neighbour: offset (entries) of my segment in its layout
   unsigned long long **d_peer_flag = nullptr;  // per neighbour: address of my slot in ITS flag array
@@ -39,13 +39,13 @@ struct Blob {  // what every rank publishes
 };
 
 __global__ void kk_pack_p2p(int h, int n, int mu, int parity, const int *__restrict__ map, const int *__restrict__ ebase, const int *__restrict__ esize,
-                            const int *__restrict__ enb, const double *__restrict__ x, double *const *__restrict__ peer_base,
+                            const int *__restrict__ enb, const K *__restrict__ x, K *const *__restrict__ peer_base,
                             const long long *__restrict__ peer_stride, const long long *__restrict__ peer_off) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= (int64_t)h * mu) return;
   const int e = (int)(t % h), c = (int)(t / h);
   const int i = enb[e];
-  double *dst = peer_base[i] + parity * peer_stride[i] + peer_off[i] * mu + (int64_t)c * esize[e] + (e - ebase[e]);
+  K *dst = peer_base[i] + parity * peer_stride[i] + peer_off[i] * mu + (int64_t)c * esize[e] + (e - ebase[e]);
   *dst = x[map[e] + (int64_t)c * n];  // NVLink store into the neighbour's HBM
 }
 __global__ void kk_signal_p2p(int nb, unsigned long long round, unsigned long long *const *__restrict__ peer_flag) {
@@ -57,7 +57,7 @@ __global__ void kk_signal_p2p(int nb, unsigned long long round, unsigned long lo
 }
 __global__ void kk_unpack_p2p(int nuniq, int n, int mu, int nb, unsigned long long round, const unsigned long long *flags, const int *__restrict__ uidx,
                               const int *__restrict__ useg, const int *__restrict__ upos, const int *__restrict__ ebase, const int *__restrict__ esize,
-                              const double *recv, double *x, int *err) {
+                              const K *recv, K *x, int *err) {
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
   __syncthreads();
@@ -79,13 +79,19 @@ __global__ void kk_unpack_p2p(int nuniq, int n, int mu, int nb, unsigned long lo
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= (int64_t)nuniq * mu) return;
   const int u = (int)(t % nuniq), c = (int)(t / nuniq);
-  double acc = x[uidx[u] + (int64_t)c * n];
+  K acc = x[uidx[u] + (int64_t)c * n];
   for (int q = useg[u]; q < useg[u + 1]; ++q) {
     const int e = upos[q];
-    const double *src = recv + (int64_t)ebase[e] * mu + (int64_t)c * esize[e] + (e - ebase[e]);
+    const K *src = recv + (int64_t)ebase[e] * mu + (int64_t)c * esize[e] + (e - ebase[e]);
+#ifdef HB_COMPLEX
+    double vr, vi;
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(vr), "=d"(vi) : "l"(src));
+    acc += mk(vr, vi);
+#else
     double v;
     asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(src));
     acc += v;
+#endif
   }
   x[uidx[u] + (int64_t)c * n] = acc;
 }
@@ -121,7 +127,7 @@ static int p2p_setup(Ctx *c, int mu) {
   mine.ok = (nb <= 64) ? 1 : 0;
   for (int i = 0; i < nb && i < 64; ++i) mine.ranks[i] = s->nb_rank[i];
   for (int i = 0; i <= nb && i < 65; ++i) mine.ptr[i] = s->nb_ptr[i];
-  if (cudaMalloc(&p->recv2, std::max<size_t>((size_t)2 * s->h * mu, 1) * sizeof(double)) != cudaSuccess) mine.ok = 0;
+  if (cudaMalloc(&p->recv2, std::max<size_t>((size_t)2 * s->h * mu, 1) * sizeof(K)) != cudaSuccess) mine.ok = 0;
   if (cudaMalloc(&p->flags, std::max(nb, 1) * sizeof(unsigned long long)) != cudaSuccess) mine.ok = 0;
   if (mine.ok) {
     cudaMemset(p->flags, 0, std::max(nb, 1) * sizeof(unsigned long long));
@@ -139,7 +145,7 @@ static int p2p_setup(Ctx *c, int mu) {
   cudaFree(dbuf);
   bool ok = true;
   for (int q = 0; q < P; ++q) ok = ok && all[q].ok && all[q].mu_cap == mu;
-  std::vector<double *> base(nb, nullptr);
+  std::vector<K *> base(nb, nullptr);
   std::vector<long long> stride(nb, 0), off(nb, 0);
   std::vector<unsigned long long *> pflag(nb, nullptr);
   if (ok) {
@@ -165,7 +171,7 @@ static int p2p_setup(Ctx *c, int mu) {
         p->opened.push_back(pf);
         open[q] = {pr, pf};
       }
-      base[i] = static_cast<double *>(open[q].first);
+      base[i] = static_cast<K *>(open[q].first);
       stride[i] = (long long)B.h * mu;
       off[i] = B.ptr[k];
       pflag[i] = static_cast<unsigned long long *>(open[q].second) + k;
@@ -189,14 +195,14 @@ static int p2p_setup(Ctx *c, int mu) {
   for (int i = 0; i < nb; ++i)
     for (int e = s->nb_ptr[i]; e < s->nb_ptr[i + 1]; ++e) enb[e] = i;
   HB_CUDA(cudaMalloc(&p->d_enb, std::max<size_t>(s->h, 1) * sizeof(int)));
-  HB_CUDA(cudaMalloc(&p->d_peer_base, std::max(nb, 1) * sizeof(double *)));
+  HB_CUDA(cudaMalloc(&p->d_peer_base, std::max(nb, 1) * sizeof(K *)));
   HB_CUDA(cudaMalloc(&p->d_peer_stride, std::max(nb, 1) * sizeof(long long)));
   HB_CUDA(cudaMalloc(&p->d_peer_off, std::max(nb, 1) * sizeof(long long)));
   HB_CUDA(cudaMalloc(&p->d_peer_flag, std::max(nb, 1) * sizeof(unsigned long long *)));
   HB_CUDA(cudaMalloc(&p->d_err, sizeof(int)));
   HB_CUDA(cudaMemsetAsync(p->d_err, 0, sizeof(int), c->stream));
   HB_CUDA(cudaMemcpyAsync(p->d_enb, enb.data(), s->h * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  HB_CUDA(cudaMemcpyAsync(p->d_peer_base, base.data(), nb * sizeof(double *), cudaMemcpyHostToDevice, c->stream));
+  HB_CUDA(cudaMemcpyAsync(p->d_peer_base, base.data(), nb * sizeof(K *), cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaMemcpyAsync(p->d_peer_stride, stride.data(), nb * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaMemcpyAsync(p->d_peer_off, off.data(), nb * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
   HB_CUDA(cudaMemcpyAsync(p->d_peer_flag, pflag.data(), nb * sizeof(unsigned long long *), cudaMemcpyHostToDevice, c->stream));
@@ -208,7 +214,7 @@ static int p2p_setup(Ctx *c, int mu) {
 }
 
 // returns 1 when the exchange was done over peer memory, 0 when the caller must use NCCL, < 0 on error
-int p2p_halo(Ctx *c, double *const *x, int mu) {
+int p2p_halo(Ctx *c, K *const *x, int mu) {
   // opt-in for now (HPDDM_B200_HALO=p2p): verified against the oracle on 2 GPUs this round, not yet on 8
   static const bool enabled = getenv("HPDDM_B200_HALO") && !strcmp(getenv("HPDDM_B200_HALO"), "p2p");
   if (!enabled || c->nproc <= 1 || c->subs.size() != 1) return 0;

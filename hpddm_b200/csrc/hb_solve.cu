@@ -28,24 +28,24 @@ __device__ __forceinline__ double2 ldg_stream(const double2 *p) {
 
 // 8 row sums spread over the warp -> lane L (L % 4 == 0) ends up with the total of row
 // 4*bit4(L) + 2*bit3(L) + bit2(L): 9 shuffles instead of 40
-__device__ __forceinline__ double reduce8(double (&a)[8], int lane) {
+__device__ __forceinline__ K reduce8(K (&a)[8], int lane) {
   const bool u16 = lane & 16, u8 = lane & 8, u4 = lane & 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const double send = u16 ? a[i] : a[i + 4], keep = u16 ? a[i + 4] : a[i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    const K send = u16 ? a[i] : a[i + 4], keep = u16 ? a[i + 4] : a[i];
+    a[i] = keep + hb_shfl_xor(send, 16);
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const double send = u8 ? a[i] : a[i + 2], keep = u8 ? a[i + 2] : a[i];
-    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    const K send = u8 ? a[i] : a[i + 2], keep = u8 ? a[i + 2] : a[i];
+    a[i] = keep + hb_shfl_xor(send, 8);
   }
   {
-    const double send = u4 ? a[0] : a[1], keep = u4 ? a[1] : a[0];
-    a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    const K send = u4 ? a[0] : a[1], keep = u4 ? a[1] : a[0];
+    a[0] = keep + hb_shfl_xor(send, 4);
   }
-  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
-  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+  a[0] += hb_shfl_xor(a[0], 2);
+  a[0] += hb_shfl_xor(a[0], 1);
   return a[0];
 }
 
@@ -53,18 +53,20 @@ __device__ __forceinline__ double reduce8(double (&a)[8], int lane) {
 // R = 8 / MU rows and JU = MU column slabs are in flight together (8 x 128-bit panel loads per
 // lane), the R * MU = 8 partial sums go through one reduce8.
 // (MU = 1 is held to 64 registers -> 4 CTAs / SM: measured +2 % at m = 128 over the 80-register build, profiles/README.md)
+// A 128-bit load carries VE elements of K: two reals or one complex (hb_scalar.h); complex accumulators
+// double the register budget, so that build runs 2 CTAs / SM.
 template <int MU>
-__global__ void __launch_bounds__(256, MU == 1 ? 4 : 3) k_fwd(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
-                                                const int *__restrict__ rowidx, const double *__restrict__ pan, double *b, double *y, int n) {
+__global__ void __launch_bounds__(256, IS_COMPLEX ? 2 : (MU == 1 ? 4 : 3)) k_fwd(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
+                                                const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n) {
   constexpr int R = 8 / MU, JU = MU, CW = FCH / MU;
-  __shared__ __align__(16) double bs[8][FCH];
+  __shared__ __align__(16) K bs[8][FCH];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = (int64_t)blockIdx.x * 8 + warp;
   if (it >= nitems) return;
   const FwdItem w = items[it];
   const Front f = fronts[w.front];
   const int s1 = f.s1, nb1 = (s1 + RB - 1) / RB;
-  const double *base;
+  const K *base;
   int nrows, stride, cmax;
   const bool pivot = w.rblk < nb1;
   if (pivot) {
@@ -81,9 +83,9 @@ __global__ void __launch_bounds__(256, MU == 1 ? 4 : 3) k_fwd(const FwdItem *__r
     cmax = s1;
   }
   const int c1 = min(cmax, w.c0 + w.cw);
-  double *mybs = bs[warp];
+  K *mybs = bs[warp];
   const double2 *bs2 = reinterpret_cast<const double2 *>(mybs);
-  const int st2 = stride >> 1;  // row stride in double2
+  const int st2 = stride / VE;  // row stride in 128-bit vectors
   const int rsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   for (int cs = w.c0; cs < c1; cs += CW) {
     const int nc = min(CW, c1 - cs);
@@ -91,16 +93,16 @@ __global__ void __launch_bounds__(256, MU == 1 ? 4 : 3) k_fwd(const FwdItem *__r
 #pragma unroll
     for (int m = 0; m < MU; ++m) {
       for (int c = lane; c < nc; c += 32) mybs[m * CW + c] = b[(int64_t)m * n + f.p0 + cs + c];
-      if ((nc & 1) && lane == 0) mybs[m * CW + nc] = 0.0;  // panels are zero-padded to even widths
+      if (VE == 2 && (nc & 1) && lane == 0) mybs[m * CW + nc] = mk(0.0);  // real panels are zero-padded to even widths
     }
     __syncwarp();
-    const int nv = (nc + 1) >> 1;
+    const int nv = (nc + VE - 1) / VE;
     for (int r = 0; r < nrows; r += R) {
       const double2 *p = reinterpret_cast<const double2 *>(base + (int64_t)r * stride + cs);
       const int nr = min(R, nrows - r);
-      double a[8];
+      K a[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) a[q] = 0.0;
+      for (int q = 0; q < 8; ++q) a[q] = mk(0.0);
       for (int j0 = lane; j0 < nv; j0 += 32 * JU) {
         double2 t[R][JU];
 #pragma unroll
@@ -112,44 +114,44 @@ __global__ void __launch_bounds__(256, MU == 1 ? 4 : 3) k_fwd(const FwdItem *__r
           if (j0 + 32 * u < nv) {
 #pragma unroll
             for (int m = 0; m < MU; ++m) {
-              const double2 bb = bs2[m * (CW / 2) + j0 + 32 * u];
+              const double2 bb = bs2[m * (CW / VE) + j0 + 32 * u];
 #pragma unroll
-              for (int q = 0; q < R; ++q) a[q * MU + m] = fma(t[q][u].x, bb.x, fma(t[q][u].y, bb.y, a[q * MU + m]));
+              for (int q = 0; q < R; ++q) a[q * MU + m] = hb_vdot(t[q][u], bb, a[q * MU + m]);
             }
           }
         }
       }
-      const double v = reduce8(a, lane);
+      const K v = reduce8(a, lane);
       const int q = rsel / MU, m = rsel % MU;
       if ((lane & 3) == 0 && q < nr) {
-        if (pivot) atomicAdd(&y[(int64_t)m * n + f.p0 + RB * w.rblk + r + q], v);
-        else atomicAdd(&b[(int64_t)m * n + rowidx[f.rptr + RB * (w.rblk - nb1) + r + q]], -v);
+        if (pivot) hb_atomic_add(&y[(int64_t)m * n + f.p0 + RB * w.rblk + r + q], v);
+        else hb_atomic_add(&b[(int64_t)m * n + rowidx[f.rptr + RB * (w.rblk - nb1) + r + q]], -v);
       }
     }
   }
 }
 
-// Backward sweep work item.  NJ = 64-column slabs covered per pass (NJ * MU <= 4 accumulator
-// pairs per lane); rows are processed in groups of 8 / NJ so that 8 128-bit loads are in flight.
+// Backward sweep work item.  NJ = slabs of 32 * VE columns covered per pass (NJ * MU <= 4 128-bit
+// accumulators per lane); rows are processed in groups of 8 / NJ so that 8 128-bit loads are in flight.
 template <int NJ, int MU>
-__device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int cbase, const int *__restrict__ rowidx, const double *__restrict__ pan,
-                                         const double *__restrict__ y, double *x, int n, int lane) {
+__device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int cbase, const int *__restrict__ rowidx, const K *__restrict__ pan,
+                                         const K *__restrict__ y, K *x, int n, int lane) {
   constexpr int G = 8 / NJ;
   const int s1 = f.s1, ldp = hb_ldp(s1);
-  const double *P = pan + f.poff;
-  const double *Pu = P + hb_upd_off(s1);
+  const K *P = pan + f.poff;
+  const K *Pu = P + hb_upd_off(s1);
   double2 acc[NJ][MU];
 #pragma unroll
   for (int j = 0; j < NJ; ++j)
 #pragma unroll
     for (int m = 0; m < MU; ++m) acc[j][m] = make_double2(0.0, 0.0);
-  const int cl = cbase + 2 * lane;  // this lane's first column
+  const int cl = cbase + VE * lane;  // this lane's first column
   for (int rb = 0; rb < w.nr; rb += 32) {
     const int r = w.r0 + rb + lane;
-    double u[MU];
+    K u[MU];
 #pragma unroll
     for (int m = 0; m < MU; ++m) {
-      u[m] = 0.0;
+      u[m] = mk(0.0);
       if (rb + lane < w.nr) u[m] = (r < s1) ? y[(int64_t)m * n + f.p0 + r] : -x[(int64_t)m * n + rowidx[f.rptr + r - s1]];
     }
     const int nq = min(32, w.nr - rb);
@@ -158,7 +160,7 @@ __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int c
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const int rr = w.r0 + rb + q + g;
-        const double *rowp;
+        const K *rowp;
         int wlim;
         if (rr < s1) {
           const int k = rr / RB;
@@ -171,7 +173,7 @@ __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int c
         if (q + g >= nq) wlim = 0;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          const int c = cl + 64 * j;
+          const int c = cl + 32 * VE * j;
           t[g][j] = (c < wlim) ? ldg_stream(reinterpret_cast<const double2 *>(rowp + c)) : make_double2(0.0, 0.0);
         }
       }
@@ -179,29 +181,23 @@ __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int c
       for (int g = 0; g < G; ++g)
 #pragma unroll
         for (int m = 0; m < MU; ++m) {
-          const double uq = __shfl_sync(0xffffffffu, u[m], (q + g) & 31);
+          const K uq = hb_shfl(u[m], (q + g) & 31);
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            acc[j][m].x = fma(t[g][j].x, uq, acc[j][m].x);
-            acc[j][m].y = fma(t[g][j].y, uq, acc[j][m].y);
-          }
+          for (int j = 0; j < NJ; ++j) hb_vaxpy(t[g][j], uq, acc[j][m]);
         }
     }
   }
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
-    const int c = cl + 64 * j;
+    const int c = cl + 32 * VE * j;
 #pragma unroll
-    for (int m = 0; m < MU; ++m) {
-      if (c < s1) atomicAdd(&x[(int64_t)m * n + f.p0 + c], acc[j][m].x);
-      if (c + 1 < s1) atomicAdd(&x[(int64_t)m * n + f.p0 + c + 1], acc[j][m].y);
-    }
+    for (int m = 0; m < MU; ++m) hb_vpublish(x + (int64_t)m * n + f.p0, c, s1, acc[j][m]);
   }
 }
 
 template <int MU>
-__global__ void __launch_bounds__(256, MU == 4 ? 2 : 3) k_bwd(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
-                                                const int *__restrict__ rowidx, const double *__restrict__ pan, const double *__restrict__ y, double *x, int n) {
+__global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : 3) k_bwd(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
+                                                const int *__restrict__ rowidx, const K *__restrict__ pan, const K *__restrict__ y, K *x, int n) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = (int64_t)blockIdx.x * 8 + warp;
   if (it >= nitems) return;
@@ -209,32 +205,33 @@ __global__ void __launch_bounds__(256, MU == 4 ? 2 : 3) k_bwd(const BwdItem *__r
   const Front f = fronts[w.front];
   const int width = min(BCH, hb_ldp(f.s1) - w.c0);
   constexpr int NJMAX = 4 / MU;  // 4, 2, 1
-  for (int cb = 0; cb < width; cb += 64 * NJMAX) {
+  constexpr int SLAB = 32 * VE;  // columns covered by one 128-bit load per lane
+  for (int cb = 0; cb < width; cb += SLAB * NJMAX) {
     const int left = width - cb;
-    if (NJMAX >= 4 && left > 128) bwd_pass<(NJMAX >= 4 ? 4 : NJMAX), MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
-    else if (NJMAX >= 2 && left > 64) bwd_pass<(NJMAX >= 2 ? 2 : NJMAX), MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
+    if (NJMAX >= 4 && left > 2 * SLAB) bwd_pass<(NJMAX >= 4 ? 4 : NJMAX), MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
+    else if (NJMAX >= 2 && left > SLAB) bwd_pass<(NJMAX >= 2 ? 2 : NJMAX), MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
     else bwd_pass<1, MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
   }
 }
 
-__global__ void k_perm_in(int n, int mu, const int *__restrict__ perm, const double *__restrict__ in, double *b, double *y, double *x) {
+__global__ void k_perm_in(int n, int mu, const int *__restrict__ perm, const K *__restrict__ in, K *b, K *y, K *x) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t < (int64_t)n * mu) {
     const int i = (int)(t % n);
     const int64_t c = t / n;
     b[t] = in[c * n + perm[i]];
-    y[t] = 0.0;
-    x[t] = 0.0;
+    y[t] = mk(0.0);
+    x[t] = mk(0.0);
   }
 }
-__global__ void k_perm_out(int n, int mu, const int *__restrict__ perm, const double *__restrict__ x, const double *__restrict__ d, double *out, int accumulate) {
+__global__ void k_perm_out(int n, int mu, const int *__restrict__ perm, const K *__restrict__ x, const double *__restrict__ d, K *out, int accumulate) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t < (int64_t)n * mu) {
     const int i = (int)(t % n);
     const int64_t c = t / n;
     const int p = perm[i];
-    double v = x[t];
-    if (d) v *= d[p];
+    K v = x[t];
+    if (d) v = d[p] * v;
     out[c * n + p] = accumulate ? out[c * n + p] + v : v;
   }
 }
@@ -264,7 +261,7 @@ static int launch_levels(Sub *s, cudaStream_t st) {
 // column stride n).  The 2 * nlevels sweep launches are replayed from a CUDA graph captured on
 // first use (their arguments never change); only the two permutation kernels see the caller's
 // pointers.
-int sptrsv_solve(Sub *s, const double *b, double *x, int mu, const double *scale, bool accumulate) {
+int sptrsv_solve(Sub *s, const K *b, K *x, int mu, const double *scale, bool accumulate) {
   DeviceFactor &D = s->fac;
   if (!D.valid) {
     set_error("solve: no factorisation (call numfact first)");

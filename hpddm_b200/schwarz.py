@@ -10,7 +10,8 @@ libhpddm_b200.so.  No arithmetic happens here.
 One `Decomposition` = the subdomains hosted by this process on one GPU (one MPI
 rank = one subdomain in the reference; several per process are allowed so a
 whole decomposition can be exercised on one GPU).  Collective calls take / return
-one array per local subdomain, column-major (n_loc, mu) float64.
+one array per local subdomain, column-major (n_loc, mu), float64 or -- Decomposition(dtype=np.complex128),
+the hpddm_b200z_* instantiation of the C ABI -- complex128.
 """
 import ctypes as C
 
@@ -20,8 +21,8 @@ import scipy.sparse as sp
 from . import capi
 
 
-def _f(a):
-    a = np.asarray(a, dtype=np.float64)
+def _f(a, dtype=np.float64):
+    a = np.asarray(a, dtype=dtype)
     if a.ndim == 1:
         a = a.reshape(-1, 1)
     return np.asfortranarray(a)
@@ -32,9 +33,11 @@ class Schwarz:
 
     def __init__(self, deco, global_rank):
         self.deco = deco
+        self.api = deco.api
+        self.dtype = deco.dtype
         self.rank = int(global_rank)
         h = C.c_void_p()
-        capi.check(capi.lib().hpddm_b200_sub_create(deco.ctx, self.rank, C.byref(h)))
+        self.api.check(self.api.sub_create(deco.ctx, self.rank, C.byref(h)))
         self.h = h
         self.n = 0
         self._keep = []
@@ -44,28 +47,28 @@ class Schwarz:
         A = sp.csr_matrix(Mat)
         ia = np.ascontiguousarray(A.indptr, dtype=np.int32)
         ja = np.ascontiguousarray(A.indices, dtype=np.int32)
-        a = np.ascontiguousarray(A.data, dtype=np.float64)
+        a = np.ascontiguousarray(A.data, dtype=self.dtype)
         self.n = A.shape[0]
-        L = capi.lib()
-        capi.check(L.hpddm_b200_sub_set_matrix(self.h, self.n, int(a.size), capi.ptr(ia), capi.ptr(ja), capi.ptr(a), int(bool(sym)), numbering.encode()))
+        L = self.api
+        self.api.check(L.sub_set_matrix(self.h, self.n, int(a.size), capi.ptr(ia), capi.ptr(ja), capi.ptr(a), int(bool(sym)), numbering.encode()))
         ranks = np.ascontiguousarray(list(o), dtype=np.int32)
         sizes = np.ascontiguousarray([len(m) for m in mapping], dtype=np.int32)
         idx = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.int32) for m in mapping]) if len(mapping) else np.zeros(0, np.int32), dtype=np.int32)
-        capi.check(L.hpddm_b200_sub_set_neighbors(self.h, len(ranks), capi.ptr(ranks), capi.ptr(sizes), capi.ptr(idx)))
+        self.api.check(L.sub_set_neighbors(self.h, len(ranks), capi.ptr(ranks), capi.ptr(sizes), capi.ptr(idx)))
         return self
 
     def setGridHint(self, nx, ny, nz=1, dof=1):
-        capi.check(capi.lib().hpddm_b200_sub_set_grid_hint(self.h, int(nx), int(ny), int(nz), int(dof)))
+        self.api.check(self.api.sub_set_grid_hint(self.h, int(nx), int(ny), int(nz), int(dof)))
 
     # Schwarz::initialize(d)  (include/HPDDM_schwarz.hpp:178)
     def setScaling(self, d):
         d = np.ascontiguousarray(d, dtype=np.float64)
         assert d.size == self.n
-        capi.check(capi.lib().hpddm_b200_sub_set_scaling(self.h, capi.ptr(d)))
+        self.api.check(self.api.sub_set_scaling(self.h, capi.ptr(d)))
 
     # Schwarz::callNumfact(A = nullptr)  (include/HPDDM_schwarz.hpp:337-368)
     def callNumfact(self, A=None, method="ras", sym=False):
-        L = capi.lib()
+        L = self.api
         if method == "none":
             t = capi.PRCNDTNR["NO"]
         elif method == "asm":
@@ -77,65 +80,67 @@ class Schwarz:
         else:
             t = capi.PRCNDTNR["GE"]
         if A is None:
-            capi.check(L.hpddm_b200_sub_numfact(self.h, t, 0, 0, None, None, None, 0, b"C"))
+            self.api.check(L.sub_numfact(self.h, t, 0, 0, None, None, None, 0, b"C"))
         else:
             A = sp.csr_matrix(A)
             ia = np.ascontiguousarray(A.indptr, dtype=np.int32)
             ja = np.ascontiguousarray(A.indices, dtype=np.int32)
-            a = np.ascontiguousarray(A.data, dtype=np.float64)
-            capi.check(L.hpddm_b200_sub_numfact(self.h, t, A.shape[0], int(a.size), capi.ptr(ia), capi.ptr(ja), capi.ptr(a), int(bool(sym)), b"C"))
+            a = np.ascontiguousarray(A.data, dtype=self.dtype)
+            self.api.check(L.sub_numfact(self.h, t, A.shape[0], int(a.size), capi.ptr(ia), capi.ptr(ja), capi.ptr(a), int(bool(sym)), b"C"))
 
     # Preconditioner::setVectors  (include/HPDDM_preconditioner.hpp:358-362)
     def setVectors(self, Z):
-        Z = _f(Z)
+        Z = _f(Z, self.dtype)
         assert Z.shape[0] == self.n
-        capi.check(capi.lib().hpddm_b200_sub_set_vectors(self.h, capi.ptr(Z), int(Z.shape[1])))
+        self.api.check(self.api.sub_set_vectors(self.h, capi.ptr(Z), int(Z.shape[1])))
 
     # Schwarz::solveGEVP<EIGENSOLVER>(MatNeumann)  (include/HPDDM_schwarz.hpp:665-715), on the GPU
     def solveGEVP(self, MatNeumann, nu=20, tol=1e-6, max_it=100, sym=False):
         A = sp.csr_matrix(MatNeumann)
         ia = np.ascontiguousarray(A.indptr, dtype=np.int32)
         ja = np.ascontiguousarray(A.indices, dtype=np.int32)
-        a = np.ascontiguousarray(A.data, dtype=np.float64)
+        a = np.ascontiguousarray(A.data, dtype=self.dtype)
         lam = np.zeros(nu)
-        it = capi.check(capi.lib().hpddm_b200_sub_solve_gevp(self.h, A.shape[0], int(a.size), capi.ptr(ia), capi.ptr(ja), capi.ptr(a), int(bool(sym)), b"C",
+        it = self.api.check(self.api.sub_solve_gevp(self.h, A.shape[0], int(a.size), capi.ptr(ia), capi.ptr(ja), capi.ptr(a), int(bool(sym)), b"C",
                                                                int(nu), float(tol), int(max_it), capi.ptr(lam)))
         return lam, it
 
     def getVectors(self):
         nu = C.c_int(0)
-        capi.check(capi.lib().hpddm_b200_sub_get_vectors(self.h, None, C.byref(nu)))
-        Z = np.zeros((self.n, nu.value), order="F")
+        self.api.check(self.api.sub_get_vectors(self.h, None, C.byref(nu)))
+        Z = np.zeros((self.n, nu.value), order="F", dtype=self.dtype)
         if nu.value:
-            capi.check(capi.lib().hpddm_b200_sub_get_vectors(self.h, capi.ptr(Z), C.byref(nu)))
+            self.api.check(self.api.sub_get_vectors(self.h, capi.ptr(Z), C.byref(nu)))
         return Z
 
     # SUBDOMAIN::solve(b, x, n)  (e.g. include/HPDDM_SuiteSparse.hpp:388-423)
     def solve(self, b):
-        b = _f(b)
+        b = _f(b, self.dtype)
         x = np.empty_like(b, order="F")
-        capi.check(capi.lib().hpddm_b200_sub_solve(self.h, capi.ptr(b), capi.ptr(x), int(b.shape[1]), capi.HOST))
+        self.api.check(self.api.sub_solve(self.h, capi.ptr(b), capi.ptr(x), int(b.shape[1]), capi.HOST))
         return x
 
     def statistics(self):
         st = capi.Stats()
-        capi.check(capi.lib().hpddm_b200_sub_stats(self.h, C.byref(st)))
+        self.api.check(self.api.sub_stats(self.h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in capi.Stats._fields_}
 
 
 class Decomposition:
     """The subdomains of this process + the collective hot-path calls."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, dtype=np.float64):
+        self.api = capi.api(dtype)
+        self.dtype = self.api.dtype
         self.ctx = C.c_void_p()
-        capi.check(capi.lib().hpddm_b200_ctx_create(int(device), C.byref(self.ctx)))
+        self.api.check(self.api.ctx_create(int(device), C.byref(self.ctx)))
         self.subs = []
         self.device = device
         self.correction = None
 
     def close(self):
         if self.ctx:
-            capi.lib().hpddm_b200_ctx_destroy(self.ctx)
+            self.api.ctx_destroy(self.ctx)
             self.ctx = None
 
     def __del__(self):
@@ -156,46 +161,46 @@ class Decomposition:
         rank, size = dist.get_rank(), dist.get_world_size()
         buf = (C.c_char * 128)()
         if rank == 0:
-            capi.check(capi.lib().hpddm_b200_nccl_unique_id(buf))
+            self.api.check(self.api.nccl_unique_id(buf))
         t = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).clone()
         if dist.get_backend() == "nccl":
             t = t.cuda()
         dist.broadcast(t, 0)
         raw = bytes(t.cpu().numpy().tobytes())
-        capi.check(capi.lib().hpddm_b200_ctx_comm_init(self.ctx, raw, rank, size))
+        self.api.check(self.api.ctx_comm_init(self.ctx, raw, rank, size))
 
     def synchronize(self):
-        capi.check(capi.lib().hpddm_b200_ctx_synchronize(self.ctx))
+        self.api.check(self.api.ctx_synchronize(self.ctx))
 
     @property
     def stream(self):
-        return capi.lib().hpddm_b200_ctx_stream(self.ctx)
+        return self.api.ctx_stream(self.ctx)
 
     @property
     def launches(self):
-        return int(capi.lib().hpddm_b200_ctx_launch_count(self.ctx))
+        return int(self.api.ctx_launch_count(self.ctx))
 
     # Schwarz::multiplicityScaling  (include/HPDDM_schwarz.hpp:381-404), then initialize(d)
     def multiplicityScaling(self, ds):
         ds = [np.ascontiguousarray(d, dtype=np.float64).copy() for d in ds]
-        capi.check(capi.lib().hpddm_b200_multiplicity_scaling(self.ctx, capi.ptr_array(ds)))
+        self.api.check(self.api.multiplicity_scaling(self.ctx, capi.ptr_array(ds)))
         for s, d in zip(self.subs, ds):
             s.setScaling(d)
         return ds
 
     # Schwarz::buildTwo  (include/HPDDM_schwarz.hpp:440-495)
     def buildTwo(self):
-        capi.check(capi.lib().hpddm_b200_build_coarse(self.ctx))
+        self.api.check(self.api.build_coarse(self.ctx))
 
     def setCoarse(self, E):
-        E = _f(E)
-        capi.check(capi.lib().hpddm_b200_set_coarse(self.ctx, capi.ptr(E), int(E.shape[0])))
+        E = _f(E, self.dtype)
+        self.api.check(self.api.set_coarse(self.ctx, capi.ptr(E), int(E.shape[0])))
 
     def getCoarse(self):
         n = C.c_int(0)
-        capi.check(capi.lib().hpddm_b200_get_coarse(self.ctx, None, C.byref(n)))
-        E = np.zeros((n.value, n.value), order="F")
-        capi.check(capi.lib().hpddm_b200_get_coarse(self.ctx, capi.ptr(E), C.byref(n)))
+        self.api.check(self.api.get_coarse(self.ctx, None, C.byref(n)))
+        E = np.zeros((n.value, n.value), order="F", dtype=self.dtype)
+        self.api.check(self.api.get_coarse(self.ctx, capi.ptr(E), C.byref(n)))
         return E
 
     # --- hot path, host vectors (what an unchanged Krylov driver passes)
@@ -203,73 +208,73 @@ class Decomposition:
         return [np.empty_like(v, order="F") for v in ins]
 
     def start(self, b, x):
-        b = [_f(v) for v in b]
-        x = [_f(v).copy(order="F") for v in x]
+        b = [_f(v, self.dtype) for v in b]
+        x = [_f(v, self.dtype).copy(order="F") for v in x]
         mu = b[0].shape[1]
-        capi.check(capi.lib().hpddm_b200_start(self.ctx, capi.ptr_array(b), capi.ptr_array(x), mu, capi.HOST))
+        self.api.check(self.api.start(self.ctx, capi.ptr_array(b), capi.ptr_array(x), mu, capi.HOST))
         return x
 
     def end(self):
-        capi.check(capi.lib().hpddm_b200_end(self.ctx))
+        self.api.check(self.api.end(self.ctx))
 
     def apply(self, ins, correction="__default__"):
         corr = self.correction if correction == "__default__" else correction
-        ins = [_f(v) for v in ins]
+        ins = [_f(v, self.dtype) for v in ins]
         outs = self._outs(ins)
-        capi.check(capi.lib().hpddm_b200_apply(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), ins[0].shape[1], capi.CORRECTION[corr], capi.HOST))
+        self.api.check(self.api.apply(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), ins[0].shape[1], capi.CORRECTION[corr], capi.HOST))
         return outs
 
     def deflation(self, ins):
-        ins = [_f(v) for v in ins]
+        ins = [_f(v, self.dtype) for v in ins]
         outs = self._outs(ins)
-        capi.check(capi.lib().hpddm_b200_deflation(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), ins[0].shape[1], capi.HOST))
+        self.api.check(self.api.deflation(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), ins[0].shape[1], capi.HOST))
         return outs
 
     def exchange(self, xs, scaled=True):
-        xs = [_f(v).copy(order="F") for v in xs]
-        capi.check(capi.lib().hpddm_b200_exchange(self.ctx, capi.ptr_array(xs), xs[0].shape[1], int(bool(scaled)), capi.HOST))
+        xs = [_f(v, self.dtype).copy(order="F") for v in xs]
+        self.api.check(self.api.exchange(self.ctx, capi.ptr_array(xs), xs[0].shape[1], int(bool(scaled)), capi.HOST))
         return xs
 
     def GMV(self, ins):
-        ins = [_f(v) for v in ins]
+        ins = [_f(v, self.dtype) for v in ins]
         outs = self._outs(ins)
-        capi.check(capi.lib().hpddm_b200_gmv(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), ins[0].shape[1], capi.HOST))
+        self.api.check(self.api.gmv(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), ins[0].shape[1], capi.HOST))
         return outs
 
     def callSolver(self, rhs):
-        rhs = [_f(v).copy(order="F") for v in rhs]
-        capi.check(capi.lib().hpddm_b200_coarse_solve(self.ctx, capi.ptr_array(rhs), rhs[0].shape[1], capi.HOST))
+        rhs = [_f(v, self.dtype).copy(order="F") for v in rhs]
+        self.api.check(self.api.coarse_solve(self.ctx, capi.ptr_array(rhs), rhs[0].shape[1], capi.HOST))
         return rhs
 
     def dot(self, x, y):
-        x = [_f(v) for v in x]
-        y = [_f(v) for v in y]
+        x = [_f(v, self.dtype) for v in x]
+        y = [_f(v, self.dtype) for v in y]
         mu = x[0].shape[1]
-        res = np.zeros(mu)
-        capi.check(capi.lib().hpddm_b200_dot(self.ctx, capi.ptr_array(x), capi.ptr_array(y), mu, capi.ptr(res), capi.HOST))
+        res = np.zeros(mu, dtype=self.dtype)
+        self.api.check(self.api.dot(self.ctx, capi.ptr_array(x), capi.ptr_array(y), mu, capi.ptr(res), capi.HOST))
         return res
 
     # IterativeMethod::solve (include/HPDDM_iterative.hpp:1013-1111) with the Krylov basis resident in HBM
     def solve(self, b, x0=None, correction="__default__", restart=40, max_it=100, tol=1e-6):
         corr = self.correction if correction == "__default__" else correction
-        b = [_f(v) for v in b]
-        x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v).copy(order="F") for v in x0]
+        b = [_f(v, self.dtype) for v in b]
+        x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v, self.dtype).copy(order="F") for v in x0]
         mu = b[0].shape[1]
         it = C.c_int(0)
         res = np.zeros(mu)
-        capi.check(capi.lib().hpddm_b200_solve(self.ctx, capi.ptr_array(b), capi.ptr_array(x), mu, capi.CORRECTION[corr], int(restart), int(max_it), float(tol),
+        self.api.check(self.api.solve(self.ctx, capi.ptr_array(b), capi.ptr_array(x), mu, capi.CORRECTION[corr], int(restart), int(max_it), float(tol),
                                                capi.HOST, C.byref(it), capi.ptr(res)))
         return it.value, x, res
 
     # --- hot path, device-resident vectors (raw addresses / torch tensors)
     def apply_device(self, ins, outs, mu, correction="__default__"):
         corr = self.correction if correction == "__default__" else correction
-        capi.check(capi.lib().hpddm_b200_apply(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), int(mu), capi.CORRECTION[corr], capi.DEVICE))
+        self.api.check(self.api.apply(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), int(mu), capi.CORRECTION[corr], capi.DEVICE))
 
     def apply_host_inplace(self, ins, outs, mu, correction="__default__"):
         """apply on caller-owned host buffers (numpy or pinned torch tensors), no allocation."""
         corr = self.correction if correction == "__default__" else correction
-        capi.check(capi.lib().hpddm_b200_apply(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), int(mu), capi.CORRECTION[corr], capi.HOST))
+        self.api.check(self.api.apply(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), int(mu), capi.CORRECTION[corr], capi.HOST))
 
 
 class KrylovOperator:

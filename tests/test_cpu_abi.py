@@ -1,5 +1,5 @@
-"""CPU-side checks: the C-ABI library loads, exports every symbol include/hpddm_b200.h
-declares, and refuses to run without a GPU (no CPU fallback)."""
+"""CPU-side checks: the C-ABI library loads, exports every symbol include/hpddm_b200.h and
+include/hpddm_b200z.h (complex instantiation) declare, and refuses to run without a GPU (no CPU fallback)."""
 import ctypes as C
 import os
 import re
@@ -12,9 +12,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "hpddm_b200.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(hpddm_b200_[a-z0-9_]+)\s*\(", src)))
+    out = set()
+    for header in ("hpddm_b200.h", "hpddm_b200z.h"):
+        src = open(os.path.join(ROOT, "include", header)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        out |= set(re.findall(r"\b(hpddm_b200z?_[a-z0-9_]+)\s*\(", src))
+    return sorted(out)
+
+
+def test_complex_header_mirrors_real_header():
+    names = declared_symbols()
+    real = {n[len("hpddm_b200_"):] for n in names if n.startswith("hpddm_b200_")}
+    cplx = {n[len("hpddm_b200z_"):] for n in names if n.startswith("hpddm_b200z_")}
+    assert real == cplx and len(real) > 30
 
 
 def test_header_and_binding_agree():
@@ -25,7 +35,7 @@ def test_library_exports_every_declared_symbol():
     L = capi.lib()
     for name in declared_symbols():
         assert hasattr(L, name), name
-    assert b"sm_100a" in L.hpddm_b200_version()
+    assert b"sm_100a" in L.hpddm_b200_version() and b"complex" in L.hpddm_b200z_version()
 
 
 def test_no_cpu_fallback():
@@ -38,6 +48,10 @@ def test_no_cpu_fallback():
     assert b"no CPU fallback" in capi.lib().hpddm_b200_last_error()
     with pytest.raises(capi.HpddmB200Error):
         capi.check(rc)
+    rc = capi.COMPLEX.ctx_create(0, C.byref(h))
+    assert rc < 0 and b"no CPU fallback" in capi.COMPLEX.last_error()
+    with pytest.raises(capi.HpddmB200Error):
+        capi.COMPLEX.check(rc)
 
 
 def test_product_does_not_import_oracle():
