@@ -27,7 +27,8 @@ def gmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40, verbose=False):
     mu = b[0].shape[1]
     x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [np.array(v, order="F", copy=True) for v in x0]
     x = op.start(b, x)                                   # initializeNorm -> A.start (iterative.hpp:444)
-    norm = np.sqrt(op.dot(b, b))                         # ||b||_D (iterative.hpp:455-468)
+    dtype = np.result_type(*[v.dtype for v in b])        # K: float64 or complex128
+    norm = np.sqrt(np.real(op.dot(b, b)))                # ||b||_D (iterative.hpp:455-468)
     norm = np.where(norm < 1e-12, 1.0, norm)             # GMRES.hpp:73
     m = restart
     applies = 0
@@ -36,17 +37,17 @@ def gmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40, verbose=False):
     while j <= max_it:
         Ax = op.GMV(x)
         v = [[b[r] - Ax[r] for r in range(P)]]           # right variant: v0 = b - A x
-        sn0 = op.dot(v[0], v[0])
+        sn0 = np.real(op.dot(v[0], v[0]))
         if j == 1 and np.any(sn0 < np.finfo(float).eps ** 2):
             j = 0
             break
-        s = np.zeros((m + 1, mu))
+        s = np.zeros((m + 1, mu), dtype=dtype)
         s[0] = np.sqrt(sn0)
         for r in range(P):
-            v[0][r] = v[0][r] / s[0]
+            v[0][r] = v[0][r] / np.sqrt(sn0)
         conv[conv > 0] = 0
-        H = np.zeros((m + 1, m, mu))
-        cs = np.zeros((m, mu))
+        H = np.zeros((m + 1, m, mu), dtype=dtype)
+        cs = np.zeros((m, mu), dtype=dtype)              # cosine lives in K, sine is real (iterative.hpp:690-710)
         sn = np.zeros((m, mu))
         i = 0
         done = False
@@ -59,7 +60,7 @@ def gmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40, verbose=False):
             for k in range(i + 1):
                 for r in range(P):
                     w[r] -= v[k][r] * h[k]
-            hn = np.sqrt(op.dot(w, w))
+            hn = np.sqrt(np.real(op.dot(w, w)))
             H[:i + 1, i] = h
             H[i + 1, i] = hn
             if i < m - 1:
@@ -67,16 +68,16 @@ def gmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40, verbose=False):
                     w[r] = w[r] / np.where(hn == 0, 1.0, hn)
             v.append(w)
             for k in range(i):                           # previous rotations
-                g = cs[k] * H[k, i] + sn[k] * H[k + 1, i]
+                g = np.conj(cs[k]) * H[k, i] + sn[k] * H[k + 1, i]
                 H[k + 1, i] = -sn[k] * H[k, i] + cs[k] * H[k + 1, i]
                 H[k, i] = g
-            delta = np.hypot(H[i, i], H[i + 1, i])
-            sn[i] = H[i + 1, i] / delta
+            delta = np.hypot(np.abs(H[i, i]), np.abs(H[i + 1, i]))
+            sn[i] = np.real(H[i + 1, i]) / delta
             cs[i] = H[i, i] / delta
             H[i, i] = delta
             H[i + 1, i] = 0.0
             s[i + 1] = -sn[i] * s[i]
-            s[i] = s[i] * cs[i]
+            s[i] = s[i] * np.conj(cs[i])
             i += 1
             res = np.abs(s[i])
             newly = (conv == -m) & (res / norm <= tol)

@@ -1,7 +1,7 @@
 """Runs oracle/_ref/ref_driver (the UNMODIFIED reference headers + examples/generate.cpp,
 built by this directory's Makefile) and stores its per-rank dumps as tests/golden/*.npz.
 
-    python oracle/ref_build/make_goldens.py
+    python oracle/ref_build/make_goldens.py [case ...]      (default: every case)
 
 The goldens pin (a) the driver-side generator, (b) the oracle restatement and (c) the CUDA
 path against outputs of the reference itself (tests/test_golden_reference.py).
@@ -17,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+DRIVER_Z = os.path.join(ROOT, "oracle", "_ref", "ref_driver_z")  # the same driver, K = std::complex<double> (-DFORCE_COMPLEX)
 OUT = os.path.join(ROOT, "tests", "golden")
 
 CASES = {
@@ -27,6 +28,10 @@ CASES = {
     "small_40x40_p4_twolevel_nu3": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40"]),
     "small_48x30_p6_ov2_twolevel_nu2": dict(np=6, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "2", "-Nx", "48", "-Ny", "30", "-overlap", "2"]),
     "small_36x36_p4_symcsr_twolevel_nu2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "2", "-Nx", "36", "-Ny", "36", "-symmetric_csr", "1"]),
+    # complex scalars (the reference's FORCE_COMPLEX build; damped-Helmholtz-like shift of the generator's matrix, see ref_driver.cpp)
+    "complex_40x40_p4_ras": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40"]),
+    "complex_40x40_p4_twolevel_nu3": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40"]),
+    "complex_48x30_p6_ov2_twolevel_nu2": dict(np=6, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "2", "-Nx", "48", "-Ny", "30", "-overlap", "2"]),
 }
 
 
@@ -41,7 +46,8 @@ def read_dump(path):
             name = f.read(ln).decode()
             t = f.read(1).decode()
             (cnt,) = struct.unpack("q", f.read(8))
-            out[name] = np.frombuffer(f.read(cnt * (8 if t == "d" else 4)), dtype=np.float64 if t == "d" else np.int32).copy()
+            size, dtype = {"d": (8, np.float64), "i": (4, np.int32), "z": (16, np.complex128)}[t]
+            out[name] = np.frombuffer(f.read(cnt * size), dtype=dtype).copy()
     return out
 
 
@@ -49,10 +55,13 @@ def main():
     if not os.path.exists(DRIVER):
         sys.exit("oracle/_ref/ref_driver missing: run `make -C oracle/ref_build` where /root/reference exists")
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             env = dict(os.environ, HPDDM_SHIM_NP=str(case["np"]), HPDDM_REF_DUMP=os.path.join(tmp, "g"))
-            res = subprocess.run([DRIVER] + case["args"], env=env, cwd=tmp, capture_output=True, text=True, timeout=600)
+            res = subprocess.run([DRIVER_Z if case.get("z") else DRIVER] + case["args"], env=env, cwd=tmp, capture_output=True, text=True, timeout=600)
             line = [ln for ln in res.stdout.splitlines() if ln.startswith("ref_driver:")]
             print(name, line)
             blob = {"args": np.array(" ".join(case["args"])), "np": np.array(case["np"])}

@@ -3,6 +3,10 @@
 // hot path per rank.  Built by oracle/ref_build/Makefile against the in-box MPI shim, the
 // dense LAPACK SUBDOMAIN/COARSEOPERATOR plugins (-DLAPACKSUB -DDLAPACK) and scipy's OpenBLAS.
 // Mirrors the control flow of the reference's examples/schwarz.cpp:40-147 (which cannot dump).
+// Built twice: K = double, and -DFORCE_COMPLEX (K = std::complex<double>, examples/schwarz.hpp:56-60); the complex
+// build shifts the generator's Poisson matrix to a damped-Helmholtz-like operator  A - (k^2 - i sigma) I  and makes
+// the right-hand side, the probe vector and the deflation vectors genuinely complex, so that every conjugation
+// convention of the reference (Wrapper<K>::transc, conj in the inner products) is exercised.
 // TEST INFRASTRUCTURE ONLY.
 #include "schwarz.hpp"  // the reference's examples/schwarz.hpp (K, symCoarse, generate())
 
@@ -16,9 +20,15 @@ static void dump(const char *name, char type, const void *data, long long count)
   fwrite(name, 1, len, g_out);
   fwrite(&type, 1, 1, g_out);
   fwrite(&count, sizeof(long long), 1, g_out);
-  fwrite(data, type == 'd' ? 8 : 4, count, g_out);
+  fwrite(data, type == 'z' ? 16 : (type == 'd' ? 8 : 4), count, g_out);
 }
 static void dumpd(const char *name, const double *d, long long n) { dump(name, 'd', d, n); }
+static void dumpd(const char *name, const std::complex<double> *d, long long n) { dump(name, 'z', d, n); }
+#ifdef FORCE_COMPLEX
+static inline K cplx_probe(double re, double im) { return K(re, im); }
+#else
+static inline K cplx_probe(double re, double) { return re; }
+#endif
 static void dumpi(const char *name, const int *d, long long n) { dump(name, 'i', d, n); }
 
 int main(int argc, char **argv) {
@@ -48,6 +58,14 @@ int main(int argc, char **argv) {
   int ndof;
   generate(rankWorld, sizeWorld, o, mapping, ndof, Mat, MatNeumann, d, f, sol);
   const int mu = 1;
+#ifdef FORCE_COMPLEX
+  // A <- A - (k^2 - i sigma) I : indefinite, complex symmetric, non-Hermitian (full CSR storage only)
+  for (int i = 0; i < ndof; ++i) {
+    for (int k = Mat->ia_[i]; k < Mat->ia_[i + 1]; ++k)
+      if (Mat->ja_[k] == i) Mat->a_[k] += K(-3.0, 1.0);
+    f[i] = K(std::real(f[i]), 0.25 * std::sin(0.05 * i + rankWorld));
+  }
+#endif
   {
     int hdr[4] = {ndof, Mat->nnz_, (int)Mat->sym_, sizeWorld};
     dumpi("header", hdr, 4);
@@ -55,7 +73,11 @@ int main(int argc, char **argv) {
     dumpi("ja", Mat->ja_, Mat->nnz_);
     dumpd("a", Mat->a_, Mat->nnz_);
     dumpd("d_ramp", d, ndof);
+#ifdef FORCE_COMPLEX
+    dumpd("f_local", f, ndof);  // perturbed per rank: not yet consistent on the overlap (made so below, like schwarz.cpp:98)
+#else
     dumpd("f", f, ndof);
+#endif
     std::vector<int> ov(o.begin(), o.end());
     dumpi("o", ov.data(), ov.size());
     for (size_t i = 0; i < mapping.size(); ++i) dumpi(("mapping" + std::to_string(i)).c_str(), mapping[i].data(), mapping[i].size());
@@ -66,6 +88,10 @@ int main(int argc, char **argv) {
   A.multiplicityScaling(d);
   A.initialize(d);
   dumpd("d", d, ndof);
+#ifdef FORCE_COMPLEX
+  A.exchange<true>(f, 1);  // consistent right-hand side (examples/schwarz.cpp:98 does the same for its random ones)
+  dumpd("f", f, ndof);
+#endif
   const int nuOpt = (int)opt.app()["deflation_vectors"];
   int nu = 0;
   if (nuOpt > 0) {
@@ -75,7 +101,8 @@ int main(int argc, char **argv) {
     *deflation = new K[(size_t)nu * ndof];
     for (int k = 0; k < nu; ++k) {
       deflation[k] = *deflation + (size_t)k * ndof;
-      for (int i = 0; i < ndof; ++i) deflation[k][i] = k == 0 ? 1.0 : std::cos(3.141592653589793 * k * (i + 0.5) / ndof) + 0.1 * ((i * 7 + k) % 5);
+      for (int i = 0; i < ndof; ++i)
+        deflation[k][i] = cplx_probe(k == 0 ? 1.0 : std::cos(3.141592653589793 * k * (i + 0.5) / ndof) + 0.1 * ((i * 7 + k) % 5), 0.3 * std::sin(0.01 * (k + 1) * i));
     }
     dumpd("Z", *deflation, (long long)nu * ndof);
     A.setVectors(deflation);
@@ -87,7 +114,7 @@ int main(int argc, char **argv) {
   A.callNumfact();
   // deterministic, consistent input vector
   std::vector<K> v(ndof), w(ndof), work(ndof);
-  for (int i = 0; i < ndof; ++i) v[i] = std::sin(0.37 * i + 0.11 * rankWorld) + 0.5;
+  for (int i = 0; i < ndof; ++i) v[i] = cplx_probe(std::sin(0.37 * i + 0.11 * rankWorld) + 0.5, std::cos(0.23 * i) - 0.2 * rankWorld);
   A.exchange<true>(v.data(), 1);
   dumpd("v", v.data(), ndof);
   {

@@ -3,8 +3,12 @@
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
 
 All "ranks" live in one process: a vector is a list (one entry per rank) of
-``(n_loc, mu)`` Fortran-ordered float64 arrays, exactly the column-major
-``n_loc x mu`` blocks the reference passes around.
+``(n_loc, mu)`` Fortran-ordered float64 (or complex128: K = std::complex<double>,
+the reference's FORCE_COMPLEX build / BASELINE config 5) arrays, exactly the column-major
+``n_loc x mu`` blocks the reference passes around.  Complex scalars
+follow the reference's conventions: conjugate transposes where it uses Wrapper<K>::transc
+(Z^H in deflation and in the Galerkin operator, conj on the first argument of inner
+products), real partition of unity (underlying_type<K>).
 
 Restated functions (reference file:line):
   Subdomain.initialize        include/HPDDM_subdomain.hpp:165-236
@@ -57,6 +61,7 @@ class LocalSolver:
     def __init__(self, A, dense_below=0):
         A = sp.csc_matrix(A)
         self.n = A.shape[0]
+        self.dtype = np.complex128 if np.iscomplexobj(A.data) else np.float64
         if self.n <= dense_below:
             self.lu = sla.lu_factor(A.toarray())
             self.dense = True
@@ -65,7 +70,7 @@ class LocalSolver:
             self.dense = False
 
     def solve(self, b):
-        b = np.asarray(b, dtype=np.float64)
+        b = np.asarray(b, dtype=np.result_type(self.dtype, np.asarray(b).dtype))
         if self.dense:
             return np.asfortranarray(sla.lu_solve(self.lu, b))
         out = np.empty_like(b, order="F")
@@ -180,7 +185,7 @@ class SchwarzWorld:
 
     # --------------------------------------------------------------- two-level
     def set_vectors(self, Z):
-        self.Z = [np.asfortranarray(z, dtype=np.float64) for z in Z]
+        self.Z = [np.asfortranarray(z, dtype=np.complex128 if np.iscomplexobj(z) else np.float64) for z in Z]
         self.nu = [z.shape[1] for z in self.Z]
 
     def scale_into_overlap(self, A, r):
@@ -252,20 +257,21 @@ class SchwarzWorld:
         solver (coarse_operator_impl.hpp:282-1247)."""
         off = np.concatenate([[0], np.cumsum(self.nu)]).astype(int)
         Nc = int(off[-1])
-        E = np.zeros((Nc, Nc))
+        dtype = np.result_type(*[z.dtype for z in self.Z], *[a.dtype for a in self.A])
+        E = np.zeros((Nc, Nc), dtype=dtype)
         W = []
         for j in range(self.P):
             dj = np.where(self.d[j] > HPDDM_EPS, self.d[j], 0.0)
             C = sp.csr_matrix(self.A[j] @ sp.diags(dj))
             W.append(np.asfortranarray(C @ self.Z[j]))  # work_ = A_j D_j Z_j
         for i in range(self.P):
-            E[off[i]:off[i + 1], off[i]:off[i + 1]] = self.Z[i].T @ (self.d[i][:, None] * W[i])
+            E[off[i]:off[i + 1], off[i]:off[i + 1]] = self.Z[i].conj().T @ (self.d[i][:, None] * W[i])
             for (j, idx) in self.map[i]:
                 kk = [q for q, (rr, _) in enumerate(self.map[j]) if rr == i][0]
                 jdx = self.map[j][kk][1]
-                tmp = np.zeros((self.n[i], self.nu[j]))
+                tmp = np.zeros((self.n[i], self.nu[j]), dtype=dtype)
                 tmp[idx, :] = self.d[i][idx, None] * W[j][jdx, :]
-                E[off[i]:off[i + 1], off[j]:off[j + 1]] = self.Z[i].T @ tmp
+                E[off[i]:off[i + 1], off[j]:off[j + 1]] = self.Z[i].conj().T @ tmp
         self.E = E
         self.off = off
         # Plugin quirk, reproduced only on request: the reference's dense LAPACK coarse solver
@@ -286,8 +292,8 @@ class SchwarzWorld:
         return [np.asfortranarray(y[self.off[r]:self.off[r + 1], :]) for r in range(self.P)]
 
     def deflation(self, x):
-        """schwarz.hpp:1602-1622: out = exchange(Z E^{-1} Z^T D in)."""
-        uc = [self.Z[r].T @ (self.d[r][:, None] * x[r]) for r in range(self.P)]
+        """schwarz.hpp:1602-1622: out = exchange(Z E^{-1} Z^H D in)  (gemm with Wrapper<K>::transc, 1616)."""
+        uc = [self.Z[r].conj().T @ (self.d[r][:, None] * x[r]) for r in range(self.P)]
         uc = self.call_solver(uc)
         out = [np.asfortranarray(self.Z[r] @ uc[r]) for r in range(self.P)]
         return self.exchange(out)
@@ -344,13 +350,13 @@ class SchwarzWorld:
             notb = np.ones(self.n[r])
             for i in bc:
                 notb[i] = 0.0
-            st[:, 1] += (self.d[r] * notb) @ (tmp[r] ** 2)
+            st[:, 1] += (self.d[r] * notb) @ (np.abs(tmp[r]) ** 2)
             fr = np.where(np.abs(f[r]) > HPDDM_EPS * HPDDM_PEN, f[r] / HPDDM_PEN, f[r])
-            st[:, 0] += self.d[r] @ (fr ** 2)
+            st[:, 0] += self.d[r] @ (np.abs(fr) ** 2)
         return np.sqrt(st)
 
     # ------------------------------------------------------------------ helpers
     def dot(self, x, y):
         """D-weighted global inner products per column (iterative.hpp:455-468,
-        GMRES.hpp:59-68): sum_r sum_i d_i x_i y_i."""
-        return sum((self.d[r][:, None] * x[r] * y[r]).sum(axis=0) for r in range(self.P))
+        GMRES.hpp:59-68): sum_r sum_i d_i conj(x_i) y_i  (iterative.hpp:503)."""
+        return sum((self.d[r][:, None] * np.conj(x[r]) * y[r]).sum(axis=0) for r in range(self.P))

@@ -34,11 +34,28 @@ def load(name):
         parts.append(dict(o=[int(v) for v in g["o"]], mapping=mapping, ndof=n, Mat=Mat, sym=bool(sym), d=g["d_ramp"].copy(),
                           f=np.asfortranarray(g["f"].reshape(-1, 1))))
         ref.append(g)
-    meta = dict(P=P, args=args, Nx=int(arg_value(args, "Nx", 100)), Ny=int(arg_value(args, "Ny", 100)), overlap=int(arg_value(args, "overlap", 1)),
+    meta = dict(P=P, args=args, complex=bool(np.iscomplexobj(ref[0]["a"])), Nx=int(arg_value(args, "Nx", 100)), Ny=int(arg_value(args, "Ny", 100)), overlap=int(arg_value(args, "overlap", 1)),
                 sym=arg_value(args, "symmetric_csr", "0") == "1", nu=int(arg_value(args, "deflation_vectors", 0)),
                 restart=int(arg_value(args, "hpddm_gmres_restart", 40)), max_it=int(arg_value(args, "hpddm_max_it", 100)))
     return parts, ref, meta
 
 
 def col(v):
-    return np.asfortranarray(np.asarray(v, dtype=np.float64).reshape(-1, 1))
+    v = np.asarray(v)
+    return np.asfortranarray(v.astype(np.complex128 if np.iscomplexobj(v) else np.float64).reshape(-1, 1))
+
+
+# the complex goldens come from the reference's FORCE_COMPLEX build with the generator's matrix shifted to
+# A - (k^2 - i sigma) I and an imaginary part added to f (oracle/ref_build/ref_driver.cpp)
+COMPLEX_SHIFT = complex(-3.0, 1.0)
+
+
+def complexify(part, rank):
+    """Apply ref_driver.cpp's documented complex perturbation to a generate2d() part."""
+    A = sp.csr_matrix(part["Mat"]).astype(np.complex128)
+    rows = np.repeat(np.arange(A.shape[0]), np.diff(A.indptr))
+    A.data[A.indices == rows] += COMPLEX_SHIFT
+    n = A.shape[0]
+    f = part["f"][:, :1].astype(np.complex128)
+    f[:, 0] = f[:, 0].real + 1j * 0.25 * np.sin(0.05 * np.arange(n) + rank)
+    return dict(part, Mat=A, f=np.asfortranarray(f))

@@ -8,7 +8,8 @@ def build_gpu_decomposition(parts, world=None, two_level=False, device=0, grid_h
                             own_coarse=True, ranks=None, deco=None, method="ras"):
     """parts: oracle.generate output for ALL ranks; `ranks` = the global ranks hosted here."""
     ranks = list(range(len(parts))) if ranks is None else list(ranks)
-    deco = Decomposition(device) if deco is None else deco
+    dtype = np.complex128 if any(np.iscomplexobj(parts[r]["Mat"].data) for r in ranks) else np.float64
+    deco = Decomposition(device, dtype=dtype) if deco is None else deco
     for r in ranks:
         p = parts[r]
         s = deco.add(r)
