@@ -364,3 +364,56 @@ def generate_elasticity3d(rank, size, Nn=(9, 9, 7), overlap=1, mu=4, grid=None, 
     MatN = _assemble_elasticity(st, en, Nn, h, Ke, penalty) if neumann else None
     return dict(o=o, mapping=mapping, ndof=ndof, Mat=Mat, MatNeumann=MatN, d=d, f=f, sym=False, box=tuple(zip(st, en)), grid=(px, py, pz),
                 dims=(dims[0], dims[1], dims[2], 3))
+
+
+# ----------------------------------------------------------------------------- 3-D Helmholtz, complex scalars (BASELINE config 5)
+def generate_helmholtz3d(rank, size, N=(16, 16, 16), overlap=1, mu=1, grid=None, k=2.0, nu=4, seed=5678):
+    """-Laplace(u) - k^2 u on [0,10]^3 with the first-order absorbing condition du/dn - i k u = 0 on the outer
+    boundary, 7-point cell-centred differences, K = complex double (config 5 of BASELINE.json; the reference has no
+    in-tree Helmholtz generator -- SURVEY.md section 8d -- this is the driver-side model of one).  Same decomposition
+    conventions as generate3d.  Returns, besides the generate3d keys:
+      Mat       local matrix = restriction of the global operator to the subdomain (what Subdomain::initialize and
+                GMV use); complex symmetric, not Hermitian
+      MatRobin  the matrix ORAS factorises (Schwarz::callNumfact(A) -> Prcndtnr::OG, schwarz.hpp:351-365): the same
+                operator with the impedance condition du/dn - i k u = 0 also on the artificial (interior) faces
+      Z         nu plane waves exp(i k dir.x) restricted to the subdomain, column-normalised: the coarse vectors a
+                driver would pass to setVectors (the reference expects user-supplied vectors / an (A, B) pencil here)
+    """
+    base = generate3d(rank, size, N=N, overlap=overlap, mu=mu, grid=grid, seed=seed)
+    Nx, Ny, Nz = N
+    (x0, x1), (y0, y1), (z0, z1) = base["box"]
+    w, h, t = base["dims"]
+    ndof = base["ndof"]
+    hs = (10.0 / Nx, 10.0 / Ny, 10.0 / Nz)
+    lo, hi, NN = (x0, y0, z0), (x1, y1, z1), (Nx, Ny, Nz)
+    # ghost-cell elimination of  (u_g - u_b) / h = i k u_b  ->  the missing neighbour contributes c * (1 + i k h) to the diagonal
+    ext = np.zeros((t, h, w), dtype=np.complex128)   # outer boundary faces
+    art = np.zeros((t, h, w), dtype=np.complex128)   # artificial faces (ORAS transmission condition)
+    for a in range(3):
+        c = -1.0 / (hs[a] * hs[a])
+        val = c * (1.0 + 1j * k * hs[a])
+        first = [slice(None)] * 3
+        last = [slice(None)] * 3
+        first[2 - a] = 0
+        last[2 - a] = -1
+        (ext if lo[a] == 0 else art)[tuple(first)] += val
+        (ext if hi[a] == NN[a] else art)[tuple(last)] += val
+    A0 = sp.csr_matrix(base["Mat"]).astype(np.complex128)
+    Mat = sp.csr_matrix(A0 + sp.diags(ext.reshape(-1) - k * k))
+    Mat.sort_indices()
+    MatRobin = sp.csr_matrix(Mat + sp.diags(art.reshape(-1)))
+    MatRobin.sort_indices()
+    rs = np.random.RandomState(seed + 17 * rank)
+    f = np.asfortranarray((rs.uniform(0.0, 1.0, size=(max(mu, 1), ndof)) + 1j * rs.uniform(-0.5, 0.5, size=(max(mu, 1), ndof))).T)
+    xs = (np.arange(x0, x1) + 0.5) * hs[0]
+    ys = (np.arange(y0, y1) + 0.5) * hs[1]
+    zs = (np.arange(z0, z1) + 0.5) * hs[2]
+    dirs = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (-1, 0, 0), (0, -1, 0), (0, 0, -1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (1, 1, 1)]
+    Z = np.empty((ndof, nu), dtype=np.complex128, order="F")
+    for c in range(nu):
+        dv = np.array(dirs[c % len(dirs)], dtype=float)
+        dv /= np.linalg.norm(dv)
+        kk = k * (1 + c // len(dirs))
+        v = np.exp(1j * kk * (dv[2] * zs[:, None, None] + dv[1] * ys[None, :, None] + dv[0] * xs[None, None, :])).reshape(-1)
+        Z[:, c] = v / np.linalg.norm(v)
+    return dict(base, Mat=Mat, MatRobin=MatRobin, MatNeumann=None, f=f, Z=Z, k=k, sym=False)

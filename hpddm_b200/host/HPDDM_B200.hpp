@@ -16,7 +16,9 @@
  *     Operator concept of the Krylov drivers (include/HPDDM_GMRES.hpp:57-62,113-117) so
  *     IterativeMethod::solve(A, f, sol, mu, comm) works on it unchanged.
  *
- * Only K = double is implemented (FP64 is the metric's precision; complex is config 5, out of scope).
+ * K = double (C ABI hpddm_b200_*, include/hpddm_b200.h) and K = std::complex<double> (hpddm_b200z_*,
+ * include/hpddm_b200z.h; the reference's FORCE_COMPLEX build, BASELINE config 5) are implemented; b200::Api<K>
+ * selects the entry points of one scalar type.
  */
 #ifndef HPDDM_B200_HPP_
 #define HPDDM_B200_HPP_
@@ -32,6 +34,7 @@
 #include <vector>
 
 #include "hpddm_b200.h"
+#include "hpddm_b200z.h"
 
 #ifndef HPDDM_NUMBERING
   #define HPDDM_NUMBERING 'C'
@@ -42,16 +45,65 @@ template <class K>
 class MatrixCSR;  // include/HPDDM_matrix.hpp:156-165 (n_, m_, nnz_, ia_, ja_, a_, sym_)
 
 namespace b200 {
+/* Api<K>: the C entry points of one scalar type behind common names (K = double -> hpddm_b200_*, K = std::complex<double> -> hpddm_b200z_*) */
+template <class K>
+struct Api;
+#define HPDDM_B200_DEFINE_API(K_, P_)                                                                                                              \
+  template <>                                                                                                                                      \
+  struct Api<K_> {                                                                                                                                 \
+    typedef P_##_ctx ctx_t;                                                                                                                        \
+    typedef P_##_sub sub_t;                                                                                                                        \
+    static const char *last_error() { return P_##_last_error(); }                                                                                  \
+    static int ctx_create(int dev, ctx_t **c) { return P_##_ctx_create(dev, c); }                                                                  \
+    static int ctx_destroy(ctx_t *c) { return P_##_ctx_destroy(c); }                                                                               \
+    static int nccl_unique_id(void *id) { return P_##_nccl_unique_id(id); }                                                                        \
+    static int ctx_comm_init(ctx_t *c, const void *id, int r, int n) { return P_##_ctx_comm_init(c, id, r, n); }                                   \
+    static int sub_create(ctx_t *c, int r, sub_t **s) { return P_##_sub_create(c, r, s); }                                                         \
+    static int sub_destroy(sub_t *s) { return P_##_sub_destroy(s); }                                                                               \
+    static int sub_set_matrix(sub_t *s, int n, int nnz, const int *ia, const int *ja, const K_ *a, int sym, char nb)                               \
+    {                                                                                                                                              \
+      return P_##_sub_set_matrix(s, n, nnz, ia, ja, a, sym, nb);                                                                                   \
+    }                                                                                                                                              \
+    static int sub_set_neighbors(sub_t *s, int c, const int *r, const int *sz, const int *idx) { return P_##_sub_set_neighbors(s, c, r, sz, idx); } \
+    static int sub_set_scaling(sub_t *s, const double *d) { return P_##_sub_set_scaling(s, d); }                                                   \
+    static int sub_set_grid_hint(sub_t *s, int nx, int ny, int nz, int dof) { return P_##_sub_set_grid_hint(s, nx, ny, nz, dof); }                 \
+    static int multiplicity_scaling(ctx_t *c, double *const *d) { return P_##_multiplicity_scaling(c, d); }                                        \
+    static int sub_numfact(sub_t *s, int t, int n, int nnz, const int *ia, const int *ja, const K_ *a, int sym, char nb)                           \
+    {                                                                                                                                              \
+      return P_##_sub_numfact(s, t, n, nnz, ia, ja, a, sym, nb);                                                                                   \
+    }                                                                                                                                              \
+    static int sub_set_vectors(sub_t *s, const K_ *Z, int nu) { return P_##_sub_set_vectors(s, Z, nu); }                                           \
+    static int sub_solve_gevp(sub_t *s, int n, int nnz, const int *ia, const int *ja, const K_ *a, int sym, char nb, int nu, double tol, int it,   \
+                              double *ev)                                                                                                          \
+    {                                                                                                                                              \
+      return P_##_sub_solve_gevp(s, n, nnz, ia, ja, a, sym, nb, nu, tol, it, ev);                                                                  \
+    }                                                                                                                                              \
+    static int build_coarse(ctx_t *c) { return P_##_build_coarse(c); }                                                                             \
+    static int start(ctx_t *c, const K_ *const *b, K_ *const *x, int mu, int w) { return P_##_start(c, b, x, mu, w); }                             \
+    static int end(ctx_t *c) { return P_##_end(c); }                                                                                               \
+    static int apply(ctx_t *c, const K_ *const *in, K_ *const *out, int mu, int corr, int w) { return P_##_apply(c, in, out, mu, corr, w); }        \
+    static int deflation(ctx_t *c, const K_ *const *in, K_ *const *out, int mu, int w) { return P_##_deflation(c, in, out, mu, w); }                \
+    static int exchange(ctx_t *c, K_ *const *x, int mu, int scaled, int w) { return P_##_exchange(c, x, mu, scaled, w); }                          \
+    static int gmv(ctx_t *c, const K_ *const *in, K_ *const *out, int mu, int w) { return P_##_gmv(c, in, out, mu, w); }                            \
+    static int sub_solve(sub_t *s, const K_ *b, K_ *x, int mu, int w) { return P_##_sub_solve(s, b, x, mu, w); }                                    \
+    static int dot(ctx_t *c, const K_ *const *x, const K_ *const *y, int mu, K_ *res, int w) { return P_##_dot(c, x, y, mu, res, w); }              \
+  }
+HPDDM_B200_DEFINE_API(double, hpddm_b200);
+HPDDM_B200_DEFINE_API(std::complex<double>, hpddm_b200z);
+#undef HPDDM_B200_DEFINE_API
+
+template <class K>
 inline void check(int rc, const char *what) {
   if (rc < 0) {
-    std::fprintf(stderr, "[hpddm_b200] %s failed (%d): %s\n", what, rc, hpddm_b200_last_error());
-    throw std::runtime_error(std::string(what) + ": " + hpddm_b200_last_error());
+    std::fprintf(stderr, "[hpddm_b200] %s failed (%d): %s\n", what, rc, Api<K>::last_error());
+    throw std::runtime_error(std::string(what) + ": " + Api<K>::last_error());
   }
 }
-/* one context per process, created on first use (after MPI_Init / fork).  Device: HPDDM_B200_DEVICE,
+/* one context per process and scalar type, created on first use (after MPI_Init / fork).  Device: HPDDM_B200_DEVICE,
  * else the local MPI rank exported by the launcher, else 0. */
-inline hpddm_b200_ctx *context(bool fresh = false) {
-  static hpddm_b200_ctx *ctx = nullptr;
+template <class K>
+inline typename Api<K>::ctx_t *context(bool fresh = false) {
+  static typename Api<K>::ctx_t *ctx = nullptr;
   if (fresh || !ctx) {
     int dev = 0;
     for (const char *v : {"HPDDM_B200_DEVICE", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID", "LOCAL_RANK"})
@@ -59,24 +111,27 @@ inline hpddm_b200_ctx *context(bool fresh = false) {
         dev = std::atoi(e);
         break;
       }
-    hpddm_b200_ctx *c = nullptr;
-    check(hpddm_b200_ctx_create(dev, &c), "hpddm_b200_ctx_create");
+    typename Api<K>::ctx_t *c = nullptr;
+    check<K>(Api<K>::ctx_create(dev, &c), "ctx_create");
     if (fresh) return c;
     ctx = c;
   }
   return ctx;
 }
+inline double real_part(double v) { return v; }
+inline double real_part(const std::complex<double> &v) { return v.real(); }
 }  // namespace b200
 
 /* ------------------------------------------------------------------ 1. SUBDOMAIN plugin */
 template <class K>
 class B200Sub {
-  static_assert(std::is_same<K, double>::value, "hpddm_b200: only K = double is implemented");
+  static_assert(std::is_same<K, double>::value || std::is_same<K, std::complex<double>>::value, "hpddm_b200: K must be double or std::complex<double>");
+  typedef b200::Api<K> A_;
 
 private:
-  hpddm_b200_ctx *ctx_;
-  hpddm_b200_sub *sub_;
-  int             n_;
+  typename A_::ctx_t *ctx_;
+  typename A_::sub_t *sub_;
+  int                 n_;
 
 public:
   B200Sub() : ctx_(), sub_(), n_() { }
@@ -85,9 +140,9 @@ public:
   static constexpr char numbering_ = 'C';
   void                  dtor()
   {
-    if (sub_) hpddm_b200_sub_destroy(sub_);
+    if (sub_) A_::sub_destroy(sub_);
     sub_ = nullptr;
-    if (ctx_) hpddm_b200_ctx_destroy(ctx_);
+    if (ctx_) A_::ctx_destroy(ctx_);
     ctx_ = nullptr;
   }
   /* SUBDOMAIN::numfact (e.g. include/HPDDM_SuiteSparse.hpp:264-371) */
@@ -95,15 +150,15 @@ public:
   void numfact(MatrixCSR<K> *const &A, bool = false, K *const & = nullptr)
   {
     dtor();
-    ctx_ = b200::context(true);  // private context: solver objects are independent of each other
-    b200::check(hpddm_b200_sub_create(ctx_, 0, &sub_), "hpddm_b200_sub_create");
+    ctx_ = b200::context<K>(true);  // private context: solver objects are independent of each other
+    b200::check<K>(A_::sub_create(ctx_, 0, &sub_), "sub_create");
     n_ = A->n_;
-    b200::check(hpddm_b200_sub_set_matrix(sub_, A->n_, A->nnz_, A->ia_, A->ja_, A->a_, A->sym_ ? 1 : 0, N), "hpddm_b200_sub_set_matrix");
+    b200::check<K>(A_::sub_set_matrix(sub_, A->n_, A->nnz_, A->ia_, A->ja_, A->a_, A->sym_ ? 1 : 0, N), "sub_set_matrix");
     if (const char *g = std::getenv("HPDDM_B200_GRID")) {  // optional "nx,ny,nz[,dof]" ordering hint
       int nx = 0, ny = 0, nz = 1, dof = 1;
-      if (std::sscanf(g, "%d,%d,%d,%d", &nx, &ny, &nz, &dof) >= 2 && (long long)nx * ny * nz * dof == A->n_) hpddm_b200_sub_set_grid_hint(sub_, nx, ny, nz, dof);
+      if (std::sscanf(g, "%d,%d,%d,%d", &nx, &ny, &nz, &dof) >= 2 && (long long)nx * ny * nz * dof == A->n_) A_::sub_set_grid_hint(sub_, nx, ny, nz, dof);
     }
-    b200::check(hpddm_b200_sub_numfact(sub_, HPDDM_B200_PRCNDTNR_GE, 0, 0, nullptr, nullptr, nullptr, 0, 'C'), "hpddm_b200_sub_numfact");
+    b200::check<K>(A_::sub_numfact(sub_, HPDDM_B200_PRCNDTNR_GE, 0, 0, nullptr, nullptr, nullptr, 0, 'C'), "sub_numfact");
   }
   template <char = HPDDM_NUMBERING>
   int inertia(MatrixCSR<K> *const &)
@@ -112,8 +167,8 @@ public:
   }
   unsigned short deficiency() const { return 0; }
   /* SUBDOMAIN::solve (include/HPDDM_SuiteSparse.hpp:388-423): host pointers in/out */
-  void solve(K *const x, const unsigned short &n = 1) const { b200::check(hpddm_b200_sub_solve(sub_, x, x, n, HPDDM_B200_HOST), "hpddm_b200_sub_solve"); }
-  void solve(const K *const b, K *const x, const unsigned short &n = 1) const { b200::check(hpddm_b200_sub_solve(sub_, b, x, n, HPDDM_B200_HOST), "hpddm_b200_sub_solve"); }
+  void solve(K *const x, const unsigned short &n = 1) const { b200::check<K>(A_::sub_solve(sub_, x, x, n, HPDDM_B200_HOST), "sub_solve"); }
+  void solve(const K *const b, K *const x, const unsigned short &n = 1) const { b200::check<K>(A_::sub_solve(sub_, b, x, n, HPDDM_B200_HOST), "sub_solve"); }
 };
 
 /* ------------------------------------------------------------------ 2. Schwarz mirror */
@@ -135,7 +190,8 @@ public:
  * include/HPDDM_subdomain.hpp:47) so that the recycling Krylov methods find storage()/k()/allocate(). */
 template <class K, class Base = b200::NoPrefix<K>>
 class B200Schwarz : public Base {
-  static_assert(std::is_same<K, double>::value, "hpddm_b200: only K = double is implemented");
+  static_assert(std::is_same<K, double>::value || std::is_same<K, std::complex<double>>::value, "hpddm_b200: K must be double or std::complex<double>");
+  typedef b200::Api<K> A_;
 
 public:
   typedef K scalar_type;
@@ -143,19 +199,19 @@ public:
   enum class Prcndtnr : char { NO = HPDDM_B200_PRCNDTNR_NO, SY = HPDDM_B200_PRCNDTNR_SY, GE = HPDDM_B200_PRCNDTNR_GE, OS = HPDDM_B200_PRCNDTNR_OS, OG = HPDDM_B200_PRCNDTNR_OG };
 
 private:
-  hpddm_b200_ctx *ctx_;
-  hpddm_b200_sub *sub_;
+  typename A_::ctx_t *ctx_;
+  typename A_::sub_t *sub_;
   MatrixCSR<K>   *a_;
   const double   *d_;
   int             dof_, rank_, size_, nu_, correction_;
   std::vector<std::pair<unsigned short, std::vector<int>>> map_;
 
 public:
-  B200Schwarz() : ctx_(b200::context()), sub_(), a_(), d_(), dof_(), rank_(), size_(1), nu_(), correction_(HPDDM_B200_CORRECTION_NONE) { }
+  B200Schwarz() : ctx_(b200::context<K>()), sub_(), a_(), d_(), dof_(), rank_(), size_(1), nu_(), correction_(HPDDM_B200_CORRECTION_NONE) { }
   B200Schwarz(const B200Schwarz &) = delete;
   ~B200Schwarz()
   {
-    if (sub_) hpddm_b200_sub_destroy(sub_);
+    if (sub_) A_::sub_destroy(sub_);
   }
   /* NCCL bootstrap for the hot path (replaces Subdomain::communicator_ there): `bcast` broadcasts
    * 128 bytes from rank 0, e.g. [&](void* p){ MPI_Bcast(p, 128, MPI_BYTE, 0, MPI_COMM_WORLD); } */
@@ -166,9 +222,9 @@ public:
     size_ = size;
     if (size > 1) {
       char id[128];
-      if (rank == 0) b200::check(hpddm_b200_nccl_unique_id(id), "hpddm_b200_nccl_unique_id");
+      if (rank == 0) b200::check<K>(A_::nccl_unique_id(id), "nccl_unique_id");
       bcast(static_cast<void *>(id));
-      b200::check(hpddm_b200_ctx_comm_init(ctx_, id, rank, size), "hpddm_b200_ctx_comm_init");
+      b200::check<K>(A_::ctx_comm_init(ctx_, id, rank, size), "ctx_comm_init");
     }
   }
   /* Subdomain::initialize(a, o, r) (include/HPDDM_subdomain.hpp:165-236) */
@@ -177,8 +233,8 @@ public:
   {
     a_   = a;
     dof_ = a->n_;
-    if (!sub_) b200::check(hpddm_b200_sub_create(ctx_, rank_, &sub_), "hpddm_b200_sub_create");
-    b200::check(hpddm_b200_sub_set_matrix(sub_, a->n_, a->nnz_, a->ia_, a->ja_, a->a_, a->sym_ ? 1 : 0, HPDDM_NUMBERING), "hpddm_b200_sub_set_matrix");
+    if (!sub_) b200::check<K>(A_::sub_create(ctx_, rank_, &sub_), "sub_create");
+    b200::check<K>(A_::sub_set_matrix(sub_, a->n_, a->nnz_, a->ia_, a->ja_, a->a_, a->sym_ ? 1 : 0, HPDDM_NUMBERING), "sub_set_matrix");
     std::vector<int> ranks(o.begin(), o.end()), sizes, idx;
     unsigned short   i = 0;
     map_.clear();
@@ -187,40 +243,40 @@ public:
       idx.insert(idx.end(), m.begin(), m.end());
       map_.emplace_back(static_cast<unsigned short>(ranks[i++]), std::vector<int>(m.begin(), m.end()));
     }
-    b200::check(hpddm_b200_sub_set_neighbors(sub_, static_cast<int>(ranks.size()), ranks.data(), sizes.data(), idx.data()), "hpddm_b200_sub_set_neighbors");
+    b200::check<K>(A_::sub_set_neighbors(sub_, static_cast<int>(ranks.size()), ranks.data(), sizes.data(), idx.data()), "sub_set_neighbors");
   }
-  void setGridHint(int nx, int ny, int nz = 1, int dof = 1) { b200::check(hpddm_b200_sub_set_grid_hint(sub_, nx, ny, nz, dof), "hpddm_b200_sub_set_grid_hint"); }
+  void setGridHint(int nx, int ny, int nz = 1, int dof = 1) { b200::check<K>(A_::sub_set_grid_hint(sub_, nx, ny, nz, dof), "sub_set_grid_hint"); }
   /* Schwarz::multiplicityScaling (include/HPDDM_schwarz.hpp:381-404) */
   void multiplicityScaling(double *const d) const
   {
     double *arr[1] = {d};
-    b200::check(hpddm_b200_multiplicity_scaling(ctx_, arr), "hpddm_b200_multiplicity_scaling");
+    b200::check<K>(A_::multiplicity_scaling(ctx_, arr), "multiplicity_scaling");
   }
   /* Schwarz::initialize(d) (schwarz.hpp:178): d stays owned by the caller */
   void initialize(double *const &d)
   {
     d_ = d;
-    b200::check(hpddm_b200_sub_set_scaling(sub_, d), "hpddm_b200_sub_set_scaling");
+    b200::check<K>(A_::sub_set_scaling(sub_, d), "sub_set_scaling");
   }
   /* Schwarz::callNumfact (schwarz.hpp:337-368) */
   template <char N = HPDDM_NUMBERING>
   void callNumfact(MatrixCSR<K> *const &A = nullptr, int prcndtnr = HPDDM_B200_PRCNDTNR_GE)
   {
-    if (A) b200::check(hpddm_b200_sub_numfact(sub_, prcndtnr, A->n_, A->nnz_, A->ia_, A->ja_, A->a_, A->sym_ ? 1 : 0, N), "hpddm_b200_sub_numfact");
-    else b200::check(hpddm_b200_sub_numfact(sub_, prcndtnr, 0, 0, nullptr, nullptr, nullptr, 0, 'C'), "hpddm_b200_sub_numfact");
+    if (A) b200::check<K>(A_::sub_numfact(sub_, prcndtnr, A->n_, A->nnz_, A->ia_, A->ja_, A->a_, A->sym_ ? 1 : 0, N), "sub_numfact");
+    else b200::check<K>(A_::sub_numfact(sub_, prcndtnr, 0, 0, nullptr, nullptr, nullptr, 0, 'C'), "sub_numfact");
   }
   /* Preconditioner::setVectors (include/HPDDM_preconditioner.hpp:358-362): ev[0] contiguous n x nu; ownership stays with the caller here */
   void setVectors(K **const &ev, unsigned short nu)
   {
     nu_ = nu;
-    b200::check(hpddm_b200_sub_set_vectors(sub_, *ev, nu), "hpddm_b200_sub_set_vectors");
+    b200::check<K>(A_::sub_set_vectors(sub_, *ev, nu), "sub_set_vectors");
   }
   /* Schwarz::solveGEVP<EIGENSOLVER>(A_Neumann) (schwarz.hpp:665-715): GenEO vectors computed on the GPU; the template
    * parameter of the reference (the eigensolver plugin) has no meaning here and is accepted for source compatibility */
   template <template <class> class Eps = B200Sub>
   void solveGEVP(MatrixCSR<K> *const &A, unsigned short nu = 20, double tol = 1.0e-6)
   {
-    b200::check(hpddm_b200_sub_solve_gevp(sub_, A->n_, A->nnz_, A->ia_, A->ja_, A->a_, A->sym_ ? 1 : 0, HPDDM_NUMBERING, nu, tol, 0, nullptr), "hpddm_b200_sub_solve_gevp");
+    b200::check<K>(A_::sub_solve_gevp(sub_, A->n_, A->nnz_, A->ia_, A->ja_, A->a_, A->sym_ ? 1 : 0, HPDDM_NUMBERING, nu, tol, 0, nullptr), "sub_solve_gevp");
     nu_ = nu;
   }
   /* Schwarz::buildTwo (schwarz.hpp:440-495) */
@@ -228,7 +284,7 @@ public:
   int buildTwo(const Comm & = Comm(), int correction = HPDDM_B200_CORRECTION_DEFLATED)
   {
     correction_ = correction;
-    b200::check(hpddm_b200_build_coarse(ctx_), "hpddm_b200_build_coarse");
+    b200::check<K>(A_::build_coarse(ctx_), "build_coarse");
     return 0;
   }
   void setCorrection(int correction) { correction_ = correction; }
@@ -236,41 +292,41 @@ public:
   template <bool excluded = false>
   bool start(const K *const b, K *const x, const unsigned short &mu = 1) const
   {
-    const double *bb[1] = {b};
-    double       *xx[1] = {x};
-    b200::check(hpddm_b200_start(ctx_, bb, xx, mu, HPDDM_B200_HOST), "hpddm_b200_start");
+    const K *bb[1] = {b};
+    K       *xx[1] = {x};
+    b200::check<K>(A_::start(ctx_, bb, xx, mu, HPDDM_B200_HOST), "start");
     return false;
   }
-  void end(const bool = true) const { hpddm_b200_end(ctx_); }
+  void end(const bool = true) const { A_::end(ctx_); }
   /* Schwarz::exchange<allocate> (schwarz.hpp:180-188) and Subdomain::exchange */
   template <bool allocate = false>
   void exchange(K *const x, const unsigned short &mu = 1) const
   {
-    double *xx[1] = {x};
-    b200::check(hpddm_b200_exchange(ctx_, xx, mu, 1, HPDDM_B200_HOST), "hpddm_b200_exchange");
+    K *xx[1] = {x};
+    b200::check<K>(A_::exchange(ctx_, xx, mu, 1, HPDDM_B200_HOST), "exchange");
   }
   /* Schwarz::apply<excluded>(in, out, mu, work) (schwarz.hpp:527-612); `in` is never clobbered */
   template <bool excluded = false>
   int apply(const K *const in, K *const out, const unsigned short &mu = 1, K * = nullptr) const
   {
-    const double *ii[1] = {in};
-    double       *oo[1] = {out};
-    return hpddm_b200_apply(ctx_, ii, oo, mu, correction_, HPDDM_B200_HOST);
+    const K *ii[1] = {in};
+    K       *oo[1] = {out};
+    return A_::apply(ctx_, ii, oo, mu, correction_, HPDDM_B200_HOST);
   }
   /* Schwarz::deflation<excluded, transpose> (schwarz.hpp:1602-1622) */
   template <bool excluded, bool transpose = false>
   void deflation(const K *const in, K *const out, const unsigned short &mu) const
   {
-    const double *ii[1] = {in};
-    double       *oo[1] = {out};
-    b200::check(hpddm_b200_deflation(ctx_, ii, oo, mu, HPDDM_B200_HOST), "hpddm_b200_deflation");
+    const K *ii[1] = {in};
+    K       *oo[1] = {out};
+    b200::check<K>(A_::deflation(ctx_, ii, oo, mu, HPDDM_B200_HOST), "deflation");
   }
   /* Schwarz::GMV (schwarz.hpp:726-747) */
   int GMV(const K *const in, K *const out, const int &mu = 1) const
   {
-    const double *ii[1] = {in};
-    double       *oo[1] = {out};
-    return hpddm_b200_gmv(ctx_, ii, oo, mu, HPDDM_B200_HOST);
+    const K *ii[1] = {in};
+    K       *oo[1] = {out};
+    return A_::gmv(ctx_, ii, oo, mu, HPDDM_B200_HOST);
   }
   /* Schwarz::computeResidual (schwarz.hpp:761-803), l2 norm: storage[2*nu] = ||f||_D, [2*nu+1] = ||Ax-f||_D */
   void computeResidual(const K *const x, const K *const f, double *const storage, const unsigned short mu = 1) const
@@ -278,13 +334,13 @@ public:
     std::vector<K> tmp(static_cast<std::size_t>(mu) * dof_);
     GMV(x, tmp.data(), mu);
     for (std::size_t i = 0; i < tmp.size(); ++i) tmp[i] -= f[i];
-    std::vector<double> r(mu), b(mu);
-    const double       *t[1] = {tmp.data()}, *ff[1] = {f};
-    b200::check(hpddm_b200_dot(ctx_, t, t, mu, r.data(), HPDDM_B200_HOST), "hpddm_b200_dot");
-    b200::check(hpddm_b200_dot(ctx_, ff, ff, mu, b.data(), HPDDM_B200_HOST), "hpddm_b200_dot");
+    std::vector<K> r(mu), b(mu);  // sum_i d_i conj(x_i) x_i: real up to rounding
+    const K       *t[1] = {tmp.data()}, *ff[1] = {f};
+    b200::check<K>(A_::dot(ctx_, t, t, mu, r.data(), HPDDM_B200_HOST), "dot");
+    b200::check<K>(A_::dot(ctx_, ff, ff, mu, b.data(), HPDDM_B200_HOST), "dot");
     for (unsigned short nu = 0; nu < mu; ++nu) {
-      storage[2 * nu]     = std::sqrt(b[nu]);
-      storage[2 * nu + 1] = std::sqrt(r[nu]);
+      storage[2 * nu]     = std::sqrt(b200::real_part(b[nu]));
+      storage[2 * nu + 1] = std::sqrt(b200::real_part(r[nu]));
     }
   }
   /* accessors used by the Krylov drivers (include/HPDDM_GMRES.hpp:40-62, HPDDM_iterative.hpp:441-468) */
@@ -294,8 +350,8 @@ public:
   const MatrixCSR<K> *getMatrix() const { return a_; }
   const std::vector<std::pair<unsigned short, std::vector<int>>> &getMap() const { return map_; }
   std::unordered_map<unsigned int, K> boundaryConditions() const { return std::unordered_map<unsigned int, K>(); }
-  hpddm_b200_ctx *context() const { return ctx_; }
-  hpddm_b200_sub *handle() const { return sub_; }
+  typename A_::ctx_t *context() const { return ctx_; }
+  typename A_::sub_t *handle() const { return sub_; }
 };
 }  // namespace HPDDM
 

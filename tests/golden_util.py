@@ -10,7 +10,9 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def cases():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """real-scalar goldens first, then the complex ones (K = std::complex<double>)"""
+    names = [os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))]
+    return sorted(names, key=lambda n: (n.startswith("complex"), n))
 
 
 def arg_value(args, key, default):

@@ -26,6 +26,26 @@ def test_reference_driver_with_b200_subdomain_solver(tmp_path):
     assert int(m.group(1)) == int(golden["r0_iterations"][0])   # identical to the all-CPU reference run (33)
 
 
+BINZ = os.path.join(ROOT, "oracle", "_ref", "schwarz_b200_z")
+
+
+@pytest.mark.skipif(not os.path.exists(BINZ), reason="oracle/_ref/schwarz_b200_z not built (needs /root/reference at build time)")
+def test_reference_driver_complex_build_with_b200_subdomain_solver(tmp_path):
+    """The same unmodified driver compiled with -DFORCE_COMPLEX (K = std::complex<double>, examples/schwarz.hpp:56-60):
+    SUBDOMAIN = HPDDM::B200Sub<std::complex<double>> -> hpddm_b200z_* (complex no-pivot LU + complex SpTRSV on the GPU).
+    The generator's matrix and right-hand side are real-valued, so complex GMRES must take exactly the iterations of
+    the real run (33, the all-CPU reference golden)."""
+    env = dict(os.environ, HPDDM_SHIM_NP="4")
+    res = subprocess.run([BINZ, "-hpddm_schwarz_method", "ras", "-hpddm_gmres_restart=25", "-hpddm_max_it", "80", "-hpddm_verbosity", "1"],
+                         env=env, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    out = res.stdout + res.stderr
+    assert res.returncode == 0, out[-2000:]
+    m = re.search(r"converges after\s+(\d+)\s+iteration", out)
+    assert m, out[-2000:]
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "config1_100x100_p4_ras.npz"))
+    assert int(m.group(1)) == int(golden["r0_iterations"][0])
+
+
 FULL = os.path.join(ROOT, "oracle", "_ref", "b200_full_driver")
 REFDRV = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 
