@@ -10,6 +10,8 @@ contract asks; `applies_per_s` is the global figure.
 
   python bench.py --gpus 1 --steps 20 --warmup 3            # this repo's CUDA path
   python bench.py --impl reference ...                       # CPU arm (oracle port on host cores)
+  python bench.py --scalar z --cells 64                      # auxiliary: BASELINE config 5 shape (3-D Helmholtz, complex FP64,
+                                                             # ORAS + plane-wave coarse space) through hpddm_b200z_*; not the headline
 """
 import argparse
 import json
@@ -25,6 +27,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "preconditioner applies/sec (FP64) 3-D Poisson, 1 subdomain/GPU, two-level RAS (deflated) + GenEO nu=20"
+METRIC_Z = "preconditioner applies/sec (complex FP64) 3-D Helmholtz, 1 subdomain/GPU, two-level ORAS (deflated) + plane-wave coarse space"
 
 
 def cosine_modes(dims, nu):
@@ -73,10 +76,9 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def algorithmic_bytes(st, nnz_a, nu, mu=1):
-    """BASELINE.md section 4 traffic model, per subdomain, s = 8 bytes."""
+def algorithmic_bytes(st, nnz_a, nu, mu=1, s=8):
+    """BASELINE.md section 4 traffic model, per subdomain, s = 8 bytes (16 for complex scalars)."""
     n, h = st["n"], st["halo"]
-    s = 8
     b_trsv = st["factor_bytes"] * (2 if st["symmetric"] else 1) + st["index_bytes"] + 4 * s * n * mu
     b_halo = (2 * s + 8) * n * mu + 2 * s * h * mu
     b_z = s * n * nu + s * n * mu + 8 * n
@@ -100,9 +102,15 @@ def run_b200(args):
     grid = split_grid_3d(world)
     m = args.m
     N = tuple(g * m for g in grid)
-    part = generate3d(rank, world, N=N, overlap=1, mu=1, grid=grid)
+    cplx = args.scalar == "z"
+    if cplx:
+        from hpddm_b200.examples.generate import generate_helmholtz3d
+        part = generate_helmholtz3d(rank, world, N=N, overlap=1, mu=1, grid=grid, k=args.wavenumber, nu=args.nu)
+    else:
+        part = generate3d(rank, world, N=N, overlap=1, mu=1, grid=grid)
     n = part["ndof"]
-    deco = Decomposition(local)
+    tdtype = torch.complex128 if cplx else torch.float64
+    deco = Decomposition(local, dtype=np.complex128 if cplx else np.float64)
     if world > 1:
         deco.comm_init_torch()
     s = deco.add(rank)
@@ -110,20 +118,23 @@ def run_b200(args):
     s.setGridHint(*part["dims"])
     deco.multiplicityScaling([part["d"]])
     t0 = time.time()
-    s.callNumfact()
+    if cplx:
+        s.callNumfact(A=part["MatRobin"], method="oras")   # ORAS: impedance transmission conditions (Prcndtnr::OG)
+    else:
+        s.callNumfact()
     deco.synchronize()
     t_fact = time.time() - t0
-    s.setVectors(cosine_modes(part["dims"], args.nu))
+    s.setVectors(part["Z"] if cplx else cosine_modes(part["dims"], args.nu))
     deco.buildTwo()
     st = s.statistics()
     nnz_a = st["nnz_a"]
-    by = algorithmic_bytes(st, nnz_a, args.nu, args.mu)
+    by = algorithmic_bytes(st, nnz_a, args.nu, args.mu, s=16 if cplx else 8)
     stream = torch.cuda.ExternalStream(deco.stream, device=local)
     mu = args.mu
-    x_dev = torch.rand(n * mu, dtype=torch.float64, device="cuda")
+    x_dev = torch.rand(n * mu, dtype=tdtype, device="cuda")
     y_dev = torch.empty_like(x_dev)
-    x_pin = torch.rand(n * mu, dtype=torch.float64).pin_memory()
-    y_pin = torch.empty(n * mu, dtype=torch.float64).pin_memory()
+    x_pin = torch.rand(n * mu, dtype=tdtype).pin_memory()
+    y_pin = torch.empty(n * mu, dtype=tdtype).pin_memory()
     torch.cuda.synchronize()
 
     def barrier():
@@ -155,26 +166,28 @@ def run_b200(args):
     launches = (deco.launches - l0) // (args.steps + args.warmup) * args.steps
     # dominant kernel alone: the local triangular solves (forward + backward sweeps)
     from hpddm_b200 import capi
-    ms_trsv = timed(lambda: capi.check(capi.lib().hpddm_b200_sub_solve(s.h, x_dev.data_ptr(), y_dev.data_ptr(), mu, capi.DEVICE)), args.steps, args.warmup)
+    ms_trsv = timed(lambda: deco.api.check(deco.api.sub_solve(s.h, x_dev.data_ptr(), y_dev.data_ptr(), mu, capi.DEVICE)), args.steps, args.warmup)
     ms_e2e = timed(lambda: deco.apply_host_inplace([x_pin], [y_pin], mu, "deflated"), args.steps, args.warmup)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     peak, peak_src = peaks()
     traffic = None
     try:  # DRAM bytes of one solve measured by ncu for this configuration (profiles/), if captured
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["cells"].get(str(m), {}).get("dram_bytes") if args.mu == 1 else None
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["cells"].get(str(m), {}).get("dram_bytes") if args.mu == 1 and not cplx else None
     except Exception:
         pass
     trsv_gbs = by["trsv"] / (ms_trsv / args.steps * 1e-3) / 1e9
     out = {
-        "metric": METRIC, "value": world * args.steps / (ms_dev * 1e-3), "unit": "subdomain-applies/s", "applies_per_s": args.steps / (ms_dev * 1e-3),
+        "metric": METRIC_Z if cplx else METRIC, "value": world * args.steps / (ms_dev * 1e-3), "unit": "subdomain-applies/s", "applies_per_s": args.steps / (ms_dev * 1e-3),
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config3 slice: 3-D Poisson {N[0]}x{N[1]}x{N[2]}, {world} subdomain(s) of {m}^3 cells + overlap 1 (n_loc={n}), two-level RAS deflated, nu={args.nu}, mu={args.mu}",
+        "vs_baseline": None, "dtype": "c128" if cplx else "f64", "data": "synthetic",
+        "config": {"workload": (f"config5 slice: 3-D Helmholtz k={args.wavenumber} {N[0]}x{N[1]}x{N[2]}, complex FP64, {world} subdomain(s) of {m}^3 cells + overlap 1 (n_loc={n}), "
+                                f"two-level ORAS deflated, {args.nu} plane waves, mu={args.mu}") if cplx else
+                               f"config3 slice: 3-D Poisson {N[0]}x{N[1]}x{N[2]}, {world} subdomain(s) of {m}^3 cells + overlap 1 (n_loc={n}), two-level RAS deflated, nu={args.nu}, mu={args.mu}",
                    "parallelism": f"{grid[0]}x{grid[1]}x{grid[2]} subdomains, 1/GPU", "l2": "inputs (factor panels) larger than L2, no flush needed",
                    "nnz_factor": st["nnz_factor"], "factor_gb": st["factor_bytes"] / 1e9, "levels": st["levels"], "fronts": st["fronts"],
                    "numfact_s": round(t_fact, 3), "symbolic_s": round(st["symbolic_seconds"], 3)},
-        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "subdomain-applies/s", "h2d_bytes_per_step": 8 * n * mu, "d2h_bytes_per_step": 8 * n * mu,
+        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "subdomain-applies/s", "h2d_bytes_per_step": (16 if cplx else 8) * n * mu, "d2h_bytes_per_step": (16 if cplx else 8) * n * mu,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "supernodal SpTRSV sweeps (k_fwd + k_bwd, all levels)", "bound": "hbm", "achieved": trsv_gbs, "peak": peak, "peak_source": peak_src,
@@ -191,7 +204,9 @@ def run_b200(args):
         it_dev, _, res = deco.solve(bvec, correction="deflated")
         t_dev = time.time() - t0
         out["krylov"] = {"device_resident_gmres_s": t_dev, "iterations": it_dev, "rel_residual": float(res[0])}
-    if args.cpu_baseline and rank == 0 and world == 1:
+    if cplx:
+        out["cpu_baseline"] = None   # the CPU arm (oracle/cpu_ras.cpp) is real-valued; the complex bench is auxiliary
+    elif args.cpu_baseline and rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_baseline(args, m=args.cpu_m or None, steps=5, budget_s=60.0)
     if rank == 0:
         print(json.dumps(out))
@@ -296,6 +311,8 @@ def main():
     ap.add_argument("--rhs", dest="mu", type=int, default=1, help="right-hand sides per apply (block methods)")
     ap.add_argument("--cpu-cells", dest="cpu_m", type=int, default=0, help="subdomain edge of the CPU sample (0 = same as --cells)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--scalar", default="d", choices=["d", "z"], help="d: real FP64 Poisson (headline); z: complex FP64 Helmholtz / ORAS (config 5 shape, auxiliary)")
+    ap.add_argument("--wavenumber", type=float, default=2.0)
     ap.add_argument("--krylov", action="store_true", help="also time a full GMRES solve: device-resident driver vs host-driven loop over the C ABI")
     args = ap.parse_args()
     if args.impl == "reference":
