@@ -12,6 +12,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def cases():
     """real-scalar goldens first, then the complex ones (K = std::complex<double>)"""
     names = [os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))]
+    names = [n for n in names if not n.startswith("refdata_")]   # the reference's own data files (load_refdata)
     return sorted(names, key=lambda n: (n.startswith("complex"), n))
 
 
@@ -61,3 +62,21 @@ def complexify(part, rank):
     f = part["f"][:, :1].astype(np.complex128)
     f[:, 0] = f[:, 0].real + 1j * 0.25 * np.sin(0.05 * np.arange(n) + rank)
     return dict(part, Mat=A, f=np.asfortranarray(f))
+
+
+def load_refdata():
+    """The reference's in-tree data fixtures, converted by oracle/ref_build/make_data_fixture.py: examples/data/40X (400.txt:
+    SPD finite-element system, kappa ~ 1e4, Fortran-numbered CSR + right-hand side; examples/driver.cpp:84-114) and mini.mtx
+    (HPDDM matrix dump format, include/HPDDM_matrix.hpp:121-135).  Returns {name: (ia, ja, a, numbering, rhs, scipy matrix)}."""
+    out = {}
+    z = np.load(os.path.join(GOLDEN_DIR, "refdata_40X_400.npz"))
+    n = int(z["n"])
+    A = sp.csr_matrix((z["a"], z["ja"] - 1, z["ia"] - 1), shape=(n, n))
+    out["40X_400"] = (z["ia"].astype(np.int32), z["ja"].astype(np.int32), z["a"].copy(), "F", z["rhs"].copy(), A)
+    m = np.load(os.path.join(GOLDEN_DIR, "refdata_mini_mtx.npz"))
+    n = int(m["n"])
+    M = sp.csr_matrix((m["v"], (m["i"] - 1, m["j"] - 1)), shape=(n, n))
+    M.sort_indices()
+    rhs = np.sin(0.1 * np.arange(n)) + 1.0
+    out["mini_mtx"] = (M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.copy(), "C", rhs, M)
+    return out

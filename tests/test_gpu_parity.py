@@ -340,3 +340,28 @@ def test_geneo_eigensolve_on_gpu_spans_the_reference_subspace():
     res = w.compute_residual(x, b)
     assert np.all(res[:, 1] / res[:, 0] < 1e-5)
     deco.close()
+
+
+@pytest.mark.parametrize("name", ["40X_400", "mini_mtx"])
+def test_local_solve_on_the_reference_data_fixtures(name):
+    """SUBDOMAIN::numfact / solve on the reference's own data files (examples/data/40X/400.txt, Fortran numbering, SPD with
+    kappa ~ 1e4; examples/data/mini.mtx) -- unstructured matrices: algebraic nested dissection, no grid hint.  The
+    reference's acceptance bound for these systems is a relative residual <= 1e-7 (examples/driver.cpp:140)."""
+    import scipy.sparse.linalg as spla
+    from hpddm_b200 import Decomposition, capi
+    from tests.golden_util import load_refdata
+    ia, ja, a, numbering, b, A = load_refdata()[name]
+    n = A.shape[0]
+    deco = Decomposition(0)
+    s = deco.add(0)
+    L = capi.lib()
+    capi.check(L.hpddm_b200_sub_set_matrix(s.h, n, int(a.size), capi.ptr(ia), capi.ptr(ja), capi.ptr(a), 0, numbering.encode()))
+    s.n = n
+    capi.check(L.hpddm_b200_sub_set_neighbors(s.h, 0, None, None, None))
+    s.setScaling(np.ones(n))
+    s.callNumfact()
+    x = s.solve(b)[:, 0]
+    ref = spla.splu(A.tocsc()).solve(b)
+    assert np.abs(A @ x - b).max() / np.abs(b).max() < 1e-10
+    assert np.abs(x - ref).max() / np.abs(ref).max() < 1e-9
+    deco.close()

@@ -83,3 +83,16 @@ def test_cpu_benchmark_arm_matches_the_oracle():
     w.build_coarse()
     ref = w.apply([x.reshape(-1, 1)], DEFLATED)[0][:, 0]
     assert np.abs(ref - y).max() / np.abs(ref).max() < 1e-12
+
+
+def test_reference_data_fixtures_load_and_solve():
+    """tests/golden/refdata_*.npz (the reference's examples/data files, converted by oracle/ref_build/make_data_fixture.py)"""
+    import scipy.sparse as sp
+    from oracle.schwarz import LocalSolver
+    from tests.golden_util import load_refdata
+    data = load_refdata()
+    assert data["40X_400"][5].shape == (3988, 3988) and data["40X_400"][5].nnz == 53608      # "3988 53608 3989" header of 400.txt
+    assert data["mini_mtx"][5].shape == (976, 976) and data["mini_mtx"][5].nnz == 6526
+    for name, (ia, ja, a, numbering, b, A) in data.items():
+        x = LocalSolver(A).solve(b)
+        assert np.abs(A @ x - b).max() / np.abs(b).max() < 1e-10
