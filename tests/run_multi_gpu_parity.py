@@ -1,7 +1,8 @@
 """Multi-GPU parity driver (launch with torchrun, one rank per GPU):
 every rank hosts one subdomain, halo + coarse gather go over NCCL; each rank
 rebuilds the whole decomposition with the CPU oracle (small sizes) and checks its
-own slice of apply / deflation / GMV / GMRES.  Exit code != 0 on mismatch."""
+own slice of apply / deflation / GMV / GMRES.  Exit code != 0 on mismatch.
+PARITY_SCALAR=z runs the complex instantiation (hpddm_b200z_*): 3-D Helmholtz, ORAS, plane-wave coarse vectors."""
 import os
 import sys
 
@@ -25,15 +26,25 @@ def main():
     grid = split_grid_3d(world)
     m = int(os.environ.get("PARITY_M", 10))
     N = tuple(g * m for g in grid)
-    parts = generate_world(world, dim=3, N=N, overlap=1, mu=2, grid=grid, neumann=True)
-    w = SchwarzWorld(parts)
-    w.multiplicity_scaling()
-    w.numfact()
-    w.solve_gevp([p["MatNeumann"] for p in parts], nu=3)
+    cplx = os.environ.get("PARITY_SCALAR", "d") == "z"
+    if cplx:
+        from hpddm_b200.examples.generate import generate_helmholtz3d
+        from oracle.schwarz import OG
+        parts = [generate_helmholtz3d(r, world, N=N, overlap=1, mu=2, grid=grid, k=2.0, nu=3) for r in range(world)]
+        w = SchwarzWorld(parts, method=OG)
+        w.multiplicity_scaling()
+        w.numfact([p["MatRobin"] for p in parts])
+        w.set_vectors([p["Z"] for p in parts])
+    else:
+        parts = generate_world(world, dim=3, N=N, overlap=1, mu=2, grid=grid, neumann=True)
+        w = SchwarzWorld(parts)
+        w.multiplicity_scaling()
+        w.numfact()
+        w.solve_gevp([p["MatNeumann"] for p in parts], nu=3)
     if os.environ.get("PARITY_NONUNIFORM"):   # different number of deflation vectors per rank (reference: -nonuniform)
         w.set_vectors([z[:, :1 + (r % 3)] for r, z in enumerate(w.Z)])
     w.build_coarse()
-    deco = Decomposition(local)
+    deco = Decomposition(local, dtype=np.complex128 if cplx else np.float64)
     deco.comm_init_torch()
     p = parts[rank]
     s = deco.add(rank)
@@ -41,13 +52,16 @@ def main():
     s.setGridHint(*p["dims"])
     d = deco.multiplicityScaling([p["d"]])[0]
     ok = np.abs(d - w.d[rank]).max() < 1e-15
-    s.callNumfact()
+    if cplx:
+        s.callNumfact(A=p["MatRobin"], method="oras")
+    else:
+        s.callNumfact()
     s.setVectors(w.Z[rank])
     deco.buildTwo()
     E = deco.getCoarse()
     errs = {"E": np.abs(E - w.E).max() / np.abs(w.E).max()}
     rs = np.random.RandomState(7)
-    x_all = [np.asfortranarray(rs.standard_normal(q["f"].shape)) for q in parts]
+    x_all = [np.asfortranarray(rs.standard_normal(q["f"].shape) + (1j * rs.standard_normal(q["f"].shape) if cplx else 0.0)) for q in parts]
     for name, corr in (("one-level", None), ("deflated", DEFLATED), ("additive", ADDITIVE), ("balanced", BALANCED)):
         ref = w.apply(x_all, corr)[rank]
         got = deco.apply([x_all[rank]], corr)[0]
@@ -60,8 +74,10 @@ def main():
     it_ref, x_ref, _ = gmres(OracleOperator(w, DEFLATED), b_all)
     it_gpu, x_gpu, _ = gmres(KrylovOperator(deco, DEFLATED), [b_all[rank]])
     errs["gmres_x"] = np.abs(x_gpu[0] - x_ref[rank]).max() / np.abs(x_ref[rank]).max()
-    bad = (not ok) or it_gpu != it_ref or any(v > 1e-10 for k, v in errs.items() if k != "gmres_x") or errs["gmres_x"] > 1e-7
-    print(f"rank {rank}/{world}: d_ok={ok} it_gpu={it_gpu} it_ref={it_ref} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()) + (" FAIL" if bad else " OK"), flush=True)
+    it_dev, x_dev, _ = deco.solve([b_all[rank]], correction=DEFLATED)     # device-resident driver (hpddm_b200[z]_solve)
+    errs["gmres_dev_x"] = np.abs(x_dev[0] - x_ref[rank]).max() / np.abs(x_ref[rank]).max()
+    bad = (not ok) or it_gpu != it_ref or it_dev != it_ref or errs["gmres_dev_x"] > 1e-7 or any(v > 1e-10 for k, v in errs.items() if not k.startswith("gmres")) or errs["gmres_x"] > 1e-7
+    print(f"rank {rank}/{world} {'complex' if cplx else 'real'}: d_ok={ok} it_gpu={it_gpu} it_dev={it_dev} it_ref={it_ref} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()) + (" FAIL" if bad else " OK"), flush=True)
     t = torch.tensor([1.0 if bad else 0.0], device="cuda")
     dist.all_reduce(t)
     deco.close()
