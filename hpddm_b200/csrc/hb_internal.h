@@ -254,8 +254,9 @@ int p2p_halo(Ctx *c, K *const *x, int mu);  // 1 = done over peer memory, 0 = us
 int p2p_check(Ctx *c);
 void p2p_free(Ctx *c);
 // Krylov helper kernels (hb_kernels.cu)
-int k_vdots(Ctx *c, const Sub *s, int k, const K *V, const K *w, K *T);               // T[j] += sum_i d_i conj(V[i,j]) w[i]
-int k_vupdate(Ctx *c, const Sub *s, int k, const K *V, const K *h, double sign, K *w);  // w += sign * V h
+// V: k vectors of length n, stride ldv between them (n, or mu * n for one column of a block basis)
+int k_vdots(Ctx *c, const Sub *s, int k, const K *V, int64_t ldv, const K *w, K *T);               // T[j] += sum_i d_i conj(V[i,j]) w[i]
+int k_vupdate(Ctx *c, const Sub *s, int k, const K *V, int64_t ldv, const K *h, double sign, K *w);  // w += sign * V h
 int k_scal_copy(Ctx *c, int64_t n, double a, const K *x, K *y);                       // y = a x
 
 }  // namespace hb

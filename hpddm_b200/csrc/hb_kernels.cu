@@ -65,8 +65,9 @@ __global__ void __launch_bounds__(256) kk_spmv(int n, int mu, const int *__restr
 // Vectors are processed in chunks of KC: KC * 4 independent 8-byte loads per thread are in flight, the
 // KC * MB partial sums are reduced once per chunk (shuffles + one shared-memory pass) and published with
 // one atomic per (CTA, vector, column).
+// ldz = stride between the vectors of Z (n for a contiguous n x nu block; mu * n for one column of a block Krylov basis)
 template <int MB>
-__global__ void __launch_bounds__(256) kk_zt(int n, int nu, int c0, const K *__restrict__ Z, const double *__restrict__ d, const K *__restrict__ x,
+__global__ void __launch_bounds__(256) kk_zt(int n, int nu, int c0, const K *__restrict__ Z, int64_t ldz, const double *__restrict__ d, const K *__restrict__ x,
                                              K *T, int ldT) {
   constexpr int KCR = 8 / MB >= 2 ? 8 / MB : 2;     // 8, 4, 2 vectors per chunk for real scalars
   constexpr int KC = KCR / KD >= 1 ? KCR / KD : 1;  // complex: half as many (same bytes in flight)
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(256) kk_zt(int n, int nu, int c0, const K *__r
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int i = base + tid + 256 * q;
-        z[kk][q] = (k0 + kk < nu && i < n) ? hb_conj(Z[i + (int64_t)(k0 + kk) * n]) : mk(0.0);
+        z[kk][q] = (k0 + kk < nu && i < n) ? hb_conj(Z[i + (int64_t)(k0 + kk) * ldz]) : mk(0.0);
       }
     K acc[KC][MB];
 #pragma unroll
@@ -225,8 +226,8 @@ __global__ void kk_bc(int nbc, int n, int mu, const int *__restrict__ idx, const
   x[idx[q] + (int64_t)c * n] = b[idx[q] + (int64_t)c * n] / val[q];
 }
 
-// w[i] += sign * sum_j V[i + j*n] h[j]   (Gram-Schmidt update / Krylov linear combination)
-__global__ void __launch_bounds__(256) kk_vupdate(int n, int k, const K *__restrict__ V, const K *__restrict__ h, double sign, K *w) {
+// w[i] += sign * sum_j V[i + j*ldv] h[j]   (Gram-Schmidt update / Krylov linear combination)
+__global__ void __launch_bounds__(256) kk_vupdate(int n, int k, const K *__restrict__ V, int64_t ldv, const K *__restrict__ h, double sign, K *w) {
   extern __shared__ __align__(16) unsigned char hs_raw[];
   K *hs = reinterpret_cast<K *>(hs_raw);
   for (int t = threadIdx.x; t < k; t += blockDim.x) hs[t] = h[t];
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(256) kk_vupdate(int n, int k, const K *__restr
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   K acc = mk(0.0);
-  for (int j = 0; j < k; ++j) acc = hb_fma(V[i + (int64_t)j * n], hs[j], acc);
+  for (int j = 0; j < k; ++j) acc = hb_fma(V[i + (int64_t)j * ldv], hs[j], acc);
   w[i] = hb_fma(sign, acc, w[i]);
 }
 __global__ void kk_scal_copy(int64_t n, double a, const K *__restrict__ x, K *y) {
@@ -297,13 +298,13 @@ int k_zt_raw(Ctx *c, int n, int nu, const K *Z, const double *d, int mu, const K
   while (c0 < mu) {
     const int left = mu - c0;
     if (left >= 4) {
-      kk_zt<4><<<g, 256, 0, c->stream>>>(n, nu, c0, Z, d, x, T, ldT);
+      kk_zt<4><<<g, 256, 0, c->stream>>>(n, nu, c0, Z, n, d, x, T, ldT);
       c0 += 4;
     } else if (left >= 2) {
-      kk_zt<2><<<g, 256, 0, c->stream>>>(n, nu, c0, Z, d, x, T, ldT);
+      kk_zt<2><<<g, 256, 0, c->stream>>>(n, nu, c0, Z, n, d, x, T, ldT);
       c0 += 2;
     } else {
-      kk_zt<1><<<g, 256, 0, c->stream>>>(n, nu, c0, Z, d, x, T, ldT);
+      kk_zt<1><<<g, 256, 0, c->stream>>>(n, nu, c0, Z, n, d, x, T, ldT);
       c0 += 1;
     }
     c->launches++;
@@ -360,14 +361,14 @@ int k_coarse_solve(Ctx *c, int mu) {
   kk_coarse<<<1, 256, 0, c->stream>>>(c->Nc, mu, c->Lnu, c->d_rowproc, c->d_rowloc, c->d_E, c->d_Einv, c->d_T, c->d_Y, c->d_R);
   HB_LAUNCH_END(c);
 }
-int k_vdots(Ctx *c, const Sub *s, int k, const K *V, const K *w, K *T) {
+int k_vdots(Ctx *c, const Sub *s, int k, const K *V, int64_t ldv, const K *w, K *T) {
   if (s->n == 0 || k == 0) return 0;
-  kk_zt<1><<<grid1(s->n, 1024), 256, 0, c->stream>>>(s->n, k, 0, V, s->d_d, w, T, k);
+  kk_zt<1><<<grid1(s->n, 1024), 256, 0, c->stream>>>(s->n, k, 0, V, ldv, s->d_d, w, T, k);
   HB_LAUNCH_END(c);
 }
-int k_vupdate(Ctx *c, const Sub *s, int k, const K *V, const K *h, double sign, K *w) {
+int k_vupdate(Ctx *c, const Sub *s, int k, const K *V, int64_t ldv, const K *h, double sign, K *w) {
   if (s->n == 0 || k == 0) return 0;
-  kk_vupdate<<<grid1(s->n), 256, k * sizeof(K), c->stream>>>(s->n, k, V, h, sign, w);
+  kk_vupdate<<<grid1(s->n), 256, k * sizeof(K), c->stream>>>(s->n, k, V, ldv, h, sign, w);
   HB_LAUNCH_END(c);
 }
 int k_scal_copy(Ctx *c, int64_t n, double a, const K *x, K *y) {

@@ -13,28 +13,36 @@ namespace hb {
 
 namespace {
 
-// D-weighted dots of k basis vectors (per subdomain V_s, n_s x k) with w, reduced over the local
-// subdomains and all processes, returned on the host
-// (conjugated on V: iterative.hpp:503,517)
-int dots(Ctx *c, int k, const std::vector<K *> &V, const std::vector<K *> &w, K *d_T, std::vector<K> &out) {
-  HB_CUDA(cudaMemsetAsync(d_T, 0, k * sizeof(K), c->stream));
-  for (size_t i = 0; i < c->subs.size(); ++i) HB_CHECK(k_vdots(c, c->subs[i], k, V[i], w[i], d_T));
-  HB_CHECK(nccl_allreduce_sum(c, reinterpret_cast<double *>(d_T), k * KD));
-  out.resize(k);
-  HB_CUDA(cudaMemcpyAsync(out.data(), d_T, k * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+// D-weighted products of the first k basis vectors of every column with that column of w (conjugated on V:
+// iterative.hpp:503,517), reduced over the local subdomains and all processes, returned on the host:
+// out[nu * k + r] = sum_i d_i conj(V_r[i, nu]) w[i, nu].  V[q] is the block basis of subdomain q (vector r = n_q x mu
+// block at V[q] + r * mu * n_q, reference layout v[r] + nu * n), so one column's vectors are mu * n apart.
+int dots(Ctx *c, int k, int mu, const std::vector<K *> &V, const std::vector<K *> &w, K *d_T, std::vector<K> &out) {
+  HB_CUDA(cudaMemsetAsync(d_T, 0, (size_t)k * mu * sizeof(K), c->stream));
+  for (size_t q = 0; q < c->subs.size(); ++q) {
+    const size_t n = c->subs[q]->n;
+    for (int nu = 0; nu < mu; ++nu) HB_CHECK(k_vdots(c, c->subs[q], k, V[q] + nu * n, (int64_t)mu * n, w[q] + nu * n, d_T + (size_t)nu * k));
+  }
+  HB_CHECK(nccl_allreduce_sum(c, reinterpret_cast<double *>(d_T), k * mu * KD));
+  out.resize((size_t)k * mu);
+  HB_CUDA(cudaMemcpyAsync(out.data(), d_T, (size_t)k * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
 }  // namespace
 
-// one right-hand side; b, x: device pointers per local subdomain (x holds the initial guess)
-int gmres_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *> &x, int correction, int restart, int max_it, double tol,
+// IterativeMethod::GMRES for mu right-hand sides advancing together (GMRES.hpp:31-158: every column has its own Krylov
+// space, Hessenberg matrix and rotations, but the preconditioner and the operator are applied to the n x mu block at once,
+// so the factor panels are streamed once per iteration for all columns).  b, x: device pointers per local subdomain,
+// column-major n x mu (x holds the initial guess).  hasConverged semantics as in the reference: a converged column keeps
+// its dimension for the next solution update and is frozen afterwards (GMRES.hpp:90-92, iterative.hpp:98-103,272-336).
+int gmres_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *> &x, int mu, int correction, int restart, int max_it, double tol,
                  int *iterations, double *rel_residual) {
   const size_t L = c->subs.size();
   const int m = restart;
   std::vector<K *> V(L, nullptr), w(L), z(L), t(L);
-  std::vector<const K *> cz(L), cw(L);
+  std::vector<const K *> cz(L), ct(L);
   K *d_T = nullptr, *d_h = nullptr;
   auto cleanup = [&]() {
     for (K *p : V) cudaFree(p);
@@ -60,126 +68,161 @@ int gmres_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *>
     if (e__ != cudaSuccess) {                                                                     \
       set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
       cleanup();                                                                                  \
-      return HPDDM_B200_ERR_CUDA;                                                                 \
+      return e__ == cudaErrorMemoryAllocation ? HPDDM_B200_ERR_NOMEM : HPDDM_B200_ERR_CUDA;        \
     }                                                                                             \
   } while (0)
   for (size_t i = 0; i < L; ++i) {
-    const size_t n = std::max<size_t>(c->subs[i]->n, 1);
+    const size_t len = std::max<size_t>((size_t)c->subs[i]->n * mu, 1);
     w[i] = z[i] = t[i] = nullptr;
-    KRC(cudaMalloc(&V[i], n * (m + 1) * sizeof(K)));
-    KRC(cudaMalloc(&w[i], n * sizeof(K)));
-    KRC(cudaMalloc(&z[i], n * sizeof(K)));
-    KRC(cudaMalloc(&t[i], n * sizeof(K)));
+    KRC(cudaMalloc(&V[i], len * (m + 1) * sizeof(K)));
+    KRC(cudaMalloc(&w[i], len * sizeof(K)));
+    KRC(cudaMalloc(&z[i], len * sizeof(K)));
+    KRC(cudaMalloc(&t[i], len * sizeof(K)));
     cz[i] = z[i];
-    cw[i] = w[i];
+    ct[i] = t[i];
   }
-  KRC(cudaMalloc(&d_T, (m + 2) * sizeof(K)));
-  KRC(cudaMalloc(&d_h, (m + 2) * sizeof(K)));
+  KRC(cudaMalloc(&d_T, (size_t)(m + 2) * mu * sizeof(K)));
+  KRC(cudaMalloc(&d_h, (size_t)(m + 2) * mu * sizeof(K)));
   std::vector<K> hv;
+  auto len_of = [&](size_t q) { return (int64_t)c->subs[q]->n * mu; };
+  auto col = [&](K *base, size_t q, int nu) { return base + (size_t)nu * c->subs[q]->n; };
+  auto vec = [&](size_t q, int r) { return V[q] + (size_t)r * mu * c->subs[q]->n; };
   // Schwarz::start (schwarz.hpp:496-514): penalised rows + exchange(x)
   for (size_t i = 0; i < L; ++i) {
     Sub *s = c->subs[i];
-    KR(k_bc(c, s, 1, b[i], x[i]));
-    KR(k_scale(c, s->n, 1, s->d_d, x[i], x[i]));
+    KR(k_bc(c, s, mu, b[i], x[i]));
+    KR(k_scale(c, s->n, mu, s->d_d, x[i], x[i]));
   }
-  KR(halo(c, x.data(), 1));
-  // ||b||_D (iterative.hpp:455-468)
+  KR(halo(c, x.data(), mu));
+  // ||b||_D per column (iterative.hpp:455-468)
+  std::vector<double> normb(mu);
   {
     std::vector<K *> bb(L);
     for (size_t i = 0; i < L; ++i) bb[i] = const_cast<K *>(b[i]);
-    KR(dots(c, 1, bb, bb, d_T, hv));
+    KR(dots(c, 1, mu, bb, bb, d_T, hv));  // (a single "vector" per column: stride irrelevant)
+    for (int nu = 0; nu < mu; ++nu) {
+      normb[nu] = std::sqrt(hb_real(hv[nu]));
+      if (normb[nu] < 1e-12) normb[nu] = 1.0;
+    }
   }
-  double normb = std::sqrt(hb_real(hv[0]));
-  if (normb < 1e-12) normb = 1.0;
-  // Givens rotations as the reference stores them (iterative.hpp:690-710): cosine in K, sine real
-  std::vector<K> H((size_t)(m + 1) * m, mk(0.0)), cs(m), sv(m + 1), y(m);
-  std::vector<double> sn(m);
+  // per column: Hessenberg (m+1) x m, Givens rotations as the reference stores them (iterative.hpp:690-710: cosine in K,
+  // sine real), rotated right-hand side sv, hasConverged
+  const size_t hs = (size_t)(m + 1) * m;
+  std::vector<K> H(hs * mu, mk(0.0)), cs((size_t)m * mu), sv((size_t)(m + 1) * mu), y(m);
+  std::vector<double> sn((size_t)m * mu), res(mu, 0.0);
+  std::vector<int> conv(mu, -m);
   int j = 1;
-  double res = 0.0;
   bool done = false;
   while (j <= max_it) {
     // v0 = b - A x
     {
       std::vector<const K *> cx(L);
       for (size_t i = 0; i < L; ++i) cx[i] = x[i];
-      KR(gmv_core(c, cx, w, 1));
+      KR(gmv_core(c, cx, w, mu));
     }
     for (size_t i = 0; i < L; ++i) {
-      KR(k_scal_copy(c, c->subs[i]->n, -1.0, w[i], w[i]));
-      KR(k_axpy(c, c->subs[i]->n, 1.0, b[i], w[i]));
+      KR(k_scal_copy(c, len_of(i), -1.0, w[i], w[i]));
+      KR(k_axpy(c, len_of(i), 1.0, b[i], w[i]));
     }
-    KR(dots(c, 1, w, w, d_T, hv));
-    if (j == 1 && hb_real(hv[0]) < 4.930380657631324e-32) {  // eps^2 (GMRES.hpp:75)
-      j = 0;
-      break;
+    KR(dots(c, 1, mu, w, w, d_T, hv));
+    if (j == 1) {
+      bool tiny = false;
+      for (int nu = 0; nu < mu; ++nu) tiny = tiny || hb_real(hv[nu]) < 4.930380657631324e-32;  // eps^2 (GMRES.hpp:75)
+      if (tiny) {
+        j = 0;
+        break;
+      }
     }
-    sv.assign(m + 1, mk(0.0));
-    const double beta0 = std::sqrt(hb_real(hv[0]));
-    sv[0] = mk(beta0);
-    for (size_t i = 0; i < L; ++i) KR(k_scal_copy(c, c->subs[i]->n, 1.0 / beta0, w[i], V[i]));
+    std::fill(sv.begin(), sv.end(), mk(0.0));
+    for (int nu = 0; nu < mu; ++nu) {
+      if (conv[nu] > 0) conv[nu] = 0;  // GMRES.hpp:91
+      const double beta0 = std::sqrt(hb_real(hv[nu]));
+      sv[(size_t)nu * (m + 1)] = mk(beta0);
+      for (size_t q = 0; q < L; ++q) KR(k_scal_copy(c, c->subs[q]->n, 1.0 / beta0, col(w[q], q, nu), col(vec(q, 0), q, nu)));
+    }
     std::fill(H.begin(), H.end(), mk(0.0));
     int i = 0;
     done = false;
     while (i < m && j <= max_it) {
       std::vector<const K *> vi(L);
-      for (size_t q = 0; q < L; ++q) vi[q] = V[q] + (size_t)i * c->subs[q]->n;
-      KR(apply_core(c, vi, z, 1, correction));  // z = M^-1 v_i   (GMRES.hpp:116)
-      KR(gmv_core(c, cz, w, 1));                // w = A z        (GMRES.hpp:117)
-      KR(dots(c, i + 1, V, w, d_T, hv));        // classical Gram-Schmidt: all products first
-      KRC(cudaMemcpyAsync(d_h, hv.data(), (i + 1) * sizeof(K), cudaMemcpyHostToDevice, c->stream));
-      for (size_t q = 0; q < L; ++q) KR(k_vupdate(c, c->subs[q], i + 1, V[q], d_h, -1.0, w[q]));
-      std::vector<K> hcol(hv);
-      KR(dots(c, 1, w, w, d_T, hv));
-      const double hn = std::sqrt(hb_real(hv[0]));
-      for (int k = 0; k <= i; ++k) H[k + (size_t)i * (m + 1)] = hcol[k];
-      H[i + 1 + (size_t)i * (m + 1)] = mk(hn);
-      if (i < m - 1)
-        for (size_t q = 0; q < L; ++q) KR(k_scal_copy(c, c->subs[q]->n, hn == 0.0 ? 1.0 : 1.0 / hn, w[q], V[q] + (size_t)(i + 1) * c->subs[q]->n));
-      K *Hc = &H[(size_t)i * (m + 1)];
-      for (int k = 0; k < i; ++k) {  // previous rotations (iterative.hpp:690-697)
-        const K g = hb_conj(cs[k]) * Hc[k] + sn[k] * Hc[k + 1];
-        Hc[k + 1] = cs[k] * Hc[k + 1] - sn[k] * Hc[k];
-        Hc[k] = g;
+      for (size_t q = 0; q < L; ++q) vi[q] = vec(q, i);
+      KR(apply_core(c, vi, z, mu, correction));  // z = M^-1 v_i   (GMRES.hpp:116), all columns at once
+      KR(gmv_core(c, cz, w, mu));                // w = A z        (GMRES.hpp:117)
+      KR(dots(c, i + 1, mu, V, w, d_T, hv));     // classical Gram-Schmidt: all products first
+      KRC(cudaMemcpyAsync(d_h, hv.data(), (size_t)(i + 1) * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+      for (size_t q = 0; q < L; ++q)
+        for (int nu = 0; nu < mu; ++nu)
+          KR(k_vupdate(c, c->subs[q], i + 1, col(V[q], q, nu), (int64_t)mu * c->subs[q]->n, d_h + (size_t)nu * (i + 1), -1.0, col(w[q], q, nu)));
+      const std::vector<K> hcol(hv);
+      KR(dots(c, 1, mu, w, w, d_T, hv));
+      for (int nu = 0; nu < mu; ++nu) {
+        const double hn = std::sqrt(hb_real(hv[nu]));
+        K *Hc = &H[hs * nu + (size_t)i * (m + 1)];
+        K *cc = &cs[(size_t)m * nu];
+        double *ss = &sn[(size_t)m * nu];
+        K *sq = &sv[(size_t)nu * (m + 1)];
+        for (int k = 0; k <= i; ++k) Hc[k] = hcol[(size_t)nu * (i + 1) + k];
+        Hc[i + 1] = mk(hn);
+        if (i < m - 1)
+          for (size_t q = 0; q < L; ++q) KR(k_scal_copy(c, c->subs[q]->n, hn == 0.0 ? 1.0 : 1.0 / hn, col(w[q], q, nu), col(vec(q, i + 1), q, nu)));
+        for (int k = 0; k < i; ++k) {  // previous rotations (iterative.hpp:690-697)
+          const K g = hb_conj(cc[k]) * Hc[k] + ss[k] * Hc[k + 1];
+          Hc[k + 1] = cc[k] * Hc[k + 1] - ss[k] * Hc[k];
+          Hc[k] = g;
+        }
+        const double delta = std::hypot(hb_abs(Hc[i]), hb_abs(Hc[i + 1]));  // nrm2 of the two entries (iterative.hpp:701)
+        ss[i] = hb_real(Hc[i + 1]) / delta;
+        cc[i] = Hc[i] / delta;
+        Hc[i] = mk(delta);
+        Hc[i + 1] = mk(0.0);
+        sq[i + 1] = -ss[i] * sq[i];
+        sq[i] = sq[i] * hb_conj(cc[i]);
       }
-      const double delta = std::hypot(hb_abs(Hc[i]), hb_abs(Hc[i + 1]));  // nrm2 of the two entries (iterative.hpp:701)
-      sn[i] = hb_real(Hc[i + 1]) / delta;
-      cs[i] = Hc[i] / delta;
-      Hc[i] = mk(delta);
-      Hc[i + 1] = mk(0.0);
-      sv[i + 1] = -sn[i] * sv[i];
-      sv[i] = sv[i] * hb_conj(cs[i]);
       ++i;
-      res = hb_abs(sv[i]);
-      if (res / normb <= tol) {  // checkConvergence (iterative.hpp:98-103)
+      bool all = true;
+      for (int nu = 0; nu < mu; ++nu) {
+        res[nu] = hb_abs(sv[(size_t)nu * (m + 1) + i]);
+        if (conv[nu] == -m && res[nu] / normb[nu] <= tol) conv[nu] = i;  // checkConvergence (iterative.hpp:98-103)
+        all = all && conv[nu] != -m;
+      }
+      if (all) {
         done = true;
         break;
       }
       ++j;
     }
-    // updateSol (iterative.hpp:272-336): y = H^-1 s, x += M^-1 (V y)
-    const int dim = i;
-    for (int k = dim - 1; k >= 0; --k) {
-      K acc = sv[k];
-      for (int l = k + 1; l < dim; ++l) acc -= H[k + (size_t)l * (m + 1)] * y[l];
-      y[k] = acc / H[k + (size_t)k * (m + 1)];
-    }
-    if (dim > 0) {
-      KRC(cudaMemcpyAsync(d_h, y.data(), dim * sizeof(K), cudaMemcpyHostToDevice, c->stream));
-      for (size_t q = 0; q < L; ++q) {
-        KRC(cudaMemsetAsync(t[q], 0, (size_t)c->subs[q]->n * sizeof(K), c->stream));
-        KR(k_vupdate(c, c->subs[q], dim, V[q], d_h, 1.0, t[q]));
+    // updateSol (iterative.hpp:272-336): per column y = H^-1 s over its own dimension, x += M^-1 (V y)
+    bool any = false;
+    for (size_t q = 0; q < L; ++q) KRC(cudaMemsetAsync(t[q], 0, (size_t)len_of(q) * sizeof(K), c->stream));
+    for (int nu = 0; nu < mu; ++nu) {
+      int dim = conv[nu] != 0 ? std::abs(conv[nu]) : 0;
+      if (!done && conv[nu] == -m) dim = i;  // restart (i == m) or iteration limit (i = iterations of this cycle)
+      if (dim == 0) continue;
+      any = true;
+      const K *Hn = &H[hs * nu];
+      const K *sq = &sv[(size_t)nu * (m + 1)];
+      for (int k = dim - 1; k >= 0; --k) {
+        K acc = sq[k];
+        for (int l = k + 1; l < dim; ++l) acc -= Hn[k + (size_t)l * (m + 1)] * y[l];
+        y[k] = acc / Hn[k + (size_t)k * (m + 1)];
       }
-      std::vector<const K *> ct(L);
-      for (size_t q = 0; q < L; ++q) ct[q] = t[q];
-      KR(apply_core(c, ct, z, 1, correction));
-      for (size_t q = 0; q < L; ++q) KR(k_axpy(c, c->subs[q]->n, 1.0, z[q], x[q]));
+      KRC(cudaMemcpyAsync(d_h + (size_t)nu * (m + 1), y.data(), dim * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+      KRC(cudaStreamSynchronize(c->stream));  // y is reused by the next column
+      for (size_t q = 0; q < L; ++q) KR(k_vupdate(c, c->subs[q], dim, col(V[q], q, nu), (int64_t)mu * c->subs[q]->n, d_h + (size_t)nu * (m + 1), 1.0, col(t[q], q, nu)));
+    }
+    if (any) {
+      KR(apply_core(c, ct, z, mu, correction));
+      for (size_t q = 0; q < L; ++q)
+        for (int nu = 0; nu < mu; ++nu)
+          if (conv[nu] != 0) KR(k_axpy(c, c->subs[q]->n, 1.0, col(z[q], q, nu), col(x[q], q, nu)));
     }
     if (done || j > max_it) break;
   }
   KRC(cudaStreamSynchronize(c->stream));
   cleanup();
   *iterations = std::min(j, max_it);
-  if (rel_residual) *rel_residual = res / normb;
+  if (rel_residual)
+    for (int nu = 0; nu < mu; ++nu) rel_residual[nu] = res[nu] / normb[nu];
   return 0;
 #undef KR
 #undef KRC
@@ -212,20 +255,9 @@ extern "C" int HB_API(solve)(hb_ctx_t *ctx, const K *const *b, K *const *x, int 
       xd[i] = x[i];
     }
   }
-  int itmax = 0, rc = 0;
-  for (int col = 0; col < mu && rc == 0; ++col) {  // every column runs its own Krylov space (pseudo-block, like the reference's non-block GMRES)
-    std::vector<const K *> bc(L);
-    std::vector<K *> xc(L);
-    for (size_t i = 0; i < L; ++i) {
-      bc[i] = bd[i] + (size_t)col * c->subs[i]->n;
-      xc[i] = xd[i] + (size_t)col * c->subs[i]->n;
-    }
-    int it = 0;
-    double rr = 0.0;
-    rc = gmres_device(c, bc, xc, correction, restart, max_it, tol, &it, &rr);
-    itmax = std::max(itmax, it);
-    if (rel_residual) rel_residual[col] = rr;
-  }
+  int itmax = 0;
+  std::vector<const K *> bc(bd.begin(), bd.end());
+  const int rc = gmres_device(c, bc, xd, mu, correction, restart, max_it, tol, &itmax, rel_residual);  // all columns advance together
   if (where == HPDDM_B200_HOST) {
     if (rc == 0)
       for (size_t i = 0; i < L; ++i) cudaMemcpyAsync(x[i], xd[i], (size_t)c->subs[i]->n * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream);

@@ -28,6 +28,13 @@ CASES = {
     "small_40x40_p4_twolevel_nu3": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40"]),
     "small_48x30_p6_ov2_twolevel_nu2": dict(np=6, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "2", "-Nx", "48", "-Ny", "30", "-overlap", "2"]),
     "small_36x36_p4_symcsr_twolevel_nu2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "2", "-Nx", "36", "-Ny", "36", "-symmetric_csr", "1"]),
+    # several right-hand sides advancing together (IterativeMethod::GMRES with mu > 1: per-column hasConverged, GMRES.hpp:90-158),
+    # with restarts so that columns converge in different cycles
+    "small_40x40_p4_mu3_gmres": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "3"]),
+    "small_40x40_p4_mu3_twolevel_restart5": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40",
+                                                             "-generate_random_rhs", "3", "-hpddm_gmres_restart", "5", "-hpddm_tol", "1e-9"]),
+    "complex_40x40_p4_mu2_twolevel": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40",
+                                                              "-generate_random_rhs", "2"]),
     # complex scalars (the reference's FORCE_COMPLEX build; damped-Helmholtz-like shift of the generator's matrix, see ref_driver.cpp)
     "complex_40x40_p4_ras": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40"]),
     "complex_40x40_p4_twolevel_nu3": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40"]),

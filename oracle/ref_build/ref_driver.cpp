@@ -57,7 +57,9 @@ int main(int argc, char **argv) {
   HPDDM::underlying_type<K> *d = nullptr;
   int ndof;
   generate(rankWorld, sizeWorld, o, mapping, ndof, Mat, MatNeumann, d, f, sol);
-  const int mu = 1;
+  // -generate_random_rhs N: N random right-hand sides from the reference's generator (made consistent with exchange<true>
+  // like examples/schwarz.cpp:98) solved together -- pins the multi-RHS semantics of IterativeMethod::GMRES / BGMRES
+  const int mu = std::max(1, (int)opt.app()["generate_random_rhs"]);
 #ifdef FORCE_COMPLEX
   // A <- A - (k^2 - i sigma) I : indefinite, complex symmetric, non-Hermitian (full CSR storage only)
   for (int i = 0; i < ndof; ++i) {
@@ -76,7 +78,7 @@ int main(int argc, char **argv) {
 #ifdef FORCE_COMPLEX
     dumpd("f_local", f, ndof);  // perturbed per rank: not yet consistent on the overlap (made so below, like schwarz.cpp:98)
 #else
-    dumpd("f", f, ndof);
+    if (mu == 1) dumpd("f", f, ndof);
 #endif
     std::vector<int> ov(o.begin(), o.end());
     dumpi("o", ov.data(), ov.size());
@@ -89,8 +91,13 @@ int main(int argc, char **argv) {
   A.initialize(d);
   dumpd("d", d, ndof);
 #ifdef FORCE_COMPLEX
-  A.exchange<true>(f, 1);  // consistent right-hand side (examples/schwarz.cpp:98 does the same for its random ones)
-  dumpd("f", f, ndof);
+  A.exchange<true>(f, mu);  // consistent right-hand side (examples/schwarz.cpp:98 does the same for its random ones)
+  dumpd("f", f, (long long)mu * ndof);
+#else
+  if (mu > 1) {
+    A.exchange<true>(f, mu);
+    dumpd("f", f, (long long)mu * ndof);
+  }
 #endif
   const int nuOpt = (int)opt.app()["deflation_vectors"];
   int nu = 0;
@@ -148,11 +155,11 @@ int main(int argc, char **argv) {
     A.end(alloc);
   }
   int it = HPDDM::IterativeMethod::solve(A, f, sol, mu, A.getCommunicator());
-  HPDDM::underlying_type<K> storage[2];
-  A.computeResidual(sol, f, storage, mu);
+  std::vector<HPDDM::underlying_type<K>> storage(2 * mu);
+  A.computeResidual(sol, f, storage.data(), mu);
   dumpi("iterations", &it, 1);
-  dumpd("sol", sol, ndof);
-  dumpd("residual", storage, 2);
+  dumpd("sol", sol, (long long)mu * ndof);
+  dumpd("residual", storage.data(), 2 * mu);
   if (rankWorld == 0) printf("ref_driver: %d ranks, ndof %d, nu %d, it %d, residual %.3e / %.3e\n", sizeWorld, ndof, nu, it, storage[1], storage[0]);
   fclose(g_out);
   delete[] d;

@@ -34,12 +34,14 @@ def load(name):
         n, nnz, sym, _ = [int(v) for v in g["header"]]
         Mat = sp.csr_matrix((g["a"], g["ja"], g["ia"]), shape=(n, n))
         mapping = [g[f"mapping{i}"] for i in range(len(g["o"]))]
+        g["sol"] = np.asfortranarray(g["sol"].reshape(-1, n).T)     # n x mu, column-major like the reference's buffers
         parts.append(dict(o=[int(v) for v in g["o"]], mapping=mapping, ndof=n, Mat=Mat, sym=bool(sym), d=g["d_ramp"].copy(),
-                          f=np.asfortranarray(g["f"].reshape(-1, 1))))
+                          f=np.asfortranarray(g["f"].reshape(-1, n).T)))
         ref.append(g)
-    meta = dict(P=P, args=args, complex=bool(np.iscomplexobj(ref[0]["a"])), Nx=int(arg_value(args, "Nx", 100)), Ny=int(arg_value(args, "Ny", 100)), overlap=int(arg_value(args, "overlap", 1)),
+    meta = dict(P=P, args=args, mu=max(1, int(arg_value(args, "generate_random_rhs", 0))), complex=bool(np.iscomplexobj(ref[0]["a"])), Nx=int(arg_value(args, "Nx", 100)), Ny=int(arg_value(args, "Ny", 100)), overlap=int(arg_value(args, "overlap", 1)),
                 sym=arg_value(args, "symmetric_csr", "0") == "1", nu=int(arg_value(args, "deflation_vectors", 0)),
-                restart=int(arg_value(args, "hpddm_gmres_restart", 40)), max_it=int(arg_value(args, "hpddm_max_it", 100)))
+                restart=int(arg_value(args, "hpddm_gmres_restart", 40)), max_it=int(arg_value(args, "hpddm_max_it", 100)),
+                tol=float(arg_value(args, "hpddm_tol", 1e-6)))
     return parts, ref, meta
 
 

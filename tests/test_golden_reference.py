@@ -31,7 +31,8 @@ def test_generator_is_bit_identical_to_examples_generate_cpp(name):
         assert mine["o"] == [int(v) for v in g["o"]]
         for a, b in zip(mine["mapping"], parts[r]["mapping"]):
             assert np.array_equal(a, b)
-        assert rel(mine["f"], g["f_local" if meta["complex"] else "f"]) < 1e-15
+        if meta["mu"] == 1:   # (random right-hand sides of -generate_random_rhs come from std::random_device: inputs, not reproducible)
+            assert rel(mine["f"], g["f_local" if meta["complex"] else "f"]) < 1e-15
 
 
 @pytest.mark.parametrize("name", cases())
@@ -62,9 +63,10 @@ def test_oracle_reproduces_the_reference(name):
             assert max(rel(got[r], ref[r][key]) for r in range(P)) < TOL, key
         corr = DEFLATED
     b = [parts[r]["f"].copy() for r in range(P)]
-    it, x, _ = gmres(OracleOperator(w, corr), b, restart=meta["restart"], max_it=meta["max_it"])
+    it, x, _ = gmres(OracleOperator(w, corr), b, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])
     assert it == int(ref[0]["iterations"][0])                      # identical Krylov iteration count
     assert max(rel(x[r], ref[r]["sol"]) for r in range(P)) < 1e-7
     res = w.compute_residual(x, b)
-    assert abs(res[0, 0] - ref[0]["residual"][0]) < 1e-10 * ref[0]["residual"][0]
-    assert abs(res[0, 1] - ref[0]["residual"][1]) < 1e-3 * ref[0]["residual"][1]
+    gold = ref[0]["residual"].reshape(-1, 2)                       # per right-hand side: ||f||_D, ||A x - f||_D
+    assert np.abs(res[:, 0] - gold[:, 0]).max() < 1e-10 * gold[:, 0].max()
+    assert np.all(np.abs(res[:, 1] - gold[:, 1]) < 1e-3 * gold[:, 1])
