@@ -228,21 +228,151 @@ int gmres_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *>
 #undef KRC
 }
 
+
+// IterativeMethod::CG (include/HPDDM_CG.hpp:31-168, non-flexible variant): preconditioned conjugate gradient with the
+// reference's D-weighted inner products sum_i d_i conj(x_i) y_i, all mu right-hand sides advancing together, convergence
+// when ||M^-1 r||_D / ||M^-1 r_0||_D <= tol per column (CG.hpp:60-64,139-140).  r, p, z stay in HBM; 2 mu scalars cross PCIe
+// twice per iteration.
+int cg_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *> &x, int mu, int correction, int max_it, double tol, int *iterations,
+              double *rel_residual) {
+  const size_t L = c->subs.size();
+  std::vector<K *> r(L, nullptr), p(L, nullptr), z(L, nullptr);
+  std::vector<const K *> cr(L), cp(L), cx(L);
+  K *d_dir = nullptr;
+  auto cleanup = [&]() {
+    for (size_t i = 0; i < L; ++i) {
+      cudaFree(r[i]);
+      cudaFree(p[i]);
+      cudaFree(z[i]);
+    }
+    cudaFree(d_dir);
+  };
+#define KR(call)        \
+  do {                  \
+    int r__ = (call);   \
+    if (r__ < 0) {      \
+      cleanup();        \
+      return r__;       \
+    }                   \
+  } while (0)
+#define KRC(call)                                                                                 \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+      cleanup();                                                                                  \
+      return e__ == cudaErrorMemoryAllocation ? HPDDM_B200_ERR_NOMEM : HPDDM_B200_ERR_CUDA;        \
+    }                                                                                             \
+  } while (0)
+  auto len_of = [&](size_t q) { return (int64_t)c->subs[q]->n * mu; };
+  auto col = [&](K *base, size_t q, int nu) { return base + (size_t)nu * c->subs[q]->n; };
+  for (size_t i = 0; i < L; ++i) {
+    const size_t len = std::max<size_t>((size_t)len_of(i), 1);
+    KRC(cudaMalloc(&r[i], len * sizeof(K)));
+    KRC(cudaMalloc(&p[i], len * sizeof(K)));
+    KRC(cudaMalloc(&z[i], len * sizeof(K)));
+    cr[i] = r[i];
+    cp[i] = p[i];
+    cx[i] = x[i];
+  }
+  KRC(cudaMalloc(&d_dir, (size_t)2 * mu * sizeof(K)));
+  std::vector<K> hd((size_t)2 * mu);
+  // two families of D-weighted products, one reduction (CG.hpp:103,120: Allreduce over 2 mu values)
+  auto dots2 = [&](const std::vector<K *> &x0, const std::vector<K *> &y0, const std::vector<K *> *x1, const std::vector<K *> *y1) -> int {
+    HB_CUDA(cudaMemsetAsync(d_dir, 0, (size_t)2 * mu * sizeof(K), c->stream));
+    for (size_t q = 0; q < L; ++q) {
+      HB_CHECK(k_dot(c, c->subs[q], mu, x0[q], y0[q], d_dir));
+      if (x1) HB_CHECK(k_dot(c, c->subs[q], mu, (*x1)[q], (*y1)[q], d_dir + mu));
+    }
+    HB_CHECK(nccl_allreduce_sum(c, reinterpret_cast<double *>(d_dir), 2 * mu * KD));
+    HB_CUDA(cudaMemcpyAsync(hd.data(), d_dir, (size_t)2 * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  };
+  // Schwarz::start, r = b - A x, p = M^-1 r (CG.hpp:60-65)
+  for (size_t i = 0; i < L; ++i) {
+    Sub *s = c->subs[i];
+    KR(k_bc(c, s, mu, b[i], x[i]));
+    KR(k_scale(c, s->n, mu, s->d_d, x[i], x[i]));
+  }
+  KR(halo(c, x.data(), mu));
+  KR(gmv_core(c, cx, z, mu));
+  for (size_t i = 0; i < L; ++i) {
+    KR(k_copy(c, len_of(i), b[i], r[i]));
+    KR(k_axpy(c, len_of(i), -1.0, z[i], r[i]));
+  }
+  KR(apply_core(c, cr, p, mu, correction));
+  KR(dots2(r, p, &p, &p));                            // (r, D p) and ||p||_D^2       (CG.hpp:66-69,87 at i = 0)
+  // rz = (r, D M^-1 r): the reference recomputes it at the top of every iteration (CG.hpp:87) from vectors that have not
+  // changed since the end of the previous one (CG.hpp:110), where it is available already -- kept instead of recomputed
+  std::vector<double> rz(mu), pAp(mu), res(mu), last(mu, 0.0);
+  std::vector<int> conv(mu, -max_it);
+  bool tiny = false;
+  for (int nu = 0; nu < mu; ++nu) {
+    rz[nu] = hb_real(hd[nu]);
+    res[nu] = std::sqrt(hb_real(hd[mu + nu]));
+    tiny = tiny || hb_real(hd[mu + nu]) < 4.930380657631324e-32;  // eps^2 (CG.hpp:85)
+  }
+  int i = 0;
+  if (!tiny) {
+    while (i < max_it) {
+      KR(gmv_core(c, cp, z, mu));                     // z = A p                     (CG.hpp:88)
+      KR(dots2(z, p, nullptr, nullptr));              // (A p, D p)                  (CG.hpp:90)
+      for (int nu = 0; nu < mu; ++nu) pAp[nu] = hb_real(hd[nu]);
+      ++i;
+      for (int nu = 0; nu < mu; ++nu)
+        if (conv[nu] == -max_it) {                    // converged columns are frozen (CG.hpp:99-105)
+          const double alpha = rz[nu] / pAp[nu];
+          for (size_t q = 0; q < L; ++q) {
+            KR(k_axpy(c, c->subs[q]->n, alpha, col(p[q], q, nu), col(x[q], q, nu)));
+            KR(k_axpy(c, c->subs[q]->n, -alpha, col(z[q], q, nu), col(r[q], q, nu)));
+          }
+        }
+      KR(apply_core(c, cr, z, mu, correction));       // z = M^-1 r                  (CG.hpp:107)
+      KR(dots2(r, z, &z, &z));                        // (r, D z) and (z, D z)       (CG.hpp:110-111)
+      for (int nu = 0; nu < mu; ++nu) {
+        const double beta = hb_real(hd[nu]) / rz[nu];
+        rz[nu] = hb_real(hd[nu]);
+        for (size_t q = 0; q < L; ++q) {              // p = z + beta p              (CG.hpp:115)
+          KR(k_scal_copy(c, c->subs[q]->n, beta, col(p[q], q, nu), col(p[q], q, nu)));
+          KR(k_axpy(c, c->subs[q]->n, 1.0, col(z[q], q, nu), col(p[q], q, nu)));
+        }
+        last[nu] = std::sqrt(hb_real(hd[mu + nu]));
+      }
+      bool all = true;
+      for (int nu = 0; nu < mu; ++nu) {
+        if (conv[nu] == -max_it && last[nu] / res[nu] <= tol) conv[nu] = i;  // checkConvergence<2> (iterative.hpp:98-103)
+        all = all && conv[nu] != -max_it;
+      }
+      if (all) {
+        --i;
+        break;
+      }
+    }
+  } else
+    i = -1;
+  ++i;
+  KRC(cudaStreamSynchronize(c->stream));
+  cleanup();
+  *iterations = std::min(i, max_it);
+  if (rel_residual)
+    for (int nu = 0; nu < mu; ++nu) rel_residual[nu] = res[nu] > 0.0 ? last[nu] / res[nu] : 0.0;
+  return 0;
+#undef KR
+#undef KRC
+}
+
 }  // namespace hb
 
 using namespace hb;
 
-extern "C" int HB_API(solve)(hb_ctx_t *ctx, const K *const *b, K *const *x, int mu, int correction, int restart, int max_it, double tol,
-                                int where, int *iterations, double *rel_residual) {
-  Ctx *c = reinterpret_cast<Ctx *>(ctx);
-  if (!iterations || restart < 1 || max_it < 1) {
-    set_error("solve: bad arguments");
-    return HPDDM_B200_ERR_ARG;
-  }
+// stage host vectors (if any), run `method`, copy the solution back
+template <class Method>
+static int krylov_entry(Ctx *c, const K *const *b, K *const *x, int mu, int where, Method method) {
   HB_CHECK(check_ready(c, std::max(mu, 1)));
   const size_t L = c->subs.size();
   // vectors live in private device buffers for the whole solve (d_in / d_out are used by nothing else here)
-  std::vector<K *> bd(L), xd(L);
+  std::vector<K *> bd(L, nullptr), xd(L, nullptr);
   for (size_t i = 0; i < L; ++i) {
     const size_t bytes = std::max<size_t>((size_t)c->subs[i]->n * mu, 1) * sizeof(K);
     if (where == HPDDM_B200_HOST) {
@@ -255,9 +385,8 @@ extern "C" int HB_API(solve)(hb_ctx_t *ctx, const K *const *b, K *const *x, int 
       xd[i] = x[i];
     }
   }
-  int itmax = 0;
   std::vector<const K *> bc(bd.begin(), bd.end());
-  const int rc = gmres_device(c, bc, xd, mu, correction, restart, max_it, tol, &itmax, rel_residual);  // all columns advance together
+  const int rc = method(bc, xd);  // all columns advance together
   if (where == HPDDM_B200_HOST) {
     if (rc == 0)
       for (size_t i = 0; i < L; ++i) cudaMemcpyAsync(x[i], xd[i], (size_t)c->subs[i]->n * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream);
@@ -267,6 +396,36 @@ extern "C" int HB_API(solve)(hb_ctx_t *ctx, const K *const *b, K *const *x, int 
       cudaFree(xd[i]);
     }
   }
-  *iterations = itmax;
   return rc;
+}
+
+extern "C" int HB_API(solve)(hb_ctx_t *ctx, const K *const *b, K *const *x, int mu, int correction, int restart, int max_it, double tol,
+                                int where, int *iterations, double *rel_residual) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !iterations || restart < 1 || max_it < 1 || mu < 1) {
+    set_error("solve: bad arguments");
+    return HPDDM_B200_ERR_ARG;
+  }
+  *iterations = 0;
+  return krylov_entry(c, b, x, mu, where, [&](const std::vector<const K *> &bd, const std::vector<K *> &xd) {
+    return gmres_device(c, bd, xd, mu, correction, restart, max_it, tol, iterations, rel_residual);
+  });
+}
+
+extern "C" int HB_API(solve_cg)(hb_ctx_t *ctx, const K *const *b, K *const *x, int mu, int correction, int max_it, double tol, int where, int *iterations,
+                                   double *rel_residual) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !iterations || max_it < 1 || mu < 1) {
+    set_error("solve_cg: bad arguments");
+    return HPDDM_B200_ERR_ARG;
+  }
+  *iterations = 0;
+  // the reference runs CG only for symmetric preconditioners -- SORAS / ASM / none without a deflated correction -- and
+  // falls back to GMRES otherwise (CG.hpp:41-44)
+  bool symmetric = correction != HPDDM_B200_CORRECTION_DEFLATED;
+  for (Sub *s : c->subs) symmetric = symmetric && (s->prcndtnr == HPDDM_B200_PRCNDTNR_OS || s->prcndtnr == HPDDM_B200_PRCNDTNR_SY || s->prcndtnr == HPDDM_B200_PRCNDTNR_NO);
+  return krylov_entry(c, b, x, mu, where, [&](const std::vector<const K *> &bd, const std::vector<K *> &xd) {
+    if (!symmetric) return gmres_device(c, bd, xd, mu, correction, 40, max_it, tol, iterations, rel_residual);
+    return cg_device(c, bd, xd, mu, correction, max_it, tol, iterations, rel_residual);
+  });
 }

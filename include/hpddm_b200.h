@@ -185,6 +185,13 @@ int hpddm_b200_dot(hpddm_b200_ctx *ctx, const double *const *x, const double *co
 int hpddm_b200_solve(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int correction, int restart, int max_it, double tol, int where,
                      int *iterations, double *rel_residual);
 
+/* IterativeMethod::CG (include/HPDDM_CG.hpp:31-168, non-flexible variant) with r, p, z resident in HBM: D-weighted inner
+ * products, all mu columns advancing together, convergence when ||M^-1 r||_D / ||M^-1 r_0||_D <= tol per column.  Like the
+ * reference (CG.hpp:41-44) it runs CG only for symmetric preconditioners -- SORAS / ASM / none, correction not deflated -- and
+ * forwards to GMRES (restart 40) otherwise.  Returns the iteration count in *iterations. */
+int hpddm_b200_solve_cg(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int correction, int max_it, double tol, int where, int *iterations,
+                        double *rel_residual);
+
 /* ---- introspection (Subdomain::statistics analogue, subdomain.hpp:405-454) -- */
 typedef struct hpddm_b200_stats {
   int64_t n;             /* dofs */

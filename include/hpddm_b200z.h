@@ -159,6 +159,10 @@ int hpddm_b200z_dot(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *x, const hp
 int hpddm_b200z_solve(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpddm_b200_z *const *x, int mu, int correction, int restart, int max_it, double tol, int where,
                       int *iterations, double *rel_residual);
 
+/* IterativeMethod::CG (include/HPDDM_CG.hpp:31-168); see hpddm_b200_solve_cg */
+int hpddm_b200z_solve_cg(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpddm_b200_z *const *x, int mu, int correction, int max_it, double tol, int where,
+                         int *iterations, double *rel_residual);
+
 /* ---- introspection (Subdomain::statistics analogue, subdomain.hpp:405-454); factor_bytes counts 16-byte scalars */
 int hpddm_b200z_sub_stats(hpddm_b200z_sub *sub, hpddm_b200_stats *st);
 

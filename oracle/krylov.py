@@ -109,6 +109,52 @@ def gmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40, verbose=False):
     return min(j, max_it), x, applies
 
 
+def cg(op, b, x0=None, tol=1e-6, max_it=100):
+    """IterativeMethod::CG (include/HPDDM_CG.hpp:31-168), non-flexible variant, restated: D-weighted products
+    sum_i d_i conj(x_i) y_i (Blas::dot conjugates its first argument for complex K, HPDDM_BLAS.hpp:173-179), all columns
+    advance together, a converged column stops being updated (CG.hpp:99-105), convergence when
+    ||M^-1 r||_D / ||M^-1 r_0||_D <= tol (CG.hpp:68,139-140).  Returns (iterations, x)."""
+    P = len(b)
+    mu = b[0].shape[1]
+    x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [np.array(v, order="F", copy=True) for v in x0]
+    x = op.start(b, x)
+    z = op.GMV(x)
+    r = [b[q] - z[q] for q in range(P)]
+    p = op.apply(r)
+    dirn = np.real(op.dot(p, p))
+    res = np.sqrt(dirn)
+    conv = np.full(mu, -max_it, dtype=int)
+    i = 0
+    if np.all(dirn >= np.finfo(float).eps ** 2):
+        zd = p                                               # `trash` = D zd : p before the loop, z = M^-1 r afterwards
+        while i < max_it:
+            rz = np.real(op.dot(r, zd))                      # CG.hpp:87
+            z = op.GMV(p)                                    # CG.hpp:88
+            pAp = np.real(op.dot(z, p))                      # CG.hpp:90
+            i += 1
+            for nu in range(mu):
+                if conv[nu] == -max_it:
+                    alpha = rz[nu] / pAp[nu]
+                    for q in range(P):
+                        x[q][:, nu] += alpha * p[q][:, nu]
+                        r[q][:, nu] -= alpha * z[q][:, nu]
+            z = op.apply(r)                                  # CG.hpp:107
+            zd = z
+            beta = np.real(op.dot(r, z)) / rz                # CG.hpp:110
+            dirn = np.real(op.dot(z, z))                     # CG.hpp:111
+            for q in range(P):
+                p[q] = z[q] + p[q] * beta[None, :]           # CG.hpp:115
+            newly = (conv == -max_it) & (np.sqrt(dirn) / res <= tol)
+            conv[newly] = i
+            if not np.any(conv == -max_it):
+                i -= 1
+                break
+    else:
+        i = -1
+    i += 1
+    return min(i, max_it), x
+
+
 class OracleOperator:
     """Adapter SchwarzWorld -> Krylov operator concept."""
 

@@ -35,6 +35,9 @@ CASES = {
                                                              "-generate_random_rhs", "3", "-hpddm_gmres_restart", "5", "-hpddm_tol", "1e-9"]),
     "complex_40x40_p4_mu2_twolevel": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40",
                                                               "-generate_random_rhs", "2"]),
+    # IterativeMethod::CG (HPDDM_CG.hpp:31-168) with the symmetric one-level method (ASM), 1 and 3 right-hand sides
+    "small_40x40_p4_asm_cg": dict(np=4, args=["-hpddm_schwarz_method", "asm", "-hpddm_krylov_method", "cg", "-Nx", "40", "-Ny", "40"]),
+    "small_40x40_p4_asm_cg_mu3": dict(np=4, args=["-hpddm_schwarz_method", "asm", "-hpddm_krylov_method", "cg", "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "3", "-hpddm_tol", "1e-8"]),
     # complex scalars (the reference's FORCE_COMPLEX build; damped-Helmholtz-like shift of the generator's matrix, see ref_driver.cpp)
     "complex_40x40_p4_ras": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40"]),
     "complex_40x40_p4_twolevel_nu3": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40"]),

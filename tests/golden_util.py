@@ -41,7 +41,8 @@ def load(name):
     meta = dict(P=P, args=args, mu=max(1, int(arg_value(args, "generate_random_rhs", 0))), complex=bool(np.iscomplexobj(ref[0]["a"])), Nx=int(arg_value(args, "Nx", 100)), Ny=int(arg_value(args, "Ny", 100)), overlap=int(arg_value(args, "overlap", 1)),
                 sym=arg_value(args, "symmetric_csr", "0") == "1", nu=int(arg_value(args, "deflation_vectors", 0)),
                 restart=int(arg_value(args, "hpddm_gmres_restart", 40)), max_it=int(arg_value(args, "hpddm_max_it", 100)),
-                tol=float(arg_value(args, "hpddm_tol", 1e-6)))
+                tol=float(arg_value(args, "hpddm_tol", 1e-6)), method=arg_value(args, "hpddm_schwarz_method", "ras"),
+                krylov=arg_value(args, "hpddm_krylov_method", "gmres"))
     return parts, ref, meta
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from hpddm_b200.examples.generate import generate2d
-from oracle.krylov import OracleOperator, gmres
+from oracle.krylov import OracleOperator, cg, gmres
 from oracle.schwarz import ADDITIVE, BALANCED, DEFLATED, SchwarzWorld
 from tests.golden_util import cases, col, complexify, load
 
@@ -39,7 +39,7 @@ def test_generator_is_bit_identical_to_examples_generate_cpp(name):
 def test_oracle_reproduces_the_reference(name):
     parts, ref, meta = load(name)
     P = meta["P"]
-    w = SchwarzWorld(parts)
+    w = SchwarzWorld(parts, method=meta["method"])
     w.multiplicity_scaling()
     for r in range(P):
         assert np.abs(w.d[r] - ref[r]["d"]).max() < 1e-15
@@ -63,7 +63,10 @@ def test_oracle_reproduces_the_reference(name):
             assert max(rel(got[r], ref[r][key]) for r in range(P)) < TOL, key
         corr = DEFLATED
     b = [parts[r]["f"].copy() for r in range(P)]
-    it, x, _ = gmres(OracleOperator(w, corr), b, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])
+    if meta["krylov"] == "cg":
+        it, x = cg(OracleOperator(w, corr), b, max_it=meta["max_it"], tol=meta["tol"])
+    else:
+        it, x, _ = gmres(OracleOperator(w, corr), b, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])
     assert it == int(ref[0]["iterations"][0])                      # identical Krylov iteration count
     assert max(rel(x[r], ref[r]["sol"]) for r in range(P)) < 1e-7
     res = w.compute_residual(x, b)

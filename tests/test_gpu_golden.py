@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from hpddm_b200 import KrylovOperator
-from oracle.krylov import gmres
+from oracle.krylov import cg, gmres
 from oracle.schwarz import SchwarzWorld
 from tests.golden_util import cases, col, load
 from tests.helpers import build_gpu_decomposition
@@ -23,7 +23,7 @@ def test_cuda_path_reproduces_the_reference(name):
     P = meta["P"]
     for p in parts:
         p["dims"] = None
-    deco = build_gpu_decomposition(parts, None, own_scaling=True, grid_hint=False)
+    deco = build_gpu_decomposition(parts, None, own_scaling=True, grid_hint=False, method=meta["method"])
     ds = deco.multiplicityScaling([p["d"] for p in parts])   # idempotent input: the ramp
     for r in range(P):
         assert np.abs(ds[r] - ref[r]["d"]).max() < 1e-15
@@ -52,11 +52,17 @@ def test_cuda_path_reproduces_the_reference(name):
             assert max(rel(got[r], ref[r][key]) for r in range(P)) < TOL, key
         corr = "deflated"
     b = [parts[r]["f"].copy() for r in range(P)]
-    it, x, _ = gmres(KrylovOperator(deco, corr), b, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])
+    if meta["krylov"] == "cg":
+        it, x = cg(KrylovOperator(deco, corr), b, max_it=meta["max_it"], tol=meta["tol"])
+    else:
+        it, x, _ = gmres(KrylovOperator(deco, corr), b, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])
     assert it == int(ref[0]["iterations"][0])                 # identical Krylov iteration count
     assert max(rel(x[r], ref[r]["sol"]) for r in range(P)) < 1e-7
     # device-resident driver (hpddm_b200[z]_solve: all right-hand sides advance together, Krylov basis in HBM)
-    it_dev, x_dev, res = deco.solve(b, correction=corr, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])
+    if meta["krylov"] == "cg":
+        it_dev, x_dev, res = deco.solve_cg(b, correction=corr, max_it=meta["max_it"], tol=meta["tol"])
+    else:
+        it_dev, x_dev, res = deco.solve(b, correction=corr, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])
     assert it_dev == int(ref[0]["iterations"][0])
     assert max(rel(x_dev[r], ref[r]["sol"]) for r in range(P)) < 1e-7
     deco.close()

@@ -365,3 +365,30 @@ def test_local_solve_on_the_reference_data_fixtures(name):
     assert np.abs(A @ x - b).max() / np.abs(b).max() < 1e-10
     assert np.abs(x - ref).max() / np.abs(ref).max() < 1e-9
     deco.close()
+
+
+def test_device_resident_cg_matches_reference_algorithm():
+    """hpddm_b200_solve_cg (IterativeMethod::CG, HPDDM_CG.hpp:31-168, r/p/z in HBM) on the symmetric one-level method (ASM),
+    3 right-hand sides advancing together: same iteration count and solution as the restated CG driving the oracle; with RAS
+    the entry point forwards to GMRES like the reference (CG.hpp:41-44)."""
+    from oracle.krylov import cg
+    from oracle.schwarz import SY
+    parts, w = make_world(3, 8, mu=3, N=(14, 14, 14), overlap=1)
+    w.type = SY
+    deco = build_gpu_decomposition(parts, w, method="asm")
+    b = w.exchange([p["f"].copy() for p in parts])
+    it_ref, x_ref = cg(OracleOperator(w, None), b, tol=1e-8)
+    it_dev, x_dev, res = deco.solve_cg(b, tol=1e-8)
+    assert 5 < it_ref < 100 and it_dev == it_ref
+    assert relerr(x_dev, x_ref) < 1e-8
+    assert np.all(res <= 1e-8)
+    deco.close()
+    # non-symmetric preconditioner (RAS): GMRES fallback
+    w2 = SchwarzWorld(parts)
+    w2.multiplicity_scaling()
+    w2.numfact()
+    deco = build_gpu_decomposition(parts, w2)
+    it_g, x_g, _ = gmres(OracleOperator(w2, None), b)
+    it_c, x_c, _ = deco.solve_cg(b)
+    assert it_c == it_g and relerr(x_c, x_g) < 1e-8
+    deco.close()
