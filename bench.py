@@ -173,7 +173,7 @@ def run_b200(args):
     peak, peak_src = peaks()
     traffic = None
     try:  # DRAM bytes of one solve measured by ncu for this configuration (profiles/), if captured
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["cells"].get(str(m), {}).get("dram_bytes") if args.mu == 1 and not cplx else None
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["cells_complex" if cplx else "cells"].get(str(m), {}).get("dram_bytes") if args.mu == 1 else None
     except Exception:
         pass
     trsv_gbs = by["trsv"] / (ms_trsv / args.steps * 1e-3) / 1e9
