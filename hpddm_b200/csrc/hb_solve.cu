@@ -14,6 +14,8 @@
 // a warp owns one work item (<= 32 rows x 512 columns forward, <= 128 rows x 256
 // columns backward; 1, 2 or 4 right-hand sides per pass over the panels), reduces with shuffles and publishes with FP64 atomics
 // (RED.ADD.F64).  Pure HBM streaming: 0.25 flop/byte.
+#include <cstring>
+
 #include "hb_internal.h"
 
 namespace hb {
@@ -131,11 +133,93 @@ __global__ void __launch_bounds__(256, IS_COMPLEX ? 2 : (MU == 1 ? 4 : 3)) k_fwd
   }
 }
 
+// VE right-hand-side values b[c .. c+VE) as one 128-bit vector, from L1 (read-only in this launch: a level's fronts only
+// update rows of their ancestors).  Real scalars: the address is only 8-byte aligned in general -> two loads; the partner of
+// the last column of an odd-width item is a zero (it multiplies the zero padding of the panel, but must not be a NaN).
+__device__ __forceinline__ double2 ld_rhs(const K *p, int c, int nc) {
+#ifdef HB_COMPLEX
+  return __ldg(reinterpret_cast<const double2 *>(p + c));
+#else
+  return make_double2(__ldg(p + c), c + 1 < nc ? __ldg(p + c + 1) : 0.0);
+#endif
+}
+
+// Forward sweep work item for MU = 2 / 4 right-hand sides.  Same data flow as k_fwd, but the right-hand-side block is read
+// through L1 instead of being staged in shared memory, so that one pass covers the whole item width (up to FCH columns) for
+// all MU columns: the shuffle reduction (reduce8) runs once per R = 8 / MU rows x FCH columns instead of once per FCH / MU
+// columns -- it dominated the staged variant at MU = 4 (profiles/README.md).
+template <int MU>
+__global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : 3) k_fwd_blk(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
+                                                                     const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n) {
+  constexpr int R = 8 / MU, JU = MU;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t it = (int64_t)blockIdx.x * 8 + warp;
+  if (it >= nitems) return;
+  const FwdItem w = items[it];
+  const Front f = fronts[w.front];
+  const int s1 = f.s1, nb1 = (s1 + RB - 1) / RB;
+  const K *base;
+  int nrows, stride, cmax;
+  const bool pivot = w.rblk < nb1;
+  if (pivot) {
+    const int k = w.rblk;
+    stride = hb_wblk(s1, k);
+    base = pan + f.poff + hb_blk_off(k);
+    nrows = min(RB, s1 - RB * k);
+    cmax = min(s1, RB * (k + 1));
+  } else {
+    const int k2 = w.rblk - nb1;
+    stride = hb_ldp(s1);
+    base = pan + f.poff + hb_upd_off(s1) + (int64_t)k2 * RB * stride;
+    nrows = min(RB, f.s2 - RB * k2);
+    cmax = s1;
+  }
+  const int nc = min(cmax, w.c0 + w.cw) - w.c0;  // columns of this item
+  if (nc <= 0) return;
+  const int nv = (nc + VE - 1) / VE;
+  const int st2 = stride / VE;  // row stride in 128-bit vectors
+  const int rsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const K *bc = b + f.p0 + w.c0;  // column m of the right-hand-side block: bc + m * n
+  for (int r = 0; r < nrows; r += R) {
+    const double2 *p = reinterpret_cast<const double2 *>(base + (int64_t)r * stride + w.c0);
+    const int nr = min(R, nrows - r);
+    K a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = mk(0.0);
+    for (int j0 = lane; j0 < nv; j0 += 32 * JU) {
+      double2 t[R][JU];
+#pragma unroll
+      for (int u = 0; u < JU; ++u)
+#pragma unroll
+        for (int q = 0; q < R; ++q) t[q][u] = (q < nr && j0 + 32 * u < nv) ? ldg_stream(p + (int64_t)q * st2 + j0 + 32 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < JU; ++u) {
+        if (j0 + 32 * u < nv) {
+#pragma unroll
+          for (int m = 0; m < MU; ++m) {
+            const double2 bb = ld_rhs(bc + (int64_t)m * n, (j0 + 32 * u) * VE, nc);
+#pragma unroll
+            for (int q = 0; q < R; ++q) a[q * MU + m] = hb_vdot(t[q][u], bb, a[q * MU + m]);
+          }
+        }
+      }
+    }
+    const K v = reduce8(a, lane);
+    const int q = rsel / MU, m = rsel % MU;
+    if ((lane & 3) == 0 && q < nr) {
+      if (pivot) hb_atomic_add(&y[(int64_t)m * n + f.p0 + RB * w.rblk + r + q], v);
+      else hb_atomic_add(&b[(int64_t)m * n + rowidx[f.rptr + RB * (w.rblk - nb1) + r + q]], -v);
+    }
+  }
+}
+
 // Backward sweep work item.  NJ = slabs of 32 * VE columns covered per pass (NJ * MU <= 4 128-bit
 // accumulators per lane); rows are processed in groups of 8 / NJ so that 8 128-bit loads are in flight.
-template <int NJ, int MU>
+// With SHARED (block right-hand sides) the multipliers u of a 32-row block are broadcast from shared memory (us: 32 * MU values
+// of this warp) instead of one shuffle per (row, column): MU = 4 needed 8 SHFL per 128-bit panel load.
+template <int NJ, int MU, bool SHARED>
 __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int cbase, const int *__restrict__ rowidx, const K *__restrict__ pan,
-                                         const K *__restrict__ y, K *x, int n, int lane) {
+                                         const K *__restrict__ y, K *x, int n, int lane, K *us) {
   constexpr int G = 8 / NJ;
   const int s1 = f.s1, ldp = hb_ldp(s1);
   const K *P = pan + f.poff;
@@ -153,6 +237,12 @@ __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int c
     for (int m = 0; m < MU; ++m) {
       u[m] = mk(0.0);
       if (rb + lane < w.nr) u[m] = (r < s1) ? y[(int64_t)m * n + f.p0 + r] : -x[(int64_t)m * n + rowidx[f.rptr + r - s1]];
+    }
+    if (SHARED) {
+      __syncwarp();  // the previous block's readers are done
+#pragma unroll
+      for (int m = 0; m < MU; ++m) us[lane * MU + m] = u[m];
+      __syncwarp();
     }
     const int nq = min(32, w.nr - rb);
     for (int q = 0; q < nq; q += G) {
@@ -181,7 +271,7 @@ __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int c
       for (int g = 0; g < G; ++g)
 #pragma unroll
         for (int m = 0; m < MU; ++m) {
-          const K uq = hb_shfl(u[m], (q + g) & 31);
+          const K uq = SHARED ? us[((q + g) & 31) * MU + m] : hb_shfl(u[m], (q + g) & 31);
 #pragma unroll
           for (int j = 0; j < NJ; ++j) hb_vaxpy(t[g][j], uq, acc[j][m]);
         }
@@ -195,10 +285,12 @@ __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int c
   }
 }
 
-template <int MU>
+template <int MU, bool SHARED>
 __global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : 3) k_bwd(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
                                                 const int *__restrict__ rowidx, const K *__restrict__ pan, const K *__restrict__ y, K *x, int n) {
+  __shared__ __align__(16) K us_all[SHARED ? 8 * 32 * MU : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  K *us = us_all + (SHARED ? warp * 32 * MU : 0);
   const int64_t it = (int64_t)blockIdx.x * 8 + warp;
   if (it >= nitems) return;
   const BwdItem w = items[it];
@@ -208,9 +300,9 @@ __global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : 3) k_bwd(co
   constexpr int SLAB = 32 * VE;  // columns covered by one 128-bit load per lane
   for (int cb = 0; cb < width; cb += SLAB * NJMAX) {
     const int left = width - cb;
-    if (NJMAX >= 4 && left > 2 * SLAB) bwd_pass<(NJMAX >= 4 ? 4 : NJMAX), MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
-    else if (NJMAX >= 2 && left > SLAB) bwd_pass<(NJMAX >= 2 ? 2 : NJMAX), MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
-    else bwd_pass<1, MU>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane);
+    if (NJMAX >= 4 && left > 2 * SLAB) bwd_pass<(NJMAX >= 4 ? 4 : NJMAX), MU, SHARED>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane, us);
+    else if (NJMAX >= 2 && left > SLAB) bwd_pass<(NJMAX >= 2 ? 2 : NJMAX), MU, SHARED>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane, us);
+    else bwd_pass<1, MU, SHARED>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane, us);
   }
 }
 
@@ -236,20 +328,26 @@ __global__ void k_perm_out(int n, int mu, const int *__restrict__ perm, const K 
   }
 }
 
+// MU >= 2: block kernels (k_fwd_blk, shared-memory multipliers in k_bwd); HPDDM_B200_BLK=staged selects the first-generation
+// block kernels (right-hand sides staged in shared memory, shuffled multipliers) for A/B measurements
 template <int MU>
 static int launch_levels(Sub *s, cudaStream_t st) {
+  static const bool staged = getenv("HPDDM_B200_BLK") && !strcmp(getenv("HPDDM_B200_BLK"), "staged");
+  const bool blk = MU > 1 && !staged;
   DeviceFactor &D = s->fac;
   const Symbolic &S = s->sym;
   const int n = S.n;
   for (int l = 0; l < S.nlevels; ++l) {
     const int64_t i0 = S.fwd_ptr[l], ni = S.fwd_ptr[l + 1] - i0;
     if (ni <= 0) continue;
-    k_fwd<MU><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+    if (blk) k_fwd_blk<(MU > 1 ? MU : 2)><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+    else k_fwd<MU><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
   }
   for (int l = S.nlevels - 1; l >= 0; --l) {
     const int64_t i0 = S.bwd_ptr[l], ni = S.bwd_ptr[l + 1] - i0;
     if (ni <= 0) continue;
-    k_bwd<MU><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n);
+    if (blk) k_bwd<MU, (MU > 1)><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n);
+    else k_bwd<MU, false><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n);
   }
   HB_CUDA(cudaGetLastError());
   return 0;
