@@ -155,6 +155,115 @@ def cg(op, b, x0=None, tol=1e-6, max_it=100):
     return min(i, max_it), x
 
 
+def _gram(op, X, Y):
+    """sum over ranks of X_r^H D_r Y_r  (mu_x x mu_y): the reduction of blockOrthogonalization / VR (iterative.hpp:523-583)"""
+    return op.gram(X, Y)
+
+
+def bgmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40):
+    """IterativeMethod::BGMRES (include/HPDDM_GMRES.hpp:160-313) with the reference defaults (iterative.hpp:192-212): right
+    preconditioning, block classical Gram-Schmidt (blockOrthogonalization, iterative.hpp:523-556), CholQR of every new block
+    (QR / VR, iterative.hpp:560-583,623-640), no deflation of right-hand sides (deflation_tol = -1), block Hessenberg reduced
+    by LAPACK Householder QRs of 2mu x mu blocks (BlockArnoldi, iterative.hpp:714-737: mqr of the previous blocks, geqrf, mqr
+    on s), convergence when, for every column nu, the norm of the FIRST nu+1 ENTRIES of column nu of the trailing mu x mu block
+    of s, over ||b_nu||_D, is <= tol (checkBlockConvergence, iterative.hpp:139-146 -- a partial norm, restated as is),
+    solution update by trtrs + gemm + one preconditioner apply (updateSol, iterative.hpp:272-336).  Returns (iterations, x)."""
+    from scipy.linalg import lapack, solve_triangular
+    P = len(b)
+    mu = b[0].shape[1]
+    dtype = np.result_type(*[v.dtype for v in b])
+    cplx = np.issubdtype(dtype, np.complexfloating)
+    geqrf = lapack.zgeqrf if cplx else lapack.dgeqrf
+    mqr = lapack.zunmqr if cplx else lapack.dormqr
+    x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [np.array(v, order="F", copy=True) for v in x0]
+    x = op.start(b, x)
+    norm = np.sqrt(np.real(op.dot(b, b)))
+    norm = np.where(norm < 1e-12, 1.0, norm)
+    m = restart
+    ldh = mu * (m + 1)
+
+    def cholqr(W, update=True):
+        G = _gram(op, W, W)
+        try:
+            R = np.linalg.cholesky(G).conj().T          # potrf("U"): G = R^H R
+        except np.linalg.LinAlgError:
+            return None
+        if update:
+            Rinv = solve_triangular(R, np.eye(mu, dtype=dtype))
+            for r in range(P):
+                W[r] = np.asfortranarray(W[r] @ Rinv)   # trsm("R", "U", "N", "N")
+        return R
+
+    def apply_qt(k, C):
+        """C[k*mu:(k+2)*mu] <- Q_k^H C[...]  (mqr "L", transc) with the reflectors stored by geqrf in block column k of H"""
+        blk = np.asfortranarray(H[k * mu:(k + 2) * mu, k * mu:(k + 1) * mu])
+        out, _, info = mqr("L", "C" if cplx else "T", blk, tau[k], np.asfortranarray(C[k * mu:(k + 2) * mu]), 64 * mu)
+        C[k * mu:(k + 2) * mu] = out
+
+    j = 1
+    dim = 0
+    V = None
+    H = None
+    sv = None
+    while j <= max_it:
+        Ax = op.GMV(x)
+        v0 = [np.asfortranarray(b[r] - Ax[r]) for r in range(P)]
+        R0 = cholqr(v0)
+        if R0 is None:
+            raise RuntimeError("BGMRES: rank-deficient block residual (the reference falls back to GMRES)")
+        V = [v0]
+        H = np.zeros((ldh, m * mu), dtype=dtype)
+        tau = [None] * m
+        sv = np.zeros((ldh, mu), dtype=dtype)
+        sv[:mu] = np.triu(R0)
+        i = 0
+        done = False
+        while i < m and j <= max_it:
+            z = op.apply(V[i])
+            w = op.GMV(z)
+            Hc = np.zeros((ldh, mu), dtype=dtype)
+            # blockOrthogonalization, classical: all products first
+            prods = [_gram(op, V[k], w) for k in range(i + 1)]
+            for k in range(i + 1):
+                Hc[k * mu:(k + 1) * mu] = prods[k]
+                for r in range(P):
+                    w[r] = np.asfortranarray(w[r] - V[k][r] @ prods[k])
+            R = cholqr(w, update=i < m - 1)
+            if R is None:
+                raise RuntimeError("BGMRES: breakdown in BlockArnoldi")
+            Hc[(i + 1) * mu:(i + 2) * mu] = np.triu(R)
+            V.append(w)
+            for k in range(i):
+                apply_qt(k, Hc)
+            blk, t, _, info = geqrf(np.asfortranarray(Hc[i * mu:(i + 2) * mu]))
+            Hc[i * mu:(i + 2) * mu] = blk
+            H[:, i * mu:(i + 1) * mu] = Hc
+            tau[i] = t
+            apply_qt(i, sv)
+            i += 1
+            res = sv[i * mu:(i + 1) * mu]
+            pt = np.array([np.linalg.norm(res[:nu + 1, nu]) for nu in range(mu)])
+            if np.all(pt / norm <= tol):
+                dim = mu * i
+                done = True
+                break
+            j += 1
+        if not done:
+            dim = mu * i                                   # restart (i == m) or iteration limit (i = max_it % m or m)
+        if dim > 0:
+            Y = solve_triangular(np.triu(H[:dim, :dim]), sv[:dim])
+            work = [np.zeros_like(x[r]) for r in range(P)]
+            for k in range(dim // mu):
+                for r in range(P):
+                    work[r] += V[k][r] @ Y[k * mu:(k + 1) * mu]
+            corr = op.apply(work)
+            for r in range(P):
+                x[r] += corr[r]
+        if done or j > max_it:
+            break
+    return min(j, max_it), x
+
+
 class OracleOperator:
     """Adapter SchwarzWorld -> Krylov operator concept."""
 
@@ -173,3 +282,6 @@ class OracleOperator:
 
     def dot(self, x, y):
         return self.w.dot(x, y)
+
+    def gram(self, X, Y):
+        return sum(X[r].conj().T @ (self.w.d[r][:, None] * Y[r]) for r in range(self.w.P))

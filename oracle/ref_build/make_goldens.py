@@ -38,6 +38,11 @@ CASES = {
     # IterativeMethod::CG (HPDDM_CG.hpp:31-168) with the symmetric one-level method (ASM), 1 and 3 right-hand sides
     "small_40x40_p4_asm_cg": dict(np=4, args=["-hpddm_schwarz_method", "asm", "-hpddm_krylov_method", "cg", "-Nx", "40", "-Ny", "40"]),
     "small_40x40_p4_asm_cg_mu3": dict(np=4, args=["-hpddm_schwarz_method", "asm", "-hpddm_krylov_method", "cg", "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "3", "-hpddm_tol", "1e-8"]),
+    # IterativeMethod::BGMRES (GMRES.hpp:160-313), 4 right-hand sides (the Krylov method of BASELINE config 4), with and without restarts
+    "small_40x40_p4_bgmres_mu4": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "bgmres", "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "4"]),
+    "small_40x40_p4_bgmres_mu4_twolevel_restart6": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-hpddm_krylov_method", "bgmres",
+                                                                    "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "4", "-hpddm_gmres_restart", "6", "-hpddm_verbosity", "4"]),
+    "complex_40x40_p4_bgmres_mu3": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "bgmres", "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "3"]),
     # complex scalars (the reference's FORCE_COMPLEX build; damped-Helmholtz-like shift of the generator's matrix, see ref_driver.cpp)
     "complex_40x40_p4_ras": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40"]),
     "complex_40x40_p4_twolevel_nu3": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40"]),
@@ -74,7 +79,7 @@ def main():
             res = subprocess.run([DRIVER_Z if case.get("z") else DRIVER] + case["args"], env=env, cwd=tmp, capture_output=True, text=True, timeout=600)
             line = [ln for ln in res.stdout.splitlines() if ln.startswith("ref_driver:")]
             print(name, line)
-            blob = {"args": np.array(" ".join(case["args"])), "np": np.array(case["np"])}
+            blob = {"args": np.array(" ".join(case["args"])), "np": np.array(case["np"]), "log": np.array(res.stdout[-20000:])}
             for r in range(case["np"]):
                 for k, v in read_dump(os.path.join(tmp, f"g_{r}.bin")).items():
                     blob[f"r{r}_{k}"] = v
