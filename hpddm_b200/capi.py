@@ -71,6 +71,7 @@ _SIGS = {
     "hpddm_b200_dot": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int]),
     "hpddm_b200_sub_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "hpddm_b200_solve": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
+    "hpddm_b200_solve_bgmres": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
     "hpddm_b200_solve_cg": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
 }
 # the complex instantiation exports the same set under the hpddm_b200z_ prefix, with identical

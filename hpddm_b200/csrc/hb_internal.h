@@ -258,5 +258,8 @@ void p2p_free(Ctx *c);
 int k_vdots(Ctx *c, const Sub *s, int k, const K *V, int64_t ldv, const K *w, K *T);               // T[j] += sum_i d_i conj(V[i,j]) w[i]
 int k_vupdate(Ctx *c, const Sub *s, int k, const K *V, int64_t ldv, const K *h, double sign, K *w);  // w += sign * V h
 int k_scal_copy(Ctx *c, int64_t n, double a, const K *x, K *y);                       // y = a x
+// block Krylov helpers: W (n x mu) += sign * V (n x k, ld n) * H (k x mu, ld ldh, device) ; W <- W * R (R mu x mu upper, device)
+int k_vupdate_blk(Ctx *c, int n, int k, int mu, const K *V, const K *H, int ldh, double sign, K *W);
+int k_rmul_upper(Ctx *c, int n, int mu, const K *R, K *W);
 
 }  // namespace hb

@@ -238,6 +238,49 @@ __global__ void __launch_bounds__(256) kk_vupdate(int n, int k, const K *__restr
   for (int j = 0; j < k; ++j) acc = hb_fma(V[i + (int64_t)j * ldv], hs[j], acc);
   w[i] = hb_fma(sign, acc, w[i]);
 }
+// W[i, c] += sign * sum_j V[i + j*n] * H[j + ldh*c]  for MB columns c0 .. c0+MB (block Gram-Schmidt update / block Krylov
+// linear combination: gemm("N", "N", n, mu, k) of blockOrthogonalization and addSol, iterative.hpp:519,544,322)
+template <int MB>
+__global__ void __launch_bounds__(256) kk_vupdate_blk(int n, int k, int c0, const K *__restrict__ V, const K *__restrict__ H, int ldh, double sign, K *W) {
+  extern __shared__ __align__(16) unsigned char hb_raw[];
+  K *hs = reinterpret_cast<K *>(hb_raw);  // k * MB
+  for (int t = threadIdx.x; t < k * MB; t += blockDim.x) hs[t] = H[(t % k) + (int64_t)ldh * (c0 + t / k)];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  K acc[MB];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) acc[m] = mk(0.0);
+  for (int j = 0; j < k; ++j) {
+    const K v = V[i + (int64_t)j * n];
+#pragma unroll
+    for (int m = 0; m < MB; ++m) acc[m] = hb_fma(v, hs[j + k * m], acc[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < MB; ++m) W[i + (int64_t)(c0 + m) * n] = hb_fma(sign, acc[m], W[i + (int64_t)(c0 + m) * n]);
+}
+// W <- W * R  in place, R = mu x mu upper triangular (column-major, ld = mu; the inverse Cholesky factor of CholQR:
+// trsm("R", "U", "N", "N") of IterativeMethod::QR, iterative.hpp:635), mu <= 8
+__global__ void __launch_bounds__(256) kk_rmul_upper(int n, int mu, const K *__restrict__ R, K *W) {
+  __shared__ K rs[64];
+  if ((int)threadIdx.x < mu * mu) rs[threadIdx.x] = R[threadIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  K w[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) w[c] = c < mu ? W[i + (int64_t)c * n] : mk(0.0);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (c < mu) {
+      K acc = mk(0.0);
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r <= c) acc = hb_fma(w[r], rs[r + mu * c], acc);
+      W[i + (int64_t)c * n] = acc;
+    }
+  }
+}
 __global__ void kk_scal_copy(int64_t n, double a, const K *__restrict__ x, K *y) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t < n) y[t] = a * x[t];
@@ -369,6 +412,36 @@ int k_vdots(Ctx *c, const Sub *s, int k, const K *V, int64_t ldv, const K *w, K 
 int k_vupdate(Ctx *c, const Sub *s, int k, const K *V, int64_t ldv, const K *h, double sign, K *w) {
   if (s->n == 0 || k == 0) return 0;
   kk_vupdate<<<grid1(s->n), 256, k * sizeof(K), c->stream>>>(s->n, k, V, ldv, h, sign, w);
+  HB_LAUNCH_END(c);
+}
+int k_vupdate_blk(Ctx *c, int n, int k, int mu, const K *V, const K *H, int ldh, double sign, K *W) {
+  if (n == 0 || k == 0 || mu == 0) return 0;
+  const unsigned g = grid1(n);
+  int c0 = 0;
+  while (c0 < mu) {
+    const int left = mu - c0;
+    if (left >= 4) {
+      kk_vupdate_blk<4><<<g, 256, (size_t)k * 4 * sizeof(K), c->stream>>>(n, k, c0, V, H, ldh, sign, W);
+      c0 += 4;
+    } else if (left >= 2) {
+      kk_vupdate_blk<2><<<g, 256, (size_t)k * 2 * sizeof(K), c->stream>>>(n, k, c0, V, H, ldh, sign, W);
+      c0 += 2;
+    } else {
+      kk_vupdate_blk<1><<<g, 256, (size_t)k * sizeof(K), c->stream>>>(n, k, c0, V, H, ldh, sign, W);
+      c0 += 1;
+    }
+    c->launches++;
+  }
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}
+int k_rmul_upper(Ctx *c, int n, int mu, const K *R, K *W) {
+  if (n == 0 || mu == 0) return 0;
+  if (mu > 8) {
+    set_error("block Krylov methods support at most 8 right-hand sides per block (got %d)", mu);
+    return HPDDM_B200_ERR_ARG;
+  }
+  kk_rmul_upper<<<grid1(n), 256, 0, c->stream>>>(n, mu, R, W);
   HB_LAUNCH_END(c);
 }
 int k_scal_copy(Ctx *c, int64_t n, double a, const K *x, K *y) {

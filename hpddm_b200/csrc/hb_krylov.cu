@@ -4,7 +4,9 @@
 // Gram-Schmidt products and the solution update stay in HBM; per iteration only i+2 scalars cross
 // PCIe.  The small Hessenberg least-squares problem (Givens rotations,
 // iterative.hpp:669-710) is solved on the host exactly as the reference does.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "hb_internal.h"
@@ -362,6 +364,286 @@ int cg_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *> &x
 #undef KRC
 }
 
+
+// ------------------------------------------------------------------ block GMRES
+namespace {
+
+// small dense helpers on the host, column-major, written against LAPACK's conventions (zpotf2, zlarfg, zgeqr2, zunm2r) because the
+// reference's convergence test reads individual entries of the Householder-transformed block residual (see bgmres_device)
+bool potrf_upper(int n, K *A, int lda) {  // A = R^H R, R upper in place; false if not positive definite
+  for (int j = 0; j < n; ++j) {
+    double ajj = hb_real(A[j + (size_t)j * lda]);
+    for (int k = 0; k < j; ++k) ajj -= hb_norm(A[k + (size_t)j * lda]);
+    if (!(ajj > 0.0)) return false;
+    ajj = std::sqrt(ajj);
+    A[j + (size_t)j * lda] = mk(ajj);
+    for (int i = j + 1; i < n; ++i) {
+      K acc = A[j + (size_t)i * lda];
+      for (int k = 0; k < j; ++k) acc -= hb_conj(A[k + (size_t)j * lda]) * A[k + (size_t)i * lda];
+      A[j + (size_t)i * lda] = acc / ajj;
+    }
+  }
+  return true;
+}
+void trtri_upper(int n, const K *R, int ldr, K *X) {  // X = R^-1 (n x n, ld n)
+  for (int c = 0; c < n; ++c) {
+    for (int r = 0; r < n; ++r) X[r + (size_t)c * n] = mk(0.0);
+    X[c + (size_t)c * n] = mk(1.0) / R[c + (size_t)c * ldr];
+    for (int r = c - 1; r >= 0; --r) {
+      K acc = mk(0.0);
+      for (int k = r + 1; k <= c; ++k) acc -= R[r + (size_t)k * ldr] * X[k + (size_t)c * n];
+      X[r + (size_t)c * n] = acc / R[r + (size_t)r * ldr];
+    }
+  }
+}
+void larfg(int n, K &alpha, K *x, K &tau) {  // elementary reflector H = I - tau v v^H, v(0) = 1, H^H (alpha; x) = (beta; 0)
+  double xn = 0.0;
+  for (int i = 0; i < n - 1; ++i) xn += hb_norm(x[i]);
+  xn = std::sqrt(xn);
+  const double ar = hb_real(alpha), ai = hb_imag(alpha);
+  if (n <= 0 || (xn == 0.0 && ai == 0.0)) {
+    tau = mk(0.0);
+    return;
+  }
+  const double beta = -std::copysign(std::sqrt(ar * ar + ai * ai + xn * xn), ar);
+  tau = mk((beta - ar) / beta, -ai / beta);
+  const K scal = mk(1.0) / (alpha - mk(beta));
+  for (int i = 0; i < n - 1; ++i) x[i] = x[i] * scal;
+  alpha = mk(beta);
+}
+// C(0:m, 0:nc) <- (I - t v v^H) C, v = (1; v1)
+void larf_left(int m, int nc, const K *v1, K t, K *C, int ldc) {
+  if (t == mk(0.0)) return;
+  for (int j = 0; j < nc; ++j) {
+    K *cj = C + (size_t)j * ldc;
+    K w = cj[0];
+    for (int r = 1; r < m; ++r) w += hb_conj(v1[r - 1]) * cj[r];
+    w = t * w;
+    cj[0] -= w;
+    for (int r = 1; r < m; ++r) cj[r] -= v1[r - 1] * w;
+  }
+}
+void geqr2(int m, int n, K *A, int lda, K *tau) {
+  for (int i = 0; i < std::min(m, n); ++i) {
+    larfg(m - i, A[i + (size_t)i * lda], A + i + 1 + (size_t)i * lda, tau[i]);
+    if (i < n - 1) larf_left(m - i, n - i - 1, A + i + 1 + (size_t)i * lda, hb_conj(tau[i]), A + i + (size_t)(i + 1) * lda, lda);
+  }
+}
+// C <- Q^H C with the k reflectors stored below the diagonal of A (unm2r "L", "C")
+void unm2r_left_c(int m, int nc, int k, const K *A, int lda, const K *tau, K *C, int ldc) {
+  for (int i = 0; i < k; ++i) larf_left(m - i, nc, A + i + 1 + (size_t)i * lda, hb_conj(tau[i]), C + i, ldc);
+}
+
+}  // namespace
+
+// IterativeMethod::BGMRES (include/HPDDM_GMRES.hpp:160-313) with the reference defaults (iterative.hpp:192-212): right
+// preconditioning, block classical Gram-Schmidt (blockOrthogonalization, iterative.hpp:523-556), CholQR of every new block (QR / VR,
+// iterative.hpp:560-583,623-640), no deflation of right-hand sides, block Hessenberg reduced by Householder QRs of 2 mu x mu blocks
+// (BlockArnoldi, iterative.hpp:714-737), convergence when for every column nu the norm of the first nu + 1 entries of column nu of the
+// trailing block of the transformed residual, over ||b_nu||_D, is <= tol (checkBlockConvergence, iterative.hpp:139-146: a partial norm,
+// kept as is).  The block basis, the Gram products and the updates stay in HBM: per iteration one block apply, one block SpMV, two
+// tall-skinny products, two small reductions to the host.  On a rank-deficient block (CholQR breakdown) the reference restarts with
+// GMRES (GMRES.hpp:307-312); so does this.
+int bgmres_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *> &x, int mu, int correction, int restart, int max_it, double tol,
+                  int *iterations, double *rel_residual) {
+  const size_t L = c->subs.size();
+  const int m = restart, ldh = mu * (m + 1);
+  if (mu > 8) {
+    set_error("solve_bgmres: at most 8 right-hand sides per block (got %d)", mu);
+    return HPDDM_B200_ERR_ARG;
+  }
+  std::vector<K *> V(L, nullptr), z(L, nullptr), t(L, nullptr);
+  std::vector<const K *> cz(L), ct(L), cx(L);
+  K *d_T = nullptr, *d_R = nullptr;
+  auto cleanup = [&]() {
+    for (size_t i = 0; i < L; ++i) {
+      cudaFree(V[i]);
+      cudaFree(z[i]);
+      cudaFree(t[i]);
+    }
+    cudaFree(d_T);
+    cudaFree(d_R);
+  };
+#define KR(call)        \
+  do {                  \
+    int r__ = (call);   \
+    if (r__ < 0) {      \
+      cleanup();        \
+      return r__;       \
+    }                   \
+  } while (0)
+#define KRC(call)                                                                                 \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__), __FILE__, __LINE__, #call); \
+      cleanup();                                                                                  \
+      return e__ == cudaErrorMemoryAllocation ? HPDDM_B200_ERR_NOMEM : HPDDM_B200_ERR_CUDA;        \
+    }                                                                                             \
+  } while (0)
+  auto len_of = [&](size_t q) { return (int64_t)c->subs[q]->n * mu; };
+  auto vec = [&](size_t q, int r) { return V[q] + (size_t)r * mu * c->subs[q]->n; };
+  for (size_t i = 0; i < L; ++i) {
+    const size_t len = std::max<size_t>((size_t)len_of(i), 1);
+    KRC(cudaMalloc(&V[i], len * (m + 1) * sizeof(K)));
+    KRC(cudaMalloc(&z[i], len * sizeof(K)));
+    KRC(cudaMalloc(&t[i], len * sizeof(K)));
+    cz[i] = z[i];
+    ct[i] = t[i];
+    cx[i] = x[i];
+  }
+  KRC(cudaMalloc(&d_T, (size_t)ldh * mu * sizeof(K)));
+  KRC(cudaMalloc(&d_R, (size_t)64 * sizeof(K)));
+  std::vector<K> hbuf;
+  // T (k x mu, ld k) = sum over subdomains / processes of X^H D W, X = n x k block (ld n); left on the device in d_T and copied to the host
+  auto gram = [&](int k, const std::vector<K *> &X, const std::vector<K *> &W) -> int {
+    HB_CUDA(cudaMemsetAsync(d_T, 0, (size_t)k * mu * sizeof(K), c->stream));
+    for (size_t q = 0; q < L; ++q) HB_CHECK(k_zt_raw(c, c->subs[q]->n, k, X[q], c->subs[q]->d_d, mu, W[q], d_T, k));
+    HB_CHECK(nccl_allreduce_sum(c, reinterpret_cast<double *>(d_T), k * mu * KD));
+    hbuf.resize((size_t)k * mu);
+    HB_CUDA(cudaMemcpyAsync(hbuf.data(), d_T, (size_t)k * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  };
+  // CholQR of the block W (IterativeMethod::QR, HPDDM_QR_CHOLQR): R (mu x mu upper, ld mu) on the host; W <- W R^-1 if update.
+  // returns 1 on breakdown (Gram matrix not positive definite)
+  std::vector<K> R((size_t)mu * mu), Rinv((size_t)mu * mu);
+  auto cholqr = [&](const std::vector<K *> &W, bool update) -> int {
+    HB_CHECK(gram(mu, W, W));
+    R = hbuf;
+    if (!potrf_upper(mu, R.data(), mu)) return 1;
+    for (int cc = 0; cc < mu; ++cc)
+      for (int r = cc + 1; r < mu; ++r) R[r + (size_t)cc * mu] = mk(0.0);
+    if (update) {
+      trtri_upper(mu, R.data(), mu, Rinv.data());
+      HB_CUDA(cudaMemcpyAsync(d_R, Rinv.data(), (size_t)mu * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+      for (size_t q = 0; q < L; ++q) HB_CHECK(k_rmul_upper(c, c->subs[q]->n, mu, d_R, W[q]));
+    }
+    return 0;
+  };
+  // Schwarz::start
+  for (size_t i = 0; i < L; ++i) {
+    Sub *s = c->subs[i];
+    KR(k_bc(c, s, mu, b[i], x[i]));
+    KR(k_scale(c, s->n, mu, s->d_d, x[i], x[i]));
+  }
+  KR(halo(c, x.data(), mu));
+  std::vector<double> normb(mu), last(mu, 0.0);
+  {
+    K *d_n = d_T;
+    KRC(cudaMemsetAsync(d_n, 0, mu * sizeof(K), c->stream));
+    for (size_t q = 0; q < L; ++q) KR(k_dot(c, c->subs[q], mu, b[q], b[q], d_n));
+    KR(nccl_allreduce_sum(c, reinterpret_cast<double *>(d_n), mu * KD));
+    hbuf.resize(mu);
+    KRC(cudaMemcpyAsync(hbuf.data(), d_n, mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+    KRC(cudaStreamSynchronize(c->stream));
+    for (int nu = 0; nu < mu; ++nu) {
+      normb[nu] = std::sqrt(hb_real(hbuf[nu]));
+      if (normb[nu] < 1e-12) normb[nu] = 1.0;
+    }
+  }
+  std::vector<K> H((size_t)ldh * m * mu), tau((size_t)m * mu), sv((size_t)ldh * mu), Hc((size_t)ldh * mu), Y((size_t)ldh * mu);
+  int j = 1, dim = 0;
+  bool done = false, breakdown = false;
+  while (j <= max_it) {
+    // block residual V_0 R_0 = b - A x
+    std::vector<K *> v0(L), w(L);
+    for (size_t q = 0; q < L; ++q) v0[q] = vec(q, 0);
+    KR(gmv_core(c, cx, v0, mu));
+    for (size_t q = 0; q < L; ++q) {
+      KR(k_scal_copy(c, len_of(q), -1.0, v0[q], v0[q]));
+      KR(k_axpy(c, len_of(q), 1.0, b[q], v0[q]));
+    }
+    int rc = cholqr(v0, true);
+    if (rc < 0) KR(rc);
+    if (rc == 1) {
+      breakdown = true;
+      break;
+    }
+    std::fill(H.begin(), H.end(), mk(0.0));
+    std::fill(tau.begin(), tau.end(), mk(0.0));
+    std::fill(sv.begin(), sv.end(), mk(0.0));
+    for (int cc = 0; cc < mu; ++cc)
+      for (int r = 0; r <= cc; ++r) sv[r + (size_t)cc * ldh] = R[r + (size_t)cc * mu];
+    int i = 0;
+    done = false;
+    while (i < m && j <= max_it) {
+      std::vector<const K *> vi(L);
+      for (size_t q = 0; q < L; ++q) {
+        vi[q] = vec(q, i);
+        w[q] = vec(q, i + 1);
+      }
+      KR(apply_core(c, vi, z, mu, correction));  // GMRES.hpp:246
+      KR(gmv_core(c, cz, w, mu));                // GMRES.hpp:247
+      // block classical Gram-Schmidt: all products first, then one update (iterative.hpp:547-555)
+      const int k = (i + 1) * mu;
+      KR(gram(k, V, w));
+      std::fill(Hc.begin(), Hc.end(), mk(0.0));
+      for (int cc = 0; cc < mu; ++cc)
+        for (int r = 0; r < k; ++r) Hc[r + (size_t)cc * ldh] = hbuf[r + (size_t)cc * k];
+      for (size_t q = 0; q < L; ++q) KR(k_vupdate_blk(c, c->subs[q]->n, k, mu, V[q], d_T, k, -1.0, w[q]));
+      rc = cholqr(w, i < m - 1);
+      if (rc < 0) KR(rc);
+      if (rc == 1) {
+        breakdown = true;
+        break;
+      }
+      for (int cc = 0; cc < mu; ++cc)
+        for (int r = 0; r <= cc; ++r) Hc[k + r + (size_t)cc * ldh] = R[r + (size_t)cc * mu];
+      // Householder reduction of the block Hessenberg matrix (BlockArnoldi, iterative.hpp:727-729)
+      for (int p = 0; p < i; ++p) unm2r_left_c(2 * mu, mu, mu, &H[(size_t)p * mu + (size_t)p * mu * ldh], ldh, &tau[(size_t)p * mu], &Hc[(size_t)p * mu], ldh);
+      geqr2(2 * mu, mu, &Hc[(size_t)i * mu], ldh, &tau[(size_t)i * mu]);
+      std::copy(Hc.begin(), Hc.end(), H.begin() + (size_t)i * mu * ldh);
+      unm2r_left_c(2 * mu, mu, mu, &H[(size_t)i * mu + (size_t)i * mu * ldh], ldh, &tau[(size_t)i * mu], &sv[(size_t)i * mu], ldh);
+      ++i;
+      bool all = true;
+      for (int nu = 0; nu < mu; ++nu) {  // checkBlockConvergence<1>, t <= 1 branch (iterative.hpp:139-146)
+        double nrm = 0.0;
+        for (int r = 0; r <= nu; ++r) nrm += hb_norm(sv[(size_t)i * mu + r + (size_t)nu * ldh]);
+        last[nu] = std::sqrt(nrm);
+        all = all && last[nu] / normb[nu] <= tol;
+      }
+      if (all) {
+        dim = mu * i;
+        done = true;
+        break;
+      }
+      ++j;
+    }
+    if (breakdown) break;
+    if (!done) dim = mu * i;  // restart (i == m) or iteration limit
+    if (dim > 0) {            // updateSol (iterative.hpp:272-336): trtrs, gemm, one apply
+      for (int cc = 0; cc < mu; ++cc)
+        for (int r = dim - 1; r >= 0; --r) {
+          K acc = sv[r + (size_t)cc * ldh];
+          for (int l = r + 1; l < dim; ++l) acc -= H[r + (size_t)l * ldh] * Y[l + (size_t)cc * dim];
+          Y[r + (size_t)cc * dim] = acc / H[r + (size_t)r * ldh];
+        }
+      KRC(cudaMemcpyAsync(d_T, Y.data(), (size_t)dim * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+      for (size_t q = 0; q < L; ++q) {
+        KRC(cudaMemsetAsync(t[q], 0, (size_t)len_of(q) * sizeof(K), c->stream));
+        KR(k_vupdate_blk(c, c->subs[q]->n, dim, mu, V[q], d_T, dim, 1.0, t[q]));
+      }
+      KR(apply_core(c, ct, z, mu, correction));
+      for (size_t q = 0; q < L; ++q) KR(k_axpy(c, len_of(q), 1.0, z[q], x[q]));
+      KRC(cudaStreamSynchronize(c->stream));  // Y (pageable) is rewritten by the next cycle
+    }
+    if (done || j > max_it) break;
+  }
+  KRC(cudaStreamSynchronize(c->stream));
+  cleanup();
+  if (breakdown) {
+    if (getenv("HPDDM_B200_DEBUG")) fprintf(stderr, "[hpddm_b200] BGMRES: rank-deficient block, continuing with GMRES (GMRES.hpp:307-312)\n");
+    return gmres_device(c, b, x, mu, correction, restart, max_it, tol, iterations, rel_residual);
+  }
+  *iterations = std::min(j, max_it);
+  if (rel_residual)
+    for (int nu = 0; nu < mu; ++nu) rel_residual[nu] = last[nu] / normb[nu];
+  return 0;
+#undef KR
+#undef KRC
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -427,5 +709,18 @@ extern "C" int HB_API(solve_cg)(hb_ctx_t *ctx, const K *const *b, K *const *x, i
   return krylov_entry(c, b, x, mu, where, [&](const std::vector<const K *> &bd, const std::vector<K *> &xd) {
     if (!symmetric) return gmres_device(c, bd, xd, mu, correction, 40, max_it, tol, iterations, rel_residual);
     return cg_device(c, bd, xd, mu, correction, max_it, tol, iterations, rel_residual);
+  });
+}
+
+extern "C" int HB_API(solve_bgmres)(hb_ctx_t *ctx, const K *const *b, K *const *x, int mu, int correction, int restart, int max_it, double tol, int where,
+                                       int *iterations, double *rel_residual) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !iterations || restart < 1 || max_it < 1 || mu < 1) {
+    set_error("solve_bgmres: bad arguments");
+    return HPDDM_B200_ERR_ARG;
+  }
+  *iterations = 0;
+  return krylov_entry(c, b, x, mu, where, [&](const std::vector<const K *> &bd, const std::vector<K *> &xd) {
+    return bgmres_device(c, bd, xd, mu, correction, std::min(restart, max_it), max_it, tol, iterations, rel_residual);
   });
 }

@@ -77,6 +77,7 @@ HB_HD bool operator==(K a, K b) { return a.re == b.re && a.im == b.im; }
 HB_HD bool operator!=(K a, K b) { return !(a == b); }
 HB_HD K hb_conj(K a) { return mk(a.re, -a.im); }
 HB_HD double hb_real(K a) { return a.re; }
+HB_HD double hb_imag(K a) { return a.im; }
 HB_HD double hb_abs(K a) { return hypot(a.re, a.im); }
 HB_HD double hb_norm(K a) { return a.re * a.re + a.im * a.im; }  // |a|^2 (HPDDM::norm)
 // c + a * b
@@ -89,6 +90,7 @@ constexpr bool IS_COMPLEX = false;
 HB_HD K mk(double re, double = 0.0) { return re; }
 HB_HD K hb_conj(K a) { return a; }
 HB_HD double hb_real(K a) { return a; }
+HB_HD double hb_imag(K) { return 0.0; }
 HB_HD double hb_abs(K a) { return fabs(a); }
 HB_HD double hb_norm(K a) { return a * a; }
 HB_HD K hb_fma(K a, K b, K c) { return fma(a, b, c); }

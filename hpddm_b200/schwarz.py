@@ -266,6 +266,18 @@ class Decomposition:
                                                capi.HOST, C.byref(it), capi.ptr(res)))
         return it.value, x, res
 
+    # IterativeMethod::BGMRES (include/HPDDM_GMRES.hpp:160-313) on the device: one block Krylov space for all right-hand sides
+    def solve_bgmres(self, b, x0=None, correction="__default__", restart=40, max_it=100, tol=1e-6):
+        corr = self.correction if correction == "__default__" else correction
+        b = [_f(v, self.dtype) for v in b]
+        x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v, self.dtype).copy(order="F") for v in x0]
+        mu = b[0].shape[1]
+        it = C.c_int(0)
+        res = np.zeros(mu)
+        self.api.check(self.api.solve_bgmres(self.ctx, capi.ptr_array(b), capi.ptr_array(x), mu, capi.CORRECTION[corr], int(restart), int(max_it), float(tol),
+                                             capi.HOST, C.byref(it), capi.ptr(res)))
+        return it.value, x, res
+
     # IterativeMethod::CG (include/HPDDM_CG.hpp:31-168) on the device (falls back to GMRES like the reference when the
     # preconditioner is not symmetric: RAS / ORAS or a deflated correction)
     def solve_cg(self, b, x0=None, correction="__default__", max_it=100, tol=1e-6):

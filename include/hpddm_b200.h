@@ -192,6 +192,13 @@ int hpddm_b200_solve(hpddm_b200_ctx *ctx, const double *const *b, double *const 
 int hpddm_b200_solve_cg(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int correction, int max_it, double tol, int where, int *iterations,
                         double *rel_residual);
 
+/* IterativeMethod::BGMRES (include/HPDDM_GMRES.hpp:160-313; the Krylov method of BASELINE config 4) with the block basis resident
+ * in HBM and the reference defaults: right preconditioning, block classical Gram-Schmidt, CholQR of every new block, no deflation of
+ * right-hand sides, Householder-reduced block Hessenberg matrix on the host, the reference's per-column convergence test
+ * (iterative.hpp:139-146).  mu <= 8.  A rank-deficient block makes it continue with GMRES, as the reference does (GMRES.hpp:307-312). */
+int hpddm_b200_solve_bgmres(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int correction, int restart, int max_it, double tol, int where,
+                            int *iterations, double *rel_residual);
+
 /* ---- introspection (Subdomain::statistics analogue, subdomain.hpp:405-454) -- */
 typedef struct hpddm_b200_stats {
   int64_t n;             /* dofs */

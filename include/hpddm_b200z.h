@@ -163,6 +163,10 @@ int hpddm_b200z_solve(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpddm_
 int hpddm_b200z_solve_cg(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpddm_b200_z *const *x, int mu, int correction, int max_it, double tol, int where,
                          int *iterations, double *rel_residual);
 
+/* IterativeMethod::BGMRES (include/HPDDM_GMRES.hpp:160-313); see hpddm_b200_solve_bgmres */
+int hpddm_b200z_solve_bgmres(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpddm_b200_z *const *x, int mu, int correction, int restart, int max_it, double tol,
+                             int where, int *iterations, double *rel_residual);
+
 /* ---- introspection (Subdomain::statistics analogue, subdomain.hpp:405-454); factor_bytes counts 16-byte scalars */
 int hpddm_b200z_sub_stats(hpddm_b200z_sub *sub, hpddm_b200_stats *st);
 

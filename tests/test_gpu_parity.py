@@ -394,3 +394,21 @@ def test_device_resident_cg_matches_reference_algorithm():
     it_c, x_c, _ = deco.solve_cg(b)
     assert it_c == it_g and relerr(x_c, x_g) < 1e-8
     deco.close()
+
+
+@pytest.mark.parametrize("correction", [None, DEFLATED])
+def test_device_resident_bgmres_matches_reference_algorithm(poisson3d, correction):
+    """hpddm_b200_solve_bgmres (IterativeMethod::BGMRES, GMRES.hpp:160-313, block basis in HBM) against the restated reference
+    algorithm driving the oracle: 3 right-hand sides in one block Krylov space, same iteration count and solution; and fewer
+    iterations than the non-block driver on the same right-hand sides."""
+    from oracle.krylov import bgmres
+    parts, w, deco = poisson3d
+    b = w.exchange([p["f"].copy() for p in parts])
+    it_ref, x_ref = bgmres(OracleOperator(w, correction), b)
+    it_dev, x_dev, res = deco.solve_bgmres(b, correction=correction)
+    assert it_dev == it_ref
+    assert relerr(x_dev, x_ref) < 1e-7
+    r = w.compute_residual(x_dev, b)
+    assert np.all(r[:, 1] / r[:, 0] < 1e-5)
+    it_gmres, _, _ = deco.solve(b, correction=correction)
+    assert it_dev <= it_gmres
