@@ -87,6 +87,18 @@ struct Api;
     static int gmv(ctx_t *c, const K_ *const *in, K_ *const *out, int mu, int w) { return P_##_gmv(c, in, out, mu, w); }                            \
     static int sub_solve(sub_t *s, const K_ *b, K_ *x, int mu, int w) { return P_##_sub_solve(s, b, x, mu, w); }                                    \
     static int dot(ctx_t *c, const K_ *const *x, const K_ *const *y, int mu, K_ *res, int w) { return P_##_dot(c, x, y, mu, res, w); }              \
+    static int solve(ctx_t *c, const K_ *const *b, K_ *const *x, int mu, int corr, int m, int it, double tol, int w, int *its, double *res)        \
+    {                                                                                                                                              \
+      return P_##_solve(c, b, x, mu, corr, m, it, tol, w, its, res);                                                                               \
+    }                                                                                                                                              \
+    static int solve_bgmres(ctx_t *c, const K_ *const *b, K_ *const *x, int mu, int corr, int m, int it, double tol, int w, int *its, double *res) \
+    {                                                                                                                                              \
+      return P_##_solve_bgmres(c, b, x, mu, corr, m, it, tol, w, its, res);                                                                        \
+    }                                                                                                                                              \
+    static int solve_cg(ctx_t *c, const K_ *const *b, K_ *const *x, int mu, int corr, int it, double tol, int w, int *its, double *res)            \
+    {                                                                                                                                              \
+      return P_##_solve_cg(c, b, x, mu, corr, it, tol, w, its, res);                                                                               \
+    }                                                                                                                                              \
   }
 HPDDM_B200_DEFINE_API(double, hpddm_b200);
 HPDDM_B200_DEFINE_API(std::complex<double>, hpddm_b200z);
@@ -342,6 +354,19 @@ public:
       storage[2 * nu]     = std::sqrt(b200::real_part(b[nu]));
       storage[2 * nu + 1] = std::sqrt(b200::real_part(r[nu]));
     }
+  }
+  /* Device-resident counterpart of IterativeMethod::solve(A, f, sol, mu, comm) (include/HPDDM_iterative.hpp:1013-1111): the Krylov
+   * vectors never leave HBM.  method: 0 = GMRES (HPDDM_KRYLOV_METHOD_GMRES), 1 = BGMRES, 2 = CG -- the values of -hpddm_krylov_method
+   * (include/HPDDM_define.hpp).  Returns the iteration count like the reference's drivers (negative = error). */
+  int solve(const K *const f, K *const x, const unsigned short mu = 1, int method = 0, int restart = 40, int max_it = 100, double tol = 1.0e-6) const
+  {
+    const K *bb[1] = {f};
+    K       *xx[1] = {x};
+    int      it = 0, rc;
+    if (method == 1) rc = A_::solve_bgmres(ctx_, bb, xx, mu, correction_, restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
+    else if (method == 2) rc = A_::solve_cg(ctx_, bb, xx, mu, correction_, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
+    else rc = A_::solve(ctx_, bb, xx, mu, correction_, restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
+    return rc < 0 ? rc : it;
   }
   /* accessors used by the Krylov drivers (include/HPDDM_GMRES.hpp:40-62, HPDDM_iterative.hpp:441-468) */
   const double *getScaling() const { return d_; }

@@ -16,7 +16,7 @@ def main():
     import torch.distributed as dist
     from hpddm_b200 import Decomposition, KrylovOperator
     from hpddm_b200.examples.generate import generate_world, split_grid_3d
-    from oracle.krylov import OracleOperator, gmres
+    from oracle.krylov import OracleOperator, bgmres, cg, gmres
     from oracle.schwarz import ADDITIVE, BALANCED, DEFLATED, SchwarzWorld
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -76,8 +76,23 @@ def main():
     errs["gmres_x"] = np.abs(x_gpu[0] - x_ref[rank]).max() / np.abs(x_ref[rank]).max()
     it_dev, x_dev, _ = deco.solve([b_all[rank]], correction=DEFLATED)     # device-resident driver (hpddm_b200[z]_solve)
     errs["gmres_dev_x"] = np.abs(x_dev[0] - x_ref[rank]).max() / np.abs(x_ref[rank]).max()
-    bad = (not ok) or it_gpu != it_ref or it_dev != it_ref or errs["gmres_dev_x"] > 1e-7 or any(v > 1e-10 for k, v in errs.items() if not k.startswith("gmres")) or errs["gmres_x"] > 1e-7
-    print(f"rank {rank}/{world} {'complex' if cplx else 'real'}: d_ok={ok} it_gpu={it_gpu} it_dev={it_dev} it_ref={it_ref} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()) + (" FAIL" if bad else " OK"), flush=True)
+    # block GMRES (2 right-hand sides in one block Krylov space) and, on the symmetric one-level ASM variant, CG: device drivers
+    # whose reductions (Gram matrices, D-weighted products) cross the processes through NCCL
+    b2_all = w.exchange([q["f"][:, :2].copy() for q in parts])
+    it_bref, x_bref = bgmres(OracleOperator(w, DEFLATED), b2_all)
+    it_bdev, x_bdev, _ = deco.solve_bgmres([b2_all[rank]], correction=DEFLATED)
+    errs["bgmres_dev_x"] = np.abs(x_bdev[0] - x_bref[rank]).max() / np.abs(x_bref[rank]).max()
+    it_cdev = it_cref = 0
+    if not cplx:
+        from oracle.schwarz import SY
+        w.type = SY
+        s.callNumfact(method="asm")
+        it_cref, x_cref = cg(OracleOperator(w, None), b2_all, tol=1e-8)
+        it_cdev, x_cdev, _ = deco.solve_cg([b2_all[rank]], correction=None, tol=1e-8)
+        errs["cg_dev_x"] = np.abs(x_cdev[0] - x_cref[rank]).max() / np.abs(x_cref[rank]).max()
+    bad = (not ok) or it_gpu != it_ref or it_dev != it_ref or errs["gmres_dev_x"] > 1e-7 or it_bdev != it_bref or errs["bgmres_dev_x"] > 1e-7 or \
+        it_cdev != it_cref or errs.get("cg_dev_x", 0.0) > 1e-6 or any(v > 1e-10 for k, v in errs.items() if not (k.startswith("gmres") or k.endswith("_dev_x"))) or errs["gmres_x"] > 1e-7
+    print(f"rank {rank}/{world} {'complex' if cplx else 'real'}: d_ok={ok} it_gpu={it_gpu} it_dev={it_dev} it_ref={it_ref} bgmres={it_bdev}/{it_bref} cg={it_cdev}/{it_cref} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()) + (" FAIL" if bad else " OK"), flush=True)
     t = torch.tensor([1.0 if bad else 0.0], device="cuda")
     dist.all_reduce(t)
     deco.close()
