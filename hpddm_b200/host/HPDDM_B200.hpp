@@ -78,6 +78,8 @@ struct Api;
     {                                                                                                                                              \
       return P_##_sub_solve_gevp(s, n, nnz, ia, ja, a, sym, nb, nu, tol, it, ev);                                                                  \
     }                                                                                                                                              \
+    static int sub_get_vectors(sub_t *s, K_ *Z, int *nu) { return P_##_sub_get_vectors(s, Z, nu); }                                                \
+    static int sub_stats(sub_t *s, hpddm_b200_stats *st) { return P_##_sub_stats(s, st); }                                                         \
     static int build_coarse(ctx_t *c) { return P_##_build_coarse(c); }                                                                             \
     static int start(ctx_t *c, const K_ *const *b, K_ *const *x, int mu, int w) { return P_##_start(c, b, x, mu, w); }                             \
     static int end(ctx_t *c) { return P_##_end(c); }                                                                                               \
@@ -367,6 +369,28 @@ public:
     else if (method == 2) rc = A_::solve_cg(ctx_, bb, xx, mu, correction_, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     else rc = A_::solve(ctx_, bb, xx, mu, correction_, restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     return rc < 0 ? rc : it;
+  }
+  /* Preconditioner::getVectors (include/HPDDM_preconditioner.hpp:366): the deflation vectors as one contiguous n x nu block
+   * (ev[0], ev[i] = ev[0] + i n), downloaded from the device (e.g. after solveGEVP); the caller owns the returned arrays */
+  K **getVectors() const
+  {
+    int nu = 0;
+    b200::check<K>(A_::sub_get_vectors(sub_, nullptr, &nu), "sub_get_vectors");
+    if (nu == 0) return nullptr;
+    K **ev = new K *[nu];
+    *ev    = new K[static_cast<std::size_t>(nu) * dof_];
+    for (int i = 1; i < nu; ++i) ev[i] = *ev + static_cast<std::size_t>(i) * dof_;
+    b200::check<K>(A_::sub_get_vectors(sub_, *ev, &nu), "sub_get_vectors");
+    return ev;
+  }
+  /* Subdomain::statistics analogue (include/HPDDM_subdomain.hpp:405-454) */
+  void statistics() const
+  {
+    hpddm_b200_stats st;
+    b200::check<K>(A_::sub_stats(sub_, &st), "sub_stats");
+    std::printf(" --- subdomain %d: %lld dofs, %lld nnz, factor %lld entries (%.2f GB, %s), %lld fronts / %lld levels, halo %lld, nu %lld\n", rank_, (long long)st.n,
+                (long long)st.nnz_a, (long long)st.nnz_factor, st.factor_bytes * 1e-9, st.symmetric ? "LL^T" : "LU", (long long)st.fronts, (long long)st.levels,
+                (long long)st.halo, (long long)st.nu);
   }
   /* accessors used by the Krylov drivers (include/HPDDM_GMRES.hpp:40-62, HPDDM_iterative.hpp:441-468) */
   const double *getScaling() const { return d_; }

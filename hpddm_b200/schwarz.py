@@ -95,7 +95,7 @@ class Schwarz:
         self.api.check(self.api.sub_set_vectors(self.h, capi.ptr(Z), int(Z.shape[1])))
 
     # Schwarz::solveGEVP<EIGENSOLVER>(MatNeumann)  (include/HPDDM_schwarz.hpp:665-715), on the GPU
-    def solveGEVP(self, MatNeumann, nu=20, tol=1e-6, max_it=100, sym=False):
+    def solveGEVP(self, MatNeumann, nu=20, tol=1e-6, max_it=100, sym=False, threshold=None):
         A = sp.csr_matrix(MatNeumann)
         ia = np.ascontiguousarray(A.indptr, dtype=np.int32)
         ja = np.ascontiguousarray(A.indices, dtype=np.int32)
@@ -103,6 +103,13 @@ class Schwarz:
         lam = np.zeros(nu)
         it = self.api.check(self.api.sub_solve_gevp(self.h, A.shape[0], int(a.size), capi.ptr(ia), capi.ptr(ja), capi.ptr(a), int(bool(sym)), b"C",
                                                                int(nu), float(tol), int(max_it), capi.ptr(lam)))
+        if threshold is not None and threshold > 0.0:
+            # -hpddm_geneo_threshold (include/HPDDM_eigensolver.hpp:69-159 selectNu): of the nu computed pairs keep those whose
+            # eigenvalue is below the threshold (at least one) -- the number of deflation vectors then differs per subdomain
+            keep = max(1, int(np.count_nonzero(lam < threshold)))
+            if keep < nu:
+                self.setVectors(self.getVectors()[:, :keep])
+                lam = lam[:keep]
         return lam, it
 
     def getVectors(self):

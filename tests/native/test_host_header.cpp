@@ -23,6 +23,7 @@ void instantiate() {
   A.start(nullptr, (K *)nullptr, 1); A.apply((const K *)nullptr, (K *)nullptr, 1); A.template deflation<false>(nullptr, (K *)nullptr, 1);
   A.GMV(nullptr, (K *)nullptr, 1); A.template exchange<true>(nullptr, 1); A.end(); A.computeResidual(nullptr, nullptr, nullptr, 1);
   A.solve(nullptr, (K *)nullptr, 1, 0); A.solve(nullptr, (K *)nullptr, 4, 1); A.solve(nullptr, (K *)nullptr, 1, 2);
+  (void)A.getVectors(); A.statistics();
   (void)A.getScaling(); (void)A.getDof(); (void)A.boundaryConditions(); (void)A.prefix();
 }
 int main() {

@@ -412,3 +412,24 @@ def test_device_resident_bgmres_matches_reference_algorithm(poisson3d, correctio
     assert np.all(r[:, 1] / r[:, 0] < 1e-5)
     it_gmres, _, _ = deco.solve(b, correction=correction)
     assert it_dev <= it_gmres
+
+
+def test_geneo_threshold_selects_a_different_nu_per_subdomain():
+    """-hpddm_geneo_threshold semantics on top of the GPU eigensolver: keep the eigenpairs below the threshold; the coarse space
+    (non-uniform nu) still builds and the two-level apply matches the oracle run on the same vectors."""
+    parts, w = make_world(3, 4, nu=4, mu=2, N=(12, 12, 6), overlap=1)
+    deco = build_gpu_decomposition(parts, w)
+    kept = []
+    for r, s in enumerate(deco.subs):
+        lam_all, _ = s.solveGEVP(parts[r]["MatNeumann"], nu=4, tol=1e-8)
+        thr = 0.5 * (lam_all[1] + lam_all[2]) if r % 2 == 0 else 2.0 * lam_all[-1]   # keep 2 on even ranks, all 4 on odd ones
+        lam, _ = s.solveGEVP(parts[r]["MatNeumann"], nu=4, tol=1e-8, threshold=thr)
+        kept.append(len(lam))
+        assert np.all(lam < thr)
+    assert kept == [2, 4, 2, 4]
+    deco.buildTwo()
+    w.set_vectors([s.getVectors() for s in deco.subs])
+    w.build_coarse()
+    x = rhs(parts, w, 5)
+    assert relerr(deco.apply(x, DEFLATED), w.apply(x, DEFLATED)) < TOL
+    deco.close()
