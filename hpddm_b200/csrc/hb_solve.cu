@@ -57,11 +57,14 @@ __device__ __forceinline__ K reduce8(K (&a)[8], int lane) {
 // (MU = 1 is held to 64 registers -> 4 CTAs / SM: measured +2 % at m = 128 over the 80-register build, profiles/README.md)
 // A 128-bit load carries VE elements of K: two reals or one complex (hb_scalar.h); complex accumulators
 // double the register budget, so that build runs 2 CTAs / SM.
-template <int MU>
+// WIDE = 2 (block right-hand sides only): the staged chunk covers 2 FCH / MU columns per pass (64 KB of dynamic shared memory per
+// CTA) -- half as many shuffle reductions per panel byte as WIDE = 1.
+template <int MU, int WIDE = 1>
 __global__ void __launch_bounds__(256, IS_COMPLEX ? 2 : (MU == 1 ? 4 : 3)) k_fwd(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
                                                 const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n) {
-  constexpr int R = 8 / MU, JU = MU, CW = FCH / MU;
-  __shared__ __align__(16) K bs[8][FCH];
+  constexpr int R = 8 / MU, JU = MU, CW = WIDE * FCH / MU;
+  extern __shared__ __align__(16) unsigned char bs_raw[];
+  K(*bs)[WIDE * FCH] = reinterpret_cast<K(*)[WIDE * FCH]>(bs_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = (int64_t)blockIdx.x * 8 + warp;
   if (it >= nitems) return;
@@ -285,8 +288,8 @@ __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int c
   }
 }
 
-template <int MU, bool SHARED>
-__global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : 3) k_bwd(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
+template <int MU, bool SHARED, int OCC = ((IS_COMPLEX || MU == 4) ? 2 : 3)>
+__global__ void __launch_bounds__(256, OCC) k_bwd(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
                                                 const int *__restrict__ rowidx, const K *__restrict__ pan, const K *__restrict__ y, K *x, int n) {
   __shared__ __align__(16) K us_all[SHARED ? 8 * 32 * MU : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -328,25 +331,41 @@ __global__ void k_perm_out(int n, int mu, const int *__restrict__ perm, const K 
   }
 }
 
-// MU >= 2: block kernels (k_fwd_blk, shared-memory multipliers in k_bwd); HPDDM_B200_BLK=staged selects the first-generation
-// block kernels (right-hand sides staged in shared memory, shuffled multipliers) for A/B measurements
+// Block right-hand sides (MU >= 2).  Forward sweep: MU = 2 -> k_fwd_blk (right-hand sides through L1, one reduction per full item
+// width); MU = 4, real scalars -> k_fwd<4, 2> (staged in 64 KB of shared memory, 2 FCH / MU columns per pass: the L1 variant is
+// occupancy-bound at 106 registers).  Backward sweep: multipliers broadcast from shared memory; MU = 4 real at 78 registers / 3 CTAs
+// per SM.  Measured at m = 96 (profiles/README.md): 4 RHS 5.04 ms (first generation) -> 4.48 ms, 2 RHS 3.12 -> 3.09 ms.
+// HPDDM_B200_BLK = staged | l1 | wide and HPDDM_B200_BWD4 = 2 | 3 override the choice for A/B measurements.
 template <int MU>
 static int launch_levels(Sub *s, cudaStream_t st) {
-  static const bool staged = getenv("HPDDM_B200_BLK") && !strcmp(getenv("HPDDM_B200_BLK"), "staged");
+  static const char *env = getenv("HPDDM_B200_BLK");
+  static const bool staged = env && !strcmp(env, "staged");
+  static const bool wide = env ? !strcmp(env, "wide") : (MU == 4 && !IS_COMPLEX);
+  static const bool bwd3 = getenv("HPDDM_B200_BWD4") ? !strcmp(getenv("HPDDM_B200_BWD4"), "3") : true;
   const bool blk = MU > 1 && !staged;
+  constexpr size_t smem1 = (size_t)8 * FCH * sizeof(K), smem2 = 2 * smem1;
+  if (MU > 1 && wide) {
+    static bool once = false;
+    if (!once) {
+      HB_CUDA(cudaFuncSetAttribute(k_fwd<(MU > 1 ? MU : 2), 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      once = true;
+    }
+  }
   DeviceFactor &D = s->fac;
   const Symbolic &S = s->sym;
   const int n = S.n;
   for (int l = 0; l < S.nlevels; ++l) {
     const int64_t i0 = S.fwd_ptr[l], ni = S.fwd_ptr[l + 1] - i0;
     if (ni <= 0) continue;
-    if (blk) k_fwd_blk<(MU > 1 ? MU : 2)><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
-    else k_fwd<MU><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+    if (MU > 1 && wide) k_fwd<(MU > 1 ? MU : 2), 2><<<(unsigned)((ni + 7) / 8), 256, smem2, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+    else if (blk) k_fwd_blk<(MU > 1 ? MU : 2)><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+    else k_fwd<MU><<<(unsigned)((ni + 7) / 8), 256, smem1, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
   }
   for (int l = S.nlevels - 1; l >= 0; --l) {
     const int64_t i0 = S.bwd_ptr[l], ni = S.bwd_ptr[l + 1] - i0;
     if (ni <= 0) continue;
-    if (blk) k_bwd<MU, (MU > 1)><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n);
+    if (blk && MU == 4 && bwd3 && !IS_COMPLEX) k_bwd<MU, (MU > 1), 3><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n);
+    else if (blk) k_bwd<MU, (MU > 1)><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n);
     else k_bwd<MU, false><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n);
   }
   HB_CUDA(cudaGetLastError());
