@@ -63,8 +63,10 @@ template <int MU, int WIDE = 1>
 __global__ void __launch_bounds__(256, IS_COMPLEX ? 2 : (MU == 1 ? 4 : 3)) k_fwd(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
                                                 const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n) {
   constexpr int R = 8 / MU, JU = MU, CW = WIDE * FCH / MU;
+  // WIDE = 1: 32 KB of static shared memory (the layout the MU = 1 kernel was tuned with); WIDE = 2: 64 KB, dynamic (opt-in size)
+  __shared__ __align__(16) K bs_static[WIDE == 1 ? 8 : 1][WIDE == 1 ? FCH : 1];
   extern __shared__ __align__(16) unsigned char bs_raw[];
-  K(*bs)[WIDE * FCH] = reinterpret_cast<K(*)[WIDE * FCH]>(bs_raw);
+  K(*bs)[WIDE * FCH] = WIDE == 1 ? reinterpret_cast<K(*)[WIDE * FCH]>(bs_static) : reinterpret_cast<K(*)[WIDE * FCH]>(bs_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = (int64_t)blockIdx.x * 8 + warp;
   if (it >= nitems) return;
@@ -152,7 +154,7 @@ __device__ __forceinline__ double2 ld_rhs(const K *p, int c, int nc) {
 // all MU columns: the shuffle reduction (reduce8) runs once per R = 8 / MU rows x FCH columns instead of once per FCH / MU
 // columns -- it dominated the staged variant at MU = 4 (profiles/README.md).
 template <int MU>
-__global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : 3) k_fwd_blk(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
+__global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : (MU == 1 ? 4 : 3)) k_fwd_blk(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
                                                                      const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n) {
   constexpr int R = 8 / MU, JU = MU;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -343,7 +345,8 @@ static int launch_levels(Sub *s, cudaStream_t st) {
   static const bool wide = env ? !strcmp(env, "wide") : (MU == 4 && !IS_COMPLEX);
   static const bool bwd3 = getenv("HPDDM_B200_BWD4") ? !strcmp(getenv("HPDDM_B200_BWD4"), "3") : true;
   const bool blk = MU > 1 && !staged;
-  constexpr size_t smem1 = (size_t)8 * FCH * sizeof(K), smem2 = 2 * smem1;
+  static const bool fwd1_l1 = getenv("HPDDM_B200_FWD1") && !strcmp(getenv("HPDDM_B200_FWD1"), "l1");  // experiment: MU = 1 forward sweep without shared staging
+  constexpr size_t smem2 = (size_t)2 * 8 * FCH * sizeof(K);
   if (MU > 1 && wide) {
     static bool once = false;
     if (!once) {
@@ -357,9 +360,10 @@ static int launch_levels(Sub *s, cudaStream_t st) {
   for (int l = 0; l < S.nlevels; ++l) {
     const int64_t i0 = S.fwd_ptr[l], ni = S.fwd_ptr[l + 1] - i0;
     if (ni <= 0) continue;
-    if (MU > 1 && wide) k_fwd<(MU > 1 ? MU : 2), 2><<<(unsigned)((ni + 7) / 8), 256, smem2, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+    if (MU == 1 && fwd1_l1) k_fwd_blk<1><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+    else if (MU > 1 && wide) k_fwd<(MU > 1 ? MU : 2), 2><<<(unsigned)((ni + 7) / 8), 256, smem2, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
     else if (blk) k_fwd_blk<(MU > 1 ? MU : 2)><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
-    else k_fwd<MU><<<(unsigned)((ni + 7) / 8), 256, smem1, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+    else k_fwd<MU><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
   }
   for (int l = S.nlevels - 1; l >= 0; --l) {
     const int64_t i0 = S.bwd_ptr[l], ni = S.bwd_ptr[l + 1] - i0;

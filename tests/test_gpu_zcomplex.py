@@ -171,3 +171,54 @@ def test_real_and_complex_contexts_coexist():
     assert np.abs(xz * (1.0 + 0.5j) - xr).max() / np.abs(xr).max() < 1e-12
     dr.close()
     dz.close()
+
+
+# ---------------------------------------------------------------- size-independent properties at a size the oracle cannot reach quickly
+@pytest.fixture(scope="module")
+def big_helmholtz():
+    m = 56
+    part = generate_helmholtz3d(0, 1, N=(m, m, m), overlap=1, mu=4, k=2.0, nu=12)
+    deco = Decomposition(0, dtype=np.complex128)
+    s = deco.add(0)
+    s.initialize(part["Mat"], part["o"], part["mapping"])
+    s.setGridHint(*part["dims"])
+    deco.multiplicityScaling([part["d"]])
+    s.callNumfact()
+    s.setVectors(part["Z"])
+    deco.buildTwo()
+    yield part, deco, s
+    deco.close()
+
+
+def test_complex_solve_round_trip_at_scale(big_helmholtz):
+    part, deco, s = big_helmholtz
+    b = part["f"]                                      # 4 complex right-hand sides: one pass over the panels
+    x = s.solve(b)
+    r = np.linalg.norm(part["Mat"] @ x - b, axis=0) / np.linalg.norm(b, axis=0)
+    assert r.max() < 1e-11
+    st = s.statistics()
+    assert st["symmetric"] == 0 and st["nnz_factor"] > 5e7
+
+
+def test_complex_apply_is_complex_linear_and_blocks_equal_columns(big_helmholtz):
+    part, deco, s = big_helmholtz
+    rs = np.random.RandomState(1)
+    x, y = (np.asfortranarray(crand(rs, part["ndof"], 1)) for _ in range(2))
+    a, b = 2.5 - 1.5j, -0.75 + 0.25j
+    for corr in (None, DEFLATED, ADDITIVE, BALANCED):
+        mx, my = deco.apply([x], corr)[0], deco.apply([y], corr)[0]
+        mz = deco.apply([a * x + b * y], corr)[0]
+        assert np.abs(mz - (a * mx + b * my)).max() / np.abs(mz).max() < 1e-11      # linear over C (no stray conjugation)
+        blk = deco.apply([np.asfortranarray(np.hstack([x, y, x + y, 1j * x]))], corr)[0]
+        assert np.abs(blk[:, :1] - mx).max() / np.abs(mx).max() < 1e-11
+        assert np.abs(blk[:, 2:3] - (mx + my)).max() / np.abs(mx).max() < 1e-11
+        assert np.abs(blk[:, 3:] - 1j * mx).max() / np.abs(mx).max() < 1e-11
+
+
+def test_complex_two_level_apply_of_A_times_coarse_vector_returns_it(big_helmholtz):
+    """M^-1 A z = z for z in the coarse space with the deflated correction: involves Z^H (conjugated), E^-1, Z, SpMV and the solve"""
+    part, deco, s = big_helmholtz
+    z = np.asfortranarray(part["Z"] @ crand(np.random.RandomState(2), part["Z"].shape[1], 1))
+    Az = deco.GMV([z])[0]
+    back = deco.apply([Az], DEFLATED)[0]
+    assert np.abs(back - z).max() / np.abs(z).max() < 1e-9
