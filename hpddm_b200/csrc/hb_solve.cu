@@ -345,7 +345,10 @@ static int launch_levels(Sub *s, cudaStream_t st) {
   static const bool wide = env ? !strcmp(env, "wide") : (MU == 4 && !IS_COMPLEX);
   static const bool bwd3 = getenv("HPDDM_B200_BWD4") ? !strcmp(getenv("HPDDM_B200_BWD4"), "3") : true;
   const bool blk = MU > 1 && !staged;
-  static const bool fwd1_l1 = getenv("HPDDM_B200_FWD1") && !strcmp(getenv("HPDDM_B200_FWD1"), "l1");  // experiment: MU = 1 forward sweep without shared staging
+  // MU = 1, real scalars: the forward sweep reads its right-hand-side chunk (4 KB per warp, L1-resident) through L1 as well instead of
+  // staging it in shared memory -- same-box A/B at m = 128: 8.51 -> 8.25 ms, at m = 64: 0.728 -> 0.693 ms (profiles/README.md);
+  // HPDDM_B200_FWD1=staged selects the shared-memory kernel
+  static const bool fwd1_l1 = getenv("HPDDM_B200_FWD1") ? !strcmp(getenv("HPDDM_B200_FWD1"), "l1") : !IS_COMPLEX;
   constexpr size_t smem2 = (size_t)2 * 8 * FCH * sizeof(K);
   if (MU > 1 && wide) {
     static bool once = false;
