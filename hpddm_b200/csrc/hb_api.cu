@@ -112,7 +112,7 @@ static Sub *local_sub(Ctx *c, int grank) {
 static int ensure_capacity(Ctx *c, int mu) {
   if (mu <= c->mu_cap) return 0;
   for (Sub *s : c->subs) {
-    for (K **p : {&s->d_in, &s->d_out, &s->d_work, &s->d_tmp}) {
+    for (K **p : {&s->d_in, &s->d_out, &s->d_work, &s->d_tmp, &s->d_tmp2}) {
       if (*p) cudaFree(*p);
       *p = nullptr;
       HB_CUDA(cudaMalloc(p, std::max<size_t>((size_t)s->n * mu, 1) * sizeof(K)));
@@ -362,14 +362,9 @@ int apply_core(Ctx *c, const std::vector<const K *> &ind, const std::vector<K *>
   if (correction == HPDDM_B200_CORRECTION_BALANCED) {                            // (593-606)
     HB_CHECK(gmv_core(c, cwork, tmp, mu));
     std::vector<K *> t2(L, nullptr);
-    // allocate a transient buffer per subdomain (rare path)
-    for (size_t i = 0; i < L; ++i) HB_CUDA(cudaMalloc(&t2[i], std::max<size_t>((size_t)c->subs[i]->n * mu, 1) * sizeof(K)));
-    int rc = deflation_core(c, ctmp, t2, mu);
-    if (rc == 0)
-      for (size_t i = 0; i < L && rc == 0; ++i) rc = k_axpy(c, (int64_t)c->subs[i]->n * mu, -1.0, t2[i], work[i]);
-    cudaStreamSynchronize(c->stream);
-    for (size_t i = 0; i < L; ++i) cudaFree(t2[i]);
-    HB_CHECK(rc);
+    for (size_t i = 0; i < L; ++i) t2[i] = c->subs[i]->d_tmp2;  // preallocated with the other work vectors: no allocation on the hot path
+    HB_CHECK(deflation_core(c, ctmp, t2, mu));
+    for (size_t i = 0; i < L; ++i) HB_CHECK(k_axpy(c, (int64_t)c->subs[i]->n * mu, -1.0, t2[i], work[i]));
   }
   for (size_t i = 0; i < L; ++i) HB_CHECK(k_axpy(c, (int64_t)c->subs[i]->n * mu, 1.0, work[i], outd[i]));  // out += work (607)
   return 0;
@@ -409,7 +404,7 @@ static void sub_free(Sub *s) {
   free_factor(s->fac);
   for (void *p : {(void *)s->d_ia, (void *)s->d_ja, (void *)s->d_a, (void *)s->d_d, (void *)s->d_map, (void *)s->d_ebase, (void *)s->d_esize, (void *)s->d_send,
                   (void *)s->d_recv, (void *)s->d_uidx, (void *)s->d_useg, (void *)s->d_upos, (void *)s->d_bc_idx, (void *)s->d_bc_val, (void *)s->d_Z,
-                  (void *)s->d_in, (void *)s->d_out, (void *)s->d_work, (void *)s->d_tmp})
+                  (void *)s->d_in, (void *)s->d_out, (void *)s->d_work, (void *)s->d_tmp, (void *)s->d_tmp2})
     if (p) cudaFree(p);
   delete s;
 }

@@ -176,7 +176,7 @@ struct Sub {
   K *d_Z = nullptr;
   int coff = 0;             // offset of this subdomain in the coarse vector
   // work vectors (n * mu_cap)
-  K *d_in = nullptr, *d_out = nullptr, *d_work = nullptr, *d_tmp = nullptr;
+  K *d_in = nullptr, *d_out = nullptr, *d_work = nullptr, *d_tmp = nullptr, *d_tmp2 = nullptr;
   int mu_cap = 0;
 };
 
@@ -201,9 +201,6 @@ struct Ctx {
   int loc_off = 0;                           // first coarse row of this process
   K *d_res = nullptr;                   // small device scratch (dots)
   std::vector<K> E_host;
-  // pinned staging
-  K *pin = nullptr;
-  size_t pin_bytes = 0;
   int mu_cap = 0;
   bool started = false;
   P2P *p2p = nullptr;  // NVLink peer-memory halo state (hb_p2p.cu)
