@@ -77,3 +77,31 @@ def test_host_cpp_header_compiles_and_links():
         subprocess.check_call(["g++", "-std=c++11", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "hpddm_b200", "host"), src,
                                "-L", os.path.join(ROOT, "hpddm_b200", "lib"), "-lhpddm_b200", "-Wl,-rpath," + os.path.join(ROOT, "hpddm_b200", "lib"), "-o", exe])
         subprocess.check_call([exe])
+
+
+def test_ctypes_signatures_match_the_headers():
+    """every declaration of include/hpddm_b200.h / hpddm_b200z.h: same number of arguments and same scalar/pointer kind as
+    the argtypes of hpddm_b200/capi.py (a wrong binding would corrupt the stack silently)"""
+    import ctypes as C
+    for header in ("hpddm_b200.h", "hpddm_b200z.h"):
+        src = open(os.path.join(ROOT, "include", header)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        for m in re.finditer(r"\b(hpddm_b200z?_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+            name, args = m.group(1), m.group(2).strip()
+            if name not in capi._SIGS:
+                continue
+            params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+            _, argtypes = capi._SIGS[name]
+            assert len(params) == len(argtypes), (name, params, argtypes)
+            for prm, at in zip(params, argtypes):
+                is_ptr = "*" in prm
+                if is_ptr:
+                    assert at in (C.c_void_p, C.c_char_p) or hasattr(at, "contents") or at is capi._P, (name, prm, at)
+                elif prm.startswith("double"):
+                    assert at is C.c_double, (name, prm, at)
+                elif prm.startswith("char"):
+                    assert at is C.c_char, (name, prm, at)
+                elif prm.startswith("size_t"):
+                    assert at is C.c_size_t, (name, prm, at)
+                else:
+                    assert at is C.c_int, (name, prm, at)

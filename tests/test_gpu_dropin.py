@@ -57,7 +57,8 @@ def _iterations(out, tag):
 
 
 @pytest.mark.skipif(not os.path.exists(FULL), reason="oracle/_ref/b200_full_driver not built")
-@pytest.mark.parametrize("extra", [[], ["-hpddm_krylov_method", "cg"], ["-deflation_vectors", "3"]])
+@pytest.mark.parametrize("extra", [[], ["-hpddm_krylov_method", "cg"], ["-deflation_vectors", "3"],
+                                   ["-hpddm_krylov_method", "bgmres", "-generate_random_rhs", "4"]])   # the reference's BGMRES, block apply with mu = 4
 def test_reference_krylov_drivers_on_b200schwarz_single_gpu(tmp_path, extra):
     """IterativeMethod::solve (GMRES / CG, unmodified reference code) driving HPDDM::B200Schwarz, 1 rank."""
     env = dict(os.environ, HPDDM_SHIM_NP="1", HPDDM_B200_NDEV="1")
