@@ -58,7 +58,8 @@ def _iterations(out, tag):
 
 @pytest.mark.skipif(not os.path.exists(FULL), reason="oracle/_ref/b200_full_driver not built")
 @pytest.mark.parametrize("extra", [[], ["-hpddm_krylov_method", "cg"], ["-deflation_vectors", "3"],
-                                   ["-hpddm_krylov_method", "bgmres", "-generate_random_rhs", "4"]])   # the reference's BGMRES, block apply with mu = 4
+                                   ["-hpddm_krylov_method", "bgmres", "-generate_random_rhs", "4"],    # the reference's BGMRES, block apply with mu = 4
+                                   ["-hpddm_krylov_method", "gcrodr", "-hpddm_recycle", "5"]])         # recycling driver (the Krylov method of config 5)
 def test_reference_krylov_drivers_on_b200schwarz_single_gpu(tmp_path, extra):
     """IterativeMethod::solve (GMRES / CG, unmodified reference code) driving HPDDM::B200Schwarz, 1 rank."""
     env = dict(os.environ, HPDDM_SHIM_NP="1", HPDDM_B200_NDEV="1")
@@ -70,7 +71,8 @@ def test_reference_krylov_drivers_on_b200schwarz_single_gpu(tmp_path, extra):
 
 
 @pytest.mark.skipif(not os.path.exists(FULL) or not os.path.exists(REFDRV), reason="oracle/_ref drivers not built")
-def test_reference_krylov_drivers_on_b200schwarz_multi_gpu(tmp_path):
+@pytest.mark.parametrize("krylov", [[], ["-hpddm_krylov_method", "gcrodr", "-hpddm_recycle", "5", "-hpddm_gmres_restart", "10"]])
+def test_reference_krylov_drivers_on_b200schwarz_multi_gpu(tmp_path, krylov):
     """One rank per GPU (NCCL halo + coarse gather), reference GMRES on top; iteration count must equal
     the all-CPU reference run of the same case (oracle/_ref/ref_driver)."""
     import torch
@@ -78,7 +80,7 @@ def test_reference_krylov_drivers_on_b200schwarz_multi_gpu(tmp_path):
     if ngpu < 2:
         pytest.skip("needs >= 2 GPUs")
     P = 4 if ngpu >= 4 else 2
-    args = ["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "60", "-Ny", "60", "-hpddm_verbosity", "1"]
+    args = ["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "60", "-Ny", "60", "-hpddm_verbosity", "1"] + krylov
     env = dict(os.environ, HPDDM_SHIM_NP=str(P), HPDDM_B200_NDEV=str(ngpu), HPDDM_REF_DUMP=str(tmp_path / "g"))
     ref = subprocess.run([REFDRV] + args, env=env, cwd=tmp_path, capture_output=True, text=True, timeout=300)
     got = subprocess.run([FULL] + args, env=env, cwd=tmp_path, capture_output=True, text=True, timeout=300)
