@@ -655,13 +655,26 @@ static int krylov_entry(Ctx *c, const K *const *b, K *const *x, int mu, int wher
   const size_t L = c->subs.size();
   // vectors live in private device buffers for the whole solve (d_in / d_out are used by nothing else here)
   std::vector<K *> bd(L, nullptr), xd(L, nullptr);
+  auto release = [&]() {
+    if (where != HPDDM_B200_HOST) return;
+    for (size_t i = 0; i < L; ++i) {
+      cudaFree(bd[i]);
+      cudaFree(xd[i]);
+    }
+  };
   for (size_t i = 0; i < L; ++i) {
-    const size_t bytes = std::max<size_t>((size_t)c->subs[i]->n * mu, 1) * sizeof(K);
+    const size_t bytes = (size_t)c->subs[i]->n * mu * sizeof(K);
     if (where == HPDDM_B200_HOST) {
-      HB_CUDA(cudaMalloc(&bd[i], bytes));
-      HB_CUDA(cudaMalloc(&xd[i], bytes));
-      HB_CUDA(cudaMemcpyAsync(bd[i], b[i], bytes, cudaMemcpyHostToDevice, c->stream));
-      HB_CUDA(cudaMemcpyAsync(xd[i], x[i], bytes, cudaMemcpyHostToDevice, c->stream));
+      cudaError_t e = cudaMalloc(&bd[i], std::max<size_t>(bytes, sizeof(K)));
+      if (e == cudaSuccess) e = cudaMalloc(&xd[i], std::max<size_t>(bytes, sizeof(K)));
+      if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(bd[i], b[i], bytes, cudaMemcpyHostToDevice, c->stream);
+      if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(xd[i], x[i], bytes, cudaMemcpyHostToDevice, c->stream);
+      if (e != cudaSuccess) {
+        set_error("CUDA error %s while staging the right-hand sides of a Krylov solve", cudaGetErrorString(e));
+        cudaStreamSynchronize(c->stream);
+        release();
+        return e == cudaErrorMemoryAllocation ? HPDDM_B200_ERR_NOMEM : HPDDM_B200_ERR_CUDA;
+      }
     } else {
       bd[i] = const_cast<K *>(b[i]);
       xd[i] = x[i];
@@ -673,10 +686,7 @@ static int krylov_entry(Ctx *c, const K *const *b, K *const *x, int mu, int wher
     if (rc == 0)
       for (size_t i = 0; i < L; ++i) cudaMemcpyAsync(x[i], xd[i], (size_t)c->subs[i]->n * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream);
     cudaStreamSynchronize(c->stream);
-    for (size_t i = 0; i < L; ++i) {
-      cudaFree(bd[i]);
-      cudaFree(xd[i]);
-    }
+    release();
   }
   return rc;
 }
