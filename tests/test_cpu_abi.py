@@ -105,3 +105,20 @@ def test_ctypes_signatures_match_the_headers():
                     assert at is C.c_size_t, (name, prm, at)
                 else:
                     assert at is C.c_int, (name, prm, at)
+
+
+@pytest.mark.parametrize("scalar", ["real", "complex"])
+def test_symbolic_phase_and_work_item_tiling_on_the_host(scalar, tmp_path):
+    """hb_symbolic.cpp on the host (tests/native/test_symbolic.cpp): valid permutation, level property of the assembly tree, a dense
+    multifrontal Cholesky driven by the same structures succeeds, and the forward / backward SpTRSV work items tile every stored panel
+    entry exactly once -- for both scalar builds (the chunk widths FCH / BCH depend on sizeof(K)), geometric and algebraic ordering."""
+    import subprocess
+    exe = str(tmp_path / "tsym")
+    cmd = ["nvcc", "-O1", "-std=c++17", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "hpddm_b200", "csrc"), "-x", "cu",
+           "-o", exe, os.path.join(ROOT, "tests", "native", "test_symbolic.cpp"), os.path.join(ROOT, "hpddm_b200", "csrc", "hb_symbolic.cpp")]
+    if scalar == "complex":
+        cmd.insert(1, "-DHB_COMPLEX")
+    subprocess.check_call(cmd)
+    for args in (["12", "12", "12", "1"], ["10", "8", "6", "0"], ["24", "24", "24", "1"], ["30", "30", "1", "0"], ["9", "7", "5", "1", "8"]):
+        out = subprocess.run([exe] + args, capture_output=True, text=True)
+        assert out.returncode == 0 and "factor ok" in out.stdout, (args, out.stdout[-300:])
