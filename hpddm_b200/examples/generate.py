@@ -318,11 +318,13 @@ def _assemble_elasticity(lo, hi, Nn, h, Ke, penalty):
     return A
 
 
-def generate_elasticity3d(rank, size, Nn=(9, 9, 7), overlap=1, mu=4, grid=None, neumann=False, seed=4321, penalty=1e30):
+def generate_elasticity3d(rank, size, Nn=(9, 9, 7), overlap=1, mu=4, grid=None, neumann=False, seed=4321, penalty=1e30, assembly="global"):
     """Q1 hexahedral linear elasticity (E = 1, nu_P = 0.3) on [0,10]^3 with Nn nodes per direction and 3
     dofs per node (config 4 of BASELINE.json, element model of the reference's examples/petsc/ex56.c);
     same decomposition conventions as generate3d, on nodes.  The local matrix is the global matrix
-    restricted to the subdomain's dofs (assembled globally: test sizes only)."""
+    restricted to the subdomain's dofs: assembly="global" assembles the whole grid and restricts (test sizes only);
+    assembly="local" assembles only the elements that touch the subdomain (its node box grown by one node layer) and
+    restricts -- identical up to the summation order of the element contributions, and scalable to config-4 sizes."""
     px, py, pz = grid if grid is not None else split_grid_3d(size)
     z = rank // (px * py)
     y = (rank - z * px * py) // px
@@ -333,11 +335,20 @@ def generate_elasticity3d(rank, size, Nn=(9, 9, 7), overlap=1, mu=4, grid=None, 
     dims = tuple(en[a] - st[a] for a in range(3))
     h = [10.0 / (Nn[a] - 1) for a in range(3)]
     Ke = _hex8_stiffness(h)
-    Aglob = _assemble_elasticity([0, 0, 0], list(Nn), Nn, h, Ke, penalty)
-    gid = np.arange(Nn[0] * Nn[1] * Nn[2]).reshape(Nn[2], Nn[1], Nn[0])
-    nodes = gid[st[2]:en[2], st[1]:en[1], st[0]:en[0]].reshape(-1)
-    dofs = (3 * nodes[:, None] + np.arange(3)[None, :]).reshape(-1)
-    Mat = sp.csr_matrix(Aglob[dofs][:, dofs])
+    if assembly == "local":
+        lo = [max(st[a] - 1, 0) for a in range(3)]
+        hi = [min(en[a] + 1, Nn[a]) for a in range(3)]
+        Aext = _assemble_elasticity(lo, hi, Nn, h, Ke, penalty)
+        eid = np.arange((hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2])).reshape(hi[2] - lo[2], hi[1] - lo[1], hi[0] - lo[0])
+        nodes = eid[st[2] - lo[2]:en[2] - lo[2], st[1] - lo[1]:en[1] - lo[1], st[0] - lo[0]:en[0] - lo[0]].reshape(-1)
+        dofs = (3 * nodes[:, None] + np.arange(3)[None, :]).reshape(-1)
+        Mat = sp.csr_matrix(Aext[dofs][:, dofs])
+    else:
+        Aglob = _assemble_elasticity([0, 0, 0], list(Nn), Nn, h, Ke, penalty)
+        gid = np.arange(Nn[0] * Nn[1] * Nn[2]).reshape(Nn[2], Nn[1], Nn[0])
+        nodes = gid[st[2]:en[2], st[1]:en[1], st[0]:en[0]].reshape(-1)
+        dofs = (3 * nodes[:, None] + np.arange(3)[None, :]).reshape(-1)
+        Mat = sp.csr_matrix(Aglob[dofs][:, dofs])
     Mat.sort_indices()
     ndof = dofs.size
     dist = np.minimum(np.minimum(_ramp(st[0] != 0, en[0] != Nn[0], st[0], en[0], overlap)[None, None, :],

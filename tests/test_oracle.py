@@ -123,3 +123,17 @@ def test_reference_on_disk_formats_round_trip(tmp_path):
     (tmp_path / "s.txt").write_text(f"{n} {len(a)} {n + 1}\n" + " ".join(f"{v:.17E}" for v in a) + "\n" + " ".join(map(str, ja)) + "\n" + " ".join(map(str, ia)) + "\n" + " ".join(f"{v:.17E}" for v in rhs) + "\n")
     S, r = read_system(tmp_path / "s.txt")
     assert S.toarray().tolist() == [[2.0, -1.0, 0.0], [-1.0, 2.0, 0.0], [0.0, 0.0, 1.0]] and r.tolist() == rhs
+
+
+def test_elasticity_generator_local_assembly_equals_restriction_of_the_global_matrix():
+    """generate_elasticity3d(assembly="local") (scalable: only the elements touching the subdomain) against the restriction of the
+    globally assembled matrix, every rank of two decompositions, including the penalised clamped face"""
+    from hpddm_b200.examples.generate import generate_elasticity3d
+    for size, grid, Nn, ov in ((4, (2, 2, 1), (9, 9, 6), 1), (8, (2, 2, 2), (8, 7, 9), 2)):
+        for r in range(size):
+            g = generate_elasticity3d(r, size, Nn=Nn, overlap=ov, mu=2, grid=grid, assembly="global")
+            l = generate_elasticity3d(r, size, Nn=Nn, overlap=ov, mu=2, grid=grid, assembly="local")
+            assert g["ndof"] == l["ndof"] and np.array_equal(g["Mat"].indptr, l["Mat"].indptr) and np.array_equal(g["Mat"].indices, l["Mat"].indices)
+            scale = np.abs(g["Mat"].data[np.abs(g["Mat"].data) < 1e29]).max()
+            assert np.abs(g["Mat"].data - l["Mat"].data).max() <= 1e-13 * scale or np.allclose(g["Mat"].data, l["Mat"].data, rtol=1e-13, atol=1e-13 * scale)
+            assert all(np.array_equal(a, b) for a, b in zip(g["mapping"], l["mapping"])) and g["o"] == l["o"]
