@@ -1,5 +1,5 @@
 import os, sys, numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.generate import generate_world
 from oracle.schwarz import SchwarzWorld
 from tests.helpers import build_gpu_decomposition, relerr

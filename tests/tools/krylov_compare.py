@@ -1,9 +1,9 @@
 """Full Krylov solves on one B200 hosting a 2 x 2 x 2 decomposition (8 subdomains of M^3 cells + overlap, two-level deflated RAS,
 nu cosine modes per subdomain), MU random right-hand sides: host-driven GMRES over the C ABI (host vectors, what an unchanged
 Krylov driver does) vs the device-resident drivers hpddm_b200_solve (GMRES, all columns together), hpddm_b200_solve_bgmres and --
-for the symmetric one-level ASM variant -- hpddm_b200_solve_cg.   usage: python profiles/krylov_compare.py [M] [MU] [nu]"""
+for the symmetric one-level ASM variant -- hpddm_b200_solve_cg.   usage: python tests/tools/krylov_compare.py [M] [MU] [nu]"""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from hpddm_b200 import Decomposition, KrylovOperator
 from hpddm_b200.examples.generate import generate3d
