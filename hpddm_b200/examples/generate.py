@@ -377,6 +377,25 @@ def generate_elasticity3d(rank, size, Nn=(9, 9, 7), overlap=1, mu=4, grid=None, 
                 dims=(dims[0], dims[1], dims[2], 3))
 
 
+def rigid_body_modes(part, Nn):
+    """The 6 rigid-body modes (3 translations, 3 infinitesimal rotations about the subdomain's centre) of a
+    generate_elasticity3d() subdomain, columns normalised: the kernel of its Neumann matrix and the natural first
+    vectors of a GenEO-shaped coarse space for config 4 (a driver would pass them to setVectors)."""
+    (x0, x1), (y0, y1), (z0, z1) = part["box"]
+    h = [10.0 / (Nn[a] - 1) for a in range(3)]
+    zz, yy, xx = np.meshgrid(np.arange(z0, z1) * h[2], np.arange(y0, y1) * h[1], np.arange(x0, x1) * h[0], indexing="ij")
+    X = np.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], axis=1)
+    X = X - X.mean(axis=0)
+    n = X.shape[0]
+    Z = np.zeros((3 * n, 6), order="F")
+    for c in range(3):
+        Z[c::3, c] = 1.0                              # translations
+    Z[0::3, 3], Z[1::3, 3] = -X[:, 1], X[:, 0]        # rotation about z
+    Z[1::3, 4], Z[2::3, 4] = -X[:, 2], X[:, 1]        # rotation about x
+    Z[2::3, 5], Z[0::3, 5] = -X[:, 0], X[:, 2]        # rotation about y
+    return np.asfortranarray(Z / np.linalg.norm(Z, axis=0, keepdims=True))
+
+
 # ----------------------------------------------------------------------------- 3-D Helmholtz, complex scalars (BASELINE config 5)
 def generate_helmholtz3d(rank, size, N=(16, 16, 16), overlap=1, mu=1, grid=None, k=2.0, nu=4, seed=5678):
     """-Laplace(u) - k^2 u on [0,10]^3 with the first-order absorbing condition du/dn - i k u = 0 on the outer

@@ -137,3 +137,26 @@ def test_elasticity_generator_local_assembly_equals_restriction_of_the_global_ma
             scale = np.abs(g["Mat"].data[np.abs(g["Mat"].data) < 1e29]).max()
             assert np.abs(g["Mat"].data - l["Mat"].data).max() <= 1e-13 * scale or np.allclose(g["Mat"].data, l["Mat"].data, rtol=1e-13, atol=1e-13 * scale)
             assert all(np.array_equal(a, b) for a, b in zip(g["mapping"], l["mapping"])) and g["o"] == l["o"]
+
+
+def test_elasticity_neumann_matrix_annihilates_the_rigid_body_modes():
+    """consistency of the Q1 elasticity generator: on a floating subdomain (no clamped face) the Neumann matrix has exactly the six
+    rigid-body modes in its kernel; on the clamped one the penalised matrix is positive definite"""
+    import scipy.sparse.linalg as spla
+    from hpddm_b200.examples.generate import generate_elasticity3d, rigid_body_modes
+    Nn = (9, 8, 7)
+    parts = [generate_elasticity3d(r, 4, Nn=Nn, overlap=1, mu=1, grid=(2, 2, 1), neumann=True, assembly="local") for r in range(4)]
+    floating = [p for p in parts if p["box"][0][0] > 0]
+    assert len(floating) == 2
+    for p in floating:
+        A = p["MatNeumann"]
+        Z = rigid_body_modes(p, Nn)
+        assert Z.shape == (p["ndof"], 6) and np.linalg.matrix_rank(Z) == 6
+        scale = abs(A).max()
+        assert np.abs(A @ Z).max() < 1e-12 * scale                        # A_Neu * RBM = 0
+        w = np.linalg.eigvalsh(A.toarray())
+        assert np.sum(np.abs(w) < 1e-10 * scale) == 6 and w.min() > -1e-10 * scale
+    clamped = [p for p in parts if p["box"][0][0] == 0][0]
+    lu = spla.splu(clamped["MatNeumann"].tocsc())                        # penalised rows: non-singular
+    x = lu.solve(np.ones(clamped["ndof"]))
+    assert np.all(np.isfinite(x))
