@@ -9,7 +9,12 @@ subdomains.  `value` counts subdomain-applies per second
 contract asks; `applies_per_s` is the global figure.
 
   python bench.py --gpus 1 --steps 20 --warmup 3            # this repo's CUDA path
-  python bench.py --impl reference ...                       # CPU arm (oracle port on host cores)
+  python bench.py --gpus 8 ...                               # without torchrun: spawns the 8 ranks itself (torch.distributed.run)
+  python bench.py --impl reference ...                       # CPU arm (oracle port on host cores), SAME subdomain size as the CUDA arm
+
+Both arms run the same workload: one subdomain of m^3 cells per GPU, m = --cells (default: 160, the largest exact FP64 factor
+that fits one B200 with its numeric phase -- DESIGN.md section 4; 128 when the host cannot hold the CPU arm's 160^3 factor,
+a rule both arms evaluate identically, see default_cells()).  The CPU arm never shrinks on its own.
   python bench.py --scalar z --cells 64                      # auxiliary: BASELINE config 5 shape (3-D Helmholtz, complex FP64,
                                                              # ORAS + plane-wave coarse space) through hpddm_b200z_*; not the headline
 """
@@ -135,6 +140,9 @@ def run_b200(args):
     y_dev = torch.empty_like(x_dev)
     x_pin = torch.rand(n * mu, dtype=tdtype).pin_memory()
     y_pin = torch.empty(n * mu, dtype=tdtype).pin_memory()
+    # ordinary (pageable) memory, what an unchanged Krylov driver allocates with new K[] (include/HPDDM_GMRES.hpp:45-50)
+    x_pag = np.random.RandomState(5).rand(n * mu).astype(np.complex128 if cplx else np.float64)
+    y_pag = np.empty_like(x_pag)
     torch.cuda.synchronize()
 
     def barrier():
@@ -168,6 +176,21 @@ def run_b200(args):
     from hpddm_b200 import capi
     ms_trsv = timed(lambda: deco.api.check(deco.api.sub_solve(s.h, x_dev.data_ptr(), y_dev.data_ptr(), mu, capi.DEVICE)), args.steps, args.warmup)
     ms_e2e = timed(lambda: deco.apply_host_inplace([x_pin], [y_pin], mu, "deflated"), args.steps, args.warmup)
+    # the same call on pageable memory: (a) outside a start()/end() bracket -> plain pageable copies every time;
+    # (b) inside one -> the two ranges are pinned in place on their 4th sighting (steady state of the work vector of a Krylov cycle)
+    ms_pag_cold = timed(lambda: deco.apply_host_inplace([x_pag], [y_pag], mu, "deflated"), args.steps, args.warmup)
+    deco.api.check(deco.api.start(deco.ctx, capi.ptr_array([x_pag]), capi.ptr_array([y_pag.copy()]), mu, capi.HOST))
+    ms_pag = timed(lambda: deco.apply_host_inplace([x_pag], [y_pag], mu, "deflated"), args.steps, max(args.warmup, 5))
+    hostreg = int(deco.api.ctx_hostreg_count(deco.ctx))
+    deco.end()
+    # where one apply goes (device pointers, each piece timed alone on the library's stream)
+    w_dev = torch.rand(n * mu, dtype=tdtype, device="cuda")
+    phases = {
+        "halo_exchange_ms": timed(lambda: deco.api.check(deco.api.exchange(deco.ctx, capi.ptr_array([w_dev]), mu, 0, capi.DEVICE)), args.steps, args.warmup) / args.steps,
+        "deflation_ms": timed(lambda: deco.api.check(deco.api.deflation(deco.ctx, capi.ptr_array([x_dev]), capi.ptr_array([y_dev]), mu, capi.DEVICE)), args.steps, args.warmup) / args.steps,
+        "gmv_ms": timed(lambda: deco.api.check(deco.api.gmv(deco.ctx, capi.ptr_array([x_dev]), capi.ptr_array([y_dev]), mu, capi.DEVICE)), args.steps, args.warmup) / args.steps,
+        "sptrsv_ms": ms_trsv / args.steps,
+    }
     sampler.stop_flag = True
     sampler.join(timeout=2)
     peak, peak_src = peaks()
@@ -177,18 +200,25 @@ def run_b200(args):
     except Exception:
         pass
     trsv_gbs = by["trsv"] / (ms_trsv / args.steps * 1e-3) / 1e9
+    if cplx:
+        wl, par = (f"config5 slice: 3-D Helmholtz k={args.wavenumber} {N[0]}x{N[1]}x{N[2]}, complex FP64, {world} subdomain(s) of {m}^3 cells + overlap 1, "
+                   f"two-level ORAS deflated, {args.nu} plane waves, mu={args.mu}"), f"{grid[0]}x{grid[1]}x{grid[2]} subdomains, 1/GPU"
+    else:
+        wl, par = workload_name(m, world, args.nu, args.mu)
     out = {
         "metric": METRIC_Z if cplx else METRIC, "value": world * args.steps / (ms_dev * 1e-3), "unit": "subdomain-applies/s", "applies_per_s": args.steps / (ms_dev * 1e-3),
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128" if cplx else "f64", "data": "synthetic",
-        "config": {"workload": (f"config5 slice: 3-D Helmholtz k={args.wavenumber} {N[0]}x{N[1]}x{N[2]}, complex FP64, {world} subdomain(s) of {m}^3 cells + overlap 1 (n_loc={n}), "
-                                f"two-level ORAS deflated, {args.nu} plane waves, mu={args.mu}") if cplx else
-                               f"config3 slice: 3-D Poisson {N[0]}x{N[1]}x{N[2]}, {world} subdomain(s) of {m}^3 cells + overlap 1 (n_loc={n}), two-level RAS deflated, nu={args.nu}, mu={args.mu}",
-                   "parallelism": f"{grid[0]}x{grid[1]}x{grid[2]} subdomains, 1/GPU", "l2": "inputs (factor panels) larger than L2, no flush needed",
-                   "nnz_factor": st["nnz_factor"], "factor_gb": st["factor_bytes"] / 1e9, "levels": st["levels"], "fronts": st["fronts"],
-                   "numfact_s": round(t_fact, 3), "symbolic_s": round(st["symbolic_seconds"], 3)},
+        "config": {"workload": wl, "parallelism": par, "cells": m, "nu": args.nu, "mu": args.mu},
+        "factor": {"n_loc": n, "nnz_factor": st["nnz_factor"], "factor_gb": st["factor_bytes"] / 1e9, "levels": st["levels"], "fronts": st["fronts"],
+                   "numfact_s": round(t_fact, 3), "symbolic_s": round(st["symbolic_seconds"], 3), "l2": "inputs (factor panels) larger than L2, no flush needed"},
         "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "subdomain-applies/s", "h2d_bytes_per_step": (16 if cplx else 8) * n * mu, "d2h_bytes_per_step": (16 if cplx else 8) * n * mu,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "host_memory": "pinned (cudaHostAlloc)",
+                "pageable": {"value": world * args.steps / (ms_pag * 1e-3), "ms_per_step": ms_pag / args.steps, "ranges_pinned_in_place": hostreg,
+                             "note": "ordinary numpy buffers inside a start()/end() bracket: pinned in place (cudaHostRegister) on their 4th sighting, i.e. during warm-up"},
+                "pageable_unregistered": {"value": world * args.steps / (ms_pag_cold * 1e-3), "ms_per_step": ms_pag_cold / args.steps,
+                                          "note": "ordinary numpy buffers outside start()/end(): plain pageable cudaMemcpyAsync each way"}},
+        "phases": phases,
         "gpu_launches": int(launches),
         "roofline": {"kernel": "supernodal SpTRSV sweeps (k_fwd + k_bwd, all levels)", "bound": "hbm", "achieved": trsv_gbs, "peak": peak, "peak_source": peak_src,
                      "unit": "GB/s", "frac": trsv_gbs / peak, "traffic": traffic, "algorithmic_bytes_per_launch_set": by["trsv"], "ms": ms_trsv / args.steps,
@@ -211,12 +241,56 @@ def run_b200(args):
     if cplx:
         out["cpu_baseline"] = None   # the CPU arm (oracle/cpu_ras.cpp) is real-valued; the complex bench is auxiliary
     elif args.cpu_baseline and rank == 0 and world == 1:
-        out["cpu_baseline"] = cpu_baseline(args, m=args.cpu_m or None, steps=5, budget_s=60.0)
+        out["cpu_baseline"] = cpu_baseline(args, steps=5, reuse=True)
     if rank == 0:
         print(json.dumps(out))
     deco.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def host_memory_bytes():
+    """Memory this process may use: MemAvailable capped by the cgroup limit."""
+    avail = None
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                avail = int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    try:
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        if lim != "max":
+            avail = min(avail, int(lim)) if avail else int(lim)
+    except Exception:
+        pass
+    return avail or 0
+
+
+CPU_ARM_BYTES = {160: 129e9, 128: 52e9}   # cpu_ras_estimate_bytes(m, 16) of oracle/cpu_ras.cpp (factor + update stack + working fronts)
+
+
+def default_cells():
+    """Subdomain edge both arms use unless --cells / HPDDM_B200_BENCH_M says otherwise: 160 (largest fit of the CUDA arm),
+    128 if the host could not hold the CPU arm's factorisation at 160 -- a function of the box only, so the `--impl reference`
+    process and the CUDA process pick the same size without talking to each other."""
+    if os.environ.get("HPDDM_B200_BENCH_M"):
+        return int(os.environ["HPDDM_B200_BENCH_M"])
+    return 160 if host_memory_bytes() >= 1.15 * CPU_ARM_BYTES[160] else 128
+
+
+def workload_name(m, world, nu, mu):
+    from hpddm_b200.examples.generate import split_grid_3d
+    grid = split_grid_3d(world)
+    N = tuple(g * m for g in grid)
+    ov = [m + (1 if g > 1 else 0) for g in grid]
+    return (f"config3 slice: 3-D Poisson {N[0]}x{N[1]}x{N[2]}, {world} subdomain(s) of {m}^3 cells + overlap 1, two-level RAS deflated, nu={nu}, mu={mu}",
+            f"{grid[0]}x{grid[1]}x{grid[2]} subdomains, 1/GPU")
+
+
+def _cache_path(m, nu, threads):
+    import socket
+    return os.path.join("/tmp", f"hpddm_b200_cpu_arm_{socket.gethostname()}_m{m}_nu{nu}_t{threads}.json")
 
 
 def usable_cpus():
@@ -245,28 +319,33 @@ def _cpu_lib():
     L.cpu_ras_nnz_factor.argtypes = [C.c_void_p]
     L.cpu_ras_factor_seconds.restype = C.c_double
     L.cpu_ras_factor_seconds.argtypes = [C.c_void_p]
+    L.cpu_ras_estimate_bytes.restype = C.c_double
+    L.cpu_ras_estimate_bytes.argtypes = [C.c_int, C.c_int]
     return L
 
 
-def cpu_baseline(args, m=None, steps=None, budget_s=150.0):
+def cpu_baseline(args, m=None, steps=None, reuse=False, ranks=1):
     """CPU arm = oracle/cpu_ras.cpp: the reference's path restated for the host cores (supernodal
     sparse Cholesky + dtrsv/dgemv supernodal solves as CHOLMOD/MUMPS do, dgemv projections, OpenMP
-    CSR SpMV), all host threads, ONE subdomain of the same workload.  The subdomain edge is reduced
-    (and reported) if the CPU factorisation would not fit the time budget."""
+    CSR SpMV), all host threads, ONE subdomain of exactly the CUDA arm's size (m^3 cells; never reduced here).
+    The "bounded sample" is the number of applies, not the size.  reuse=True (the in-line leg of the CUDA arm):
+    take the measurement the `--impl reference` run left on this box for the same (m, nu, threads) instead of
+    factoring the same matrix on the host a second time."""
     L = _cpu_lib()
     # scipy's OpenBLAS is built for at most 128 threads *including callers*: stay well below
     avail = usable_cpus()
-    threads = max(1, min(avail, 64))
+    threads = max(1, min(avail // max(1, ranks), 64))   # the host cores one of `ranks` concurrent subdomain processes would get
     m = m or args.m
-    # probe: factorisation time scales ~ m^6
-    probe = min(m, 48)
-    t0 = time.time()
-    Zp = cosine_modes((probe,) * 3, args.nu)
-    h = L.cpu_ras_create(probe, args.nu, Zp.ctypes.data, threads)
-    t_probe = time.time() - t0
-    L.cpu_ras_destroy(h)
-    while m > probe and t_probe * (m / probe) ** 6 > budget_s:
-        m -= 16
+    cache = _cache_path(m, args.nu, threads)
+    if reuse and os.path.exists(cache) and time.time() - os.path.getmtime(cache) < 6 * 3600:
+        cb = json.load(open(cache))
+        cb["sample"] += f" [measured {int(time.time() - os.path.getmtime(cache))} s earlier on this box by `bench.py --impl reference`, not repeated]"
+        return cb
+    need = L.cpu_ras_estimate_bytes(m, threads)
+    have = host_memory_bytes()
+    if have and need > 0.95 * have:
+        raise SystemExit(f"bench.py: the CPU arm needs {need / 1e9:.0f} GB of host memory for a {m}^3 subdomain, the box offers {have / 1e9:.0f} GB; "
+                         f"run both arms with a smaller --cells (the arms never use different sizes)")
     Z = cosine_modes((m, m, m), args.nu)
     t0 = time.time()
     h = L.cpu_ras_create(m, args.nu, Z.ctypes.data, threads)
@@ -284,24 +363,47 @@ def cpu_baseline(args, m=None, steps=None, budget_s=150.0):
     nnz = L.cpu_ras_nnz_factor(h)
     tf = L.cpu_ras_factor_seconds(h)
     L.cpu_ras_destroy(h)
-    return {"value": 1.0 / dt, "unit": "subdomain-applies/s", "cores": threads, "host_cpus": os.cpu_count(), "affinity_cpus": avail, "kind": "port", "ms_per_apply": dt * 1e3,
-            "effective_gbs": (2 * 8 * nnz + 8 * n * (2 * args.nu + 12 + 7 * 1.5)) / dt / 1e9,
-            "sample": f"oracle/cpu_ras.cpp (supernodal Cholesky + BLAS-2 supernodal solves, OpenMP x {threads} threads), one subdomain of {m}^3 cells"
-                      f"{'' if m == args.m else f' (reduced from {args.m}^3 to fit the CPU time budget)'}, nu={args.nu}, {k} applies, nnz(L)={nnz:.3g}, CPU analysis+numfact {tf:.1f}s (setup {t_create:.1f}s)"}
+    cb = {"value": 1.0 / dt, "unit": "subdomain-applies/s", "cores": threads, "host_cpus": os.cpu_count(), "affinity_cpus": avail, "kind": "port", "ms_per_apply": dt * 1e3,
+          "cells": m, "nnz_factor": int(nnz), "effective_gbs": (2 * 8 * nnz + 8 * n * (2 * args.nu + 12 + 7 * 1.5)) / dt / 1e9,
+          "sample": f"oracle/cpu_ras.cpp (supernodal Cholesky + BLAS-2 supernodal solves, OpenMP x {threads} threads), one subdomain of {m}^3 cells "
+                    f"(the CUDA arm's size), nu={args.nu}, {k} timed applies after 2 warm-up, nnz(L)={nnz:.4g}, CPU analysis+numfact {tf:.1f}s (setup {t_create:.1f}s)"}
+    try:
+        json.dump(cb, open(cache, "w"))
+    except Exception:
+        pass
+    return cb
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
+    world = int(os.environ.get("WORLD_SIZE", args.gpus))
     if rank != 0:
         return
-    cb = cpu_baseline(args, steps=args.steps)
-    # the host cores are shared by all subdomains of the job: N subdomains advance at the rate of one
+    # N subdomains = N reference processes sharing the host cores (MPI ranks x OpenMP threads): ONE of them is timed with
+    # cores/N threads and the job is credited N times its rate -- optimistic for the CPU (the N - 1 concurrent ranks would
+    # compete for memory bandwidth), never for this repo.  The measurement for a given (m, nu, threads) is taken once per box.
+    cb = cpu_baseline(args, steps=args.steps, reuse=world > 1, ranks=world)
+    wl, par = workload_name(args.m, world, args.nu, args.mu)
+    if world > 1:
+        cb = dict(cb, value=world * cb["value"], one_subdomain_value=cb["value"],
+                  sample=cb["sample"] + f"; job value = {world} x the one-subdomain rate ({world} concurrent ranks x {cb['cores']} threads assumed interference-free)")
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": cb["unit"], "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic", "config": {"workload": cb["sample"]}, "cpu_baseline": cb,
+           "warmup": args.warmup, "ms_per_step": 1e3 * world / cb["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": {"workload": wl, "parallelism": par, "cells": args.m, "nu": args.nu, "mu": args.mu},
+           "factor": {"nnz_factor": cb["nnz_factor"]}, "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
+
+
+def respawn_under_torchrun(args):
+    """`python bench.py --gpus N` without a launcher: start the N ranks ourselves (one per GPU, as the driver does)."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    raise SystemExit(subprocess.call(cmd))
 
 
 def main():
@@ -310,15 +412,20 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cells", dest="m", type=int, default=int(os.environ.get("HPDDM_B200_BENCH_M", 128)), help="cells per subdomain edge")
+    ap.add_argument("--cells", dest="m", type=int, default=0, help="cells per subdomain edge, both arms (0 = default_cells(): 160, or 128 on a small host)")
     ap.add_argument("--nu", type=int, default=20)
     ap.add_argument("--rhs", dest="mu", type=int, default=1, help="right-hand sides per apply (block methods)")
-    ap.add_argument("--cpu-cells", dest="cpu_m", type=int, default=0, help="subdomain edge of the CPU sample (0 = same as --cells)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--scalar", default="d", choices=["d", "z"], help="d: real FP64 Poisson (headline); z: complex FP64 Helmholtz / ORAS (config 5 shape, auxiliary)")
     ap.add_argument("--wavenumber", type=float, default=2.0)
     ap.add_argument("--krylov", action="store_true", help="also time a full GMRES solve: device-resident driver vs host-driven loop over the C ABI")
     args = ap.parse_args()
+    if not args.m:
+        args.m = default_cells()
+    if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) != args.gpus:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but the launcher started WORLD_SIZE={os.environ['WORLD_SIZE']} ranks")
+    if "WORLD_SIZE" not in os.environ and args.gpus > 1 and args.impl != "reference":
+        respawn_under_torchrun(args)
     if args.impl == "reference":
         run_reference(args)
     else:

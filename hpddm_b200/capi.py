@@ -43,6 +43,7 @@ _SIGS = {
     "hpddm_b200_ctx_synchronize": (C.c_int, [_P]),
     "hpddm_b200_ctx_stream": (C.c_void_p, [_P]),
     "hpddm_b200_ctx_launch_count": (C.c_int64, [_P]),
+    "hpddm_b200_ctx_hostreg_count": (C.c_int64, [_P]),
     "hpddm_b200_malloc": (C.c_int, [_P, C.c_size_t, _PP]),
     "hpddm_b200_free": (C.c_int, [_P, _P]),
     "hpddm_b200_memcpy": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int, C.c_int]),

@@ -236,13 +236,92 @@ int check_ready(Ctx *c, int mu) {
   return ensure_capacity(c, mu);
 }
 
+
+// ------------------------------------------------------------------ caller host memory
+// An unchanged Krylov driver passes ordinary `new K[]` memory (include/HPDDM_GMRES.hpp:45-50,116): a cudaMemcpyAsync from
+// pageable memory is staged by the driver at a fraction of the PCIe rate.  Between start() and end() -- the bracket in which the
+// caller's Krylov arena is alive -- a host range is pinned in place (cudaHostRegister) the FOURTH time it is passed (the
+// work vector every apply writes to; basis vectors only in long restarted solves).  Measured on the pool's B200 boxes
+// (profiles/r02_sysinfo.txt, 32 MB): pageable copy 2.3 ms, registered copy 0.63 ms, cudaHostRegister 18.7 ms +
+// cudaHostUnregister 10.8 ms -- pinning pays for itself after ~18 uses, so ranges seen once or twice are left alone.  Registered ranges are page-aligned, disjoint and sorted; a copy is split at their
+// boundaries so that every piece lies inside one registration (or inside none).  end() / ctx_destroy drop all registrations:
+// memory the caller frees after end() is never left pinned (a stale registration of a recycled virtual range would make
+// later DMA silently hit the old pages).  HPDDM_B200_HOSTREG=0 disables the mechanism.
+static bool hostreg_enabled() {
+  static const bool on = !(getenv("HPDDM_B200_HOSTREG") && !strcmp(getenv("HPDDM_B200_HOSTREG"), "0"));
+  return on;
+}
+void hostreg_release(Ctx *c) {
+  for (const Ctx::HostRange &r : c->hostreg) cudaHostUnregister(reinterpret_cast<void *>(r.a));
+  cudaGetLastError();
+  c->hostreg.clear();
+  c->host_seen.clear();
+}
+static void hostreg_cover(Ctx *c, uintptr_t a, uintptr_t b) {
+  static const uintptr_t page = 4096;
+  a &= ~(page - 1);
+  b = (b + page - 1) & ~(page - 1);
+  std::vector<Ctx::HostRange> add;
+  uintptr_t cur = a;
+  for (const Ctx::HostRange &r : c->hostreg) {  // gaps of [a, b) not covered yet
+    if (r.b <= cur) continue;
+    if (r.a >= b) break;
+    if (r.a > cur) add.push_back({cur, r.a});
+    cur = std::max(cur, r.b);
+  }
+  if (cur < b) add.push_back({cur, b});
+  for (const Ctx::HostRange &g : add) {
+    cudaError_t e = cudaHostRegister(reinterpret_cast<void *>(g.a), g.b - g.a, cudaHostRegisterPortable);
+    if (e == cudaSuccess) {
+      c->hostreg.push_back(g);
+      ++c->hostreg_calls;
+    } else
+      cudaGetLastError();  // e.g. already registered by the caller, or the locked-memory limit: the copy simply stays pageable
+  }
+  std::sort(c->hostreg.begin(), c->hostreg.end(), [](const Ctx::HostRange &x, const Ctx::HostRange &y) { return x.a < y.a; });
+}
+int host_copy(Ctx *c, void *dst, const void *src, size_t bytes, bool to_device) {
+  if (bytes == 0) return 0;
+  const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  const uintptr_t h0 = reinterpret_cast<uintptr_t>(to_device ? src : dst);
+  if (c->started && hostreg_enabled() && bytes >= (1u << 16)) {
+    int &seen = c->host_seen[h0];
+    if (++seen == 4) {
+      cudaPointerAttributes at;
+      const bool known = cudaPointerGetAttributes(&at, reinterpret_cast<const void *>(h0)) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+      cudaGetLastError();
+      if (!known) hostreg_cover(c, h0, h0 + bytes);  // cudaHostAlloc'ed / already registered memory needs nothing
+    }
+  }
+  // pieces: [h0, h0 + bytes) cut at the boundaries of the registered ranges
+  uintptr_t cur = h0;
+  const uintptr_t end = h0 + bytes;
+  auto piece = [&](uintptr_t p, uintptr_t q) -> cudaError_t {
+    const size_t off = p - h0;
+    return cudaMemcpyAsync((char *)dst + off, (const char *)src + off, q - p, kind, c->stream);
+  };
+  for (const Ctx::HostRange &r : c->hostreg) {
+    if (r.b <= cur) continue;
+    if (r.a >= end) break;
+    if (r.a > cur) {
+      HB_CUDA(piece(cur, r.a));
+      cur = r.a;
+    }
+    const uintptr_t q = std::min(end, r.b);
+    HB_CUDA(piece(cur, q));
+    cur = q;
+  }
+  if (cur < end) HB_CUDA(piece(cur, end));
+  return 0;
+}
+
 // stage user vectors: returns device pointers to use for reading
 int stage_in(Ctx *c, const K *const *in, int mu, int where, std::vector<const K *> &dev) {
   dev.resize(c->subs.size());
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     if (where == HPDDM_B200_HOST) {
-      HB_CUDA(cudaMemcpyAsync(s->d_in, in[i], (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+      HB_CHECK(host_copy(c, s->d_in, in[i], (size_t)s->n * mu * sizeof(K), true));
       dev[i] = s->d_in;
     } else
       dev[i] = in[i];
@@ -257,7 +336,7 @@ int stage_out(Ctx *c, K *const *out, int mu, int where) {
   if (where != HPDDM_B200_HOST) return 0;
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
-    HB_CUDA(cudaMemcpyAsync(out[i], s->d_out, (size_t)s->n * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+    HB_CHECK(host_copy(c, out[i], s->d_out, (size_t)s->n * mu * sizeof(K), false));
   }
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return p2p_check(c);
@@ -414,6 +493,7 @@ int HB_API(ctx_destroy)(hb_ctx_t *ctx) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  hostreg_release(c);
   p2p_free(c);
   for (Sub *s : c->subs) sub_free(s);
   for (void *p : {(void *)c->d_E, (void *)c->d_Einv, (void *)c->d_T, (void *)c->d_Y, (void *)c->d_R, (void *)c->d_res, (void *)c->d_rowproc, (void *)c->d_rowloc})
@@ -452,6 +532,7 @@ int HB_API(ctx_synchronize)(hb_ctx_t *ctx) {
 }
 void *HB_API(ctx_stream)(hb_ctx_t *ctx) { return reinterpret_cast<Ctx *>(ctx)->stream; }
 int64_t HB_API(ctx_launch_count)(hb_ctx_t *ctx) { return reinterpret_cast<Ctx *>(ctx)->launches; }
+int64_t HB_API(ctx_hostreg_count)(hb_ctx_t *ctx) { return reinterpret_cast<Ctx *>(ctx)->hostreg_calls; }
 
 int HB_API(malloc)(hb_ctx_t *ctx, size_t bytes, void **dptr) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
@@ -939,7 +1020,7 @@ int HB_API(start)(hb_ctx_t *ctx, const K *const *b, K *const *x, int mu, int whe
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     if (where == HPDDM_B200_HOST) {
-      HB_CUDA(cudaMemcpyAsync(s->d_out, x[i], (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+      HB_CHECK(host_copy(c, s->d_out, x[i], (size_t)s->n * mu * sizeof(K), true));
       xd[i] = s->d_out;
     } else
       xd[i] = x[i];
@@ -955,6 +1036,9 @@ int HB_API(end)(hb_ctx_t *ctx) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   if (!c) return HPDDM_B200_ERR_ARG;
   c->started = false;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  hostreg_release(c);  // the caller's Krylov arena may be freed after end(): nothing stays pinned
   return 0;
 }
 
@@ -965,7 +1049,7 @@ int HB_API(exchange)(hb_ctx_t *ctx, K *const *x, int mu, int scaled, int where) 
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     if (where == HPDDM_B200_HOST) {
-      HB_CUDA(cudaMemcpyAsync(s->d_out, x[i], (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+      HB_CHECK(host_copy(c, s->d_out, x[i], (size_t)s->n * mu * sizeof(K), true));
       xd[i] = s->d_out;
     } else
       xd[i] = x[i];
@@ -1016,13 +1100,13 @@ int HB_API(sub_solve)(hb_sub_t *sub, const K *b, K *x, int mu, int where) {
   const K *bd = b;
   K *xd = x;
   if (where == HPDDM_B200_HOST) {
-    HB_CUDA(cudaMemcpyAsync(s->d_in, b, (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+    HB_CHECK(host_copy(c, s->d_in, b, (size_t)s->n * mu * sizeof(K), true));
     bd = s->d_in;
     xd = s->d_out;
   }
   HB_CHECK(solve_cols(s, bd, xd, mu, nullptr, false));
   if (where == HPDDM_B200_HOST) {
-    HB_CUDA(cudaMemcpyAsync(x, s->d_out, (size_t)s->n * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+    HB_CHECK(host_copy(c, x, s->d_out, (size_t)s->n * mu * sizeof(K), false));
     HB_CUDA(cudaStreamSynchronize(c->stream));
   }
   return 0;
@@ -1062,8 +1146,8 @@ int HB_API(dot)(hb_ctx_t *ctx, const K *const *x, const K *const *y, int mu, K *
     Sub *s = c->subs[i];
     const K *xd = x[i], *yd = y[i];
     if (where == HPDDM_B200_HOST) {
-      HB_CUDA(cudaMemcpyAsync(s->d_in, x[i], (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
-      HB_CUDA(cudaMemcpyAsync(s->d_tmp, y[i], (size_t)s->n * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+      HB_CHECK(host_copy(c, s->d_in, x[i], (size_t)s->n * mu * sizeof(K), true));
+      HB_CHECK(host_copy(c, s->d_tmp, y[i], (size_t)s->n * mu * sizeof(K), true));
       xd = s->d_in;
       yd = s->d_tmp;
     }

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "hb_scalar.h"
@@ -204,6 +205,14 @@ struct Ctx {
   int mu_cap = 0;
   bool started = false;
   P2P *p2p = nullptr;  // NVLink peer-memory halo state (hb_p2p.cu)
+  // caller host memory pinned lazily (cudaHostRegister) between start() and end(): page-aligned, disjoint, sorted ranges;
+  // host_seen counts how often a host pointer was passed in this bracket (a range is registered on its second sighting)
+  struct HostRange {
+    uintptr_t a, b;
+  };
+  std::vector<HostRange> hostreg;
+  std::unordered_map<uintptr_t, int> host_seen;
+  int64_t hostreg_calls = 0;  // successful cudaHostRegister calls (statistics / tests)
 };
 
 // ---------------------------------------------------------------- kernels (launchers)
@@ -245,6 +254,9 @@ int gmv_core(Ctx *c, const std::vector<const K *> &in, const std::vector<K *> &o
 int stage_in(Ctx *c, const K *const *in, int mu, int where, std::vector<const K *> &dev);
 void out_ptrs(Ctx *c, K *const *out, int where, std::vector<K *> &dev);
 int stage_out(Ctx *c, K *const *out, int mu, int where);
+// copy between a caller HOST pointer and device memory on the context's stream; pins the host range lazily (see Ctx::hostreg)
+int host_copy(Ctx *c, void *dst, const void *src, size_t bytes, bool to_device);
+void hostreg_release(Ctx *c);
 int nccl_allreduce_sum(Ctx *c, double *buf, int count);  // count doubles (a K is KD doubles)
 int nccl_allgather_bytes(Ctx *c, const void *send, void *recv, size_t bytes_per_rank);
 int p2p_halo(Ctx *c, K *const *x, int mu);  // 1 = done over peer memory, 0 = use NCCL

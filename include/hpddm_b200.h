@@ -24,10 +24,13 @@
  *    context: context p of `nproc` hosts ranks [p*L, (p+1)*L), L = local count.
  *  - collective calls (hpddm_b200_apply & co.) take arrays with one pointer per
  *    LOCAL subdomain, in the order the subdomains were created.
- *  - `where` says where the caller's vectors live: HPDDM_B200_HOST pointers are
- *    staged through pinned buffers inside the call (this is what an unchanged
- *    Krylov driver passes, include/HPDDM_GMRES.hpp:116); HPDDM_B200_DEVICE
- *    pointers are used in place on the context's stream.
+ *  - `where` says where the caller's vectors live: HPDDM_B200_HOST pointers (what
+ *    an unchanged Krylov driver passes, include/HPDDM_GMRES.hpp:116) are copied
+ *    to / from the device inside the call, straight from the caller's memory:
+ *    pageable at first, pinned in place (cudaHostRegister) from the fourth
+ *    time a range is passed between start() and end() -- see
+ *    hpddm_b200_ctx_hostreg_count; HPDDM_B200_DEVICE pointers are used in place
+ *    on the context's stream.
  */
 #ifndef HPDDM_B200_H
 #define HPDDM_B200_H
@@ -88,6 +91,10 @@ int hpddm_b200_ctx_synchronize(hpddm_b200_ctx *ctx);
 void *hpddm_b200_ctx_stream(hpddm_b200_ctx *ctx);
 /* number of kernels this library launched on the context since creation */
 int64_t hpddm_b200_ctx_launch_count(hpddm_b200_ctx *ctx);
+/* number of caller host ranges pinned in place (cudaHostRegister) since creation: HOST pointers are read / written where they are;
+ * a range passed a fourth time between start() and end() is registered lazily (the Krylov arena of an unchanged driver,
+ * include/HPDDM_GMRES.hpp:45-50), all registrations are dropped by end().  HPDDM_B200_HOSTREG=0 disables this. */
+int64_t hpddm_b200_ctx_hostreg_count(hpddm_b200_ctx *ctx);
 /* device allocation helpers for callers without a CUDA runtime binding */
 int hpddm_b200_malloc(hpddm_b200_ctx *ctx, size_t bytes, void **dptr);
 int hpddm_b200_free(hpddm_b200_ctx *ctx, void *dptr);

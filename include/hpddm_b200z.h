@@ -62,6 +62,10 @@ int hpddm_b200z_ctx_synchronize(hpddm_b200z_ctx *ctx);
 void *hpddm_b200z_ctx_stream(hpddm_b200z_ctx *ctx);
 /* number of kernels this library launched on the context since creation */
 int64_t hpddm_b200z_ctx_launch_count(hpddm_b200z_ctx *ctx);
+/* number of caller host ranges pinned in place (cudaHostRegister) since creation: HOST pointers are read / written where they are;
+ * a range passed a fourth time between start() and end() is registered lazily (the Krylov arena of an unchanged driver,
+ * include/HPDDM_GMRES.hpp:45-50), all registrations are dropped by end().  HPDDM_B200_HOSTREG=0 disables this. */
+int64_t hpddm_b200z_ctx_hostreg_count(hpddm_b200z_ctx *ctx);
 /* device allocation helpers for callers without a CUDA runtime binding */
 int hpddm_b200z_malloc(hpddm_b200z_ctx *ctx, size_t bytes, void **dptr);
 int hpddm_b200z_free(hpddm_b200z_ctx *ctx, void *dptr);

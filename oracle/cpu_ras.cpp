@@ -126,7 +126,7 @@ void analyze(Problem &P) {
 
 void factor(Problem &P) {
   const int F = (int)P.fronts.size();
-  std::vector<std::vector<double>> U(F);  // update matrices (s2 x s2, lower)
+  std::vector<std::vector<double>> U(F);  // update matrices: packed lower triangles (column j starts at j*s2 - j(j-1)/2)
   const double one = 1.0, mone = -1.0;
   for (size_t l = 0; l < P.levels.size(); ++l) {
     const std::vector<int> &lv = P.levels[l];
@@ -143,7 +143,10 @@ void factor(Problem &P) {
       }
       for (int c : P.children[f]) {
         const Front &cf = P.fronts[c]; const int *r = P.rel.data() + cf.rptr; const std::vector<double> &Uc = U[c];
-        for (int j = 0; j < cf.s2; ++j) for (int i = j; i < cf.s2; ++i) M[r[i] + (size_t)r[j] * s] += Uc[i + (size_t)j * cf.s2];
+        for (int j = 0; j < cf.s2; ++j) {
+          const double *col = Uc.data() + ((size_t)j * cf.s2 - (size_t)j * (j - 1) / 2) - j;  // col[i] = U(i, j), i >= j
+          for (int i = j; i < cf.s2; ++i) M[r[i] + (size_t)r[j] * s] += col[i];
+        }
         std::vector<double>().swap(U[c]);
       }
       int info = 0;
@@ -152,8 +155,8 @@ void factor(Problem &P) {
       if (s2 > 0) {
         scipy_dtrsm_("R", "L", "T", "N", &s2, &s1, &one, M.data(), &s, M.data() + s1, &s);
         scipy_dsyrk_("L", "N", &s2, &s1, &mone, M.data() + s1, &s, &one, M.data() + s1 + (size_t)s1 * s, &s);
-        U[f].resize((size_t)s2 * s2);
-        for (int j = 0; j < s2; ++j) memcpy(&U[f][(size_t)j * s2 + j], &M[s1 + j + (size_t)(s1 + j) * s], (size_t)(s2 - j) * sizeof(double));
+        U[f].resize((size_t)s2 * (s2 + 1) / 2);
+        for (int j = 0; j < s2; ++j) memcpy(&U[f][(size_t)j * s2 - (size_t)j * (j - 1) / 2], &M[s1 + j + (size_t)(s1 + j) * s], (size_t)(s2 - j) * sizeof(double));
       }
       fr.L.resize((size_t)s * s1);
       for (int j = 0; j < s1; ++j) memcpy(&fr.L[(size_t)j * s], &M[(size_t)j * s], (size_t)s * sizeof(double));
@@ -337,6 +340,39 @@ void cpu_ras_solve(void *h, const double *b, double *x) {
   for (int i = 0; i < P.n; ++i) P.work[P.iperm[i]] = b[i];
   solve(P, P.work.data());
   for (int i = 0; i < P.n; ++i) x[i] = P.work[P.iperm[i]];
+}
+// host bytes cpu_ras_create(m, ...) needs at its peak (analysis only, no numerics): factor storage + the update matrices of two
+// consecutive levels + the frontal matrices being factored concurrently.  bench.py uses it to refuse a size the host cannot hold.
+double cpu_ras_estimate_bytes(int m, int nthreads) {
+  Problem P;
+  P.m = m; P.n = m * m * m; P.nthreads = nthreads > 0 ? nthreads : omp_get_max_threads();
+  P.ia.assign(1, 0);
+  auto id = [&](int i, int j, int k) { return (k * m + j) * m + i; };
+  for (int k = 0; k < m; ++k) for (int j = 0; j < m; ++j) for (int i = 0; i < m; ++i) {
+    if (k > 0) P.ja.push_back(id(i, j, k - 1));
+    if (j > 0) P.ja.push_back(id(i, j - 1, k));
+    if (i > 0) P.ja.push_back(id(i - 1, j, k));
+    P.ja.push_back(id(i, j, k));
+    if (i < m - 1) P.ja.push_back(id(i + 1, j, k));
+    if (j < m - 1) P.ja.push_back(id(i, j + 1, k));
+    if (k < m - 1) P.ja.push_back(id(i, j, k + 1));
+    P.ia.push_back((int)P.ja.size());
+  }
+  analyze(P);
+  double Lb = 0, peak = 0, prevU = 0;
+  for (const Front &fr : P.fronts) Lb += 8.0 * (double)(fr.s1 + fr.s2) * fr.s1;
+  for (size_t l = 0; l < P.levels.size(); ++l) {
+    double U = 0, Mmax = 0;
+    for (int f : P.levels[l]) {
+      const Front &fr = P.fronts[f];
+      U += 4.0 * (double)fr.s2 * (fr.s2 + 1);
+      Mmax = std::max(Mmax, 8.0 * (double)(fr.s1 + fr.s2) * (fr.s1 + fr.s2));
+    }
+    const bool par = (int)P.levels[l].size() >= 2 * P.nthreads;
+    peak = std::max(peak, prevU + U + Mmax * (par ? P.nthreads : 1));
+    prevU = U;
+  }
+  return Lb + peak + 8.0 * P.n * 40 + 12.0 * P.ja.size();
 }
 long cpu_ras_nnz_factor(void *h) { return ((Problem *)h)->nnzL; }
 double cpu_ras_factor_seconds(void *h) { return ((Problem *)h)->t_fact; }

@@ -142,3 +142,19 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+    # both arms describe the SAME workload: the config object is a function of (cells, gpus, nu, mu) only and the CPU sample is never shrunk
+    import bench
+    wl, par = bench.workload_name(24, 1, 20, 1)
+    assert d["config"] == {"workload": wl, "parallelism": par, "cells": 24, "nu": 20, "mu": 1}
+    assert d["cpu_baseline"]["cells"] == 24 and "24^3" in d["cpu_baseline"]["sample"]
+
+
+def test_bench_default_size_rule_is_shared_by_both_arms(monkeypatch):
+    import bench
+    monkeypatch.delenv("HPDDM_B200_BENCH_M", raising=False)
+    monkeypatch.setattr(bench, "host_memory_bytes", lambda: 200e9)
+    assert bench.default_cells() == 160
+    monkeypatch.setattr(bench, "host_memory_bytes", lambda: 100e9)
+    assert bench.default_cells() == 128
+    monkeypatch.setenv("HPDDM_B200_BENCH_M", "96")
+    assert bench.default_cells() == 96

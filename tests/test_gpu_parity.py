@@ -434,3 +434,30 @@ def test_geneo_threshold_selects_a_different_nu_per_subdomain():
     x = rhs(parts, w, 5)
     assert relerr(deco.apply(x, DEFLATED), w.apply(x, DEFLATED)) < TOL
     deco.close()
+
+
+def test_pageable_host_vectors_are_pinned_in_place_inside_a_start_end_bracket():
+    """Host boundary (include/HPDDM_GMRES.hpp:45-50,116: the Krylov driver passes ordinary new K[] memory): a range passed for the
+    fourth time between start() and end() is registered in place, results are unchanged, and end() drops every registration."""
+    parts, w = make_world(3, 1, mu=1, N=(40, 40, 40), overlap=1)   # 64 000 dofs = 512 KB per vector (>= the 64 KB registration floor)
+    deco = build_gpu_decomposition(parts, w)
+    rs = np.random.RandomState(3)
+    x = [np.asfortranarray(rs.standard_normal(p["f"].shape)) for p in parts]
+    ref = deco.apply(x)                                            # outside a bracket: plain pageable copies
+    assert deco.api.ctx_hostreg_count(deco.ctx) == 0
+    y = [np.empty_like(v, order="F") for v in x]
+    deco.start([p["f"] for p in parts], [np.zeros_like(p["f"]) for p in parts])
+    for k in range(6):
+        y[0][:] = 0.0
+        deco.apply_host_inplace(x, y, 1, None)
+        assert np.array_equal(y[0], ref[0]), k
+        # an unaligned view straddling the registered range: the copy is split at the registration boundaries
+        z = np.empty_like(y[0])
+        deco.apply_host_inplace(x, [z], 1, None)
+        assert np.array_equal(z, ref[0])
+    assert deco.api.ctx_hostreg_count(deco.ctx) >= 2               # x and y (z is a fresh range every time: never registered)
+    deco.end()
+    n0 = deco.api.ctx_hostreg_count(deco.ctx)
+    deco.apply_host_inplace(x, y, 1, None)                         # after end(): pageable again, still correct
+    assert np.array_equal(y[0], ref[0]) and deco.api.ctx_hostreg_count(deco.ctx) == n0
+    deco.close()
