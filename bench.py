@@ -364,7 +364,7 @@ def cpu_baseline(args, m=None, steps=None, reuse=False, ranks=1):
     tf = L.cpu_ras_factor_seconds(h)
     L.cpu_ras_destroy(h)
     cb = {"value": 1.0 / dt, "unit": "subdomain-applies/s", "cores": threads, "host_cpus": os.cpu_count(), "affinity_cpus": avail, "kind": "port", "ms_per_apply": dt * 1e3,
-          "cells": m, "nnz_factor": int(nnz), "effective_gbs": (2 * 8 * nnz + 8 * n * (2 * args.nu + 12 + 7 * 1.5)) / dt / 1e9,
+          "cells": m, "nnz_factor": int(nnz), "max_rss_gb": round(__import__("resource").getrusage(__import__("resource").RUSAGE_SELF).ru_maxrss / 1e6, 1), "effective_gbs": (2 * 8 * nnz + 8 * n * (2 * args.nu + 12 + 7 * 1.5)) / dt / 1e9,
           "sample": f"oracle/cpu_ras.cpp (supernodal Cholesky + BLAS-2 supernodal solves, OpenMP x {threads} threads), one subdomain of {m}^3 cells "
                     f"(the CUDA arm's size), nu={args.nu}, {k} timed applies after 2 warm-up, nnz(L)={nnz:.4g}, CPU analysis+numfact {tf:.1f}s (setup {t_create:.1f}s)"}
     try:

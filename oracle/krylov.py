@@ -22,13 +22,25 @@ def _axpy(a, x, y):
         y[r] += x[r] * a
 
 
+def _rhs_norm(op, b):
+    """initializeNorm (iterative.hpp:441-470): operators that know their boundary conditions rescale penalised entries."""
+    if hasattr(op, "rhs_norm"):
+        return op.rhs_norm(b)
+    return np.sqrt(np.real(op.dot(b, b)))
+
+
+def _converged(res, norm, tol):
+    """checkConvergence (iterative.hpp:98-103): tol > 0 relative to ||b||, tol < 0 absolute."""
+    return res / norm <= tol if tol > 0 else res <= -tol
+
+
 def gmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40, verbose=False):
     P = len(b)
     mu = b[0].shape[1]
     x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [np.array(v, order="F", copy=True) for v in x0]
     x = op.start(b, x)                                   # initializeNorm -> A.start (iterative.hpp:444)
     dtype = np.result_type(*[v.dtype for v in b])        # K: float64 or complex128
-    norm = np.sqrt(np.real(op.dot(b, b)))                # ||b||_D (iterative.hpp:455-468)
+    norm = _rhs_norm(op, b)                              # ||b||_D, penalised rows / PEN (iterative.hpp:455-468)
     norm = np.where(norm < 1e-12, 1.0, norm)             # GMRES.hpp:73
     m = restart
     applies = 0
@@ -80,7 +92,7 @@ def gmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40, verbose=False):
             s[i] = s[i] * np.conj(cs[i])
             i += 1
             res = np.abs(s[i])
-            newly = (conv == -m) & (res / norm <= tol)
+            newly = (conv == -m) & _converged(res, norm, tol)
             conv[newly] = i
             if verbose:
                 print(f"GMRES: {j:3d} {res.max():.6e} {(res / norm).max():.6e} < {tol}")
@@ -177,7 +189,7 @@ def bgmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40):
     mqr = lapack.zunmqr if cplx else lapack.dormqr
     x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [np.array(v, order="F", copy=True) for v in x0]
     x = op.start(b, x)
-    norm = np.sqrt(np.real(op.dot(b, b)))
+    norm = _rhs_norm(op, b)
     norm = np.where(norm < 1e-12, 1.0, norm)
     m = restart
     ldh = mu * (m + 1)
@@ -243,7 +255,7 @@ def bgmres(op, b, x0=None, tol=1e-6, max_it=100, restart=40):
             i += 1
             res = sv[i * mu:(i + 1) * mu]
             pt = np.array([np.linalg.norm(res[:nu + 1, nu]) for nu in range(mu)])
-            if np.all(pt / norm <= tol):
+            if np.all(_converged(pt, norm, tol)):
                 dim = mu * i
                 done = True
                 break
@@ -282,6 +294,9 @@ class OracleOperator:
 
     def dot(self, x, y):
         return self.w.dot(x, y)
+
+    def rhs_norm(self, b):
+        return self.w.rhs_norm(b)
 
     def gram(self, X, Y):
         return sum(X[r].conj().T @ (self.w.d[r][:, None] * Y[r]) for r in range(self.w.P))

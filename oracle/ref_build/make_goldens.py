@@ -43,6 +43,13 @@ CASES = {
     "small_40x40_p4_bgmres_mu4_twolevel_restart6": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-hpddm_krylov_method", "bgmres",
                                                                     "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "4", "-hpddm_gmres_restart", "6", "-hpddm_verbosity", "4"]),
     "complex_40x40_p4_bgmres_mu3": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "bgmres", "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "3"]),
+    # non-homogeneous Dirichlet data imposed by penalisation on one side (diag = 1e30, f = 1e30 g): boundaryConditions, the x = b / diag
+    # of Schwarz::start, the penalised entries of ||b|| (iterative.hpp:461-468) and the masked rows of computeResidual (schwarz.hpp:761-803)
+    "small_40x40_p4_penalised_ras": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40", "-penalise", "1"]),
+    "small_40x40_p4_penalised_twolevel_mu2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40",
+                                                              "-generate_random_rhs", "2", "-penalise", "1"]),
+    "small_40x40_p4_penalised_bgmres_mu4": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "bgmres", "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "4", "-penalise", "1"]),
+    "complex_40x40_p4_penalised_ras": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40", "-penalise", "1"]),
     # complex scalars (the reference's FORCE_COMPLEX build; damped-Helmholtz-like shift of the generator's matrix, see ref_driver.cpp)
     "complex_40x40_p4_ras": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40"]),
     "complex_40x40_p4_twolevel_nu3": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40"]),

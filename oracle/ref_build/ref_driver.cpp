@@ -45,6 +45,7 @@ int main(int argc, char **argv) {
              std::forward_as_tuple("symmetric_csr=(0|1)", "Assemble symmetric matrices.", HPDDM::Option::Arg::argument),
              std::forward_as_tuple("nonuniform=(0|1)", "Use a different number of eigenpairs to compute on each subdomain.", HPDDM::Option::Arg::argument),
              std::forward_as_tuple("deflation_vectors=<0>", "Number of analytic deflation vectors per subdomain (golden runs).", HPDDM::Option::Arg::integer),
+             std::forward_as_tuple("penalise=(0|1)", "Impose non-homogeneous Dirichlet data on the side y = 0 by penalisation (golden runs).", HPDDM::Option::Arg::argument),
              std::forward_as_tuple("prefix=<string>", "Use a prefix.", HPDDM::Option::Arg::argument)});
   std::string out = getenv("HPDDM_REF_DUMP") ? getenv("HPDDM_REF_DUMP") : "golden";
   out += "_" + std::to_string(rankWorld) + ".bin";
@@ -68,6 +69,29 @@ int main(int argc, char **argv) {
     f[i] = K(std::real(f[i]), 0.25 * std::sin(0.05 * i + rankWorld));
   }
 #endif
+  if (opt.app().find("penalise") != opt.app().cend() && opt.app()["penalise"] == 1) {
+    // Non-homogeneous Dirichlet data g on the side y = 0 of the domain, imposed the way HPDDM users do it (HPDDM_PEN,
+    // include/HPDDM_define.hpp:48): diagonal = 1e30, right-hand side = 1e30 * g.  Exercises Subdomain::boundaryConditions
+    // (subdomain.hpp:310-336), the division of x in Schwarz::start (schwarz.hpp:501-505), the penalised entries of ||b||
+    // (iterative.hpp:461-468) and the masked rows of Schwarz::computeResidual (schwarz.hpp:761-803).
+    // Applied after the complex shift so that the penalised diagonal is exactly (1e30, 0): with a diagonal like (1e30, 1) the
+    // initial residual b - A (b / diag) on these rows is an ulp of 1e30 ~ 1e14 of rounding noise that depends on how the platform
+    // rounds complex products, i.e. nothing a parity test can pin.
+    // Local layout of examples/generate.cpp:51-61: row k = (i - iStart) + (iEnd - iStart) * (j - jStart).
+    const int Nx = opt.app()["Nx"], Ny = opt.app()["Ny"], overlap = opt.app()["overlap"];
+    int xGrid = int(sqrt(sizeWorld));
+    while (sizeWorld % xGrid != 0) --xGrid;
+    const int yGrid = sizeWorld / xGrid, y = rankWorld / xGrid, x = rankWorld - xGrid * y;
+    const int iStart = std::max(x * Nx / xGrid - overlap, 0), iEnd = std::min((x + 1) * Nx / xGrid + overlap, Nx);
+    const int jStart = std::max(y * Ny / yGrid - overlap, 0);
+    if (jStart == 0)
+      for (int i = iStart; i < iEnd; ++i) {
+        const int k = i - iStart;
+        for (int p = Mat->ia_[k]; p < Mat->ia_[k + 1]; ++p)
+          if (Mat->ja_[p] == k) Mat->a_[p] = K(HPDDM_PEN);
+        for (int nu = 0; nu < mu; ++nu) f[k + nu * ndof] = K(HPDDM_PEN) * cplx_probe(1.0 + 0.5 * std::sin(0.3 * i + nu), 0.25 * std::cos(0.2 * i));
+      }
+  }
   {
     int hdr[4] = {ndof, Mat->nnz_, (int)Mat->sym_, sizeWorld};
     dumpi("header", hdr, 4);

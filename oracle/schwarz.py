@@ -355,6 +355,20 @@ class SchwarzWorld:
             st[:, 0] += self.d[r] @ (np.abs(fr) ** 2)
         return np.sqrt(st)
 
+    def rhs_norm(self, b):
+        """||b|| of IterativeMethod::initializeNorm, right-preconditioned branch (iterative.hpp:455-468): D-weighted l2 norm per
+        column in which an entry on a boundary-condition row (Subdomain::boundaryConditions) larger than PEN * EPS is first
+        divided by HPDDM_PEN -- a penalised Dirichlet value b_i = 1e30 g_i counts as g_i."""
+        mu = b[0].shape[1]
+        out = np.zeros(mu)
+        for r in range(self.P):
+            br = np.array(b[r], copy=True)
+            for i in self.boundary_conditions(r):
+                big = np.abs(br[i, :]) > HPDDM_PEN * HPDDM_EPS
+                br[i, big] = br[i, big] / HPDDM_PEN
+            out += self.d[r] @ (np.abs(br) ** 2)
+        return np.sqrt(out)
+
     # ------------------------------------------------------------------ helpers
     def dot(self, x, y):
         """D-weighted global inner products per column (iterative.hpp:455-468,

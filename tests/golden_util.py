@@ -42,7 +42,7 @@ def load(name):
                 sym=arg_value(args, "symmetric_csr", "0") == "1", nu=int(arg_value(args, "deflation_vectors", 0)),
                 restart=int(arg_value(args, "hpddm_gmres_restart", 40)), max_it=int(arg_value(args, "hpddm_max_it", 100)),
                 tol=float(arg_value(args, "hpddm_tol", 1e-6)), method=arg_value(args, "hpddm_schwarz_method", "ras"),
-                krylov=arg_value(args, "hpddm_krylov_method", "gmres"))
+                krylov=arg_value(args, "hpddm_krylov_method", "gmres"), penalised=arg_value(args, "penalise", "0") == "1")
     return parts, ref, meta
 
 
@@ -65,6 +65,28 @@ def complexify(part, rank):
     f = part["f"][:, :1].astype(np.complex128)
     f[:, 0] = f[:, 0].real + 1j * 0.25 * np.sin(0.05 * np.arange(n) + rank)
     return dict(part, Mat=A, f=np.asfortranarray(f))
+
+
+def penalise(part, rank, P, Nx, Ny, overlap):
+    """ref_driver.cpp's `-penalise 1`: Dirichlet data on the side y = 0 by penalisation (diag = HPDDM_PEN, f = HPDDM_PEN * g),
+    local layout of examples/generate.cpp:51-61."""
+    xg = int(np.sqrt(P))
+    while P % xg:
+        xg -= 1
+    yg = P // xg
+    y, x = divmod(rank, xg)
+    i0, i1 = max(x * Nx // xg - overlap, 0), min((x + 1) * Nx // xg + overlap, Nx)
+    j0 = max(y * Ny // yg - overlap, 0)
+    A = sp.csr_matrix(part["Mat"]).copy()
+    f = np.array(part["f"], order="F", copy=True)
+    if j0 == 0:
+        for i in range(i0, i1):
+            k = i - i0
+            lo, hi = A.indptr[k], A.indptr[k + 1]
+            A.data[lo:hi][A.indices[lo:hi] == k] = 1e30
+            for nu in range(f.shape[1]):
+                f[k, nu] = 1e30 * ((1.0 + 0.5 * np.sin(0.3 * i + nu)) + (1j * 0.25 * np.cos(0.2 * i) if np.iscomplexobj(f) else 0.0))
+    return dict(part, Mat=A, f=f)
 
 
 def load_refdata():

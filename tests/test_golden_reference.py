@@ -7,7 +7,7 @@ import pytest
 from hpddm_b200.examples.generate import generate2d
 from oracle.krylov import OracleOperator, bgmres, cg, gmres
 from oracle.schwarz import ADDITIVE, BALANCED, DEFLATED, SchwarzWorld
-from tests.golden_util import cases, col, complexify, load
+from tests.golden_util import cases, col, complexify, load, penalise
 
 TOL = 1e-10
 
@@ -23,6 +23,8 @@ def test_generator_is_bit_identical_to_examples_generate_cpp(name):
         mine = generate2d(r, meta["P"], Nx=meta["Nx"], Ny=meta["Ny"], overlap=meta["overlap"], mu=0, sym=meta["sym"])
         if meta["complex"]:
             mine = complexify(mine, r)
+        if meta["penalised"]:
+            mine = penalise(mine, r, meta["P"], meta["Nx"], meta["Ny"], meta["overlap"])
         g = ref[r]
         assert mine["ndof"] == int(g["header"][0])
         assert np.array_equal(mine["Mat"].indptr, g["ia"]) and np.array_equal(mine["Mat"].indices, g["ja"])

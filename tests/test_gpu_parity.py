@@ -450,14 +450,14 @@ def test_pageable_host_vectors_are_pinned_in_place_inside_a_start_end_bracket():
     for k in range(6):
         y[0][:] = 0.0
         deco.apply_host_inplace(x, y, 1, None)
-        assert np.array_equal(y[0], ref[0]), k
+        assert relerr(y, ref) < 1e-13, k                           # (FP64 atomics in the sweeps: equal to round-off, not bit-wise)
         # an unaligned view straddling the registered range: the copy is split at the registration boundaries
         z = np.empty_like(y[0])
         deco.apply_host_inplace(x, [z], 1, None)
-        assert np.array_equal(z, ref[0])
+        assert relerr([z], ref) < 1e-13
     assert deco.api.ctx_hostreg_count(deco.ctx) >= 2               # x and y (z is a fresh range every time: never registered)
     deco.end()
     n0 = deco.api.ctx_hostreg_count(deco.ctx)
     deco.apply_host_inplace(x, y, 1, None)                         # after end(): pageable again, still correct
-    assert np.array_equal(y[0], ref[0]) and deco.api.ctx_hostreg_count(deco.ctx) == n0
+    assert relerr(y, ref) < 1e-13 and deco.api.ctx_hostreg_count(deco.ctx) == n0
     deco.close()
