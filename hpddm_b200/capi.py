@@ -40,6 +40,8 @@ _SIGS = {
     "hpddm_b200_ctx_destroy": (C.c_int, [_P]),
     "hpddm_b200_nccl_unique_id": (C.c_int, [_P]),
     "hpddm_b200_ctx_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "hpddm_b200_ctx_comm_init_host": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "hpddm_b200_ctx_transport": (C.c_int, [_P]),
     "hpddm_b200_ctx_synchronize": (C.c_int, [_P]),
     "hpddm_b200_ctx_stream": (C.c_void_p, [_P]),
     "hpddm_b200_ctx_launch_count": (C.c_int64, [_P]),
@@ -71,6 +73,9 @@ _SIGS = {
     "hpddm_b200_coarse_solve": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "hpddm_b200_dot": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int]),
     "hpddm_b200_sub_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "hpddm_b200_sub_boundary_conditions": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int)]),
+    "hpddm_b200_rhs_norm": (C.c_int, [_P, _P, C.c_int, _P, C.c_int]),
+    "hpddm_b200_compute_residual": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int]),
     "hpddm_b200_solve": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
     "hpddm_b200_solve_bgmres": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
     "hpddm_b200_solve_cg": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
@@ -79,6 +84,9 @@ _SIGS = {
 # argument shapes (scalars travel behind pointers)
 _SIGS.update({k.replace("hpddm_b200_", "hpddm_b200z_", 1): v for k, v in list(_SIGS.items())})
 EXPORTS = sorted(_SIGS)
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)   # hpddm_b200_allgather_fn
 
 
 def lib():

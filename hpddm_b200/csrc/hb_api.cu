@@ -78,14 +78,52 @@ static int nccl_load() {
   } while (0)
 constexpr int NCCL_INT32 = 2, NCCL_F64 = 8, NCCL_SUM = 0;
 
-// uploads are issued on the context's (non-blocking) stream and waited for: a plain cudaMemcpy
-// from pageable memory is neither ordered against that stream nor guaranteed to have landed
-int nccl_allgather_bytes(Ctx *c, const void *send, void *recv, size_t bytes_per_rank) {
-  if (c->nproc > 1) HB_NCCL(g_nccl.AllGather(send, recv, bytes_per_rank, 0 /* ncclChar */, c->nccl, c->stream));
+// small reductions of the Krylov layer: the peer-memory fabric when it is up (deterministic rank-order sums), else NCCL
+int nccl_allreduce_max(Ctx *c, double *buf, int count) {
+  if (c->nproc <= 1) return 0;
+  const int done = fabric_allreduce(c, buf, count, 1);
+  if (done != 0) return done < 0 ? done : 0;
+  HB_NCCL(g_nccl.AllReduce(buf, buf, count, NCCL_F64, 2 /* ncclMax */, c->nccl, c->stream));
   return 0;
 }
 int nccl_allreduce_sum(Ctx *c, double *buf, int count) {
-  if (c->nproc > 1) HB_NCCL(g_nccl.AllReduce(buf, buf, count, NCCL_F64, NCCL_SUM, c->nccl, c->stream));
+  if (c->nproc <= 1) return 0;
+  const int done = fabric_allreduce(c, buf, count, 0);
+  if (done != 0) return done < 0 ? done : 0;
+  HB_NCCL(g_nccl.AllReduce(buf, buf, count, NCCL_F64, NCCL_SUM, c->nccl, c->stream));
+  return 0;
+}
+// CoarseOperator::callSolver gather (coarse_operator_impl.hpp:1708): every process block of d_T to every process
+static int coarse_gather(Ctx *c, int mu) {
+  if (c->nproc <= 1) return 0;
+  const int done = fabric_allgather(c, c->d_T, c->Lnu * mu);
+  if (done != 0) return done < 0 ? done : 0;
+  HB_NCCL(g_nccl.AllGather(c->d_T + (size_t)c->proc_rank * c->Lnu * mu, c->d_T, (size_t)c->Lnu * mu * KD, NCCL_F64, c->nccl, c->stream));
+  return 0;
+}
+int ctrl_allgather(Ctx *c, const void *send, void *recv, size_t bytes) {
+  if (c->nproc <= 1) {
+    memcpy(recv, send, bytes);
+    return 0;
+  }
+  if (c->host_allgather) {
+    if (c->host_allgather(send, recv, bytes, c->host_allgather_user) != 0) {
+      set_error("the host program's all-gather callback failed");
+      return HPDDM_B200_ERR_NCCL;
+    }
+    return 0;
+  }
+  if (!c->nccl) {
+    set_error("no communicator: call ctx_comm_init (NCCL) or ctx_comm_init_host first");
+    return HPDDM_B200_ERR_STATE;
+  }
+  char *dbuf = nullptr;
+  HB_CUDA(cudaMalloc(&dbuf, bytes * c->nproc));
+  HB_CUDA(cudaMemcpyAsync(dbuf + bytes * c->proc_rank, send, bytes, cudaMemcpyHostToDevice, c->stream));
+  HB_NCCL(g_nccl.AllGather(dbuf + bytes * c->proc_rank, dbuf, bytes, 0 /* ncclChar */, c->nccl, c->stream));
+  HB_CUDA(cudaMemcpyAsync(recv, dbuf, bytes * c->nproc, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(dbuf);
   return 0;
 }
 
@@ -132,6 +170,7 @@ static int ensure_capacity(Ctx *c, int mu) {
   if (c->d_res) cudaFree(c->d_res);
   HB_CUDA(cudaMalloc(&c->d_res, std::max(mu, 64) * sizeof(K)));
   c->mu_cap = mu;
+  if (c->nproc > 1) HB_CHECK(fabric_setup(c, mu));  // collective: every process reaches this with the same mu (SPMD call sequence)
   return 0;
 }
 
@@ -163,11 +202,11 @@ static int build_links(Ctx *c) {
 
 // halo sum  x_s[map] += neighbours' values  (Subdomain::exchange, subdomain.hpp:115-130),
 // all mu columns and all neighbours in one round.  x[] = device pointers per local subdomain.
-int halo(Ctx *c, K *const *x, int mu, bool allow_p2p) {
+int halo(Ctx *c, K *const *x, int mu) {
   bool any = false;
   for (Sub *s : c->subs) any = any || s->h > 0;
   if (!any) return 0;
-  if (allow_p2p) {
+  {
     const int done = p2p_halo(c, x, mu);  // one subdomain per process: NVLink peer-memory path (hb_p2p.cu)
     if (done < 0) return done;
     if (done == 1) return 0;
@@ -186,6 +225,10 @@ int halo(Ctx *c, K *const *x, int mu, bool allow_p2p) {
       } else
         remote = true;
     }
+  if (remote && !c->nccl) {
+    set_error("halo: remote neighbours but neither the peer-memory fabric nor an NCCL communicator is available (several subdomains per process need NCCL)");
+    return HPDDM_B200_ERR_STATE;
+  }
   if (remote) {
     // order both directions by (destination subdomain, source subdomain) so that
     // the k-th send A->B matches the k-th receive posted by B
@@ -218,6 +261,18 @@ int halo(Ctx *c, K *const *x, int mu, bool allow_p2p) {
   li = 0;
   for (Sub *s : c->subs) HB_CHECK(k_unpack(c, s, mu, x[li++]));
   return 0;
+}
+
+// host copy of the values received by the last single-column halo round of subdomain s (h entries, neighbour order)
+static int halo_received(Ctx *c, Sub *s, K *out) {
+  const K *src = s->d_recv;
+  if (fabric_on(c)) {
+    const K *w = p2p_last_halo_window(c);
+    if (w) src = w;
+  }
+  HB_CUDA(cudaMemcpyAsync(out, src, (size_t)s->h * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return p2p_check(c);
 }
 
 int check_ready(Ctx *c, int mu) {
@@ -353,10 +408,7 @@ static int deflation_core(Ctx *c, const std::vector<const K *> &in, const std::v
   }
   HB_CUDA(cudaMemsetAsync(c->d_T, 0, (size_t)c->Lnu * c->nproc * mu * sizeof(K), c->stream));
   for (size_t i = 0; i < c->subs.size(); ++i) HB_CHECK(k_zt_project(c, c->subs[i], mu, in[i], coarse_block(c, c->d_T, c->subs[i], mu), c->Lnu));
-  if (c->nproc > 1) {
-    // CoarseOperator::callSolver gather (coarse_operator_impl.hpp:1708) -> all-gather + replicated solve
-    HB_NCCL(g_nccl.AllGather(c->d_T + (size_t)c->proc_rank * c->Lnu * mu, c->d_T, (size_t)c->Lnu * mu * KD, NCCL_F64, c->nccl, c->stream));
-  }
+  HB_CHECK(coarse_gather(c, mu));  // CoarseOperator::callSolver gather -> all-gather + replicated solve, no scatter
   HB_CHECK(k_coarse_solve(c, mu));
   for (size_t i = 0; i < c->subs.size(); ++i) HB_CHECK(k_z_expand(c, c->subs[i], mu, coarse_block(c, c->d_Y, c->subs[i], mu), c->Lnu, out[i]));
   return halo(c, out.data(), mu);
@@ -449,6 +501,17 @@ int apply_core(Ctx *c, const std::vector<const K *> &ind, const std::vector<K *>
   return 0;
 }
 
+int rhs_norms(Ctx *c, const std::vector<const K *> &b, int mu, std::vector<double> &out) {
+  double *d_n = reinterpret_cast<double *>(c->d_res);  // >= 64 scalars (ensure_capacity)
+  HB_CUDA(cudaMemsetAsync(d_n, 0, mu * sizeof(double), c->stream));
+  for (size_t q = 0; q < c->subs.size(); ++q) HB_CHECK(k_rhs_norm(c, c->subs[q], mu, b[q], d_n));
+  HB_CHECK(nccl_allreduce_sum(c, d_n, mu));
+  out.resize(mu);
+  HB_CUDA(cudaMemcpyAsync(out.data(), d_n, mu * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (double &v : out) v = std::sqrt(v);
+  return 0;
+}
 
 }  // namespace hb
 
@@ -482,7 +545,7 @@ int HB_API(ctx_create)(int device, hb_ctx_t **ctx) {
 static void sub_free(Sub *s) {
   free_factor(s->fac);
   for (void *p : {(void *)s->d_ia, (void *)s->d_ja, (void *)s->d_a, (void *)s->d_d, (void *)s->d_map, (void *)s->d_ebase, (void *)s->d_esize, (void *)s->d_send,
-                  (void *)s->d_recv, (void *)s->d_uidx, (void *)s->d_useg, (void *)s->d_upos, (void *)s->d_bc_idx, (void *)s->d_bc_val, (void *)s->d_Z,
+                  (void *)s->d_recv, (void *)s->d_uidx, (void *)s->d_useg, (void *)s->d_upos, (void *)s->d_bc_idx, (void *)s->d_bc_val, (void *)s->d_bcflag, (void *)s->d_Z,
                   (void *)s->d_in, (void *)s->d_out, (void *)s->d_work, (void *)s->d_tmp, (void *)s->d_tmp2})
     if (p) cudaFree(p);
   delete s;
@@ -525,10 +588,29 @@ int HB_API(ctx_comm_init)(hb_ctx_t *ctx, const void *id128, int proc_rank, int n
   return 0;
 }
 
+int HB_API(ctx_comm_init_host)(hb_ctx_t *ctx, int proc_rank, int nproc, int (*allgather)(const void *, void *, size_t, void *), void *user) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !allgather || nproc < 1 || proc_rank < 0 || proc_rank >= nproc || (c->nccl && (nproc != c->nproc || proc_rank != c->proc_rank))) {
+    set_error("ctx_comm_init_host: bad arguments (rank / size must match an NCCL communicator initialised earlier)");
+    return HPDDM_B200_ERR_ARG;
+  }
+  c->host_allgather = allgather;
+  c->host_allgather_user = user;
+  c->proc_rank = proc_rank;
+  c->nproc = nproc;
+  c->mu_cap = 0;
+  return 0;
+}
+
 int HB_API(ctx_synchronize)(hb_ctx_t *ctx) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CUDA(cudaStreamSynchronize(c->stream));
-  return 0;
+  return p2p_check(c);  // a peer-memory collective that gave up waiting surfaces here for DEVICE-pointer callers
+}
+int HB_API(ctx_transport)(hb_ctx_t *ctx) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || c->nproc <= 1) return 0;
+  return fabric_on(c) ? 2 : 1;
 }
 void *HB_API(ctx_stream)(hb_ctx_t *ctx) { return reinterpret_cast<Ctx *>(ctx)->stream; }
 int64_t HB_API(ctx_launch_count)(hb_ctx_t *ctx) { return reinterpret_cast<Ctx *>(ctx)->launches; }
@@ -574,6 +656,8 @@ int HB_API(sub_destroy)(hb_sub_t *sub) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->subs.erase(std::remove(c->subs.begin(), c->subs.end(), s), c->subs.end());
+  for (Sub *o : c->subs) o->peer_seg.clear();  // links into the destroyed subdomain are rebuilt by the next check_ready
+  c->mu_cap = 0;
   sub_free(s);
   return 0;
 }
@@ -669,6 +753,12 @@ int HB_API(sub_set_matrix)(hb_sub_t *sub, int n, int nnz, const int *ia, const i
   }
   HB_CHECK(up(bi, &s->d_bc_idx, s->ctx->stream));
   HB_CHECK(up(bv, &s->d_bc_val, s->ctx->stream));
+  std::vector<unsigned char> flag;
+  if (!bi.empty()) {
+    flag.assign(n, 0);
+    for (int i : bi) flag[i] = 1;
+  }
+  HB_CHECK(up(flag, &s->d_bcflag, s->ctx->stream));
   s->ctx->mu_cap = 0;  // work vectors depend on n
   return 0;
 }
@@ -763,15 +853,14 @@ int HB_API(multiplicity_scaling)(hb_ctx_t *ctx, double *const *d) {
     HB_CUDA(cudaMemcpyAsync(s->d_work, dk[i].data(), (size_t)s->n * sizeof(K), cudaMemcpyHostToDevice, c->stream));
     src[i] = s->d_work;
   }
-  HB_CHECK(halo(c, src.data(), 1, false));  // the send / recv staging buffers themselves are read back below: NCCL path
+  // one unscaled halo round of d: what every neighbour holds on the shared dofs ends up, entry by entry, in the receive
+  // buffer (NCCL path: d_recv; peer-memory path: the window slot of this round, same [neighbour segment][entry] layout)
+  HB_CHECK(halo(c, src.data(), 1));
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
     std::vector<K> recv(s->h), send(s->h);
-    if (s->h) {
-      HB_CUDA(cudaMemcpyAsync(recv.data(), s->d_recv, s->h * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
-      HB_CUDA(cudaMemcpyAsync(send.data(), s->d_send, s->h * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
-    }
-    HB_CUDA(cudaStreamSynchronize(c->stream));
+    if (s->h) HB_CHECK(halo_received(c, s, recv.data()));
+    for (int e = 0; e < s->h; ++e) send[e] = dk[i][s->nb_idx[e]];  // what this subdomain sent: its own d on the shared dofs
     std::fill(d[i], d[i] + s->n, 1.0);  // schwarz.hpp:391
     for (int e = 0; e < s->h; ++e) {    // schwarz.hpp:392-401, neighbour order
       const int j = s->nb_idx[e];
@@ -829,15 +918,7 @@ static int coarse_layout(Ctx *c) {
     Lnu += s->nu;
   }
   std::vector<int> all(c->nproc, Lnu);
-  if (c->nproc > 1) {
-    int *dbuf = nullptr;
-    HB_CUDA(cudaMalloc(&dbuf, c->nproc * sizeof(int)));
-    HB_CUDA(cudaMemcpyAsync(dbuf + c->proc_rank, &Lnu, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    HB_NCCL(g_nccl.AllGather(dbuf + c->proc_rank, dbuf, 1, NCCL_INT32, c->nccl, c->stream));
-    HB_CUDA(cudaMemcpyAsync(all.data(), dbuf, c->nproc * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    HB_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(dbuf);
-  }
+  HB_CHECK(ctrl_allgather(c, &Lnu, all.data(), sizeof(int)));
   c->Lnu_p = all;
   c->coarse_off.assign(c->nproc + 1, 0);
   int Lmax = 0;
@@ -948,16 +1029,7 @@ int HB_API(build_coarse)(hb_ctx_t *ctx) {
   {
     std::vector<int> mine(L);
     for (int i = 0; i < L; ++i) mine[i] = c->subs[i]->nu;
-    if (c->nproc > 1) {
-      int *dbuf = nullptr;
-      HB_CUDA(cudaMalloc(&dbuf, P * sizeof(int)));
-      HB_CUDA(cudaMemcpyAsync(dbuf + c->proc_rank * L, mine.data(), L * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-      HB_NCCL(g_nccl.AllGather(dbuf + c->proc_rank * L, dbuf, L, NCCL_INT32, c->nccl, c->stream));
-      HB_CUDA(cudaMemcpyAsync(nu_all.data(), dbuf, P * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      HB_CUDA(cudaStreamSynchronize(c->stream));
-      cudaFree(dbuf);
-    } else
-      nu_all = mine;
+    HB_CHECK(ctrl_allgather(c, mine.data(), nu_all.data(), L * sizeof(int)));
   }
   for (int v : nu_all) numax = std::max(numax, v);
   HB_CHECK(ensure_capacity(c, numax));
@@ -992,13 +1064,10 @@ int HB_API(build_coarse)(hb_ctx_t *ctx) {
   }
   std::vector<K> E((size_t)N * N, mk(0.0));
   if (c->nproc > 1) {
-    K *d_all = nullptr;
-    HB_CUDA(cudaMalloc(&d_all, std::max<size_t>((size_t)Lnu * c->nproc * N, 1) * sizeof(K)));
-    HB_NCCL(g_nccl.AllGather(d_rows, d_all, (size_t)Lnu * N * KD, NCCL_F64, c->nccl, c->stream));
-    std::vector<K> tmp((size_t)Lnu * c->nproc * N);
-    HB_CUDA(cudaMemcpyAsync(tmp.data(), d_all, tmp.size() * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<K> rows((size_t)Lnu * N), tmp((size_t)Lnu * c->nproc * N);
+    HB_CUDA(cudaMemcpyAsync(rows.data(), d_rows, rows.size() * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
     HB_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d_all);
+    HB_CHECK(ctrl_allgather(c, rows.data(), tmp.data(), rows.size() * sizeof(K)));  // setup: the row blocks of E travel over the control plane
     for (int p = 0; p < c->nproc; ++p)
       for (int col = 0; col < N; ++col)
         for (int r = 0; r < c->Lnu_p[p]; ++r) E[(size_t)c->coarse_off[p] + r + (size_t)col * N] = tmp[(size_t)p * Lnu * N + (size_t)col * Lnu + r];
@@ -1127,7 +1196,7 @@ int HB_API(coarse_solve)(hb_ctx_t *ctx, K *const *rhs, int mu, int where) {
     if (s->nu == 0) continue;
     HB_CUDA(cudaMemcpy2DAsync(coarse_block(c, c->d_T, s, mu), c->Lnu * sizeof(K), rhs[i], s->nu * sizeof(K), s->nu * sizeof(K), mu, kin, c->stream));
   }
-  if (c->nproc > 1) HB_NCCL(g_nccl.AllGather(c->d_T + (size_t)c->proc_rank * c->Lnu * mu, c->d_T, (size_t)c->Lnu * mu * KD, NCCL_F64, c->nccl, c->stream));
+  HB_CHECK(coarse_gather(c, mu));
   HB_CHECK(k_coarse_solve(c, mu));
   for (size_t i = 0; i < c->subs.size(); ++i) {
     Sub *s = c->subs[i];
@@ -1156,6 +1225,68 @@ int HB_API(dot)(hb_ctx_t *ctx, const K *const *x, const K *const *y, int mu, K *
   if (c->nproc > 1) HB_NCCL(g_nccl.AllReduce(c->d_res, c->d_res, mu * KD, NCCL_F64, NCCL_SUM, c->nccl, c->stream));
   HB_CUDA(cudaMemcpyAsync(result, c->d_res, mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int HB_API(sub_boundary_conditions)(hb_sub_t *sub, int *idx, K *val, int *count) {
+  Sub *s = reinterpret_cast<Sub *>(sub);
+  if (!s || !count) return HPDDM_B200_ERR_ARG;
+  *count = (int)s->bc.size();
+  for (size_t q = 0; q < s->bc.size(); ++q) {
+    if (idx) idx[q] = s->bc[q].first;
+    if (val) val[q] = s->bc[q].second;
+  }
+  return 0;
+}
+
+int HB_API(rhs_norm)(hb_ctx_t *ctx, const K *const *b, int mu, double *norm, int where) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  HB_CHECK(check_ready(c, mu));
+  if (!norm || mu > 64) {
+    set_error("rhs_norm: bad arguments (mu <= 64)");
+    return HPDDM_B200_ERR_ARG;
+  }
+  std::vector<const K *> bd;
+  HB_CHECK(stage_in(c, b, mu, where, bd));
+  std::vector<double> out;
+  HB_CHECK(rhs_norms(c, bd, mu, out));
+  std::copy(out.begin(), out.end(), norm);
+  return 0;
+}
+
+int HB_API(compute_residual)(hb_ctx_t *ctx, const K *const *x, const K *const *f, double *storage, int mu, int norm, int where) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  HB_CHECK(check_ready(c, mu));
+  if (!storage || mu > 32 || norm < 0 || norm > 2) {
+    set_error("compute_residual: bad arguments (mu <= 32, norm in {0: l2, 1: l1, 2: l-infinity})");
+    return HPDDM_B200_ERR_ARG;
+  }
+  const size_t L = c->subs.size();
+  std::vector<const K *> xd, fd(L);
+  std::vector<K *> t(L);
+  HB_CHECK(stage_in(c, x, mu, where, xd));
+  for (size_t i = 0; i < L; ++i) {
+    Sub *s = c->subs[i];
+    t[i] = s->d_work;
+    if (where == HPDDM_B200_HOST) {
+      HB_CHECK(host_copy(c, s->d_tmp, f[i], (size_t)s->n * mu * sizeof(K), true));
+      fd[i] = s->d_tmp;
+    } else
+      fd[i] = f[i];
+  }
+  HB_CHECK(gmv_core(c, xd, t, mu));                                                                     // tmp = A x        (schwarz.hpp:766)
+  for (size_t i = 0; i < L; ++i) HB_CHECK(k_axpy(c, (int64_t)c->subs[i]->n * mu, -1.0, fd[i], t[i]));   // tmp -= f         (768)
+  double *d_n = reinterpret_cast<double *>(c->d_res);
+  HB_CUDA(cudaMemsetAsync(d_n, 0, 2 * mu * sizeof(double), c->stream));
+  for (size_t i = 0; i < L; ++i) HB_CHECK(k_residual_norms(c, c->subs[i], mu, norm, fd[i], t[i], d_n));
+  if (c->nproc > 1) {
+    if (norm == 2) HB_CHECK(nccl_allreduce_max(c, d_n, 2 * mu));
+    else HB_CHECK(nccl_allreduce_sum(c, d_n, 2 * mu));
+  }
+  HB_CUDA(cudaMemcpyAsync(storage, d_n, 2 * mu * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  if (norm == 0)
+    for (int q = 0; q < 2 * mu; ++q) storage[q] = std::sqrt(storage[q]);
   return 0;
 }
 

@@ -167,6 +167,7 @@ struct Sub {
   std::vector<std::pair<int, K>> bc;  // penalised rows
   int *d_bc_idx = nullptr;
   K *d_bc_val = nullptr;
+  unsigned char *d_bcflag = nullptr;  // n flags: 1 on boundary-condition rows (nullptr when there is none)
   // factor
   Symbolic sym;
   DeviceFactor fac;
@@ -189,6 +190,10 @@ struct Ctx {
   // communicator
   void *nccl = nullptr;  // ncclComm_t
   int proc_rank = 0, nproc = 1;
+  // control-plane all-gather supplied by the host program (hpddm_b200_ctx_comm_init_host; e.g. MPI_Allgather on the
+  // communicator of Subdomain::communicator_): host buffers, blocking.  nullptr -> NCCL carries the control plane too.
+  int (*host_allgather)(const void *, void *, size_t, void *) = nullptr;
+  void *host_allgather_user = nullptr;
   // coarse
   int Nc = 0;
   std::vector<int> coarse_off;  // per global rank, size P+1
@@ -236,7 +241,14 @@ int k_z_expand(Ctx *c, const Sub *s, int mu, const K *Y, int ldY, K *out);
 int k_pack(Ctx *c, const Sub *s, int mu, const K *x, K *send);
 int k_unpack(Ctx *c, const Sub *s, int mu, K *x);  // x[map] += d_recv, deterministic order
 int k_dot(Ctx *c, const Sub *s, int mu, const K *x, const K *y, K *res);  // res[col] += sum_i d_i conj(x_i) y_i
-int k_coarse_solve(Ctx *c, int mu);  // d_Y = E^{-1} d_T with one refinement step
+int k_coarse_solve(Ctx *c, int mu);
+// res[col] += sum_i d_i |b_i|^2 with penalised boundary rows divided by HPDDM_PEN (initializeNorm, iterative.hpp:455-468)
+int k_rhs_norm(Ctx *c, const Sub *s, int mu, const K *b, double *res);
+// Schwarz::computeResidual reductions (schwarz.hpp:761-803): res[2 col] from f, res[2 col + 1] from t = A x - f off the boundary rows;
+// norm: 0 = l2 (sums of squares), 1 = l1, 2 = l-infinity (HPDDM_COMPUTE_RESIDUAL_*)
+int k_residual_norms(Ctx *c, const Sub *s, int mu, int norm, const K *f, const K *t, double *res);
+// ||b||_D per column over all subdomains and processes, penalised rows rescaled (host result)
+int rhs_norms(Ctx *c, const std::vector<const K *> &b, int mu, std::vector<double> &out);  // d_Y = E^{-1} d_T with one refinement step
 int k_bc(Ctx *c, const Sub *s, int mu, const K *b, K *x);
 
 int k_zt_raw(Ctx *c, int n, int nu, const K *Z, const double *d, int mu, const K *x, K *T, int ldT);
@@ -248,7 +260,7 @@ int to_host_csr(int n, int nnz, const int *ia, const int *ja, const K *a, int sy
 int solve_cols(Sub *s, const K *b, K *x, int mu, const double *scale, bool acc);
 // orchestration helpers shared by hb_api.cu and hb_krylov.cu (device pointers, one per local subdomain)
 int check_ready(Ctx *c, int mu);
-int halo(Ctx *c, K *const *x, int mu, bool allow_p2p = true);
+int halo(Ctx *c, K *const *x, int mu);
 int apply_core(Ctx *c, const std::vector<const K *> &in, const std::vector<K *> &out, int mu, int correction);
 int gmv_core(Ctx *c, const std::vector<const K *> &in, const std::vector<K *> &out, int mu);
 int stage_in(Ctx *c, const K *const *in, int mu, int where, std::vector<const K *> &dev);
@@ -257,11 +269,19 @@ int stage_out(Ctx *c, K *const *out, int mu, int where);
 // copy between a caller HOST pointer and device memory on the context's stream; pins the host range lazily (see Ctx::hostreg)
 int host_copy(Ctx *c, void *dst, const void *src, size_t bytes, bool to_device);
 void hostreg_release(Ctx *c);
-int nccl_allreduce_sum(Ctx *c, double *buf, int count);  // count doubles (a K is KD doubles)
-int nccl_allgather_bytes(Ctx *c, const void *send, void *recv, size_t bytes_per_rank);
-int p2p_halo(Ctx *c, K *const *x, int mu);  // 1 = done over peer memory, 0 = use NCCL
+int nccl_allreduce_sum(Ctx *c, double *buf, int count);
+int nccl_allreduce_max(Ctx *c, double *buf, int count);  // count doubles (a K is KD doubles)
+// control plane: all-gather of `bytes` per rank between HOST buffers (host callback, else NCCL through a device bounce buffer)
+int ctrl_allgather(Ctx *c, const void *send, void *recv, size_t bytes);
+// peer-memory fabric (hb_p2p.cu): each returns 1 = done over peer memory, 0 = caller uses NCCL, < 0 = error
+int fabric_setup(Ctx *c, int mu);  // collective; called by ensure_capacity
+bool fabric_on(Ctx *c);
+int p2p_halo(Ctx *c, K *const *x, int mu);
+int fabric_allgather(Ctx *c, K *buf, int count);               // buf: nproc blocks of `count` elements, own block in place
+int fabric_allreduce(Ctx *c, double *buf, int count, int op);  // op 0: sum in rank order, 1: max
 int p2p_check(Ctx *c);
 void p2p_free(Ctx *c);
+const K *p2p_last_halo_window(Ctx *c);  // receive slot of the last peer-memory halo round (nullptr: that round went over NCCL)
 // Krylov helper kernels (hb_kernels.cu)
 // V: k vectors of length n, stride ldv between them (n, or mu * n for one column of a block basis)
 int k_vdots(Ctx *c, const Sub *s, int k, const K *V, int64_t ldv, const K *w, K *T);               // T[j] += sum_i d_i conj(V[i,j]) w[i]

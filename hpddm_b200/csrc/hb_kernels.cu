@@ -185,6 +185,70 @@ __global__ void __launch_bounds__(256) kk_dot(int n, int mu, const double *__res
   }
 }
 
+// Reductions of the Krylov layer that know the boundary-condition rows (bcflag[i] != 0, Subdomain::boundaryConditions).
+//  MODE 0: res[c] += sum_i d_i |b'_ic|^2 with b' = b / HPDDM_PEN on flagged rows whose entry exceeds PEN * EPS -- the ||b|| of
+//          IterativeMethod::initializeNorm (include/HPDDM_iterative.hpp:455-468);
+//  MODE 1..3 (Schwarz::computeResidual, include/HPDDM_schwarz.hpp:761-803; 1 = l2, 2 = l1, 3 = l-infinity), two values per column:
+//          res[2c] from f (every entry larger than EPS * PEN divided by PEN), res[2c+1] from t = A x - f with flagged rows skipped.
+template <int MODE>
+__global__ void __launch_bounds__(256) kk_bcnorm(int n, int mu, const double *__restrict__ d, const unsigned char *__restrict__ bcflag, const K *__restrict__ f,
+                                                 const K *__restrict__ t, double *res) {
+  __shared__ double red[2][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr double PEN = 1.0e30, EPS = 1.0e-12;
+  for (int c = 0; c < mu; ++c) {
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + tid; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const K fv = f[i + (int64_t)c * n];
+      const bool flagged = bcflag && bcflag[i];
+      if (MODE == 0) {
+        const double af = hb_abs(fv);
+        a0 += d[i] * ((af > PEN * EPS && flagged) ? hb_norm(fv / PEN) : hb_norm(fv));
+      } else {
+        const double af = hb_abs(fv) > EPS * PEN ? hb_abs(fv / PEN) : hb_abs(fv);
+        const double at = flagged ? 0.0 : hb_abs(t[i + (int64_t)c * n]);
+        if (MODE == 1) {
+          a0 += d[i] * af * af;
+          a1 += d[i] * at * at;
+        } else if (MODE == 2) {
+          a0 += d[i] * af;
+          a1 += d[i] * at;
+        } else {
+          a0 = fmax(a0, af);
+          a1 = fmax(a1, at);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double b0 = __shfl_xor_sync(0xffffffffu, a0, o), b1 = __shfl_xor_sync(0xffffffffu, a1, o);
+      a0 = MODE == 3 ? fmax(a0, b0) : a0 + b0;
+      a1 = MODE == 3 ? fmax(a1, b1) : a1 + b1;
+    }
+    if (lane == 0) {
+      red[0][warp] = a0;
+      red[1][warp] = a1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double s0 = 0.0, s1 = 0.0;
+      for (int q = 0; q < 8; ++q) {
+        s0 = MODE == 3 ? fmax(s0, red[0][q]) : s0 + red[0][q];
+        s1 = MODE == 3 ? fmax(s1, red[1][q]) : s1 + red[1][q];
+      }
+      if (MODE == 0) atomicAdd(&res[c], s0);
+      else if (MODE == 3) {  // non-negative doubles order like their bit patterns
+        atomicMax(reinterpret_cast<unsigned long long *>(&res[2 * c]), (unsigned long long)__double_as_longlong(s0));
+        atomicMax(reinterpret_cast<unsigned long long *>(&res[2 * c + 1]), (unsigned long long)__double_as_longlong(s1));
+      } else {
+        atomicAdd(&res[2 * c], s0);
+        atomicAdd(&res[2 * c + 1], s1);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Replicated coarse solve (one CTA): Y = Einv T ; R = T - E Y ; Y += Einv R.
 // Coarse vectors use the communication layout [proc][col][row-in-proc]:
 //   v(r, c) = buf[rowproc[r] * Lmax * mu + c * Lmax + rowloc[r]]   (process blocks padded to Lmax rows)
@@ -397,6 +461,22 @@ int k_dot(Ctx *c, const Sub *s, int mu, const K *x, const K *y, K *res) {
   unsigned g = grid1(s->n);
   if (g > 1184) g = 1184;
   kk_dot<<<g, 256, 0, c->stream>>>(s->n, mu, s->d_d, x, y, res);
+  HB_LAUNCH_END(c);
+}
+int k_rhs_norm(Ctx *c, const Sub *s, int mu, const K *b, double *res) {
+  if (s->n == 0) return 0;
+  unsigned g = grid1(s->n);
+  if (g > 1184) g = 1184;
+  kk_bcnorm<0><<<g, 256, 0, c->stream>>>(s->n, mu, s->d_d, s->d_bcflag, b, nullptr, res);
+  HB_LAUNCH_END(c);
+}
+int k_residual_norms(Ctx *c, const Sub *s, int mu, int norm, const K *f, const K *t, double *res) {
+  if (s->n == 0) return 0;
+  unsigned g = grid1(s->n);
+  if (g > 1184) g = 1184;
+  if (norm == 1) kk_bcnorm<2><<<g, 256, 0, c->stream>>>(s->n, mu, s->d_d, s->d_bcflag, f, t, res);
+  else if (norm == 2) kk_bcnorm<3><<<g, 256, 0, c->stream>>>(s->n, mu, s->d_d, s->d_bcflag, f, t, res);
+  else kk_bcnorm<1><<<g, 256, 0, c->stream>>>(s->n, mu, s->d_d, s->d_bcflag, f, t, res);
   HB_LAUNCH_END(c);
 }
 int k_coarse_solve(Ctx *c, int mu) {

@@ -96,17 +96,13 @@ int gmres_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *>
     KR(k_scale(c, s->n, mu, s->d_d, x[i], x[i]));
   }
   KR(halo(c, x.data(), mu));
-  // ||b||_D per column (iterative.hpp:455-468)
+  // ||b||_D per column, entries of penalised boundary rows divided by HPDDM_PEN (initializeNorm, iterative.hpp:455-468)
   std::vector<double> normb(mu);
-  {
-    std::vector<K *> bb(L);
-    for (size_t i = 0; i < L; ++i) bb[i] = const_cast<K *>(b[i]);
-    KR(dots(c, 1, mu, bb, bb, d_T, hv));  // (a single "vector" per column: stride irrelevant)
-    for (int nu = 0; nu < mu; ++nu) {
-      normb[nu] = std::sqrt(hb_real(hv[nu]));
-      if (normb[nu] < 1e-12) normb[nu] = 1.0;
-    }
-  }
+  KR(rhs_norms(c, b, mu, normb));
+  for (int nu = 0; nu < mu; ++nu)
+    if (normb[nu] < 1e-12) normb[nu] = 1.0;  // GMRES.hpp:73
+  // checkConvergence (iterative.hpp:98-103): tol > 0 relative to ||b||, tol < 0 absolute
+  auto converged = [&](double r, int nu) { return tol > 0.0 ? r / normb[nu] <= tol : r <= -tol; };
   // per column: Hessenberg (m+1) x m, Givens rotations as the reference stores them (iterative.hpp:690-710: cosine in K,
   // sine real), rotated right-hand side sv, hasConverged
   const size_t hs = (size_t)(m + 1) * m;
@@ -184,7 +180,7 @@ int gmres_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *>
       bool all = true;
       for (int nu = 0; nu < mu; ++nu) {
         res[nu] = hb_abs(sv[(size_t)nu * (m + 1) + i]);
-        if (conv[nu] == -m && res[nu] / normb[nu] <= tol) conv[nu] = i;  // checkConvergence (iterative.hpp:98-103)
+        if (conv[nu] == -m && converged(res[nu], nu)) conv[nu] = i;  // checkConvergence (iterative.hpp:98-103)
         all = all && conv[nu] != -m;
       }
       if (all) {
@@ -529,19 +525,9 @@ int bgmres_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *
   }
   KR(halo(c, x.data(), mu));
   std::vector<double> normb(mu), last(mu, 0.0);
-  {
-    K *d_n = d_T;
-    KRC(cudaMemsetAsync(d_n, 0, mu * sizeof(K), c->stream));
-    for (size_t q = 0; q < L; ++q) KR(k_dot(c, c->subs[q], mu, b[q], b[q], d_n));
-    KR(nccl_allreduce_sum(c, reinterpret_cast<double *>(d_n), mu * KD));
-    hbuf.resize(mu);
-    KRC(cudaMemcpyAsync(hbuf.data(), d_n, mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
-    KRC(cudaStreamSynchronize(c->stream));
-    for (int nu = 0; nu < mu; ++nu) {
-      normb[nu] = std::sqrt(hb_real(hbuf[nu]));
-      if (normb[nu] < 1e-12) normb[nu] = 1.0;
-    }
-  }
+  KR(rhs_norms(c, b, mu, normb));  // penalised boundary rows / HPDDM_PEN (initializeNorm, iterative.hpp:455-468)
+  for (int nu = 0; nu < mu; ++nu)
+    if (normb[nu] < 1e-12) normb[nu] = 1.0;
   std::vector<K> H((size_t)ldh * m * mu), tau((size_t)m * mu), sv((size_t)ldh * mu), Hc((size_t)ldh * mu), Y((size_t)ldh * mu);
   int j = 1, dim = 0;
   bool done = false, breakdown = false;
@@ -601,7 +587,7 @@ int bgmres_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *
         double nrm = 0.0;
         for (int r = 0; r <= nu; ++r) nrm += hb_norm(sv[(size_t)i * mu + r + (size_t)nu * ldh]);
         last[nu] = std::sqrt(nrm);
-        all = all && last[nu] / normb[nu] <= tol;
+        all = all && (tol > 0.0 ? last[nu] / normb[nu] <= tol : last[nu] <= -tol);  // checkBlockConvergence (iterative.hpp:139-146)
       }
       if (all) {
         dim = mu * i;

@@ -127,6 +127,16 @@ class Schwarz:
         self.api.check(self.api.sub_solve(self.h, capi.ptr(b), capi.ptr(x), int(b.shape[1]), capi.HOST))
         return x
 
+    # Subdomain::boundaryConditions  (include/HPDDM_subdomain.hpp:327-336)
+    def boundaryConditions(self):
+        cnt = C.c_int(0)
+        self.api.check(self.api.sub_boundary_conditions(self.h, None, None, C.byref(cnt)))
+        idx = np.zeros(cnt.value, dtype=np.int32)
+        val = np.zeros(cnt.value, dtype=self.dtype)
+        if cnt.value:
+            self.api.check(self.api.sub_boundary_conditions(self.h, capi.ptr(idx), capi.ptr(val), C.byref(cnt)))
+        return dict(zip(idx.tolist(), val.tolist()))
+
     def statistics(self):
         st = capi.Stats()
         self.api.check(self.api.sub_stats(self.h, C.byref(st)))
@@ -175,6 +185,41 @@ class Decomposition:
         dist.broadcast(t, 0)
         raw = bytes(t.cpu().numpy().tobytes())
         self.api.check(self.api.ctx_comm_init(self.ctx, raw, rank, size))
+
+    # --- host-bootstrapped communicator: the host program's own all-gather carries the control plane (CUDA-IPC handles, coarse
+    # sizes), the library's peer-memory fabric carries the hot path; no NCCL needed, several processes may share one GPU
+    def comm_init_host(self, rank, size, allgather):
+        """allgather(bytes) -> list of `size` bytes objects in rank order (e.g. built on MPI_Allgather / torch.distributed)."""
+        def cb(send, recv, nbytes, user):
+            try:
+                parts = allgather(C.string_at(send, nbytes))
+                C.memmove(recv, b"".join(parts), nbytes * size)
+                return 0
+            except Exception as e:   # never let an exception cross the C boundary
+                print(f"[hpddm_b200] host all-gather callback failed: {e!r}")
+                return -1
+        self._allgather_cb = capi.ALLGATHER_FN(cb)   # keep the trampoline alive as long as the context
+        self.api.check(self.api.ctx_comm_init_host(self.ctx, int(rank), int(size), C.cast(self._allgather_cb, C.c_void_p), None))
+
+    def comm_init_host_torch(self):
+        """control plane over torch.distributed (any backend, e.g. gloo between processes that share one GPU)"""
+        import torch
+        import torch.distributed as dist
+        rank, size = dist.get_rank(), dist.get_world_size()
+        on_gpu = dist.get_backend() == "nccl"
+
+        def allgather(data):
+            t = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+            if on_gpu:
+                t = t.cuda()
+            out = [torch.empty_like(t) for _ in range(size)]
+            dist.all_gather(out, t)
+            return [bytes(o.cpu().numpy().tobytes()) for o in out]
+        self.comm_init_host(rank, size, allgather)
+
+    @property
+    def transport(self):
+        return {0: "single process", 1: "nccl", 2: "peer-memory fabric"}[int(self.api.ctx_transport(self.ctx))]
 
     def synchronize(self):
         self.api.check(self.api.ctx_synchronize(self.ctx))
@@ -261,6 +306,23 @@ class Decomposition:
         self.api.check(self.api.dot(self.ctx, capi.ptr_array(x), capi.ptr_array(y), mu, capi.ptr(res), capi.HOST))
         return res
 
+    # ||b|| of IterativeMethod::initializeNorm (include/HPDDM_iterative.hpp:455-468): penalised boundary rows count as b_i / HPDDM_PEN
+    def rhs_norm(self, b):
+        b = [_f(v, self.dtype) for v in b]
+        mu = b[0].shape[1]
+        out = np.zeros(mu)
+        self.api.check(self.api.rhs_norm(self.ctx, capi.ptr_array(b), mu, capi.ptr(out), capi.HOST))
+        return out
+
+    # Schwarz::computeResidual (include/HPDDM_schwarz.hpp:761-803): (mu, 2) array of ||f||, ||A x - f||; norm in {"l2", "l1", "linfty"}
+    def computeResidual(self, x, f, norm="l2"):
+        x = [_f(v, self.dtype) for v in x]
+        f = [_f(v, self.dtype) for v in f]
+        mu = x[0].shape[1]
+        st = np.zeros(2 * mu)
+        self.api.check(self.api.compute_residual(self.ctx, capi.ptr_array(x), capi.ptr_array(f), capi.ptr(st), mu, {"l2": 0, "l1": 1, "linfty": 2}[norm], capi.HOST))
+        return st.reshape(mu, 2)
+
     # IterativeMethod::solve (include/HPDDM_iterative.hpp:1013-1111) with the Krylov basis resident in HBM
     def solve(self, b, x0=None, correction="__default__", restart=40, max_it=100, tol=1e-6):
         corr = self.correction if correction == "__default__" else correction
@@ -328,3 +390,6 @@ class KrylovOperator:
 
     def dot(self, x, y):
         return self.deco.dot(x, y)
+
+    def rhs_norm(self, b):
+        return self.deco.rhs_norm(b)

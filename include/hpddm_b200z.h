@@ -57,6 +57,17 @@ int hpddm_b200z_ctx_destroy(hpddm_b200z_ctx *ctx);
  * calls comm_init.  Not calling comm_init = single-process decomposition. */
 int hpddm_b200z_nccl_unique_id(void *id128);
 int hpddm_b200z_ctx_comm_init(hpddm_b200z_ctx *ctx, const void *id128, int proc_rank, int nproc);
+/* Alternative / complement to the NCCL bootstrap: the host program lends its own communicator for the CONTROL plane (exchange of
+ * CUDA-IPC handles, coarse-space sizes, the rows of E at setup) as a blocking all-gather between host buffers -- in an MPI
+ * program `MPI_Allgather(send, bytes, MPI_BYTE, recv, bytes, MPI_BYTE, comm)` on Subdomain::communicator_
+ * (include/HPDDM_subdomain.hpp:49-63).  The DATA plane of the hot path (halo sums, coarse gather, Krylov reductions) then runs
+ * over the library's peer-memory fabric (CUDA IPC + NVLink stores, hb_p2p.cu); NCCL is only needed when a peer is not IPC-reachable
+ * or a process hosts several subdomains.  Several processes may share one GPU.  Returns 0 / a negative error code. */
+typedef int (*hpddm_b200z_allgather_fn)(const void *send, void *recv, size_t bytes_per_rank, void *user);
+int hpddm_b200z_ctx_comm_init_host(hpddm_b200z_ctx *ctx, int proc_rank, int nproc, hpddm_b200z_allgather_fn allgather, void *user);
+/* which transport carries the hot-path collectives: 0 = single process, 1 = NCCL, 2 = peer-memory fabric (decided collectively the
+ * first time work space is sized, i.e. after the first hot-path or setup call) */
+int hpddm_b200z_ctx_transport(hpddm_b200z_ctx *ctx);
 int hpddm_b200z_ctx_synchronize(hpddm_b200z_ctx *ctx);
 /* raw cudaStream_t of the context (for callers that time with CUDA events) */
 void *hpddm_b200z_ctx_stream(hpddm_b200z_ctx *ctx);
@@ -153,6 +164,18 @@ int hpddm_b200z_coarse_solve(hpddm_b200z_ctx *ctx, hpddm_b200_z *const *rhs, int
  * reduction the Krylov layer performs (include/HPDDM_GMRES.hpp:59-68,
  * include/HPDDM_iterative.hpp:455-468).  result[mu] on the host. */
 int hpddm_b200z_dot(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *x, const hpddm_b200_z *const *y, int mu, hpddm_b200_z *result, int where);
+/* Subdomain::boundaryConditions (include/HPDDM_subdomain.hpp:310-336): the rows of the matrix given to set_matrix that impose a
+ * (penalised or identity-row) Dirichlet condition, with their diagonal values.  idx / val may be NULL to query *count. */
+int hpddm_b200z_sub_boundary_conditions(hpddm_b200z_sub *sub, int *idx, hpddm_b200_z *val, int *count);
+/* ||b|| as IterativeMethod::initializeNorm computes it for right preconditioning (include/HPDDM_iterative.hpp:455-468): D-weighted l2
+ * norm per column, entries larger than HPDDM_PEN * HPDDM_EPS on boundary-condition rows divided by HPDDM_PEN first.  norm[mu], host.
+ * The device-resident Krylov drivers use the same reduction. */
+int hpddm_b200z_rhs_norm(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, int mu, double *norm, int where);
+/* Schwarz::computeResidual(x, f, storage, mu, norm) (include/HPDDM_schwarz.hpp:761-803): storage[2 nu] = ||f||, storage[2 nu + 1] =
+ * ||A x - f|| off the boundary-condition rows, per column; norm = 0 (l2, HPDDM_COMPUTE_RESIDUAL_L2), 1 (l1) or 2 (l-infinity);
+ * D-weighted, reduced over all subdomains and processes; storage on the host. */
+int hpddm_b200z_compute_residual(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *x, const hpddm_b200_z *const *f, double *storage, int mu, int norm, int where);
+
 
 /* ---- device-resident Krylov driver ("next" row of SURVEY.md section 8f) ------------------------------ */
 /* IterativeMethod::solve -> GMRES (include/HPDDM_iterative.hpp:1013-1111, include/HPDDM_GMRES.hpp:31-158) with the

@@ -339,8 +339,9 @@ class SchwarzWorld:
         return out
 
     # --------------------------------------------------------------- residual
-    def compute_residual(self, x, f):
-        """schwarz.hpp:761-803, l2 norm: returns (||f||_D, ||A x - f||_D) per column."""
+    def compute_residual(self, x, f, norm="l2"):
+        """schwarz.hpp:761-803: returns (||f||, ||A x - f||) per column; D-weighted l2 / l1 sums or the plain l-infinity norm.  Rows
+        that carry a boundary condition are left out of the residual, entries of f larger than EPS * PEN are divided by PEN."""
         tmp = self.GMV(x)
         mu = x[0].shape[1]
         st = np.zeros((mu, 2))
@@ -350,10 +351,18 @@ class SchwarzWorld:
             notb = np.ones(self.n[r])
             for i in bc:
                 notb[i] = 0.0
-            st[:, 1] += (self.d[r] * notb) @ (np.abs(tmp[r]) ** 2)
-            fr = np.where(np.abs(f[r]) > HPDDM_EPS * HPDDM_PEN, f[r] / HPDDM_PEN, f[r])
-            st[:, 0] += self.d[r] @ (np.abs(fr) ** 2)
-        return np.sqrt(st)
+            fr = np.abs(np.where(np.abs(f[r]) > HPDDM_EPS * HPDDM_PEN, f[r] / HPDDM_PEN, f[r]))
+            tr = np.abs(tmp[r]) * notb[:, None]
+            if norm == "l2":
+                st[:, 1] += self.d[r] @ tr ** 2
+                st[:, 0] += self.d[r] @ fr ** 2
+            elif norm == "l1":
+                st[:, 1] += self.d[r] @ tr
+                st[:, 0] += self.d[r] @ fr
+            else:
+                st[:, 1] = np.maximum(st[:, 1], tr.max(axis=0))
+                st[:, 0] = np.maximum(st[:, 0], fr.max(axis=0))
+        return np.sqrt(st) if norm == "l2" else st
 
     def rhs_norm(self, b):
         """||b|| of IterativeMethod::initializeNorm, right-preconditioned branch (iterative.hpp:455-468): D-weighted l2 norm per

@@ -67,8 +67,11 @@ def complexify(part, rank):
     return dict(part, Mat=A, f=np.asfortranarray(f))
 
 
+PEN_GOLD = 2.0 ** 100   # the power of two next to HPDDM_PEN = 1e30: keeps b / diag and diag * x exact (see ref_driver.cpp)
+
+
 def penalise(part, rank, P, Nx, Ny, overlap):
-    """ref_driver.cpp's `-penalise 1`: Dirichlet data on the side y = 0 by penalisation (diag = HPDDM_PEN, f = HPDDM_PEN * g),
+    """ref_driver.cpp's `-penalise 1`: Dirichlet data on the side y = 0 by penalisation (diag = 2^100, f = 2^100 * g),
     local layout of examples/generate.cpp:51-61."""
     xg = int(np.sqrt(P))
     while P % xg:
@@ -83,9 +86,9 @@ def penalise(part, rank, P, Nx, Ny, overlap):
         for i in range(i0, i1):
             k = i - i0
             lo, hi = A.indptr[k], A.indptr[k + 1]
-            A.data[lo:hi][A.indices[lo:hi] == k] = 1e30
+            A.data[lo:hi][A.indices[lo:hi] == k] = PEN_GOLD
             for nu in range(f.shape[1]):
-                f[k, nu] = 1e30 * ((1.0 + 0.5 * np.sin(0.3 * i + nu)) + (1j * 0.25 * np.cos(0.2 * i) if np.iscomplexobj(f) else 0.0))
+                f[k, nu] = PEN_GOLD * ((1.0 + 0.5 * np.sin(0.3 * i + nu)) + (1j * 0.25 * np.cos(0.2 * i) if np.iscomplexobj(f) else 0.0))
     return dict(part, Mat=A, f=f)
 
 

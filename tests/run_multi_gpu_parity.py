@@ -2,7 +2,10 @@
 every rank hosts one subdomain, halo + coarse gather go over NCCL; each rank
 rebuilds the whole decomposition with the CPU oracle (small sizes) and checks its
 own slice of apply / deflation / GMV / GMRES.  Exit code != 0 on mismatch.
-PARITY_SCALAR=z runs the complex instantiation (hpddm_b200z_*): 3-D Helmholtz, ORAS, plane-wave coarse vectors."""
+PARITY_SCALAR=z runs the complex instantiation (hpddm_b200z_*): 3-D Helmholtz, ORAS, plane-wave coarse vectors.
+PARITY_BOOT=nccl (default): NCCL bootstrap, collectives over the peer-memory fabric (HPDDM_B200_HALO=nccl forces NCCL everywhere);
+PARITY_BOOT=host: control plane over torch.distributed/gloo through hpddm_b200_ctx_comm_init_host, no NCCL at all;
+PARITY_SAME_GPU=1 (with PARITY_BOOT=host): every rank uses device 0 -- several processes sharing one GPU over CUDA IPC."""
 import os
 import sys
 
@@ -21,8 +24,14 @@ def main():
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
+    boot = os.environ.get("PARITY_BOOT", "nccl")
+    if os.environ.get("PARITY_SAME_GPU"):
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if boot == "host":
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     grid = split_grid_3d(world)
     m = int(os.environ.get("PARITY_M", 10))
     N = tuple(g * m for g in grid)
@@ -45,7 +54,10 @@ def main():
         w.set_vectors([z[:, :1 + (r % 3)] for r, z in enumerate(w.Z)])
     w.build_coarse()
     deco = Decomposition(local, dtype=np.complex128 if cplx else np.float64)
-    deco.comm_init_torch()
+    if boot == "host":
+        deco.comm_init_host_torch()
+    else:
+        deco.comm_init_torch()
     p = parts[rank]
     s = deco.add(rank)
     s.initialize(p["Mat"], p["o"], p["mapping"])
@@ -92,8 +104,11 @@ def main():
         errs["cg_dev_x"] = np.abs(x_cdev[0] - x_cref[rank]).max() / np.abs(x_cref[rank]).max()
     bad = (not ok) or it_gpu != it_ref or it_dev != it_ref or errs["gmres_dev_x"] > 1e-7 or it_bdev != it_bref or errs["bgmres_dev_x"] > 1e-7 or \
         it_cdev != it_cref or errs.get("cg_dev_x", 0.0) > 1e-6 or any(v > 1e-10 for k, v in errs.items() if not (k.startswith("gmres") or k.endswith("_dev_x"))) or errs["gmres_x"] > 1e-7
-    print(f"rank {rank}/{world} {'complex' if cplx else 'real'}: d_ok={ok} it_gpu={it_gpu} it_dev={it_dev} it_ref={it_ref} bgmres={it_bdev}/{it_bref} cg={it_cdev}/{it_cref} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()) + (" FAIL" if bad else " OK"), flush=True)
-    t = torch.tensor([1.0 if bad else 0.0], device="cuda")
+    want = os.environ.get("PARITY_EXPECT_TRANSPORT")
+    if want and deco.transport != want:
+        bad = True
+    print(f"rank {rank}/{world} {'complex' if cplx else 'real'} [{deco.transport}]: d_ok={ok} it_gpu={it_gpu} it_dev={it_dev} it_ref={it_ref} bgmres={it_bdev}/{it_bref} cg={it_cdev}/{it_cref} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()) + (" FAIL" if bad else " OK"), flush=True)
+    t = torch.tensor([1.0 if bad else 0.0], device="cuda" if boot != "host" else "cpu")
     dist.all_reduce(t)
     deco.close()
     dist.destroy_process_group()

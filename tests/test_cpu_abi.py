@@ -94,7 +94,7 @@ def test_ctypes_signatures_match_the_headers():
             _, argtypes = capi._SIGS[name]
             assert len(params) == len(argtypes), (name, params, argtypes)
             for prm, at in zip(params, argtypes):
-                is_ptr = "*" in prm
+                is_ptr = "*" in prm or "_fn " in prm   # (function-pointer typedefs, e.g. hpddm_b200_allgather_fn)
                 if is_ptr:
                     assert at in (C.c_void_p, C.c_char_p) or hasattr(at, "contents") or at is capi._P, (name, prm, at)
                 elif prm.startswith("double"):

@@ -73,4 +73,22 @@ def test_cuda_path_reproduces_the_reference(name):
         it_dev, x_dev, res = deco.solve(b, correction=corr, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])
     assert abs(it_dev - it_ref) <= slack
     assert max(rel(x_dev[r], ref[r]["sol"]) for r in range(P)) < xtol
+    # Schwarz::computeResidual on the reference's own solution (schwarz.hpp:761-803): ||f|| with penalised entries / PEN and
+    # ||A x - f|| off the boundary rows, against the reference's numbers; l1 / l-infinity variants against the oracle
+    sol = [ref[r]["sol"] for r in range(P)]
+    gold = ref[0]["residual"].reshape(-1, 2)
+    res = deco.computeResidual(sol, b)
+    assert np.abs(res[:, 0] - gold[:, 0]).max() < 1e-12 * gold[:, 0].max()
+    assert np.all(np.abs(res[:, 1] - gold[:, 1]) < 1e-6 * gold[:, 1] + 1e-12 * gold[:, 0])
+    assert np.abs(deco.rhs_norm(b) - gold[:, 0]).max() < 1e-12 * gold[:, 0].max()     # the ||b|| of initializeNorm = storage[0] here
+    w = SchwarzWorld(parts, method=meta["method"])
+    w.multiplicity_scaling()
+    for kind in ("l1", "linfty"):
+        want = w.compute_residual(sol, b, kind)
+        got = deco.computeResidual(sol, b, kind)
+        assert np.abs(got - want).max() < 1e-9 * np.abs(want).max(), kind
+    if meta["penalised"]:
+        for r, s in enumerate(deco.subs):
+            bc = s.boundaryConditions()
+            assert bc == {k: v for k, v in w.boundary_conditions(r).items()} and (len(bc) > 0) == (r < 2)
     deco.close()
