@@ -36,6 +36,7 @@ _PP = C.POINTER(C.c_void_p)
 _SIGS = {
     "hpddm_b200_last_error": (C.c_char_p, []),
     "hpddm_b200_version": (C.c_char_p, []),
+    "hpddm_b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "hpddm_b200_ctx_create": (C.c_int, [C.c_int, _PP]),
     "hpddm_b200_ctx_destroy": (C.c_int, [_P]),
     "hpddm_b200_nccl_unique_id": (C.c_int, [_P]),

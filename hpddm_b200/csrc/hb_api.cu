@@ -78,11 +78,17 @@ static int nccl_load() {
   } while (0)
 constexpr int NCCL_INT32 = 2, NCCL_F64 = 8, NCCL_SUM = 0;
 
+static int need_nccl(Ctx *c) {
+  if (c->nccl) return 0;
+  set_error("this collective needs NCCL (the peer-memory fabric is not up) but no NCCL communicator was initialised: call ctx_comm_init");
+  return HPDDM_B200_ERR_STATE;
+}
 // small reductions of the Krylov layer: the peer-memory fabric when it is up (deterministic rank-order sums), else NCCL
 int nccl_allreduce_max(Ctx *c, double *buf, int count) {
   if (c->nproc <= 1) return 0;
   const int done = fabric_allreduce(c, buf, count, 1);
   if (done != 0) return done < 0 ? done : 0;
+  HB_CHECK(need_nccl(c));
   HB_NCCL(g_nccl.AllReduce(buf, buf, count, NCCL_F64, 2 /* ncclMax */, c->nccl, c->stream));
   return 0;
 }
@@ -90,6 +96,7 @@ int nccl_allreduce_sum(Ctx *c, double *buf, int count) {
   if (c->nproc <= 1) return 0;
   const int done = fabric_allreduce(c, buf, count, 0);
   if (done != 0) return done < 0 ? done : 0;
+  HB_CHECK(need_nccl(c));
   HB_NCCL(g_nccl.AllReduce(buf, buf, count, NCCL_F64, NCCL_SUM, c->nccl, c->stream));
   return 0;
 }
@@ -98,6 +105,7 @@ static int coarse_gather(Ctx *c, int mu) {
   if (c->nproc <= 1) return 0;
   const int done = fabric_allgather(c, c->d_T, c->Lnu * mu);
   if (done != 0) return done < 0 ? done : 0;
+  HB_CHECK(need_nccl(c));
   HB_NCCL(g_nccl.AllGather(c->d_T + (size_t)c->proc_rank * c->Lnu * mu, c->d_T, (size_t)c->Lnu * mu * KD, NCCL_F64, c->nccl, c->stream));
   return 0;
 }
@@ -549,6 +557,18 @@ static void sub_free(Sub *s) {
                   (void *)s->d_in, (void *)s->d_out, (void *)s->d_work, (void *)s->d_tmp, (void *)s->d_tmp2})
     if (p) cudaFree(p);
   delete s;
+}
+
+int HB_API(device_count)(int *count) {
+  if (!count) return HPDDM_B200_ERR_ARG;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  return 0;
 }
 
 int HB_API(ctx_destroy)(hb_ctx_t *ctx) {
@@ -1222,7 +1242,7 @@ int HB_API(dot)(hb_ctx_t *ctx, const K *const *x, const K *const *y, int mu, K *
     }
     HB_CHECK(k_dot(c, s, mu, xd, yd, c->d_res));
   }
-  if (c->nproc > 1) HB_NCCL(g_nccl.AllReduce(c->d_res, c->d_res, mu * KD, NCCL_F64, NCCL_SUM, c->nccl, c->stream));
+  HB_CHECK(nccl_allreduce_sum(c, reinterpret_cast<double *>(c->d_res), mu * KD));
   HB_CUDA(cudaMemcpyAsync(result, c->d_res, mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -81,6 +81,15 @@ struct Api;
     static int sub_get_vectors(sub_t *s, K_ *Z, int *nu) { return P_##_sub_get_vectors(s, Z, nu); }                                                \
     static int sub_stats(sub_t *s, hpddm_b200_stats *st) { return P_##_sub_stats(s, st); }                                                         \
     static int build_coarse(ctx_t *c) { return P_##_build_coarse(c); }                                                                             \
+    static int ctx_comm_init_host(ctx_t *c, int r, int n, P_##_allgather_fn f, void *u) { return P_##_ctx_comm_init_host(c, r, n, f, u); }         \
+    static int ctx_transport(ctx_t *c) { return P_##_ctx_transport(c); }                                                                           \
+    static long long launch_count(ctx_t *c) { return static_cast<long long>(P_##_ctx_launch_count(c)); }                                           \
+    static int sub_boundary_conditions(sub_t *s, int *idx, K_ *val, int *cnt) { return P_##_sub_boundary_conditions(s, idx, val, cnt); }           \
+    static int rhs_norm(ctx_t *c, const K_ *const *b, int mu, double *nrm, int w) { return P_##_rhs_norm(c, b, mu, nrm, w); }                      \
+    static int compute_residual(ctx_t *c, const K_ *const *x, const K_ *const *f, double *st, int mu, int nrm, int w)                              \
+    {                                                                                                                                              \
+      return P_##_compute_residual(c, x, f, st, mu, nrm, w);                                                                                       \
+    }                                                                                                                                              \
     static int start(ctx_t *c, const K_ *const *b, K_ *const *x, int mu, int w) { return P_##_start(c, b, x, mu, w); }                             \
     static int end(ctx_t *c) { return P_##_end(c); }                                                                                               \
     static int apply(ctx_t *c, const K_ *const *in, K_ *const *out, int mu, int corr, int w) { return P_##_apply(c, in, out, mu, corr, w); }        \
@@ -132,6 +141,8 @@ inline typename Api<K>::ctx_t *context(bool fresh = false) {
   }
   return ctx;
 }
+template <class K>
+inline long long launch_count(typename Api<K>::ctx_t *c) { return Api<K>::launch_count(c); }
 inline double real_part(double v) { return v; }
 inline double real_part(const std::complex<double> &v) { return v.real(); }
 }  // namespace b200
@@ -342,20 +353,12 @@ public:
     K       *oo[1] = {out};
     return A_::gmv(ctx_, ii, oo, mu, HPDDM_B200_HOST);
   }
-  /* Schwarz::computeResidual (schwarz.hpp:761-803), l2 norm: storage[2*nu] = ||f||_D, [2*nu+1] = ||Ax-f||_D */
-  void computeResidual(const K *const x, const K *const f, double *const storage, const unsigned short mu = 1) const
+  /* Schwarz::computeResidual (schwarz.hpp:761-803): storage[2*nu] = ||f|| (entries larger than EPS * PEN divided by PEN),
+   * storage[2*nu+1] = ||A x - f|| off the boundary-condition rows; norm = HPDDM_COMPUTE_RESIDUAL_L2 (0) / _L1 (1) / _LINFTY (2) */
+  void computeResidual(const K *const x, const K *const f, double *const storage, const unsigned short mu = 1, const unsigned short norm = 0) const
   {
-    std::vector<K> tmp(static_cast<std::size_t>(mu) * dof_);
-    GMV(x, tmp.data(), mu);
-    for (std::size_t i = 0; i < tmp.size(); ++i) tmp[i] -= f[i];
-    std::vector<K> r(mu), b(mu);  // sum_i d_i conj(x_i) x_i: real up to rounding
-    const K       *t[1] = {tmp.data()}, *ff[1] = {f};
-    b200::check<K>(A_::dot(ctx_, t, t, mu, r.data(), HPDDM_B200_HOST), "dot");
-    b200::check<K>(A_::dot(ctx_, ff, ff, mu, b.data(), HPDDM_B200_HOST), "dot");
-    for (unsigned short nu = 0; nu < mu; ++nu) {
-      storage[2 * nu]     = std::sqrt(b200::real_part(b[nu]));
-      storage[2 * nu + 1] = std::sqrt(b200::real_part(r[nu]));
-    }
+    const K *xx[1] = {x}, *ff[1] = {f};
+    b200::check<K>(A_::compute_residual(ctx_, xx, ff, storage, mu, norm, HPDDM_B200_HOST), "compute_residual");
   }
   /* Device-resident counterpart of IterativeMethod::solve(A, f, sol, mu, comm) (include/HPDDM_iterative.hpp:1013-1111): the Krylov
    * vectors never leave HBM.  method: 0 = GMRES (HPDDM_KRYLOV_METHOD_GMRES), 1 = BGMRES, 2 = CG -- the values of -hpddm_krylov_method
@@ -398,7 +401,19 @@ public:
   unsigned short getLocal() const { return static_cast<unsigned short>(nu_); }
   const MatrixCSR<K> *getMatrix() const { return a_; }
   const std::vector<std::pair<unsigned short, std::vector<int>>> &getMap() const { return map_; }
-  std::unordered_map<unsigned int, K> boundaryConditions() const { return std::unordered_map<unsigned int, K>(); }
+  /* Subdomain::boundaryConditions (include/HPDDM_subdomain.hpp:327-336): penalised / identity rows with their diagonal values --
+   * what IterativeMethod::initializeNorm needs to rescale penalised entries of the right-hand side (iterative.hpp:461-468) */
+  std::unordered_map<unsigned int, K> boundaryConditions() const
+  {
+    int cnt = 0;
+    b200::check<K>(A_::sub_boundary_conditions(sub_, nullptr, nullptr, &cnt), "sub_boundary_conditions");
+    std::vector<int> idx(cnt);
+    std::vector<K>   val(cnt);
+    if (cnt) b200::check<K>(A_::sub_boundary_conditions(sub_, idx.data(), val.data(), &cnt), "sub_boundary_conditions");
+    std::unordered_map<unsigned int, K> map;
+    for (int i = 0; i < cnt; ++i) map[static_cast<unsigned int>(idx[i])] = val[i];
+    return map;
+  }
   typename A_::ctx_t *context() const { return ctx_; }
   typename A_::sub_t *handle() const { return sub_; }
 };

@@ -49,6 +49,8 @@ const char *hpddm_b200z_version(void);
 /* ---- context ------------------------------------------------------------- */
 /* One per process (or per GPU).  Replaces MPI_Init + Subdomain::communicator_
  * ownership (include/HPDDM_subdomain.hpp:49-63). */
+/* number of CUDA devices visible to this process (0 when there is none: nothing in this library runs without one) */
+int hpddm_b200z_device_count(int *count);
 int hpddm_b200z_ctx_create(int device, hpddm_b200z_ctx **ctx);
 int hpddm_b200z_ctx_destroy(hpddm_b200z_ctx *ctx);
 /* NCCL bootstrap (replaces the MPI communicator on the hot path only, SURVEY.md
