@@ -32,6 +32,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "preconditioner applies/sec (FP64) 3-D Poisson, 1 subdomain/GPU, two-level RAS (deflated) + GenEO nu=20"
+METRIC_E = "preconditioner block-applies/sec (FP64) 3-D linear elasticity (Q1, 3 dof/node), 1 subdomain/GPU, two-level RAS (deflated), nu=30, mu=4 (Block-GMRES shape)"
 METRIC_Z = "preconditioner applies/sec (complex FP64) 3-D Helmholtz, 1 subdomain/GPU, two-level ORAS (deflated) + plane-wave coarse space"
 
 
@@ -48,6 +49,29 @@ def cosine_modes(dims, nu):
         v = np.cos(np.pi * k * z)[:, None, None] * np.cos(np.pi * j * y)[None, :, None] * np.cos(np.pi * i * x)[None, None, :]
         v = v.reshape(-1)
         Z[:, c] = v / np.linalg.norm(v)
+    return Z
+
+
+def elasticity_modes(part, Nn, nu):
+    """GenEO-shaped coarse space for the elasticity workload: the 6 rigid-body modes of the subdomain (the kernel of its Neumann
+    matrix, what GenEO finds first) modulated by low-frequency cosines of the box -- nu vectors, column-normalised."""
+    from hpddm_b200.examples.generate import rigid_body_modes
+    R = rigid_body_modes(part, Nn)
+    w, h, t = part["dims"][:3]
+    x = (np.arange(w) + 0.5) / w
+    y = (np.arange(h) + 0.5) / h
+    z = (np.arange(t) + 0.5) / t
+    ks = sorted(((i, j, k) for i in range(3) for j in range(3) for k in range(3)), key=lambda q: q[0] ** 2 + q[1] ** 2 + q[2] ** 2)
+    Z = np.empty((R.shape[0], nu), order="F")
+    c = 0
+    for (i, j, k) in ks:
+        m = (np.cos(np.pi * k * z)[:, None, None] * np.cos(np.pi * j * y)[None, :, None] * np.cos(np.pi * i * x)[None, None, :]).reshape(-1)
+        for r in range(6):
+            if c == nu:
+                break
+            v = R[:, r] * np.repeat(m, 3)
+            Z[:, c] = v / np.linalg.norm(v)
+            c += 1
     return Z
 
 
@@ -108,7 +132,11 @@ def run_b200(args):
     m = args.m
     N = tuple(g * m for g in grid)
     cplx = args.scalar == "z"
-    if cplx:
+    elas = args.workload == "elasticity"
+    if elas:   # BASELINE config 4 shape: Q1 elasticity, m nodes per subdomain edge (3 m^3 dofs + overlap), block of mu right-hand sides
+        from hpddm_b200.examples.generate import generate_elasticity3d
+        part = generate_elasticity3d(rank, world, Nn=N, overlap=1, mu=args.mu, grid=grid, assembly="local")
+    elif cplx:
         from hpddm_b200.examples.generate import generate_helmholtz3d
         part = generate_helmholtz3d(rank, world, N=N, overlap=1, mu=1, grid=grid, k=args.wavenumber, nu=args.nu)
     else:
@@ -129,7 +157,7 @@ def run_b200(args):
         s.callNumfact()
     deco.synchronize()
     t_fact = time.time() - t0
-    s.setVectors(part["Z"] if cplx else cosine_modes(part["dims"], args.nu))
+    s.setVectors(elasticity_modes(part, N, args.nu) if elas else (part["Z"] if cplx else cosine_modes(part["dims"], args.nu)))
     deco.buildTwo()
     st = s.statistics()
     nnz_a = st["nnz_a"]
@@ -200,13 +228,16 @@ def run_b200(args):
     except Exception:
         pass
     trsv_gbs = by["trsv"] / (ms_trsv / args.steps * 1e-3) / 1e9
-    if cplx:
+    if elas:
+        wl, par = (f"config4 slice: 3-D Q1 linear elasticity {N[0]}x{N[1]}x{N[2]} nodes x 3 dof, {world} subdomain(s) of {m}^3 nodes + overlap 1, face x = 0 clamped by penalisation, "
+                   f"two-level RAS deflated, nu={args.nu}, mu={args.mu}"), f"{grid[0]}x{grid[1]}x{grid[2]} subdomains, 1/GPU"
+    elif cplx:
         wl, par = (f"config5 slice: 3-D Helmholtz k={args.wavenumber} {N[0]}x{N[1]}x{N[2]}, complex FP64, {world} subdomain(s) of {m}^3 cells + overlap 1, "
                    f"two-level ORAS deflated, {args.nu} plane waves, mu={args.mu}"), f"{grid[0]}x{grid[1]}x{grid[2]} subdomains, 1/GPU"
     else:
         wl, par = workload_name(m, world, args.nu, args.mu)
     out = {
-        "metric": METRIC_Z if cplx else METRIC, "value": world * args.steps / (ms_dev * 1e-3), "unit": "subdomain-applies/s", "applies_per_s": args.steps / (ms_dev * 1e-3),
+        "metric": METRIC_E if elas else (METRIC_Z if cplx else METRIC), "value": world * args.steps / (ms_dev * 1e-3), "unit": "subdomain-applies/s", "applies_per_s": args.steps / (ms_dev * 1e-3),
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128" if cplx else "f64", "data": "synthetic",
         "config": {"workload": wl, "parallelism": par, "cells": m, "nu": args.nu, "mu": args.mu},
@@ -238,8 +269,8 @@ def run_b200(args):
             t0 = time.time()
             it_k, _, res = fn(bvec, correction="deflated")
             out["krylov"][name] = {"seconds": time.time() - t0, "iterations": it_k, "max_rel_residual": float(np.max(res)), "rhs": mu}
-    if cplx:
-        out["cpu_baseline"] = None   # the CPU arm (oracle/cpu_ras.cpp) is real-valued; the complex bench is auxiliary
+    if cplx or elas:
+        out["cpu_baseline"] = None   # the CPU arm (oracle/cpu_ras.cpp) is the scalar Poisson workload; these benches are auxiliary
     elif args.cpu_baseline and rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_baseline(args, steps=5, reuse=True)
     if rank == 0:
@@ -416,12 +447,14 @@ def main():
     ap.add_argument("--nu", type=int, default=20)
     ap.add_argument("--rhs", dest="mu", type=int, default=1, help="right-hand sides per apply (block methods)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--workload", default="poisson", choices=["poisson", "elasticity"],
+                    help="poisson: the headline (config 3 slice); elasticity: config 4 shape (Q1 3 dof/node, use --rhs 4 --nu 30; --cells = nodes per subdomain edge)")
     ap.add_argument("--scalar", default="d", choices=["d", "z"], help="d: real FP64 Poisson (headline); z: complex FP64 Helmholtz / ORAS (config 5 shape, auxiliary)")
     ap.add_argument("--wavenumber", type=float, default=2.0)
     ap.add_argument("--krylov", action="store_true", help="also time a full GMRES solve: device-resident driver vs host-driven loop over the C ABI")
     args = ap.parse_args()
     if not args.m:
-        args.m = default_cells()
+        args.m = 64 if args.workload == "elasticity" else default_cells()
     if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) != args.gpus:
         raise SystemExit(f"bench.py: --gpus {args.gpus} but the launcher started WORLD_SIZE={os.environ['WORLD_SIZE']} ranks")
     if "WORLD_SIZE" not in os.environ and args.gpus > 1 and args.impl != "reference":

@@ -424,8 +424,8 @@ static int deflation_core(Ctx *c, const std::vector<const K *> &in, const std::v
 
 int solve_cols(Sub *s, const K *b, K *x, int mu, const double *scale, bool acc) {
   int col = 0;
-  while (col < mu) {  // panels are streamed once per group of 4 / 2 / 1 right-hand sides
-    const int g = (mu - col >= 4) ? 4 : ((mu - col >= 2) ? 2 : 1);
+  while (col < mu) {  // panels are streamed once per group of right-hand sides (up to 8 on the tensor-pipe kernels, else 4 / 2 / 1)
+    const int g = sptrsv_group(mu - col);
     HB_CHECK(sptrsv_solve(s, b + (size_t)col * s->n, x + (size_t)col * s->n, g, scale, acc));
     col += g;
   }
@@ -1040,19 +1040,17 @@ int HB_API(build_coarse)(hb_ctx_t *ctx) {
   if (!c) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(c->device));
   HB_CHECK(coarse_layout(c));
-  int numax = 1;
-  for (Sub *s : c->subs) numax = std::max(numax, s->nu);
-  HB_CHECK(check_ready(c, numax));
   const int L = local_count(c), P = L * c->nproc, N = c->Nc, Lnu = c->Lnu;
-  // nu of every global subdomain
+  // nu of every global subdomain (control plane), then work space for the widest block -- the same width on every process
   std::vector<int> nu_all(P, 0);
   {
     std::vector<int> mine(L);
     for (int i = 0; i < L; ++i) mine[i] = c->subs[i]->nu;
     HB_CHECK(ctrl_allgather(c, mine.data(), nu_all.data(), L * sizeof(int)));
   }
+  int numax = 1;
   for (int v : nu_all) numax = std::max(numax, v);
-  HB_CHECK(ensure_capacity(c, numax));
+  HB_CHECK(check_ready(c, numax));
   K *d_rows = nullptr;  // Lnu x N, column-major
   HB_CUDA(cudaMalloc(&d_rows, std::max<size_t>((size_t)Lnu * N, 1) * sizeof(K)));
   HB_CUDA(cudaMemsetAsync(d_rows, 0, (size_t)Lnu * N * sizeof(K), c->stream));

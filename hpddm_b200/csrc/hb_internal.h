@@ -134,8 +134,8 @@ struct DeviceFactor {
   FwdItem *fwd = nullptr;
   BwdItem *bwd = nullptr;
   int *perm = nullptr;   // perm[new] = old
-  K *b = nullptr, *y = nullptr, *x = nullptr;  // permuted work vectors (n * 4 each: up to 4 RHS per pass)
-  cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};  // captured sweep launches for mu = 1, 2, 4
+  K *b = nullptr, *y = nullptr, *x = nullptr;  // permuted work vectors (n * 8 each: up to 8 RHS per pass)
+  cudaGraphExec_t graph[9] = {};  // captured sweep launches, indexed by the number of right-hand sides of the pass (1 .. 8)
   int sweep_launches = 0;                                  // kernels inside one captured graph
 };
 
@@ -224,9 +224,13 @@ struct Ctx {
 // K = scalar type of this build (hb_scalar.h); `d` / `scale` (partition of unity) are always real
 int numfact_device(Sub *s, const HostCSR &A);
 void free_factor(DeviceFactor &f);
-// x = A^{-1} b for mu in {1,2,4} columns (column stride n), natural ordering in/out, device pointers.
+// x = A^{-1} b for mu columns in ONE pass over the panels (column stride n), natural ordering in/out, device pointers: mu in {1, 2, 4}
+// on the register-tiled kernels, any mu <= sptrsv_max_block() at or above the tensor-pipe threshold (hb_solve.cu).
 // scale: optional d (natural order) applied on output (out = d .* x); accumulate: out += instead of =
 int sptrsv_solve(Sub *s, const K *b, K *x, int mu, const double *scale, bool accumulate);
+int sptrsv_group(int left);   // how many of `left` remaining columns the next pass takes
+int sptrsv_prepare(Sub *s);   // per-device kernel attributes (opt-in shared memory), called once per factorisation
+int sptrsv_max_block();
 
 int k_scale(Ctx *c, int n, int mu, const double *d, const K *in, K *out);      // out = d.*in
 int k_axpy(Ctx *c, int64_t n, double a, const K *x, K *y);                     // y += a x

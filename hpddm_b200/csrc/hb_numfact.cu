@@ -609,9 +609,10 @@ int numfact_device(Sub *s, const HostCSR &A) {
   HB_CHECK(upload(S.fwd, &D.fwd, st));
   HB_CHECK(upload(S.bwd, &D.bwd, st));
   HB_CHECK(upload(S.perm, &D.perm, st));
-  HB_CUDA(cudaMalloc(&D.b, (size_t)S.n * 4 * sizeof(K)));
-  HB_CUDA(cudaMalloc(&D.y, (size_t)S.n * 4 * sizeof(K)));
-  HB_CUDA(cudaMalloc(&D.x, (size_t)S.n * 4 * sizeof(K)));
+  HB_CUDA(cudaMalloc(&D.b, (size_t)S.n * 8 * sizeof(K)));
+  HB_CUDA(cudaMalloc(&D.y, (size_t)S.n * 8 * sizeof(K)));
+  HB_CUDA(cudaMalloc(&D.x, (size_t)S.n * 8 * sizeof(K)));
+  HB_CHECK(sptrsv_prepare(s));
   D.sweep_launches = 0;
   for (int l = 0; l < S.nlevels; ++l) D.sweep_launches += (S.fwd_ptr[l + 1] > S.fwd_ptr[l]) + (S.bwd_ptr[l + 1] > S.bwd_ptr[l]);
   int rc = HPDDM_B200_ERR_NUMERIC;

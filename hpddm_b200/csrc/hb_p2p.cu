@@ -206,6 +206,12 @@ int fabric_setup(Ctx *c, int mu) {
   P2P *p = c->p2p = new P2P;
   p->tried = true;
   p->P = P;
+  {  // size the window for the largest request of any rank (ranks may have grown their work space at different times)
+    int want[2] = {mu, std::max(c->Lnu, 1)};
+    std::vector<int> wants(2 * P);
+    HB_CHECK(ctrl_allgather(c, want, wants.data(), sizeof(want)));
+    for (int q = 0; q < P; ++q) mu = std::max(mu, wants[2 * q]);
+  }
   const bool one_sub = c->subs.size() == 1;
   Sub *s = one_sub ? c->subs[0] : nullptr;
   const int nb = s ? (int)s->nb_rank.size() : 0, h = s ? s->h : 0;

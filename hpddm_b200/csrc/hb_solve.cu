@@ -14,6 +14,7 @@
 // a warp owns one work item (<= 32 rows x 512 columns forward, <= 128 rows x 256
 // columns backward; 1, 2 or 4 right-hand sides per pass over the panels), reduces with shuffles and publishes with FP64 atomics
 // (RED.ADD.F64).  Pure HBM streaming: 0.25 flop/byte.
+#include <algorithm>
 #include <cstring>
 
 #include "hb_internal.h"
@@ -350,13 +351,6 @@ static int launch_levels(Sub *s, cudaStream_t st) {
   // HPDDM_B200_FWD1=staged selects the shared-memory kernel
   static const bool fwd1_l1 = getenv("HPDDM_B200_FWD1") ? !strcmp(getenv("HPDDM_B200_FWD1"), "l1") : !IS_COMPLEX;
   constexpr size_t smem2 = (size_t)2 * 8 * FCH * sizeof(K);
-  if (MU > 1 && wide) {
-    static bool once = false;
-    if (!once) {
-      HB_CUDA(cudaFuncSetAttribute(k_fwd<(MU > 1 ? MU : 2), 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      once = true;
-    }
-  }
   DeviceFactor &D = s->fac;
   const Symbolic &S = s->sym;
   const int n = S.n;
@@ -381,41 +375,435 @@ static int launch_levels(Sub *s, cudaStream_t st) {
 
 }  // namespace
 
+#ifndef HB_COMPLEX
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Block right-hand sides on the FP64 tensor pipe: 1 .. 8 columns per pass over the panels.
+//
+// Data path: every warp is a self-contained producer/consumer pipeline.  Panel tiles (32 rows x 64 columns, one row = one 512-byte
+// 1-D bulk copy, cp.async.bulk -> SASS UBLKCP) land in a per-warp ring of NST shared-memory stages; completion is tracked by one
+// mbarrier per stage (expect_tx / complete_tx), so no register holds data in flight -- the limit of the register-tiled kernels above
+// (MU = 4: 106 registers, 25 % occupancy, latency-bound at 0.5 of the HBM roofline).  The warp walks a STREAM of stages that runs
+// across work-item boundaries (persistent warps: item = global warp index + k * total warps), so the ring stays full on the levels
+// made of thousands of small fronts too.  The products are mma.sync.aligned.m8n8k4.f64 (SASS DMMA) with the right-hand-side block
+// as the N dimension (padded to 8: one kernel serves 1 .. 8 columns):
+//   forward   D[8 rows x 8 rhs]  += P[8 rows x 4 cols]   * b[4 cols x 8 rhs]      -- no cross-lane reduction left
+//   backward  D[8 cols x 8 rhs]  += P^T[8 cols x 4 rows] * u[4 rows x 8 rhs]
+// A fragments are 128-bit shared-memory loads feeding two MMAs each (even / odd columns); the row pitch of the stage (72 resp. 68
+// doubles) makes them bank-conflict free for the two access patterns.  Panel bytes are still read exactly once per sweep.
+namespace mma {
+constexpr int ST_ROWS = 32, ST_COLS = 64, NST = 3, WARPS = 4;
+constexpr int PITCH_F = ST_COLS + 8;  // forward: lanes (g, t) read [8 rg + g][8 j + 2 t]
+constexpr int PITCH_B = ST_COLS + 4;  // backward: lanes (g, t) read [4 ks + t][16 jj + 2 g]
+
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// 1-D bulk copy global -> shared (bytes: multiple of 16; both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+
+// one stage of the stream = one 32 x 64 tile of one work item
+struct FStage {  // forward
+  int64_t it;    // item index (>= nitems: stream exhausted)
+  int cs;        // first column of the tile
+  // decoded item
+  const double *base;  // first row of the item's row block
+  int stride, nrows, c0, c1, p0, rblk, nb1;
+  int64_t rptr;
+  bool pivot;
+};
+__device__ __forceinline__ void f_decode(FStage &s, const FwdItem *items, const Front *fronts, const double *pan) {
+  const FwdItem w = items[s.it];
+  const Front f = fronts[w.front];
+  const int s1 = f.s1;
+  s.nb1 = (s1 + RB - 1) / RB;
+  s.pivot = w.rblk < s.nb1;
+  int cmax;
+  if (s.pivot) {
+    s.stride = hb_wblk(s1, w.rblk);
+    s.base = pan + f.poff + hb_blk_off(w.rblk);
+    s.nrows = min(RB, s1 - RB * w.rblk);
+    cmax = min(s1, RB * (w.rblk + 1));
+  } else {
+    const int k2 = w.rblk - s.nb1;
+    s.stride = hb_ldp(s1);
+    s.base = pan + f.poff + hb_upd_off(s1) + (int64_t)k2 * RB * s.stride;
+    s.nrows = min(RB, f.s2 - RB * k2);
+    cmax = s1;
+  }
+  s.c0 = w.c0;
+  s.c1 = min(cmax, w.c0 + w.cw);
+  s.p0 = f.p0;
+  s.rblk = w.rblk;
+  s.rptr = f.rptr;
+  s.cs = w.c0;
+}
+// advance to the next tile of the stream (next column tile of the item, else first tile of the warp's next non-empty item)
+__device__ __forceinline__ void f_next(FStage &s, bool first, int64_t nitems, int64_t stride_items, const FwdItem *items, const Front *fronts, const double *pan) {
+  if (!first) {
+    s.cs += ST_COLS;
+    if (s.cs < s.c1) return;
+    s.it += stride_items;
+  }
+  while (s.it < nitems) {
+    f_decode(s, items, fronts, pan);
+    if (s.cs < s.c1) return;
+    s.it += stride_items;
+  }
+}
+
+__global__ void __launch_bounds__(WARPS * 32, 1) k_fwd_mma(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
+                                                           const double *__restrict__ pan, double *b, double *y, int n, int mu) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * NST * ST_ROWS * PITCH_F;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * NST * ST_ROWS * PITCH_F * sizeof(double)) + warp * NST;
+  for (int i = lane; i < NST * ST_ROWS * PITCH_F; i += 32) ring[i] = 0.0;  // stale tails are multiplied by zeros: keep them finite
+  if (lane == 0)
+    for (int q = 0; q < NST; ++q) mbar_init(bars + q, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, gstride = (int64_t)gridDim.x * WARPS;
+  FStage prod, cons;
+  prod.it = cons.it = gw;
+  f_next(prod, true, nitems, gstride, items, fronts, pan);
+  f_next(cons, true, nitems, gstride, items, fronts, pan);
+  auto produce = [&](int slot) {  // all lanes: lane r copies row r of the tile
+    const int nc = min(ST_COLS, prod.stride - prod.cs);  // the stored row is zero-padded up to its stride: copy whole 32-byte groups
+    const uint32_t bytes = (uint32_t)nc * 8u;
+    if (lane == 0) mbar_expect_tx(bars + slot, bytes * (uint32_t)prod.nrows);
+    __syncwarp();
+    if (lane < prod.nrows) bulk_g2s(ring + ((size_t)slot * ST_ROWS + lane) * PITCH_F, prod.base + (int64_t)lane * prod.stride + prod.cs, bytes, bars + slot);
+  };
+  int pslot = 0, cslot = 0;
+  uint32_t cphase = 0;
+  for (int q = 0; q < NST - 1 && prod.it < nitems; ++q) {  // prologue: fill NST - 1 stages
+    produce(pslot);
+    pslot = (pslot + 1) % NST;
+    f_next(prod, false, nitems, gstride, items, fronts, pan);
+  }
+  double acc[4][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+  while (cons.it < nitems) {
+    // keep the ring full: the slot freed by the previous iteration (all lanes are past their reads of it: __syncwarp below)
+    if (prod.it < nitems) {
+      produce(pslot);
+      pslot = (pslot + 1) % NST;
+      f_next(prod, false, nitems, gstride, items, fronts, pan);
+    }
+    // right-hand-side fragments of this tile: B[k = t][n = g] for the even / odd column of each group of 8
+    double bx[8], by[8];
+    {
+      const double *bc = b + (int64_t)g * n + cons.p0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cons.cs + 8 * j + 2 * t;
+        bx[j] = (g < mu && c < cons.c1) ? __ldg(bc + c) : 0.0;
+        by[j] = (g < mu && c + 1 < cons.c1) ? __ldg(bc + c + 1) : 0.0;
+      }
+    }
+    mbar_wait(bars + cslot, cphase);
+    const double *tile = ring + (size_t)cslot * ST_ROWS * PITCH_F;
+#pragma unroll
+    for (int rg = 0; rg < 4; ++rg) {
+      if (8 * rg < cons.nrows) {
+        const double2 *row = reinterpret_cast<const double2 *>(tile + (size_t)(8 * rg + g) * PITCH_F) + t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const double2 a = row[4 * j];
+          dmma(acc[rg], a.x, bx[j]);
+          dmma(acc[rg], a.y, by[j]);
+        }
+      }
+    }
+    __syncwarp();  // every lane is done reading this slot before it is refilled
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    cslot = (cslot + 1) % NST;
+    cphase ^= (cslot == 0);
+    const bool last = cons.cs + ST_COLS >= cons.c1;
+    if (last) {  // publish the item: D[row = 8 rg + g][rhs = 2 t, 2 t + 1]
+#pragma unroll
+      for (int rg = 0; rg < 4; ++rg) {
+        const int r = 8 * rg + g;
+        if (r < cons.nrows) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int m = 2 * t + h;
+            if (m < mu) {
+              if (cons.pivot) atomicAdd(&y[(int64_t)m * n + cons.p0 + RB * cons.rblk + r], acc[rg][h]);
+              else atomicAdd(&b[(int64_t)m * n + rowidx[cons.rptr + RB * (cons.rblk - cons.nb1) + r]], -acc[rg][h]);
+            }
+          }
+        }
+        acc[rg][0] = acc[rg][1] = 0.0;
+      }
+    }
+    f_next(cons, false, nitems, gstride, items, fronts, pan);
+  }
+}
+
+struct BStage {  // backward: tile = rows [rr, rr + 32) x columns [cc, cc + 64) of one item
+  int64_t it;
+  int cc, rr;
+  const double *P, *Pu;
+  int s1, ldp, p0, r0, r1, cend;
+  int64_t rptr;
+};
+__device__ __forceinline__ void b_decode(BStage &s, const BwdItem *items, const Front *fronts, const double *pan) {
+  const BwdItem w = items[s.it];
+  const Front f = fronts[w.front];
+  s.s1 = f.s1;
+  s.ldp = hb_ldp(f.s1);
+  s.P = pan + f.poff;
+  s.Pu = s.P + hb_upd_off(f.s1);
+  s.p0 = f.p0;
+  s.rptr = f.rptr;
+  s.r0 = w.r0;
+  s.r1 = w.r0 + w.nr;
+  s.cend = min(w.c0 + BCH, s.ldp);
+  s.cc = w.c0;
+  s.rr = w.r0;
+}
+__device__ __forceinline__ void b_next(BStage &s, bool first, int64_t nitems, int64_t stride_items, const BwdItem *items, const Front *fronts, const double *pan) {
+  if (!first) {
+    s.rr += ST_ROWS;
+    if (s.rr < s.r1) return;
+    s.rr = s.r0;
+    s.cc += ST_COLS;
+    if (s.cc < s.cend) return;
+    s.it += stride_items;
+  }
+  while (s.it < nitems) {
+    b_decode(s, items, fronts, pan);
+    if (s.cc < s.cend && s.rr < s.r1) return;
+    s.it += stride_items;
+  }
+}
+
+__global__ void __launch_bounds__(WARPS * 32, 1) k_bwd_mma(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
+                                                           const double *__restrict__ pan, const double *__restrict__ y, double *x, int n, int mu) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * NST * ST_ROWS * PITCH_B;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * NST * ST_ROWS * PITCH_B * sizeof(double)) + warp * NST;
+  for (int i = lane; i < NST * ST_ROWS * PITCH_B; i += 32) ring[i] = 0.0;
+  if (lane == 0)
+    for (int q = 0; q < NST; ++q) mbar_init(bars + q, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, gstride = (int64_t)gridDim.x * WARPS;
+  BStage prod, cons;
+  prod.it = cons.it = gw;
+  b_next(prod, true, nitems, gstride, items, fronts, pan);
+  b_next(cons, true, nitems, gstride, items, fronts, pan);
+  auto produce = [&](int slot) {  // lane r: row rr + r of the panel (pivot rows live in the trapezoid: their stored width grows with the row block)
+    const int r = prod.rr + lane;
+    const double *src = nullptr;
+    int width = 0;  // stored columns of this row
+    if (r < prod.r1) {
+      if (r < prod.s1) {
+        const int k = r / RB;
+        width = hb_wblk(prod.s1, k);
+        src = prod.P + hb_blk_off(k) + (int64_t)(r - k * RB) * width;
+      } else {
+        width = prod.ldp;
+        src = prod.Pu + (int64_t)(r - prod.s1) * prod.ldp;
+      }
+    }
+    const int nc = max(0, min(ST_COLS, width - prod.cc));
+    double *dst = ring + ((size_t)slot * ST_ROWS + lane) * PITCH_B;
+    for (int c = nc; c < ST_COLS; ++c) dst[c] = 0.0;  // columns this row does not store (structural zeros / rows past the item) must read as zeros
+    unsigned total = 8u * (unsigned)nc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) mbar_expect_tx(bars + slot, total);
+    __syncwarp();
+    if (nc > 0) bulk_g2s(dst, src + prod.cc, 8u * (unsigned)nc, bars + slot);
+  };
+  int pslot = 0, cslot = 0;
+  uint32_t cphase = 0;
+  for (int q = 0; q < NST - 1 && prod.it < nitems; ++q) {
+    produce(pslot);
+    pslot = (pslot + 1) % NST;
+    b_next(prod, false, nitems, gstride, items, fronts, pan);
+  }
+  double accE[4][2], accO[4][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) accE[q][0] = accE[q][1] = accO[q][0] = accO[q][1] = 0.0;
+  while (cons.it < nitems) {
+    if (prod.it < nitems) {
+      produce(pslot);
+      pslot = (pslot + 1) % NST;
+      b_next(prod, false, nitems, gstride, items, fronts, pan);
+    }
+    // multipliers of the 32 rows of this tile: B[k = t][n = g] = u[row 4 ks + t][rhs g]
+    double ub[8];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const int r = cons.rr + 4 * ks + t;
+      double v = 0.0;
+      if (g < mu && r < cons.r1) v = (r < cons.s1) ? y[(int64_t)g * n + cons.p0 + r] : -x[(int64_t)g * n + rowidx[cons.rptr + r - cons.s1]];
+      ub[ks] = v;
+    }
+    mbar_wait(bars + cslot, cphase);
+    __syncwarp();  // the zero tails written by other lanes at produce time are visible
+    const double *tile = ring + (size_t)cslot * ST_ROWS * PITCH_B;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const double2 *row = reinterpret_cast<const double2 *>(tile + (size_t)(4 * ks + t) * PITCH_B) + g;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const double2 a = row[8 * jj];
+        dmma(accE[jj], a.x, ub[ks]);
+        dmma(accO[jj], a.y, ub[ks]);
+      }
+    }
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    cslot = (cslot + 1) % NST;
+    cphase ^= (cslot == 0);
+    const bool last = cons.rr + ST_ROWS >= cons.r1;
+    if (last) {  // all rows of this 64-column chunk are in: D[col = 16 jj + 2 g (+ 1)][rhs = 2 t, 2 t + 1]
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int c = cons.cc + 16 * jj + 2 * g;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m = 2 * t + h;
+          if (m < mu) {
+            if (c < cons.s1) atomicAdd(&x[(int64_t)m * n + cons.p0 + c], accE[jj][h]);
+            if (c + 1 < cons.s1) atomicAdd(&x[(int64_t)m * n + cons.p0 + c + 1], accO[jj][h]);
+          }
+        }
+        accE[jj][0] = accE[jj][1] = accO[jj][0] = accO[jj][1] = 0.0;
+      }
+    }
+    b_next(cons, false, nitems, gstride, items, fronts, pan);
+  }
+}
+
+constexpr size_t SMEM_F = (size_t)WARPS * NST * ST_ROWS * PITCH_F * sizeof(double) + WARPS * NST * sizeof(uint64_t);
+constexpr size_t SMEM_B = (size_t)WARPS * NST * ST_ROWS * PITCH_B * sizeof(double) + WARPS * NST * sizeof(uint64_t);
+}  // namespace mma
+
+// sweeps for 1 .. 8 right-hand sides on the tensor pipe (one persistent launch per level and sweep)
+static int launch_levels_mma(Sub *s, cudaStream_t st, int mu) {
+  DeviceFactor &D = s->fac;
+  const Symbolic &S = s->sym;
+  const int n = S.n;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  auto grid = [&](int64_t ni) { return (unsigned)std::min<int64_t>(sms, (ni + mma::WARPS - 1) / mma::WARPS); };
+  for (int l = 0; l < S.nlevels; ++l) {
+    const int64_t i0 = S.fwd_ptr[l], ni = S.fwd_ptr[l + 1] - i0;
+    if (ni > 0) mma::k_fwd_mma<<<grid(ni), mma::WARPS * 32, mma::SMEM_F, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
+  }
+  for (int l = S.nlevels - 1; l >= 0; --l) {
+    const int64_t i0 = S.bwd_ptr[l], ni = S.bwd_ptr[l + 1] - i0;
+    if (ni > 0) mma::k_bwd_mma<<<grid(ni), mma::WARPS * 32, mma::SMEM_B, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
+  }
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}
+// HPDDM_B200_MMA: "0" = register-tiled kernels only; "1" (default) = tensor-pipe kernels for 3 .. 8 right-hand sides;
+// "2" = also for 2; "all" = also for a single right-hand side (A/B measurements, profiles/README.md)
+static int mma_min_mu() {
+  static const int v = [] {
+    const char *e = getenv("HPDDM_B200_MMA");
+    if (!e) return 3;
+    if (!strcmp(e, "0")) return 1000;
+    if (!strcmp(e, "2")) return 2;
+    if (!strcmp(e, "all")) return 1;
+    return 3;
+  }();
+  return v;
+}
+int sptrsv_prepare(Sub *s) {  // once per factorisation, outside any stream capture: opt-in shared-memory sizes are per device
+  HB_CUDA(cudaFuncSetAttribute(mma::k_fwd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma::SMEM_F));
+  HB_CUDA(cudaFuncSetAttribute(mma::k_bwd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma::SMEM_B));
+  HB_CUDA(cudaFuncSetAttribute(k_fwd<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 8 * FCH * sizeof(K))));
+  HB_CUDA(cudaFuncSetAttribute(k_fwd<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 8 * FCH * sizeof(K))));
+  (void)s;
+  return 0;
+}
+int sptrsv_max_block() { return mma_min_mu() <= 8 ? 8 : 4; }
+#else
+int sptrsv_prepare(Sub *s) {
+  HB_CUDA(cudaFuncSetAttribute(k_fwd<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 8 * FCH * sizeof(K))));
+  HB_CUDA(cudaFuncSetAttribute(k_fwd<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 8 * FCH * sizeof(K))));
+  (void)s;
+  return 0;
+}
+int sptrsv_max_block() { return 4; }
+#endif
+
 // x = A^{-1} b for mu in {1, 2, 4} columns at once (natural ordering in/out, device pointers,
 // column stride n).  The 2 * nlevels sweep launches are replayed from a CUDA graph captured on
 // first use (their arguments never change); only the two permutation kernels see the caller's
 // pointers.
+int sptrsv_group(int left) {
+#ifndef HB_COMPLEX
+  if (left >= mma_min_mu()) return std::min(left, 8);
+#endif
+  return left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+}
+
 int sptrsv_solve(Sub *s, const K *b, K *x, int mu, const double *scale, bool accumulate) {
   DeviceFactor &D = s->fac;
   if (!D.valid) {
     set_error("solve: no factorisation (call numfact first)");
     return HPDDM_B200_ERR_STATE;
   }
-  if (mu != 1 && mu != 2 && mu != 4) {
-    set_error("sptrsv_solve: mu must be 1, 2 or 4");
+  bool tensor = false;
+#ifndef HB_COMPLEX
+  tensor = mu >= mma_min_mu() && mu <= 8;
+#endif
+  if (!tensor && mu != 1 && mu != 2 && mu != 4) {
+    set_error("sptrsv_solve: %d right-hand sides in one pass are not supported by the register-tiled kernels (1, 2 or 4)", mu);
     return HPDDM_B200_ERR_ARG;
   }
   const Symbolic &S = s->sym;
   cudaStream_t st = s->ctx->stream;
   const int n = S.n;
   if (n == 0) return 0;
-  const int gi = mu == 1 ? 0 : (mu == 2 ? 1 : 2);
+  auto sweeps = [&]() -> int {
+#ifndef HB_COMPLEX
+    if (tensor) return launch_levels_mma(s, st, mu);
+#endif
+    return mu == 1 ? launch_levels<1>(s, st) : (mu == 2 ? launch_levels<2>(s, st) : launch_levels<4>(s, st));
+  };
   static const bool use_graph = getenv("HPDDM_B200_NO_GRAPH") == nullptr;
   k_perm_in<<<(unsigned)(((int64_t)n * mu + 255) / 256), 256, 0, st>>>(n, mu, D.perm, b, D.b, D.y, D.x);
-  if (use_graph && !D.graph[gi]) {
+  if (use_graph && !D.graph[mu]) {
     cudaGraph_t g = nullptr;
     HB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    int rc = mu == 1 ? launch_levels<1>(s, st) : (mu == 2 ? launch_levels<2>(s, st) : launch_levels<4>(s, st));
+    int rc = sweeps();
     cudaError_t e = cudaStreamEndCapture(st, &g);
     if (rc < 0 || e != cudaSuccess) {
       set_error("CUDA graph capture of the SpTRSV sweeps failed (%s)", cudaGetErrorString(e));
       return HPDDM_B200_ERR_CUDA;
     }
-    HB_CUDA(cudaGraphInstantiate(&D.graph[gi], g, 0));
+    HB_CUDA(cudaGraphInstantiate(&D.graph[mu], g, 0));
     cudaGraphDestroy(g);
   }
-  if (use_graph) HB_CUDA(cudaGraphLaunch(D.graph[gi], st));
-  else HB_CHECK((mu == 1 ? launch_levels<1>(s, st) : (mu == 2 ? launch_levels<2>(s, st) : launch_levels<4>(s, st))));
+  if (use_graph) HB_CUDA(cudaGraphLaunch(D.graph[mu], st));
+  else HB_CHECK(sweeps());
   k_perm_out<<<(unsigned)(((int64_t)n * mu + 255) / 256), 256, 0, st>>>(n, mu, D.perm, D.x, scale, x, accumulate ? 1 : 0);
   s->ctx->launches += 2 + D.sweep_launches;
   HB_CUDA(cudaGetLastError());

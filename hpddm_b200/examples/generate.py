@@ -308,13 +308,12 @@ def _assemble_elasticity(lo, hi, Nn, h, Ke, penalty):
     V = np.tile(Ke.reshape(-1), conn.shape[0])
     n = 3 * w * hh * t
     A = sp.csr_matrix((V, (R, C)), shape=(n, n))
+    A.sort_indices()
     if penalty and lo[0] == 0:
         clamp = (3 * nid[:, :, 0].reshape(-1)[:, None] + np.arange(3)[None, :]).reshape(-1)
-        A = A.tolil()
-        for i in clamp:
-            A[i, i] = penalty
-        A = A.tocsr()
-    A.sort_indices()
+        rows = np.repeat(np.arange(n), np.diff(A.indptr))
+        on_diag = np.nonzero(A.indices == rows)[0]          # every row has a stored diagonal entry (element stiffness)
+        A.data[on_diag[clamp]] = penalty
     return A
 
 
