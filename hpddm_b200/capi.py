@@ -37,6 +37,8 @@ _SIGS = {
     "hpddm_b200_last_error": (C.c_char_p, []),
     "hpddm_b200_version": (C.c_char_p, []),
     "hpddm_b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "hpddm_b200_debug_coarse_layout": (C.c_int, [C.c_int, _P, _P, C.POINTER(C.c_int)]),
+    "hpddm_b200_debug_halo_schedule": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.POINTER(C.c_int)]),
     "hpddm_b200_ctx_create": (C.c_int, [C.c_int, _PP]),
     "hpddm_b200_ctx_destroy": (C.c_int, [_P]),
     "hpddm_b200_nccl_unique_id": (C.c_int, [_P]),

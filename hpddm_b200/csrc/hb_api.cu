@@ -177,6 +177,9 @@ static int ensure_capacity(Ctx *c, int mu) {
   }
   if (c->d_res) cudaFree(c->d_res);
   HB_CUDA(cudaMalloc(&c->d_res, std::max(mu, 64) * sizeof(K)));
+  if (c->d_R) cudaFree(c->d_R);
+  c->d_R = nullptr;
+  HB_CUDA(cudaMalloc(&c->d_R, std::max<size_t>((size_t)std::max(c->Nc, 1) * mu, 1) * sizeof(K)));  // residual of the coarse refinement step
   c->mu_cap = mu;
   if (c->nproc > 1) HB_CHECK(fabric_setup(c, mu));  // collective: every process reaches this with the same mu (SPMD call sequence)
   return 0;
@@ -206,6 +209,43 @@ static int build_links(Ctx *c) {
     }
   }
   return 0;
+}
+
+// ---- host-only planning (no GPU involved; also reachable through hpddm_b200_debug_* so that CPU tests exercise the product's logic)
+// Message schedule of one halo round over NCCL for the subdomains hosted by one process: every (subdomain, neighbour) pair whose
+// neighbour lives in another process gives one send and one receive; both lists are ordered by (destination subdomain, source
+// subdomain) so that the k-th send A -> B matches the k-th receive posted by B.  Quadruples (dst, src, local subdomain, neighbour slot).
+void plan_halo_messages(const std::vector<int> &granks, const std::vector<int> &nbcnt, const std::vector<int> &nbr, std::vector<int> &sends, std::vector<int> &recvs) {
+  struct M {
+    int dst, src, sub, slot;
+  };
+  std::vector<M> sv, rv;
+  auto local = [&](int g) { return std::find(granks.begin(), granks.end(), g) != granks.end(); };
+  size_t at = 0;
+  for (size_t q = 0; q < granks.size(); ++q)
+    for (int i = 0; i < nbcnt[q]; ++i, ++at) {
+      const int nb = nbr[at];
+      if (local(nb)) continue;
+      sv.push_back({nb, granks[q], (int)q, i});
+      rv.push_back({granks[q], nb, (int)q, i});
+    }
+  auto cmp = [](const M &a, const M &b) { return a.dst != b.dst ? a.dst < b.dst : a.src < b.src; };
+  std::sort(sv.begin(), sv.end(), cmp);
+  std::sort(rv.begin(), rv.end(), cmp);
+  sends.clear();
+  recvs.clear();
+  for (const M &m : sv) sends.insert(sends.end(), {m.dst, m.src, m.sub, m.slot});
+  for (const M &m : rv) recvs.insert(recvs.end(), {m.dst, m.src, m.sub, m.slot});
+}
+// Coarse numbering [process][local subdomain][vector]: offsets of the process blocks and the padded block length of the
+// communication layout (every block padded to the longest one so that a single all-gather moves them)
+void plan_coarse_layout(const std::vector<int> &rows_per_proc, std::vector<int> &off, int &lmax) {
+  off.assign(rows_per_proc.size() + 1, 0);
+  lmax = 0;
+  for (size_t p = 0; p < rows_per_proc.size(); ++p) {
+    off[p + 1] = off[p] + rows_per_proc[p];
+    lmax = std::max(lmax, rows_per_proc[p]);
+  }
 }
 
 // halo sum  x_s[map] += neighbours' values  (Subdomain::exchange, subdomain.hpp:115-130),
@@ -238,23 +278,25 @@ int halo(Ctx *c, K *const *x, int mu) {
     return HPDDM_B200_ERR_STATE;
   }
   if (remote) {
-    // order both directions by (destination subdomain, source subdomain) so that
-    // the k-th send A->B matches the k-th receive posted by B
+    // both directions ordered by (destination subdomain, source subdomain): the k-th send A -> B matches the k-th receive posted by B
+    std::vector<int> granks, nbcnt, nbr, sflat, rflat;
+    for (Sub *s : c->subs) {
+      granks.push_back(s->grank);
+      nbcnt.push_back((int)s->nb_rank.size());
+      nbr.insert(nbr.end(), s->nb_rank.begin(), s->nb_rank.end());
+    }
+    plan_halo_messages(granks, nbcnt, nbr, sflat, rflat);
     struct Msg {
       int dst, src;
       Sub *s;
       int i;
     };
+    auto expand = [&](const std::vector<int> &flat, std::vector<Msg> &out) {
+      for (size_t q = 0; q + 3 < flat.size(); q += 4) out.push_back({flat[q], flat[q + 1], c->subs[flat[q + 2]], flat[q + 3]});
+    };
     std::vector<Msg> sends, recvs;
-    for (Sub *s : c->subs)
-      for (int i = 0; i < (int)s->nb_rank.size(); ++i)
-        if (s->peer_seg[i] < 0) {
-          sends.push_back({s->nb_rank[i], s->grank, s, i});
-          recvs.push_back({s->grank, s->nb_rank[i], s, i});
-        }
-    auto cmp = [](const Msg &a, const Msg &b) { return a.dst != b.dst ? a.dst < b.dst : a.src < b.src; };
-    std::sort(sends.begin(), sends.end(), cmp);
-    std::sort(recvs.begin(), recvs.end(), cmp);
+    expand(sflat, sends);
+    expand(rflat, recvs);
     HB_NCCL(g_nccl.GroupStart());
     for (const Msg &m : recvs) {
       const size_t cnt = (size_t)(m.s->nb_ptr[m.i + 1] - m.s->nb_ptr[m.i]) * mu;
@@ -402,6 +444,7 @@ int stage_out(Ctx *c, K *const *out, int mu, int where) {
     HB_CHECK(host_copy(c, out[i], s->d_out, (size_t)s->n * mu * sizeof(K), false));
   }
   HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (Sub *s : c->subs) HB_CHECK(sptrsv_check(s));
   return p2p_check(c);
 }
 
@@ -559,6 +602,25 @@ static void sub_free(Sub *s) {
   delete s;
 }
 
+int HB_API(debug_coarse_layout)(int nproc, const int *rows_per_proc, int *offsets, int *lmax) {
+  if (nproc < 1 || !rows_per_proc || !offsets || !lmax) return HPDDM_B200_ERR_ARG;
+  std::vector<int> off;
+  plan_coarse_layout(std::vector<int>(rows_per_proc, rows_per_proc + nproc), off, *lmax);
+  std::copy(off.begin(), off.end(), offsets);
+  return 0;
+}
+int HB_API(debug_halo_schedule)(int nlocal, const int *granks, const int *nb_count, const int *nb_ranks, int *sends, int *recvs, int *nmsg) {
+  if (nlocal < 0 || !nmsg || (nlocal > 0 && (!granks || !nb_count))) return HPDDM_B200_ERR_ARG;
+  int tot = 0;
+  for (int q = 0; q < nlocal; ++q) tot += nb_count[q];
+  std::vector<int> sv, rv;
+  plan_halo_messages(std::vector<int>(granks, granks + nlocal), std::vector<int>(nb_count, nb_count + nlocal), std::vector<int>(nb_ranks, nb_ranks + tot), sv, rv);
+  *nmsg = (int)sv.size() / 4;
+  if (sends) std::copy(sv.begin(), sv.end(), sends);
+  if (recvs) std::copy(rv.begin(), rv.end(), recvs);
+  return 0;
+}
+
 int HB_API(device_count)(int *count) {
   if (!count) return HPDDM_B200_ERR_ARG;
   int n = 0;
@@ -625,6 +687,7 @@ int HB_API(ctx_comm_init_host)(hb_ctx_t *ctx, int proc_rank, int nproc, int (*al
 int HB_API(ctx_synchronize)(hb_ctx_t *ctx) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CUDA(cudaStreamSynchronize(c->stream));
+  for (Sub *s : c->subs) HB_CHECK(sptrsv_check(s));
   return p2p_check(c);  // a peer-memory collective that gave up waiting surfaces here for DEVICE-pointer callers
 }
 int HB_API(ctx_transport)(hb_ctx_t *ctx) {
@@ -940,12 +1003,8 @@ static int coarse_layout(Ctx *c) {
   std::vector<int> all(c->nproc, Lnu);
   HB_CHECK(ctrl_allgather(c, &Lnu, all.data(), sizeof(int)));
   c->Lnu_p = all;
-  c->coarse_off.assign(c->nproc + 1, 0);
   int Lmax = 0;
-  for (int p = 0; p < c->nproc; ++p) {
-    c->coarse_off[p + 1] = c->coarse_off[p] + all[p];
-    Lmax = std::max(Lmax, all[p]);
-  }
+  plan_coarse_layout(all, c->coarse_off, Lmax);
   c->Lnu = Lmax;
   c->Nc = c->coarse_off[c->nproc];
   c->loc_off = c->coarse_off[c->proc_rank];
@@ -1006,12 +1065,24 @@ static int invert_dense(int N, const std::vector<K> &E, std::vector<K> &Einv) {
 static int install_coarse(Ctx *c, const std::vector<K> &E) {
   const int N = c->Nc;
   c->E_host = E;
-  std::vector<K> Einv;
-  HB_CHECK(invert_dense(N, E, Einv));
   HB_CHECK(up(c->E_host, &c->d_E, c->stream));
-  HB_CHECK(up(Einv, &c->d_Einv, c->stream));
+  // E^-1: extended precision on the host up to N_c = 1024 (BASELINE sizes: 160 .. 240), cuSOLVER LU on the device beyond (O(N_c^3)
+  // on one host core would take minutes at the N_c ~ 1e4 of a thousand-subdomain run); kk_coarse adds one refinement step either way
+  const int host_limit = getenv("HPDDM_B200_COARSE_HOST_LIMIT") ? atoi(getenv("HPDDM_B200_COARSE_HOST_LIMIT")) : 1024;
+  c->coarse_multipass = N > (getenv("HPDDM_B200_COARSE_ONE_CTA_LIMIT") ? atoi(getenv("HPDDM_B200_COARSE_ONE_CTA_LIMIT")) : 512);
+  if (N > host_limit) {
+    if (c->d_Einv) cudaFree(c->d_Einv);
+    c->d_Einv = nullptr;
+    HB_CUDA(cudaMalloc(&c->d_Einv, (size_t)N * N * sizeof(K)));
+    HB_CHECK(dense_inverse_device(c, N, c->d_E, c->d_Einv));
+  } else {
+    std::vector<K> Einv;
+    HB_CHECK(invert_dense(N, E, Einv));
+    HB_CHECK(up(Einv, &c->d_Einv, c->stream));
+  }
   if (c->d_R) cudaFree(c->d_R);
-  HB_CUDA(cudaMalloc(&c->d_R, std::max(N, 1) * sizeof(K)));
+  c->d_R = nullptr;
+  HB_CUDA(cudaMalloc(&c->d_R, std::max<size_t>((size_t)std::max(N, 1) * std::max(c->mu_cap, 1), 1) * sizeof(K)));
   return 0;
 }
 

@@ -135,6 +135,14 @@ struct DeviceFactor {
   BwdItem *bwd = nullptr;
   int *perm = nullptr;   // perm[new] = old
   K *b = nullptr, *y = nullptr, *x = nullptr;  // permuted work vectors (n * 8 each: up to 8 RHS per pass)
+  // dependency-driven persistent sweeps (hb_solve.cu): per-front child counts / item counts, the backward items in launch order
+  // (root level first), and the counters a solve works on
+  int *fwd_children = nullptr, *fwd_total = nullptr, *bwd_total = nullptr;
+  BwdItem *bwd_ordered = nullptr;
+  int *sync_pending = nullptr, *sync_done = nullptr;
+  unsigned long long *sync_next = nullptr;
+  int *sync_err_host = nullptr, *sync_err = nullptr;  // mapped pinned word set by a warp that gave up waiting
+  int nfronts = 0;
   cudaGraphExec_t graph[9] = {};  // captured sweep launches, indexed by the number of right-hand sides of the pass (1 .. 8)
   int sweep_launches = 0;                                  // kernels inside one captured graph
 };
@@ -200,7 +208,8 @@ struct Ctx {
   std::vector<int> nu_all;
   K *d_E = nullptr, *d_Einv = nullptr;  // Nc x Nc column-major
   K *d_T = nullptr, *d_Y = nullptr;     // Nc x mu_cap, layout [proc][col][row-in-proc]
-  K *d_R = nullptr;                     // Nc residual of the coarse refinement step
+  K *d_R = nullptr;                     // Nc x mu_cap residual of the coarse refinement step
+  bool coarse_multipass = false;        // large N_c: the replicated solve runs as three grid-wide passes instead of one CTA
   int Lnu = 0;                               // Lmax: coarse rows per process block in the (padded) communication layout
   std::vector<int> Lnu_p;                    // actual coarse rows of every process
   int *d_rowproc = nullptr, *d_rowloc = nullptr;  // coarse row -> (process, row inside its block)
@@ -224,12 +233,14 @@ struct Ctx {
 // K = scalar type of this build (hb_scalar.h); `d` / `scale` (partition of unity) are always real
 int numfact_device(Sub *s, const HostCSR &A);
 void free_factor(DeviceFactor &f);
+int dense_inverse_device(Ctx *c, int N, const K *dE, K *dEinv);  // cuSOLVER LU inverse of a large coarse operator
 // x = A^{-1} b for mu columns in ONE pass over the panels (column stride n), natural ordering in/out, device pointers: mu in {1, 2, 4}
 // on the register-tiled kernels, any mu <= sptrsv_max_block() at or above the tensor-pipe threshold (hb_solve.cu).
 // scale: optional d (natural order) applied on output (out = d .* x); accumulate: out += instead of =
 int sptrsv_solve(Sub *s, const K *b, K *x, int mu, const double *scale, bool accumulate);
 int sptrsv_group(int left);   // how many of `left` remaining columns the next pass takes
-int sptrsv_prepare(Sub *s);   // per-device kernel attributes (opt-in shared memory), called once per factorisation
+int sptrsv_prepare(Sub *s);   // per-device kernel attributes (opt-in shared memory) + persistent-sweep tables, once per factorisation
+int sptrsv_check(Sub *s);     // after a stream synchronisation: did a persistent sweep give up waiting on a dependency?
 int sptrsv_max_block();
 
 int k_scale(Ctx *c, int n, int mu, const double *d, const K *in, K *out);      // out = d.*in
@@ -263,6 +274,8 @@ int k_flush_tiny(Ctx *c, int64_t n, double tiny, K *v);
 int to_host_csr(int n, int nnz, const int *ia, const int *ja, const K *a, int sym, char numbering, HostCSR &H);
 int solve_cols(Sub *s, const K *b, K *x, int mu, const double *scale, bool acc);
 // orchestration helpers shared by hb_api.cu and hb_krylov.cu (device pointers, one per local subdomain)
+void plan_halo_messages(const std::vector<int> &granks, const std::vector<int> &nbcnt, const std::vector<int> &nbr, std::vector<int> &sends, std::vector<int> &recvs);
+void plan_coarse_layout(const std::vector<int> &rows_per_proc, std::vector<int> &off, int &lmax);
 int check_ready(Ctx *c, int mu);
 int halo(Ctx *c, K *const *x, int mu);
 int apply_core(Ctx *c, const std::vector<const K *> &in, const std::vector<K *> &out, int mu, int correction);

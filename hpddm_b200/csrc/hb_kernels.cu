@@ -277,6 +277,28 @@ __global__ void __launch_bounds__(256) kk_coarse(int Nc, int mu, int Lnu, const 
   }
 }
 
+// Large coarse spaces (N_c > 512): the same three passes as kk_coarse, one launch each over all SMs (thread per row, columns of the
+// matrix read coalesced).  PASS 0: Y = Einv T   PASS 1: R = T - E Y   PASS 2: Y += Einv R     (R: N_c x mu, column-major)
+template <int PASS>
+__global__ void __launch_bounds__(256) kk_coarse_pass(int Nc, int mu, int Lnu, const int *__restrict__ rowproc, const int *__restrict__ rowloc,
+                                                      const K *__restrict__ M, const K *__restrict__ T, K *Y, K *R) {
+  auto at = [&](int r, int c) -> int64_t { return (int64_t)rowproc[r] * Lnu * mu + (int64_t)c * Lnu + rowloc[r]; };
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Nc) return;
+  for (int c = 0; c < mu; ++c) {
+    K acc = PASS == 1 ? T[at(r, c)] : mk(0.0);
+    if (PASS == 0)
+      for (int k = 0; k < Nc; ++k) acc = hb_fma(M[r + (int64_t)k * Nc], T[at(k, c)], acc);
+    else if (PASS == 1)
+      for (int k = 0; k < Nc; ++k) acc = hb_fma(-M[r + (int64_t)k * Nc], Y[at(k, c)], acc);
+    else
+      for (int k = 0; k < Nc; ++k) acc = hb_fma(M[r + (int64_t)k * Nc], R[k + (int64_t)c * Nc], acc);
+    if (PASS == 0) Y[at(r, c)] = acc;
+    else if (PASS == 1) R[r + (int64_t)c * Nc] = acc;
+    else Y[at(r, c)] += acc;
+  }
+}
+
 // v[i] = 0 where |v[i]| < tiny (Schwarz::solveGEVP post-processing, schwarz.hpp:713)
 __global__ void kk_flush_tiny(int64_t n, double tiny, K *v) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -481,6 +503,14 @@ int k_residual_norms(Ctx *c, const Sub *s, int mu, int norm, const K *f, const K
 }
 int k_coarse_solve(Ctx *c, int mu) {
   if (c->Nc == 0) return 0;
+  if (c->coarse_multipass) {  // d_R holds N_c x mu_cap values (install_coarse / ensure_capacity)
+    const unsigned g = grid1(c->Nc);
+    kk_coarse_pass<0><<<g, 256, 0, c->stream>>>(c->Nc, mu, c->Lnu, c->d_rowproc, c->d_rowloc, c->d_Einv, c->d_T, c->d_Y, c->d_R);
+    kk_coarse_pass<1><<<g, 256, 0, c->stream>>>(c->Nc, mu, c->Lnu, c->d_rowproc, c->d_rowloc, c->d_E, c->d_T, c->d_Y, c->d_R);
+    kk_coarse_pass<2><<<g, 256, 0, c->stream>>>(c->Nc, mu, c->Lnu, c->d_rowproc, c->d_rowloc, c->d_Einv, c->d_T, c->d_Y, c->d_R);
+    c->launches += 2;
+    HB_LAUNCH_END(c);
+  }
   kk_coarse<<<1, 256, 0, c->stream>>>(c->Nc, mu, c->Lnu, c->d_rowproc, c->d_rowloc, c->d_E, c->d_Einv, c->d_T, c->d_Y, c->d_R);
   HB_LAUNCH_END(c);
 }

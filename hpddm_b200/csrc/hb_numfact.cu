@@ -276,7 +276,9 @@ typedef double CK;
 static inline CK *ck(K *p) { return reinterpret_cast<CK *>(p); }
 static inline const CK *ck(const K *p) { return reinterpret_cast<const CK *>(p); }
 
-static int factor_large(Libs &L, cudaStream_t st, K *F, int s1, int s2, bool symmetric, K *panL, K *panU) {
+// `info`: this front's own 4 status words (every cuSOLVER call overwrites its devInfo, a successful one with 0: a slot shared by the
+// fronts of a level would only remember the last front)
+static int factor_large(Libs &L, cudaStream_t st, K *F, int s1, int s2, bool symmetric, K *panL, K *panU, int *info) {
   const int ld = s1 + s2;
   const K one = mk(1.0), mone = mk(-1.0);
   K *F11 = F, *F21 = F + s1, *F12 = F + (int64_t)s1 * ld, *F22 = F + s1 + (int64_t)s1 * ld;
@@ -289,14 +291,14 @@ static int factor_large(Libs &L, cudaStream_t st, K *F, int s1, int s2, bool sym
     int lwork = 0;
     HB_SOLVER(cusolverDnDpotrf_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, s1, F11, ld, &lwork));
     HB_CHECK(L.ensure((size_t)lwork * sizeof(double), 0));
-    HB_SOLVER(cusolverDnDpotrf(L.so, CUBLAS_FILL_MODE_LOWER, s1, F11, ld, (double *)L.work, lwork, L.dinfo));
+    HB_SOLVER(cusolverDnDpotrf(L.so, CUBLAS_FILL_MODE_LOWER, s1, F11, ld, (double *)L.work, lwork, info));
     if (s2 > 0) {
       HB_BLAS(cublasDtrsm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, F11, ld, F21, ld));
       HB_BLAS(cublasDsyrk(L.bl, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, s2, s1, &mone, F21, ld, &one, F22, ld));
     }
     HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, &wd, &wh));
     HB_CHECK(L.ensure(wd, wh));
-    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 1));
+    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, CUDA_R_64F, F11, ld, L.work, wd, L.hwork, wh, info + 1));
     if (s2 > 0) HB_BLAS(cublasDtrmm(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, &one, F11, ld, F21, ld, F21, ld));
     k_to_panel<<<(s1 + s2 + 31) / 32, dim3(32, 8), 0, st>>>(F, ld, F, s1, s2, 0, panL);
 #endif
@@ -304,7 +306,7 @@ static int factor_large(Libs &L, cudaStream_t st, K *F, int s1, int s2, bool sym
     int lwork = 0;
     HB_SOLVER(HB_LIB(cusolverDnDgetrf_bufferSize, cusolverDnZgetrf_bufferSize)(L.so, s1, s1, ck(F11), ld, &lwork));
     HB_CHECK(L.ensure((size_t)lwork * sizeof(K), 0));
-    HB_SOLVER(HB_LIB(cusolverDnDgetrf, cusolverDnZgetrf)(L.so, s1, s1, ck(F11), ld, (CK *)L.work, nullptr, L.dinfo));  // devIpiv = NULL: no pivoting
+    HB_SOLVER(HB_LIB(cusolverDnDgetrf, cusolverDnZgetrf)(L.so, s1, s1, ck(F11), ld, (CK *)L.work, nullptr, info));  // devIpiv = NULL: no pivoting
     if (s2 > 0) {
       HB_BLAS(HB_LIB(cublasDtrsm, cublasZtrsm)(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, ck(&one), ck(F11), ld, ck(F21), ld));
       HB_BLAS(HB_LIB(cublasDtrsm, cublasZtrsm)(L.bl, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_UNIT, s1, s2, ck(&one), ck(F11), ld, ck(F12), ld));
@@ -322,10 +324,10 @@ static int factor_large(Libs &L, cudaStream_t st, K *F, int s1, int s2, bool sym
     k_unit_lower<<<(unsigned)(((int64_t)s1 * s1 + 255) / 256), 256, 0, st>>>(F11, s1, ld, S);
     HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, HB_CUDA_K, S, s1, &wd, &wh));
     HB_CHECK(L.ensure(wd, wh));
-    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, HB_CUDA_K, S, s1, L.work, wd, L.hwork, wh, L.dinfo + 1));
+    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, s1, HB_CUDA_K, S, s1, L.work, wd, L.hwork, wh, info + 1));
     HB_SOLVER(cusolverDnXtrtri_bufferSize(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, HB_CUDA_K, F11, ld, &wd, &wh));
     HB_CHECK(L.ensure(wd, wh));
-    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, HB_CUDA_K, F11, ld, L.work, wd, L.hwork, wh, L.dinfo + 2));
+    HB_SOLVER(cusolverDnXtrtri(L.so, CUBLAS_FILL_MODE_UPPER, CUBLAS_DIAG_NON_UNIT, s1, HB_CUDA_K, F11, ld, L.work, wd, L.hwork, wh, info + 2));
     if (s2 > 0) {
       HB_BLAS(HB_LIB(cublasDtrmm, cublasZtrmm)(L.bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s2, s1, ck(&one), ck(S), s1, ck(F21), ld, ck(F21), ld));
       HB_BLAS(HB_LIB(cublasDtrmm, cublasZtrmm)(L.bl, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, s1, s2, ck(&one), ck(F11), ld, ck(F12), ld, ck(F12), ld));
@@ -480,8 +482,7 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
   }
   cusolverDnSetStream(L.so, st);
   cublasSetStream(L.bl, st);
-  NF_CUDA(cudaMalloc(&L.dinfo, 4 * sizeof(int)));
-  NF_CUDA(cudaMemset(L.dinfo, 0, 4 * sizeof(int)));
+  int dinfo_cap = 0;  // status slots (4 words per cuSOLVER front of the current level)
   // ---- panel store
   if (!D.panL) NF_CUDA(cudaMalloc(&D.panL, std::max<int64_t>(S.panel_elems, 16) * sizeof(K)));
   if (!symmetric) {
@@ -528,18 +529,36 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
       k_factor_small<<<(unsigned)small_list.size(), 256, 0, st>>>(d_list, D.fronts, d_foff, Fcur, D.panL, D.panU, symmetric ? 1 : 0, d_info);
       s->ctx->launches++;
     }
+    int nlarge = 0;
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) nlarge += fs[S.level_order[q]] > SMALL;
+    if (nlarge > dinfo_cap) {
+      if (L.dinfo) cudaFree(L.dinfo);
+      L.dinfo = nullptr;
+      NF_CUDA(cudaMalloc(&L.dinfo, (size_t)4 * nlarge * sizeof(int)));
+      dinfo_cap = nlarge;
+    }
+    if (nlarge) NF_CUDA(cudaMemsetAsync(L.dinfo, 0, (size_t)4 * nlarge * sizeof(int), st));
+    std::vector<int> large_fronts;
     for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
       int f = S.level_order[q];
       if (fs[f] <= SMALL) continue;
       const Front &fr = S.fronts[f];
-      NF_CHECK(factor_large(L, st, Fcur + foff[f], fr.s1, fr.s2, symmetric, D.panL + fr.poff, D.panU + fr.poff));
+      NF_CHECK(factor_large(L, st, Fcur + foff[f], fr.s1, fr.s2, symmetric, D.panL + fr.poff, D.panU + fr.poff, L.dinfo + 4 * large_fronts.size()));
+      large_fronts.push_back(f);
       s->ctx->launches += 8;
     }
-    // pivots / library status of this level
+    // pivots / library status of this level: every cuSOLVER front has its own slot
     int hinfo[4] = {0, 0, 0, 0}, linfo[4] = {0, 0, 0, 0};
+    std::vector<int> slots((size_t)4 * nlarge, 0);
     NF_CUDA(cudaMemcpyAsync(hinfo, d_info, sizeof(hinfo), cudaMemcpyDeviceToHost, st));
-    NF_CUDA(cudaMemcpyAsync(linfo, L.dinfo, sizeof(linfo), cudaMemcpyDeviceToHost, st));
+    if (nlarge) NF_CUDA(cudaMemcpyAsync(slots.data(), L.dinfo, slots.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
     NF_CUDA(cudaStreamSynchronize(st));
+    int bad_large = -1;
+    for (int q = 0; q < nlarge && bad_large < 0; ++q)
+      if (slots[4 * q] != 0 || slots[4 * q + 1] != 0 || slots[4 * q + 2] != 0) {
+        bad_large = large_fronts[q];
+        for (int k = 0; k < 3; ++k) linfo[k] = slots[4 * q + k];
+      }
     if (getenv("HPDDM_B200_DEBUG")) {
       int nl = 0;
       for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) nl += fs[S.level_order[q]] > SMALL;
@@ -560,8 +579,8 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
       }
     }
     if (hinfo[0] != 0 || linfo[0] != 0 || linfo[1] != 0 || linfo[2] != 0) {
-      set_error("numfact: %s pivot breakdown at level %d (front %d, potrf/getrf info %d, trtri info %d)", symmetric ? "Cholesky" : "LU", l, hinfo[0] - 1,
-                linfo[0], linfo[1]);
+      set_error("numfact: %s pivot breakdown at level %d (front %d, potrf/getrf info %d, trtri info %d)", symmetric ? "Cholesky" : "LU", l,
+                hinfo[0] != 0 ? hinfo[0] - 1 : bad_large, linfo[0], linfo[1]);
       cleanup();
       return HPDDM_B200_ERR_NUMERIC;
     }
@@ -576,6 +595,46 @@ static int numfact_try(Sub *s, const HostCSR &A, bool symmetric) {
 
 }  // namespace
 
+// Einv = E^-1 on the device for large coarse operators (N_c beyond what a host Gauss-Jordan should do): LU with partial pivoting
+// (cuSOLVER getrf) + getrs on the identity.  dE is overwritten by its factors' input copy only through a scratch buffer.
+__global__ void k_identity(int N, K *M) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t < (int64_t)N * N) M[t] = mk((t % N) == (t / N) ? 1.0 : 0.0);
+}
+int dense_inverse_device(Ctx *c, int N, const K *dE, K *dEinv) {
+  cudaStream_t st = c->stream;
+  Libs L;
+  if (cusolverDnCreate(&L.so) != CUSOLVER_STATUS_SUCCESS) {
+    set_error("cannot create a cuSOLVER handle");
+    return HPDDM_B200_ERR_CUDA;
+  }
+  cusolverDnSetStream(L.so, st);
+  K *LU = nullptr;
+  int *ipiv = nullptr, *info = nullptr, lwork = 0, hinfo = 0;
+  auto done = [&](int rc) {
+    cudaFree(LU);
+    cudaFree(ipiv);
+    cudaFree(info);
+    return rc;
+  };
+  if (cudaMalloc(&LU, (size_t)N * N * sizeof(K)) != cudaSuccess || cudaMalloc(&ipiv, N * sizeof(int)) != cudaSuccess || cudaMalloc(&info, sizeof(int)) != cudaSuccess) {
+    set_error("out of device memory inverting the %d x %d coarse operator", N, N);
+    return done(HPDDM_B200_ERR_NOMEM);
+  }
+  cudaMemcpyAsync(LU, dE, (size_t)N * N * sizeof(K), cudaMemcpyDeviceToDevice, st);
+  if (HB_LIB(cusolverDnDgetrf_bufferSize, cusolverDnZgetrf_bufferSize)(L.so, N, N, ck(LU), N, &lwork) != CUSOLVER_STATUS_SUCCESS || L.ensure((size_t)lwork * sizeof(K), 0) < 0)
+    return done(HPDDM_B200_ERR_CUDA);
+  if (HB_LIB(cusolverDnDgetrf, cusolverDnZgetrf)(L.so, N, N, ck(LU), N, (CK *)L.work, ipiv, info) != CUSOLVER_STATUS_SUCCESS) return done(HPDDM_B200_ERR_CUDA);
+  k_identity<<<(unsigned)(((int64_t)N * N + 255) / 256), 256, 0, st>>>(N, dEinv);
+  if (HB_LIB(cusolverDnDgetrs, cusolverDnZgetrs)(L.so, CUBLAS_OP_N, N, N, ck(LU), N, ipiv, ck(dEinv), N, info) != CUSOLVER_STATUS_SUCCESS) return done(HPDDM_B200_ERR_CUDA);
+  cudaMemcpyAsync(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess || hinfo != 0) {
+    set_error("coarse operator is singular (cuSOLVER info %d)", hinfo);
+    return done(HPDDM_B200_ERR_NUMERIC);
+  }
+  return done(0);
+}
+
 void free_factor(DeviceFactor &f) {
   for (cudaGraphExec_t &g : f.graph)
     if (g) cudaGraphExecDestroy(g);
@@ -589,6 +648,9 @@ void free_factor(DeviceFactor &f) {
   cudaFree(f.b);
   cudaFree(f.y);
   cudaFree(f.x);
+  for (void *q : {(void *)f.fwd_children, (void *)f.fwd_total, (void *)f.bwd_total, (void *)f.bwd_ordered, (void *)f.sync_pending, (void *)f.sync_done, (void *)f.sync_next})
+    if (q) cudaFree(q);
+  if (f.sync_err_host) cudaFreeHost(f.sync_err_host);
   f = DeviceFactor();
 }
 

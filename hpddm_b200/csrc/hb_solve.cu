@@ -142,11 +142,22 @@ __global__ void __launch_bounds__(256, IS_COMPLEX ? 2 : (MU == 1 ? 4 : 3)) k_fwd
 // VE right-hand-side values b[c .. c+VE) as one 128-bit vector, from L1 (read-only in this launch: a level's fronts only
 // update rows of their ancestors).  Real scalars: the address is only 8-byte aligned in general -> two loads; the partner of
 // the last column of an odd-width item is a zero (it multiplies the zero padding of the panel, but must not be a NaN).
+template <bool COHERENT = false>
 __device__ __forceinline__ double2 ld_rhs(const K *p, int c, int nc) {
+  // COHERENT (persistent kernels: the vector is updated by other SMs during the launch): read through L2, never a stale L1 line
 #ifdef HB_COMPLEX
-  return __ldg(reinterpret_cast<const double2 *>(p + c));
+  return COHERENT ? __ldcg(reinterpret_cast<const double2 *>(p + c)) : __ldg(reinterpret_cast<const double2 *>(p + c));
 #else
+  if (COHERENT) return make_double2(__ldcg(p + c), c + 1 < nc ? __ldcg(p + c + 1) : 0.0);
   return make_double2(__ldg(p + c), c + 1 < nc ? __ldg(p + c + 1) : 0.0);
+#endif
+}
+__device__ __forceinline__ K ld_cg(const K *p) {
+#ifdef HB_COMPLEX
+  const double2 v = __ldcg(reinterpret_cast<const double2 *>(p));
+  return mk(v.x, v.y);
+#else
+  return __ldcg(p);
 #endif
 }
 
@@ -154,14 +165,9 @@ __device__ __forceinline__ double2 ld_rhs(const K *p, int c, int nc) {
 // through L1 instead of being staged in shared memory, so that one pass covers the whole item width (up to FCH columns) for
 // all MU columns: the shuffle reduction (reduce8) runs once per R = 8 / MU rows x FCH columns instead of once per FCH / MU
 // columns -- it dominated the staged variant at MU = 4 (profiles/README.md).
-template <int MU>
-__global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : (MU == 1 ? 4 : 3)) k_fwd_blk(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
-                                                                     const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n) {
+template <int MU, bool COHERENT>
+__device__ __forceinline__ void fwd_blk_item(const FwdItem &w, int lane, const Front *__restrict__ fronts, const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n) {
   constexpr int R = 8 / MU, JU = MU;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t it = (int64_t)blockIdx.x * 8 + warp;
-  if (it >= nitems) return;
-  const FwdItem w = items[it];
   const Front f = fronts[w.front];
   const int s1 = f.s1, nb1 = (s1 + RB - 1) / RB;
   const K *base;
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : (MU == 1 ? 
         if (j0 + 32 * u < nv) {
 #pragma unroll
           for (int m = 0; m < MU; ++m) {
-            const double2 bb = ld_rhs(bc + (int64_t)m * n, (j0 + 32 * u) * VE, nc);
+            const double2 bb = ld_rhs<COHERENT>(bc + (int64_t)m * n, (j0 + 32 * u) * VE, nc);
 #pragma unroll
             for (int q = 0; q < R; ++q) a[q * MU + m] = hb_vdot(t[q][u], bb, a[q * MU + m]);
           }
@@ -219,11 +225,21 @@ __global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : (MU == 1 ? 
   }
 }
 
+
+template <int MU>
+__global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : (MU == 1 ? 4 : 3)) k_fwd_blk(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
+                                                                     const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t it = (int64_t)blockIdx.x * 8 + warp;
+  if (it >= nitems) return;
+  fwd_blk_item<MU, false>(items[it], lane, fronts, rowidx, pan, b, y, n);
+}
+
 // Backward sweep work item.  NJ = slabs of 32 * VE columns covered per pass (NJ * MU <= 4 128-bit
 // accumulators per lane); rows are processed in groups of 8 / NJ so that 8 128-bit loads are in flight.
 // With SHARED (block right-hand sides) the multipliers u of a 32-row block are broadcast from shared memory (us: 32 * MU values
 // of this warp) instead of one shuffle per (row, column): MU = 4 needed 8 SHFL per 128-bit panel load.
-template <int NJ, int MU, bool SHARED>
+template <int NJ, int MU, bool SHARED, bool COHERENT = false>
 __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int cbase, const int *__restrict__ rowidx, const K *__restrict__ pan,
                                          const K *__restrict__ y, K *x, int n, int lane, K *us) {
   constexpr int G = 8 / NJ;
@@ -242,7 +258,11 @@ __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int c
 #pragma unroll
     for (int m = 0; m < MU; ++m) {
       u[m] = mk(0.0);
-      if (rb + lane < w.nr) u[m] = (r < s1) ? y[(int64_t)m * n + f.p0 + r] : -x[(int64_t)m * n + rowidx[f.rptr + r - s1]];
+      if (rb + lane < w.nr) {
+        const K *src = (r < s1) ? y + (int64_t)m * n + f.p0 + r : x + (int64_t)m * n + rowidx[f.rptr + r - s1];
+        const K v = COHERENT ? ld_cg(src) : *src;  // persistent kernel: other SMs finished these entries during this launch
+        u[m] = (r < s1) ? v : -v;
+      }
     }
     if (SHARED) {
       __syncwarp();  // the previous block's readers are done
@@ -291,6 +311,21 @@ __device__ __forceinline__ void bwd_pass(const BwdItem &w, const Front &f, int c
   }
 }
 
+template <int MU, bool SHARED, bool COHERENT>
+__device__ __forceinline__ void bwd_item(const BwdItem &w, int lane, const Front *__restrict__ fronts, const int *__restrict__ rowidx, const K *__restrict__ pan, const K *y, K *x, int n,
+                                         K *us) {
+  const Front f = fronts[w.front];
+  const int width = min(BCH, hb_ldp(f.s1) - w.c0);
+  constexpr int NJMAX = 4 / MU;  // 4, 2, 1
+  constexpr int SLAB = 32 * VE;  // columns covered by one 128-bit load per lane
+  for (int cb = 0; cb < width; cb += SLAB * NJMAX) {
+    const int left = width - cb;
+    if (NJMAX >= 4 && left > 2 * SLAB) bwd_pass<(NJMAX >= 4 ? 4 : NJMAX), MU, SHARED, COHERENT>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane, us);
+    else if (NJMAX >= 2 && left > SLAB) bwd_pass<(NJMAX >= 2 ? 2 : NJMAX), MU, SHARED, COHERENT>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane, us);
+    else bwd_pass<1, MU, SHARED, COHERENT>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane, us);
+  }
+}
+
 template <int MU, bool SHARED, int OCC = ((IS_COMPLEX || MU == 4) ? 2 : 3)>
 __global__ void __launch_bounds__(256, OCC) k_bwd(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
                                                 const int *__restrict__ rowidx, const K *__restrict__ pan, const K *__restrict__ y, K *x, int n) {
@@ -299,16 +334,89 @@ __global__ void __launch_bounds__(256, OCC) k_bwd(const BwdItem *__restrict__ it
   K *us = us_all + (SHARED ? warp * 32 * MU : 0);
   const int64_t it = (int64_t)blockIdx.x * 8 + warp;
   if (it >= nitems) return;
-  const BwdItem w = items[it];
-  const Front f = fronts[w.front];
-  const int width = min(BCH, hb_ldp(f.s1) - w.c0);
-  constexpr int NJMAX = 4 / MU;  // 4, 2, 1
-  constexpr int SLAB = 32 * VE;  // columns covered by one 128-bit load per lane
-  for (int cb = 0; cb < width; cb += SLAB * NJMAX) {
-    const int left = width - cb;
-    if (NJMAX >= 4 && left > 2 * SLAB) bwd_pass<(NJMAX >= 4 ? 4 : NJMAX), MU, SHARED>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane, us);
-    else if (NJMAX >= 2 && left > SLAB) bwd_pass<(NJMAX >= 2 ? 2 : NJMAX), MU, SHARED>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane, us);
-    else bwd_pass<1, MU, SHARED>(w, f, w.c0 + cb, rowidx, pan, y, x, n, lane, us);
+  bwd_item<MU, SHARED, false>(items[it], lane, fronts, rowidx, pan, y, x, n, us);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Dependency-driven persistent sweeps (one launch per sweep instead of one per elimination-tree level).  CTAs claim groups of 8
+// work items in list order (level order: leaves first in the forward sweep, root first in the backward sweep) from a global counter;
+// a warp starts its item as soon as the fronts it depends on are complete --
+//   forward:  every child of the item's front has finished all its items   (their updates to b[pivots of this front] are in)
+//   backward: the parent front has finished all its items                  (x[struct rows of this front] is final)
+// -- instead of waiting for the whole previous level: the tails of the many small levels overlap, and the launch / drain gaps between
+// levels disappear.  An item only ever waits for items EARLIER in the list, which have been claimed by resident CTAs: no deadlock;
+// the spin is bounded anyway (error flag, checked at the next synchronisation point).  Vectors written during the launch (b, y, x)
+// are read through L2 (COHERENT).
+struct SweepSync {
+  int *pending;       // forward: children of front f not yet complete (reset from pending0 before every solve)
+  int *done;          // items of front f completed in the running sweep
+  const int *total;   // items of front f in this sweep
+  unsigned long long *next;  // item claim counter
+  int *err;
+};
+__device__ __forceinline__ bool spin_until_zero(const int *p) {
+  for (long long k = 0; k < (1LL << 24); ++k) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v <= 0) return true;
+    __nanosleep(64);
+  }
+  return false;
+}
+template <int OCC>
+__global__ void __launch_bounds__(256, OCC) k_fwd_persistent(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
+                                                             const K *__restrict__ pan, K *b, K *y, int n, SweepSync sy) {
+  __shared__ unsigned long long base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) base_s = atomicAdd(sy.next, 8ULL);
+    __syncthreads();
+    const int64_t it = (int64_t)base_s + warp;
+    if ((int64_t)base_s >= nitems) return;
+    if (it >= nitems) continue;
+    const FwdItem w = items[it];
+    bool ok = true;
+    if (lane == 0) ok = spin_until_zero(sy.pending + w.front);
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) {
+      if (lane == 0) *reinterpret_cast<volatile int *>(sy.err) = 1;
+    } else
+      fwd_blk_item<1, true>(w, lane, fronts, rowidx, pan, b, y, n);
+    __threadfence();  // this item's updates are visible device-wide before it is counted
+    __syncwarp();
+    if (lane == 0) {
+      if (atomicAdd(sy.done + w.front, 1) + 1 == sy.total[w.front]) {  // last item of the front: release the parent
+        const int parent = fronts[w.front].parent;
+        if (parent >= 0) atomicSub(sy.pending + parent, 1);
+      }
+    }
+  }
+}
+template <int OCC>
+__global__ void __launch_bounds__(256, OCC) k_bwd_persistent(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
+                                                             const K *__restrict__ pan, const K *y, K *x, int n, SweepSync sy) {
+  __shared__ unsigned long long base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) base_s = atomicAdd(sy.next, 8ULL);
+    __syncthreads();
+    const int64_t it = (int64_t)base_s + warp;
+    if ((int64_t)base_s >= nitems) return;
+    if (it >= nitems) continue;
+    const BwdItem w = items[it];
+    const int parent = fronts[w.front].parent;
+    bool ok = true;
+    if (lane == 0 && parent >= 0) ok = spin_until_zero(sy.pending + parent);  // backward: pending[f] = items of f still to do
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (!ok) {
+      if (lane == 0) *reinterpret_cast<volatile int *>(sy.err) = 1;
+    } else
+      bwd_item<1, false, true>(w, lane, fronts, rowidx, pan, y, x, n, nullptr);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicSub(sy.pending + w.front, 1);
   }
 }
 
@@ -374,6 +482,76 @@ static int launch_levels(Sub *s, cudaStream_t st) {
 }
 
 }  // namespace
+
+
+// tables of the persistent sweeps, built once per factorisation from the host-side symbolic structure
+static int persistent_tables(Sub *s) {
+  DeviceFactor &D = s->fac;
+  const Symbolic &S = s->sym;
+  cudaStream_t st = s->ctx->stream;
+  const int F = (int)S.fronts.size();
+  D.nfronts = F;
+  std::vector<int> children(F, 0), ft(F, 0), bt(F, 0);
+  for (int f = 0; f < F; ++f)
+    if (S.fronts[f].parent >= 0) children[S.fronts[f].parent]++;
+  for (const FwdItem &w : S.fwd) ft[w.front]++;
+  for (const BwdItem &w : S.bwd) bt[w.front]++;
+  // a front without forward items (no columns) would never release its parent: count it as complete from the start
+  for (int f = 0; f < F; ++f)
+    if (ft[f] == 0 && S.fronts[f].parent >= 0) children[S.fronts[f].parent]--;
+  std::vector<BwdItem> ordered;
+  ordered.reserve(S.bwd.size());
+  for (int l = S.nlevels - 1; l >= 0; --l) ordered.insert(ordered.end(), S.bwd.begin() + S.bwd_ptr[l], S.bwd.begin() + S.bwd_ptr[l + 1]);
+  auto upl = [&](const void *h, size_t bytes, void **d) -> int {
+    HB_CUDA(cudaMalloc(d, std::max<size_t>(bytes, 16)));
+    if (bytes) HB_CUDA(cudaMemcpyAsync(*d, h, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+  };
+  HB_CHECK(upl(children.data(), F * sizeof(int), (void **)&D.fwd_children));
+  HB_CHECK(upl(ft.data(), F * sizeof(int), (void **)&D.fwd_total));
+  HB_CHECK(upl(bt.data(), F * sizeof(int), (void **)&D.bwd_total));
+  HB_CHECK(upl(ordered.data(), ordered.size() * sizeof(BwdItem), (void **)&D.bwd_ordered));
+  HB_CUDA(cudaMalloc(&D.sync_pending, std::max<size_t>(F, 4) * sizeof(int)));
+  HB_CUDA(cudaMalloc(&D.sync_done, std::max<size_t>(F, 4) * sizeof(int)));
+  HB_CUDA(cudaMalloc(&D.sync_next, sizeof(unsigned long long)));
+  HB_CUDA(cudaHostAlloc(&D.sync_err_host, sizeof(int), cudaHostAllocMapped));
+  *D.sync_err_host = 0;
+  HB_CUDA(cudaHostGetDevicePointer(&D.sync_err, D.sync_err_host, 0));
+  HB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+int sptrsv_check(Sub *s) {
+  if (s->fac.sync_err_host && *reinterpret_cast<volatile int *>(s->fac.sync_err_host)) {
+    set_error("persistent SpTRSV sweep: a work item timed out waiting for the fronts it depends on");
+    return HPDDM_B200_ERR_STATE;
+  }
+  return 0;
+}
+// HPDDM_B200_PERSISTENT=1: single right-hand side sweeps as two dependency-driven persistent launches instead of one launch per level
+static bool persistent_on() {
+  static const bool on = getenv("HPDDM_B200_PERSISTENT") && !strcmp(getenv("HPDDM_B200_PERSISTENT"), "1");
+  return on;
+}
+static int launch_persistent(Sub *s, cudaStream_t st) {
+  DeviceFactor &D = s->fac;
+  const Symbolic &S = s->sym;
+  const int n = S.n, F = D.nfronts;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  constexpr int OCC = IS_COMPLEX ? 2 : 3;
+  const int64_t nf = (int64_t)S.fwd.size(), nb = (int64_t)S.bwd.size();
+  SweepSync sy{D.sync_pending, D.sync_done, D.fwd_total, D.sync_next, D.sync_err};
+  HB_CUDA(cudaMemcpyAsync(D.sync_pending, D.fwd_children, F * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  HB_CUDA(cudaMemsetAsync(D.sync_done, 0, F * sizeof(int), st));
+  HB_CUDA(cudaMemsetAsync(D.sync_next, 0, sizeof(unsigned long long), st));
+  if (nf > 0) k_fwd_persistent<OCC><<<(unsigned)std::min<int64_t>((int64_t)sms * OCC, (nf + 7) / 8), 256, 0, st>>>(D.fwd, nf, D.fronts, D.rowidx, D.panL, D.b, D.y, n, sy);
+  HB_CUDA(cudaMemcpyAsync(D.sync_pending, D.bwd_total, F * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  HB_CUDA(cudaMemsetAsync(D.sync_next, 0, sizeof(unsigned long long), st));
+  if (nb > 0) k_bwd_persistent<OCC><<<(unsigned)std::min<int64_t>((int64_t)sms * OCC, (nb + 7) / 8), 256, 0, st>>>(D.bwd_ordered, nb, D.fronts, D.rowidx, D.panU, D.y, D.x, n, sy);
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}
 
 #ifndef HB_COMPLEX
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -701,8 +879,167 @@ constexpr size_t SMEM_F = (size_t)WARPS * NST * ST_ROWS * PITCH_F * sizeof(doubl
 constexpr size_t SMEM_B = (size_t)WARPS * NST * ST_ROWS * PITCH_B * sizeof(double) + WARPS * NST * sizeof(uint64_t);
 }  // namespace mma
 
+
+// ---- register-staged tensor-pipe sweeps (the shipped block kernels): same DMMA formulation as above, but the A fragments come
+// straight from HBM -- lane (g, t) issues 128-bit streaming loads of [row g][columns 8 j + 2 t, + 1] (forward) or
+// [row 4 ks + t][columns 16 jj + 2 g, + 1] (backward), 8 in flight per lane, i.e. the access pattern of the scalar kernels with the
+// FMA / shuffle-reduction work moved to the tensor pipe.  One warp = one work item, 8 warps per CTA.
+template <int OCC>
+__global__ void __launch_bounds__(256, OCC) k_fwd_dmma(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
+                                                       const double *__restrict__ pan, double *b, double *y, int n, int mu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t it = (int64_t)blockIdx.x * 8 + warp;
+  if (it >= nitems) return;
+  const FwdItem w = items[it];
+  const Front f = fronts[w.front];
+  const int s1 = f.s1, nb1 = (s1 + RB - 1) / RB;
+  const double *base;
+  int nrows, stride, cmax;
+  const bool pivot = w.rblk < nb1;
+  if (pivot) {
+    stride = hb_wblk(s1, w.rblk);
+    base = pan + f.poff + hb_blk_off(w.rblk);
+    nrows = min(RB, s1 - RB * w.rblk);
+    cmax = min(s1, RB * (w.rblk + 1));
+  } else {
+    const int k2 = w.rblk - nb1;
+    stride = hb_ldp(s1);
+    base = pan + f.poff + hb_upd_off(s1) + (int64_t)k2 * RB * stride;
+    nrows = min(RB, f.s2 - RB * k2);
+    cmax = s1;
+  }
+  const int c1 = min(cmax, w.c0 + w.cw);
+  if (c1 <= w.c0) return;
+  const double *bc = b + (int64_t)g * n + f.p0;              // right-hand side g (B fragment: n = g), L1-resident chunk
+  // accumulators of the 4 row groups (two partial sums each: breaks the dependent DMMA chain), kept over the column chunks
+  double acc[4][2][2];
+#pragma unroll
+  for (int rg = 0; rg < 4; ++rg)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) acc[rg][q][0] = acc[rg][q][1] = 0.0;
+  for (int cs = w.c0; cs < c1; cs += 64) {                  // 64 columns = 8 groups of 8 = 16 k-steps; their B fragments serve all 4 row groups
+    double bx[8], by[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = cs + 8 * u + 2 * t;
+      bx[u] = (g < mu && c < c1) ? __ldg(bc + c) : 0.0;
+      by[u] = (g < mu && c + 1 < c1) ? __ldg(bc + c + 1) : 0.0;
+    }
+#pragma unroll
+    for (int rg = 0; rg < 4; ++rg) {
+      if (8 * rg < nrows) {
+        const bool rowok = 8 * rg + g < nrows;
+        const double2 *row = reinterpret_cast<const double2 *>(base + (int64_t)(8 * rg + g) * stride + cs) + t;
+        double2 a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = (rowok && cs + 8 * u + 2 * t < stride) ? ldg_stream(row + 4 * u) : make_double2(0.0, 0.0);  // rows are zero-padded to an even width
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          mma::dmma(acc[rg][u & 1], a[u].x, bx[u]);
+          mma::dmma(acc[rg][u & 1], a[u].y, by[u]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int rg = 0; rg < 4; ++rg) {
+    const int r = 8 * rg + g;
+    if (r < nrows) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = 2 * t + h;
+        const double v = acc[rg][0][h] + acc[rg][1][h];
+        if (m < mu) {
+          if (pivot) atomicAdd(&y[(int64_t)m * n + f.p0 + RB * w.rblk + r], v);
+          else atomicAdd(&b[(int64_t)m * n + rowidx[f.rptr + RB * (w.rblk - nb1) + r]], -v);
+        }
+      }
+    }
+  }
+}
+
+template <int OCC>
+__global__ void __launch_bounds__(256, OCC) k_bwd_dmma(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
+                                                       const double *__restrict__ pan, const double *__restrict__ y, double *x, int n, int mu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t it = (int64_t)blockIdx.x * 8 + warp;
+  if (it >= nitems) return;
+  const BwdItem w = items[it];
+  const Front f = fronts[w.front];
+  const int s1 = f.s1, ldp = hb_ldp(s1);
+  const double *P = pan + f.poff, *Pu = P + hb_upd_off(s1);
+  const int cend = min(w.c0 + BCH, ldp), r1 = w.r0 + w.nr;
+  for (int cc = w.c0; cc < cend; cc += 64) {               // 64-column sub-chunks: 4 groups of 16 columns = 8 accumulator fragments
+    double accE[4][2], accO[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) accE[q][0] = accE[q][1] = accO[q][0] = accO[q][1] = 0.0;
+    // multipliers u[row][rhs g] of a trip (B fragments), fetched one trip ahead: the struct rows need two dependent loads (index, value)
+    auto multipliers = [&](int rr, double (&ub)[2]) {
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int r = rr + 4 * ks + t;
+        double v = 0.0;
+        if (g < mu && r < r1) v = (r < s1) ? y[(int64_t)g * n + f.p0 + r] : -x[(int64_t)g * n + rowidx[f.rptr + r - s1]];
+        ub[ks] = v;
+      }
+    };
+    double ub[2], ubn[2];
+    multipliers(w.r0, ub);
+    for (int rr = w.r0; rr < r1; rr += 8) {                  // two k-steps (8 rows) per trip: 8 loads in flight per lane
+      double2 a[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int r = rr + 4 * ks + t;
+        const double *rowp = P;
+        int width = 0;
+        if (r < r1) {
+          if (r < s1) {
+            const int k = r / RB;
+            width = hb_wblk(s1, k);
+            rowp = P + hb_blk_off(k) + (int64_t)(r - k * RB) * width;
+          } else {
+            width = ldp;
+            rowp = Pu + (int64_t)(r - s1) * ldp;
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int c = cc + 16 * jj + 2 * g;
+          a[ks][jj] = (c < width) ? ldg_stream(reinterpret_cast<const double2 *>(rowp + c)) : make_double2(0.0, 0.0);
+        }
+      }
+      multipliers(rr + 8, ubn);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          mma::dmma(accE[jj], a[ks][jj].x, ub[ks]);
+          mma::dmma(accO[jj], a[ks][jj].y, ub[ks]);
+        }
+      ub[0] = ubn[0];
+      ub[1] = ubn[1];
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int c = cc + 16 * jj + 2 * g;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = 2 * t + h;
+        if (m < mu) {
+          if (c < s1) atomicAdd(&x[(int64_t)m * n + f.p0 + c], accE[jj][h]);
+          if (c + 1 < s1) atomicAdd(&x[(int64_t)m * n + f.p0 + c + 1], accO[jj][h]);
+        }
+      }
+    }
+  }
+}
+
 // sweeps for 1 .. 8 right-hand sides on the tensor pipe (one persistent launch per level and sweep)
+// HPDDM_B200_MMA_VARIANT = reg (default: A fragments by 128-bit loads from HBM) | tma (per-warp cp.async.bulk ring, measured slower:
+// 512-byte row copies are issue-bound on the copy engine, profiles/README.md)
 static int launch_levels_mma(Sub *s, cudaStream_t st, int mu) {
+  static const bool tma = getenv("HPDDM_B200_MMA_VARIANT") && !strcmp(getenv("HPDDM_B200_MMA_VARIANT"), "tma");
+  static const int occ = getenv("HPDDM_B200_MMA_OCC") ? atoi(getenv("HPDDM_B200_MMA_OCC")) : 2;
   DeviceFactor &D = s->fac;
   const Symbolic &S = s->sym;
   const int n = S.n;
@@ -712,11 +1049,17 @@ static int launch_levels_mma(Sub *s, cudaStream_t st, int mu) {
   auto grid = [&](int64_t ni) { return (unsigned)std::min<int64_t>(sms, (ni + mma::WARPS - 1) / mma::WARPS); };
   for (int l = 0; l < S.nlevels; ++l) {
     const int64_t i0 = S.fwd_ptr[l], ni = S.fwd_ptr[l + 1] - i0;
-    if (ni > 0) mma::k_fwd_mma<<<grid(ni), mma::WARPS * 32, mma::SMEM_F, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
+    if (ni <= 0) continue;
+    if (tma) mma::k_fwd_mma<<<grid(ni), mma::WARPS * 32, mma::SMEM_F, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
+    else if (occ == 2) k_fwd_dmma<2><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
+    else k_fwd_dmma<3><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
   }
   for (int l = S.nlevels - 1; l >= 0; --l) {
     const int64_t i0 = S.bwd_ptr[l], ni = S.bwd_ptr[l + 1] - i0;
-    if (ni > 0) mma::k_bwd_mma<<<grid(ni), mma::WARPS * 32, mma::SMEM_B, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
+    if (ni <= 0) continue;
+    if (tma) mma::k_bwd_mma<<<grid(ni), mma::WARPS * 32, mma::SMEM_B, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
+    else if (occ == 2) k_bwd_dmma<2><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
+    else k_bwd_dmma<3><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
   }
   HB_CUDA(cudaGetLastError());
   return 0;
@@ -739,16 +1082,14 @@ int sptrsv_prepare(Sub *s) {  // once per factorisation, outside any stream capt
   HB_CUDA(cudaFuncSetAttribute(mma::k_bwd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma::SMEM_B));
   HB_CUDA(cudaFuncSetAttribute(k_fwd<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 8 * FCH * sizeof(K))));
   HB_CUDA(cudaFuncSetAttribute(k_fwd<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 8 * FCH * sizeof(K))));
-  (void)s;
-  return 0;
+  return persistent_tables(s);
 }
 int sptrsv_max_block() { return mma_min_mu() <= 8 ? 8 : 4; }
 #else
 int sptrsv_prepare(Sub *s) {
   HB_CUDA(cudaFuncSetAttribute(k_fwd<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 8 * FCH * sizeof(K))));
   HB_CUDA(cudaFuncSetAttribute(k_fwd<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 8 * FCH * sizeof(K))));
-  (void)s;
-  return 0;
+  return persistent_tables(s);
 }
 int sptrsv_max_block() { return 4; }
 #endif
@@ -786,6 +1127,7 @@ int sptrsv_solve(Sub *s, const K *b, K *x, int mu, const double *scale, bool acc
 #ifndef HB_COMPLEX
     if (tensor) return launch_levels_mma(s, st, mu);
 #endif
+    if (mu == 1 && persistent_on()) return launch_persistent(s, st);
     return mu == 1 ? launch_levels<1>(s, st) : (mu == 2 ? launch_levels<2>(s, st) : launch_levels<4>(s, st));
   };
   static const bool use_graph = getenv("HPDDM_B200_NO_GRAPH") == nullptr;

@@ -196,6 +196,14 @@ int hpddm_b200z_solve_cg(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpd
 int hpddm_b200z_solve_bgmres(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpddm_b200_z *const *x, int mu, int correction, int restart, int max_it, double tol,
                              int where, int *iterations, double *rel_residual);
 
+/* ---- host-only planning entry points (no GPU needed): the N > 1 logic the hot path uses, exposed so that CPU-only multi-process
+ * tests exercise the product's own code.  coarse_layout: offsets[nproc + 1] of the process blocks of the coarse vector and the padded
+ * block length of the communication layout.  halo_schedule: the ordered NCCL sends / receives of one halo round for the `nlocal`
+ * subdomains of a process (global ranks granks[], nb_count[q] neighbours each, their global ranks concatenated in nb_ranks[]):
+ * quadruples (destination subdomain, source subdomain, local subdomain index, neighbour slot); sends / recvs may be NULL to query *nmsg. */
+int hpddm_b200z_debug_coarse_layout(int nproc, const int *rows_per_proc, int *offsets, int *lmax);
+int hpddm_b200z_debug_halo_schedule(int nlocal, const int *granks, const int *nb_count, const int *nb_ranks, int *sends, int *recvs, int *nmsg);
+
 /* ---- introspection (Subdomain::statistics analogue, subdomain.hpp:405-454); factor_bytes counts 16-byte scalars */
 int hpddm_b200z_sub_stats(hpddm_b200z_sub *sub, hpddm_b200_stats *st);
 

@@ -461,3 +461,48 @@ def test_pageable_host_vectors_are_pinned_in_place_inside_a_start_end_bracket():
     deco.apply_host_inplace(x, y, 1, None)                         # after end(): pageable again, still correct
     assert relerr(y, ref) < 1e-13 and deco.api.ctx_hostreg_count(deco.ctx) == n0
     deco.close()
+
+
+@pytest.mark.parametrize("xnode", [5, 18])
+def test_cholesky_breakdown_in_any_large_front_of_a_level_falls_back_to_lu(xnode):
+    """A symmetric INDEFINITE matrix whose negative pivot sits in one of the two second-level separators (288 unknowns each: both go
+    through cuSOLVER, same level).  Every large front has its own status slot, so the failed potrf is seen whichever front of the
+    level it hits (a shared slot is overwritten with 0 by the next successful front) and numfact retries with LU."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    from hpddm_b200 import Decomposition
+    m = 24
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(m, m))
+    I = sp.identity(m)
+    A = (sp.kron(sp.kron(I, I), T) + sp.kron(sp.kron(I, T), I) + sp.kron(sp.kron(T, I), I)).tolil()
+    i = (7 * m + 12) * m + xnode                # node (x, y, z) = (xnode, 12, 7): inside the y = 12 separator of one x-half
+    A[i, i] = -5.0
+    A = sp.csr_matrix(A)
+    deco = Decomposition(0)
+    s = deco.add(0)
+    s.initialize(A, [], [])
+    s.setGridHint(m, m, m)
+    s.callNumfact()
+    st = s.statistics()
+    assert st["symmetric"] == 0                 # Cholesky was refused, LU took over
+    b = np.random.RandomState(1).standard_normal((m ** 3, 1))
+    x = s.solve(b)
+    ref = spl.spsolve(sp.csc_matrix(A), b[:, 0])
+    assert np.abs(x[:, 0] - ref).max() < 1e-9 * np.abs(ref).max()
+    deco.close()
+
+
+def test_large_coarse_space_paths_device_inverse_and_grid_wide_solve(poisson3d, monkeypatch):
+    """The code paths taken by coarse spaces too large for one CTA / a host inversion (E^-1 by cuSOLVER LU on the device, the
+    replicated solve as three grid-wide passes), forced on the small fixture: same deflation as the oracle."""
+    parts, w, deco = poisson3d
+    monkeypatch.setenv("HPDDM_B200_COARSE_HOST_LIMIT", "0")
+    monkeypatch.setenv("HPDDM_B200_COARSE_ONE_CTA_LIMIT", "0")
+    deco.setCoarse(w.E)
+    x = rhs(parts, w, 11)
+    assert relerr(deco.deflation(x), w.deflation(x)) < TOL
+    assert relerr(deco.apply(x, "balanced"), w.apply(x, BALANCED)) < TOL
+    monkeypatch.delenv("HPDDM_B200_COARSE_HOST_LIMIT")
+    monkeypatch.delenv("HPDDM_B200_COARSE_ONE_CTA_LIMIT")
+    deco.setCoarse(w.E)      # back to the default paths for the remaining tests of the module
+    assert relerr(deco.deflation(x), w.deflation(x)) < TOL
