@@ -445,7 +445,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", dest="m", type=int, default=0, help="cells per subdomain edge, both arms (0 = default_cells(): 160, or 128 on a small host)")
-    ap.add_argument("--nu", type=int, default=20)
+    ap.add_argument("--nu", "--nvec", dest="nu", type=int, default=20, help="deflation vectors per subdomain (use --nvec under torchrun: its parser claims --nu)")
     ap.add_argument("--rhs", dest="mu", type=int, default=1, help="right-hand sides per apply (block methods)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--workload", default="poisson", choices=["poisson", "elasticity"],

@@ -519,10 +519,28 @@ int apply_core(Ctx *c, const std::vector<const K *> &ind, const std::vector<K *>
     ctmp[i] = tmp[i];
   }
   if (correction == HPDDM_B200_CORRECTION_ADDITIVE) {  // schwarz.hpp:552-571
-    HB_CHECK(deflation_core(c, ind, outd, mu));
+    // The coarse correction Q in and the local solves A^-1 in are independent: the reference overlaps them with a non-blocking
+    // gather (HPDDM_ICOLLECTIVE, schwarz.hpp:553-563); here the whole deflation (projection, coarse gather + solve, prolongation, its
+    // halo sum) runs on a second stream while the sweeps stream the factor on the first one.
+    std::vector<K *> t2(L, nullptr);
+    for (size_t i = 0; i < L; ++i) t2[i] = c->subs[i]->d_tmp2;
+    if (!c->side) {
+      HB_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+      HB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      HB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    HB_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    HB_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    std::swap(c->stream, c->side);                                               // every launcher uses c->stream
+    const int rc = deflation_core(c, ind, t2, mu);                               // t2 = Q in (on the second stream)
+    std::swap(c->stream, c->side);
+    HB_CHECK(rc);
+    HB_CUDA(cudaEventRecord(c->ev_join, c->side));
+    for (size_t i = 0; i < L; ++i) HB_CHECK(solve_cols(c->subs[i], ind[i], outd[i], mu, nullptr, false));  // out = A^-1 in
+    HB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     for (size_t i = 0; i < L; ++i) {
       Sub *s = c->subs[i];
-      HB_CHECK(solve_cols(s, ind[i], outd[i], mu, nullptr, true));             // out += A^-1 in
+      HB_CHECK(k_axpy(c, (int64_t)s->n * mu, 1.0, t2[i], outd[i]));            // out += Q in
       HB_CHECK(k_scale(c, s->n, mu, s->d_d, outd[i], outd[i]));                // exchange(out): D ...
     }
     HB_CHECK(halo(c, outd.data(), mu));                                          // ... then halo sum
@@ -645,6 +663,9 @@ int HB_API(ctx_destroy)(hb_ctx_t *ctx) {
     if (p) cudaFree(p);
   if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
   cudaStreamDestroy(c->stream);
+  if (c->side) cudaStreamDestroy(c->side);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
   return 0;
 }

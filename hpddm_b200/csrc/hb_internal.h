@@ -193,6 +193,8 @@ struct Sub {
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;                 // second stream: the coarse correction of the additive variant runs beside the local solves
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<Sub *> subs;
   int64_t launches = 0;
   // communicator

@@ -527,8 +527,11 @@ int sptrsv_check(Sub *s) {
   }
   return 0;
 }
-// HPDDM_B200_PERSISTENT=1: single right-hand side sweeps as two dependency-driven persistent launches instead of one launch per level
-static bool persistent_on() {
+// HPDDM_B200_PERSISTENT=1: single right-hand side sweeps as two dependency-driven persistent launches instead of one launch per level.
+// Opt-in: same-box A/B pairs (profiles/README.md) are mixed -- 128^3: 7.92 -> 7.73 ms (0.928 -> 0.950 of the HBM roofline), 160^3:
+// 19.65 -> 20.15 ms, 64^3: 0.694 -> 0.748 ms; what the overlap of the level tails gains, the L2-coherent vector reads, the lower
+// occupancy of the forward kernel (80 registers) and the claim / release traffic take back.
+static bool persistent_on(const Symbolic &) {
   static const bool on = getenv("HPDDM_B200_PERSISTENT") && !strcmp(getenv("HPDDM_B200_PERSISTENT"), "1");
   return on;
 }
@@ -569,9 +572,17 @@ static int launch_persistent(Sub *s, cudaStream_t st) {
 // A fragments are 128-bit shared-memory loads feeding two MMAs each (even / odd columns); the row pitch of the stage (72 resp. 68
 // doubles) makes them bank-conflict free for the two access patterns.  Panel bytes are still read exactly once per sweep.
 namespace mma {
-constexpr int ST_ROWS = 32, ST_COLS = 64, NST = 3, WARPS = 4;
-constexpr int PITCH_F = ST_COLS + 8;  // forward: lanes (g, t) read [8 rg + g][8 j + 2 t]
-constexpr int PITCH_B = ST_COLS + 4;  // backward: lanes (g, t) read [4 ks + t][16 jj + 2 g]
+// Two ways of filling the ring: KIND 0 = one 1-D bulk copy per tile row (cp.async.bulk, SASS UBLKCP, mbarrier complete_tx; 32-row
+// tiles, 4 warps per CTA); KIND 1 = per-lane 16-byte asynchronous copies (cp.async.cg, SASS LDGSTS, commit / wait groups; 16-row
+// tiles, 8 warps per CTA).  Same consumers.
+template <int KIND>
+struct Cfg {
+  static constexpr int ROWS = KIND == 0 ? 32 : 16, COLS = 64, NST = 3, WARPS = KIND == 0 ? 4 : 8;
+  static constexpr int PITCH_F = COLS + 8;  // forward: lanes (g, t) read [8 rg + g][8 j + 2 t]
+  static constexpr int PITCH_B = COLS + 4;  // backward: lanes (g, t) read [4 ks + t][16 jj + 2 g]
+  static constexpr size_t SMEM_F = (size_t)WARPS * NST * ROWS * PITCH_F * sizeof(double) + WARPS * NST * sizeof(uint64_t);
+  static constexpr size_t SMEM_B = (size_t)WARPS * NST * ROWS * PITCH_B * sizeof(double) + WARPS * NST * sizeof(uint64_t);
+};
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count) : "memory"); }
@@ -588,15 +599,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
 }
+// 16-byte asynchronous copy global -> shared, bypassing L1; src_bytes = 0 writes zeros without touching global memory
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
 
-// one stage of the stream = one 32 x 64 tile of one work item
+// one stage of the stream = one ROWS x 64 tile of one work item
 struct FStage {  // forward
   int64_t it;    // item index (>= nitems: stream exhausted)
   int cs;        // first column of the tile
-  // decoded item
+  int rs;        // first row of the tile inside the item's 32-row block
   const double *base;  // first row of the item's row block
   int stride, nrows, c0, c1, p0, rblk, nb1;
   int64_t rptr;
@@ -627,65 +645,86 @@ __device__ __forceinline__ void f_decode(FStage &s, const FwdItem *items, const 
   s.rblk = w.rblk;
   s.rptr = f.rptr;
   s.cs = w.c0;
+  s.rs = 0;
 }
-// advance to the next tile of the stream (next column tile of the item, else first tile of the warp's next non-empty item)
+// advance to the next tile of the stream: next row tile of the column chunk, next column chunk, else the warp's next non-empty item
+template <int ROWS>
 __device__ __forceinline__ void f_next(FStage &s, bool first, int64_t nitems, int64_t stride_items, const FwdItem *items, const Front *fronts, const double *pan) {
   if (!first) {
-    s.cs += ST_COLS;
+    s.rs += ROWS;
+    if (s.rs < s.nrows) return;
+    s.rs = 0;
+    s.cs += 64;
     if (s.cs < s.c1) return;
     s.it += stride_items;
   }
   while (s.it < nitems) {
     f_decode(s, items, fronts, pan);
-    if (s.cs < s.c1) return;
+    if (s.cs < s.c1 && s.nrows > 0) return;
     s.it += stride_items;
   }
 }
 
-__global__ void __launch_bounds__(WARPS * 32, 1) k_fwd_mma(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
-                                                           const double *__restrict__ pan, double *b, double *y, int n, int mu) {
+template <int KIND>
+__global__ void __launch_bounds__(Cfg<KIND>::WARPS * 32, 1) k_fwd_mma(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
+                                                                     const double *__restrict__ pan, double *b, double *y, int n, int mu) {
+  typedef Cfg<KIND> C;
+  constexpr int ROWS = C::ROWS, NST = C::NST, WARPS = C::WARPS, PITCH = C::PITCH_F, RG = ROWS / 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * NST * ST_ROWS * PITCH_F;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * NST * ST_ROWS * PITCH_F * sizeof(double)) + warp * NST;
-  for (int i = lane; i < NST * ST_ROWS * PITCH_F; i += 32) ring[i] = 0.0;  // stale tails are multiplied by zeros: keep them finite
-  if (lane == 0)
-    for (int q = 0; q < NST; ++q) mbar_init(bars + q, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * NST * ROWS * PITCH;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * NST * ROWS * PITCH * sizeof(double)) + warp * NST;
+  if (KIND == 0) {
+    for (int i = lane; i < NST * ROWS * PITCH; i += 32) ring[i] = 0.0;  // stale tails are multiplied by zeros: keep them finite
+    if (lane == 0)
+      for (int q = 0; q < NST; ++q) mbar_init(bars + q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __syncwarp();
   const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, gstride = (int64_t)gridDim.x * WARPS;
   FStage prod, cons;
   prod.it = cons.it = gw;
-  f_next(prod, true, nitems, gstride, items, fronts, pan);
-  f_next(cons, true, nitems, gstride, items, fronts, pan);
-  auto produce = [&](int slot) {  // all lanes: lane r copies row r of the tile
-    const int nc = min(ST_COLS, prod.stride - prod.cs);  // the stored row is zero-padded up to its stride: copy whole 32-byte groups
-    const uint32_t bytes = (uint32_t)nc * 8u;
-    if (lane == 0) mbar_expect_tx(bars + slot, bytes * (uint32_t)prod.nrows);
-    __syncwarp();
-    if (lane < prod.nrows) bulk_g2s(ring + ((size_t)slot * ST_ROWS + lane) * PITCH_F, prod.base + (int64_t)lane * prod.stride + prod.cs, bytes, bars + slot);
+  f_next<ROWS>(prod, true, nitems, gstride, items, fronts, pan);
+  f_next<ROWS>(cons, true, nitems, gstride, items, fronts, pan);
+  auto produce = [&](int slot) {
+    double *tile = ring + (size_t)slot * ROWS * PITCH;
+    if (prod.it >= nitems) {
+      if (KIND == 1) cp_async_commit();  // keep one group per iteration so that wait_group counts stages
+      return;
+    }
+    const int nr = min(ROWS, prod.nrows - prod.rs);
+    if (KIND == 0) {  // lane r copies row r of the tile with one bulk copy
+      const int nc = min(64, prod.stride - prod.cs);  // the stored row is zero-padded up to its stride: copy whole 32-byte groups
+      const uint32_t bytes = (uint32_t)nc * 8u;
+      if (lane == 0) mbar_expect_tx(bars + slot, bytes * (uint32_t)nr);
+      __syncwarp();
+      if (lane < nr) bulk_g2s(tile + (size_t)lane * PITCH, prod.base + (int64_t)(prod.rs + lane) * prod.stride + prod.cs, bytes, bars + slot);
+    } else {  // every instruction moves one 512-byte row: lane l its 16 bytes at column 2 l (zeros past the stored width / the last row)
+      const bool colok = prod.cs + 2 * lane < prod.stride;
+      const double *src = prod.base + (int64_t)prod.rs * prod.stride + prod.cs + 2 * lane;
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) cp_async16(tile + (size_t)r * PITCH + 2 * lane, (colok && r < nr) ? src + (int64_t)r * prod.stride : prod.base, (colok && r < nr) ? 16 : 0);
+      cp_async_commit();
+    }
   };
   int pslot = 0, cslot = 0;
   uint32_t cphase = 0;
-  for (int q = 0; q < NST - 1 && prod.it < nitems; ++q) {  // prologue: fill NST - 1 stages
+  for (int q = 0; q < NST - 1; ++q) {  // prologue: fill NST - 1 stages
     produce(pslot);
     pslot = (pslot + 1) % NST;
-    f_next(prod, false, nitems, gstride, items, fronts, pan);
+    if (prod.it < nitems) f_next<ROWS>(prod, false, nitems, gstride, items, fronts, pan);
   }
   double acc[4][2];
 #pragma unroll
   for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = 0.0;
+  double bx[8], by[8];
   while (cons.it < nitems) {
     // keep the ring full: the slot freed by the previous iteration (all lanes are past their reads of it: __syncwarp below)
-    if (prod.it < nitems) {
-      produce(pslot);
-      pslot = (pslot + 1) % NST;
-      f_next(prod, false, nitems, gstride, items, fronts, pan);
-    }
-    // right-hand-side fragments of this tile: B[k = t][n = g] for the even / odd column of each group of 8
-    double bx[8], by[8];
-    {
+    produce(pslot);
+    pslot = (pslot + 1) % NST;
+    if (prod.it < nitems) f_next<ROWS>(prod, false, nitems, gstride, items, fronts, pan);
+    if (cons.rs == 0) {  // right-hand-side fragments of this column chunk: B[k = t][n = g] for the even / odd column of each group of 8
       const double *bc = b + (int64_t)g * n + cons.p0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -694,25 +733,34 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_fwd_mma(const FwdItem *__rest
         by[j] = (g < mu && c + 1 < cons.c1) ? __ldg(bc + c + 1) : 0.0;
       }
     }
-    mbar_wait(bars + cslot, cphase);
-    const double *tile = ring + (size_t)cslot * ST_ROWS * PITCH_F;
+    if (KIND == 0) mbar_wait(bars + cslot, cphase);
+    else {
+      cp_async_wait<NST - 1>();  // all but the NST - 1 youngest groups have landed: the stage being consumed is complete for this lane
+      __syncwarp();              // ... and for every other lane of the warp
+    }
+    const double *tile = ring + (size_t)cslot * ROWS * PITCH;
 #pragma unroll
-    for (int rg = 0; rg < 4; ++rg) {
-      if (8 * rg < cons.nrows) {
-        const double2 *row = reinterpret_cast<const double2 *>(tile + (size_t)(8 * rg + g) * PITCH_F) + t;
+    for (int part = 0; part < 4 / RG; ++part) {  // which of the item's 4 row groups this tile holds (static accumulator indices)
+      if (cons.rs == part * ROWS) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const double2 a = row[4 * j];
-          dmma(acc[rg], a.x, bx[j]);
-          dmma(acc[rg], a.y, by[j]);
+        for (int rg = 0; rg < RG; ++rg) {
+          if (cons.rs + 8 * rg < cons.nrows) {
+            const double2 *row = reinterpret_cast<const double2 *>(tile + (size_t)(8 * rg + g) * PITCH) + t;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const double2 a = row[4 * j];
+              dmma(acc[part * RG + rg], a.x, bx[j]);
+              dmma(acc[part * RG + rg], a.y, by[j]);
+            }
+          }
         }
       }
     }
     __syncwarp();  // every lane is done reading this slot before it is refilled
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (KIND == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     cslot = (cslot + 1) % NST;
     cphase ^= (cslot == 0);
-    const bool last = cons.cs + ST_COLS >= cons.c1;
+    const bool last = cons.cs + 64 >= cons.c1 && cons.rs + ROWS >= cons.nrows;
     if (last) {  // publish the item: D[row = 8 rg + g][rhs = 2 t, 2 t + 1]
 #pragma unroll
       for (int rg = 0; rg < 4; ++rg) {
@@ -730,11 +778,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_fwd_mma(const FwdItem *__rest
         acc[rg][0] = acc[rg][1] = 0.0;
       }
     }
-    f_next(cons, false, nitems, gstride, items, fronts, pan);
+    f_next<ROWS>(cons, false, nitems, gstride, items, fronts, pan);
   }
+  if (KIND == 1) cp_async_wait<0>();
 }
 
-struct BStage {  // backward: tile = rows [rr, rr + 32) x columns [cc, cc + 64) of one item
+struct BStage {  // backward: tile = rows [rr, rr + ROWS) x columns [cc, cc + 64) of one item
   int64_t it;
   int cc, rr;
   const double *P, *Pu;
@@ -756,12 +805,13 @@ __device__ __forceinline__ void b_decode(BStage &s, const BwdItem *items, const 
   s.cc = w.c0;
   s.rr = w.r0;
 }
+template <int ROWS>
 __device__ __forceinline__ void b_next(BStage &s, bool first, int64_t nitems, int64_t stride_items, const BwdItem *items, const Front *fronts, const double *pan) {
   if (!first) {
-    s.rr += ST_ROWS;
+    s.rr += ROWS;
     if (s.rr < s.r1) return;
     s.rr = s.r0;
-    s.cc += ST_COLS;
+    s.cc += 64;
     if (s.cc < s.cend) return;
     s.it += stride_items;
   }
@@ -771,79 +821,102 @@ __device__ __forceinline__ void b_next(BStage &s, bool first, int64_t nitems, in
     s.it += stride_items;
   }
 }
+// stored row r of a panel: address of its first column and its stored width (pivot rows live in the trapezoid)
+__device__ __forceinline__ const double *panel_row(const BStage &s, int r, int &width) {
+  if (r < s.s1) {
+    const int k = r / RB;
+    width = hb_wblk(s.s1, k);
+    return s.P + hb_blk_off(k) + (int64_t)(r - k * RB) * width;
+  }
+  width = s.ldp;
+  return s.Pu + (int64_t)(r - s.s1) * s.ldp;
+}
 
-__global__ void __launch_bounds__(WARPS * 32, 1) k_bwd_mma(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
-                                                           const double *__restrict__ pan, const double *__restrict__ y, double *x, int n, int mu) {
+template <int KIND>
+__global__ void __launch_bounds__(Cfg<KIND>::WARPS * 32, 1) k_bwd_mma(const BwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
+                                                                     const double *__restrict__ pan, const double *__restrict__ y, double *x, int n, int mu) {
+  typedef Cfg<KIND> C;
+  constexpr int ROWS = C::ROWS, NST = C::NST, WARPS = C::WARPS, PITCH = C::PITCH_B, KS = ROWS / 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * NST * ST_ROWS * PITCH_B;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * NST * ST_ROWS * PITCH_B * sizeof(double)) + warp * NST;
-  for (int i = lane; i < NST * ST_ROWS * PITCH_B; i += 32) ring[i] = 0.0;
-  if (lane == 0)
-    for (int q = 0; q < NST; ++q) mbar_init(bars + q, 1);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  double *ring = reinterpret_cast<double *>(smem_raw) + (size_t)warp * NST * ROWS * PITCH;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)WARPS * NST * ROWS * PITCH * sizeof(double)) + warp * NST;
+  if (KIND == 0) {
+    for (int i = lane; i < NST * ROWS * PITCH; i += 32) ring[i] = 0.0;
+    if (lane == 0)
+      for (int q = 0; q < NST; ++q) mbar_init(bars + q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __syncwarp();
   const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, gstride = (int64_t)gridDim.x * WARPS;
   BStage prod, cons;
   prod.it = cons.it = gw;
-  b_next(prod, true, nitems, gstride, items, fronts, pan);
-  b_next(cons, true, nitems, gstride, items, fronts, pan);
-  auto produce = [&](int slot) {  // lane r: row rr + r of the panel (pivot rows live in the trapezoid: their stored width grows with the row block)
-    const int r = prod.rr + lane;
-    const double *src = nullptr;
-    int width = 0;  // stored columns of this row
-    if (r < prod.r1) {
-      if (r < prod.s1) {
-        const int k = r / RB;
-        width = hb_wblk(prod.s1, k);
-        src = prod.P + hb_blk_off(k) + (int64_t)(r - k * RB) * width;
-      } else {
-        width = prod.ldp;
-        src = prod.Pu + (int64_t)(r - prod.s1) * prod.ldp;
-      }
+  b_next<ROWS>(prod, true, nitems, gstride, items, fronts, pan);
+  b_next<ROWS>(cons, true, nitems, gstride, items, fronts, pan);
+  auto produce = [&](int slot) {
+    double *tile = ring + (size_t)slot * ROWS * PITCH;
+    if (prod.it >= nitems) {
+      if (KIND == 1) cp_async_commit();
+      return;
     }
-    const int nc = max(0, min(ST_COLS, width - prod.cc));
-    double *dst = ring + ((size_t)slot * ST_ROWS + lane) * PITCH_B;
-    for (int c = nc; c < ST_COLS; ++c) dst[c] = 0.0;  // columns this row does not store (structural zeros / rows past the item) must read as zeros
-    unsigned total = 8u * (unsigned)nc;
+    if (KIND == 0) {  // lane r: row rr + r of the panel by one bulk copy; columns it does not store are zero-filled by hand
+      const int r = prod.rr + lane;
+      const double *src = prod.P;
+      int width = 0;
+      if (r < prod.r1) src = panel_row(prod, r, width);
+      const int nc = max(0, min(64, width - prod.cc));
+      double *dst = tile + (size_t)lane * PITCH;
+      for (int c = nc; c < 64; ++c) dst[c] = 0.0;
+      unsigned total = 8u * (unsigned)nc;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    if (lane == 0) mbar_expect_tx(bars + slot, total);
-    __syncwarp();
-    if (nc > 0) bulk_g2s(dst, src + prod.cc, 8u * (unsigned)nc, bars + slot);
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (lane == 0) mbar_expect_tx(bars + slot, total);
+      __syncwarp();
+      if (nc > 0) bulk_g2s(dst, src + prod.cc, 8u * (unsigned)nc, bars + slot);
+    } else {
+#pragma unroll
+      for (int q = 0; q < ROWS; ++q) {
+        const int r = prod.rr + q;
+        int width = 0;
+        const double *src = prod.P;
+        if (r < prod.r1) src = panel_row(prod, r, width);
+        const bool ok = prod.cc + 2 * lane < width;  // structural zeros / rows past the item read as zeros
+        cp_async16(tile + (size_t)q * PITCH + 2 * lane, ok ? src + prod.cc + 2 * lane : prod.P, ok ? 16 : 0);
+      }
+      cp_async_commit();
+    }
   };
   int pslot = 0, cslot = 0;
   uint32_t cphase = 0;
-  for (int q = 0; q < NST - 1 && prod.it < nitems; ++q) {
+  for (int q = 0; q < NST - 1; ++q) {
     produce(pslot);
     pslot = (pslot + 1) % NST;
-    b_next(prod, false, nitems, gstride, items, fronts, pan);
+    if (prod.it < nitems) b_next<ROWS>(prod, false, nitems, gstride, items, fronts, pan);
   }
   double accE[4][2], accO[4][2];
 #pragma unroll
   for (int q = 0; q < 4; ++q) accE[q][0] = accE[q][1] = accO[q][0] = accO[q][1] = 0.0;
   while (cons.it < nitems) {
-    if (prod.it < nitems) {
-      produce(pslot);
-      pslot = (pslot + 1) % NST;
-      b_next(prod, false, nitems, gstride, items, fronts, pan);
-    }
-    // multipliers of the 32 rows of this tile: B[k = t][n = g] = u[row 4 ks + t][rhs g]
-    double ub[8];
+    produce(pslot);
+    pslot = (pslot + 1) % NST;
+    if (prod.it < nitems) b_next<ROWS>(prod, false, nitems, gstride, items, fronts, pan);
+    // multipliers of the rows of this tile: B[k = t][n = g] = u[row 4 ks + t][rhs g]
+    double ub[KS];
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
+    for (int ks = 0; ks < KS; ++ks) {
       const int r = cons.rr + 4 * ks + t;
       double v = 0.0;
       if (g < mu && r < cons.r1) v = (r < cons.s1) ? y[(int64_t)g * n + cons.p0 + r] : -x[(int64_t)g * n + rowidx[cons.rptr + r - cons.s1]];
       ub[ks] = v;
     }
-    mbar_wait(bars + cslot, cphase);
-    __syncwarp();  // the zero tails written by other lanes at produce time are visible
-    const double *tile = ring + (size_t)cslot * ST_ROWS * PITCH_B;
+    if (KIND == 0) mbar_wait(bars + cslot, cphase);
+    else cp_async_wait<NST - 1>();
+    __syncwarp();  // other lanes' copies / zero tails are visible
+    const double *tile = ring + (size_t)cslot * ROWS * PITCH;
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const double2 *row = reinterpret_cast<const double2 *>(tile + (size_t)(4 * ks + t) * PITCH_B) + g;
+    for (int ks = 0; ks < KS; ++ks) {
+      const double2 *row = reinterpret_cast<const double2 *>(tile + (size_t)(4 * ks + t) * PITCH) + g;
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const double2 a = row[8 * jj];
@@ -852,10 +925,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_bwd_mma(const BwdItem *__rest
       }
     }
     __syncwarp();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (KIND == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     cslot = (cslot + 1) % NST;
     cphase ^= (cslot == 0);
-    const bool last = cons.rr + ST_ROWS >= cons.r1;
+    const bool last = cons.rr + ROWS >= cons.r1;
     if (last) {  // all rows of this 64-column chunk are in: D[col = 16 jj + 2 g (+ 1)][rhs = 2 t, 2 t + 1]
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
@@ -871,12 +944,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_bwd_mma(const BwdItem *__rest
         accE[jj][0] = accE[jj][1] = accO[jj][0] = accO[jj][1] = 0.0;
       }
     }
-    b_next(cons, false, nitems, gstride, items, fronts, pan);
+    b_next<ROWS>(cons, false, nitems, gstride, items, fronts, pan);
   }
+  if (KIND == 1) cp_async_wait<0>();
 }
-
-constexpr size_t SMEM_F = (size_t)WARPS * NST * ST_ROWS * PITCH_F * sizeof(double) + WARPS * NST * sizeof(uint64_t);
-constexpr size_t SMEM_B = (size_t)WARPS * NST * ST_ROWS * PITCH_B * sizeof(double) + WARPS * NST * sizeof(uint64_t);
 }  // namespace mma
 
 
@@ -911,35 +982,36 @@ __global__ void __launch_bounds__(256, OCC) k_fwd_dmma(const FwdItem *__restrict
   const int c1 = min(cmax, w.c0 + w.cw);
   if (c1 <= w.c0) return;
   const double *bc = b + (int64_t)g * n + f.p0;              // right-hand side g (B fragment: n = g), L1-resident chunk
-  // accumulators of the 4 row groups (two partial sums each: breaks the dependent DMMA chain), kept over the column chunks
-  double acc[4][2][2];
+  // ncu (profiles/r02_ncu_dmma4_m96.csv) showed the first version of this kernel latency-bound: 16 warps per SM, 8 loads each = 64 KB
+  // in flight per SM (warps stalled on long scoreboard 19 : 1 per issue, DRAM at 55-65 %).  Registers are the budget for bytes in
+  // flight, so the chunk is narrow (32 columns: 8 B-fragment registers) and covers all 4 row groups: 16 x 128-bit loads per lane.
+  double acc[4][2];
 #pragma unroll
-  for (int rg = 0; rg < 4; ++rg)
+  for (int rg = 0; rg < 4; ++rg) acc[rg][0] = acc[rg][1] = 0.0;
+  const double2 *row0 = reinterpret_cast<const double2 *>(base + (int64_t)g * stride) + t;
+  const int64_t rgstep = (int64_t)8 * stride / 2;          // 8 rows further, in 128-bit units
+  for (int cs = w.c0; cs < c1; cs += 32) {
+    double2 a[4][4];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) acc[rg][q][0] = acc[rg][q][1] = 0.0;
-  for (int cs = w.c0; cs < c1; cs += 64) {                  // 64 columns = 8 groups of 8 = 16 k-steps; their B fragments serve all 4 row groups
-    double bx[8], by[8];
+    for (int rg = 0; rg < 4; ++rg)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u)
+        a[rg][u] = (8 * rg + g < nrows && cs + 8 * u + 2 * t < stride) ? ldg_stream(row0 + rg * rgstep + cs / 2 + 4 * u) : make_double2(0.0, 0.0);  // rows are zero-padded to an even width
+    double bx[4], by[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
       const int c = cs + 8 * u + 2 * t;
       bx[u] = (g < mu && c < c1) ? __ldg(bc + c) : 0.0;
       by[u] = (g < mu && c + 1 < c1) ? __ldg(bc + c + 1) : 0.0;
     }
 #pragma unroll
-    for (int rg = 0; rg < 4; ++rg) {
-      if (8 * rg < nrows) {
-        const bool rowok = 8 * rg + g < nrows;
-        const double2 *row = reinterpret_cast<const double2 *>(base + (int64_t)(8 * rg + g) * stride + cs) + t;
-        double2 a[8];
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] = (rowok && cs + 8 * u + 2 * t < stride) ? ldg_stream(row + 4 * u) : make_double2(0.0, 0.0);  // rows are zero-padded to an even width
+      for (int rg = 0; rg < 4; ++rg) mma::dmma(acc[rg], a[rg][u].x, bx[u]);  // consecutive MMAs go to different accumulators
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          mma::dmma(acc[rg][u & 1], a[u].x, bx[u]);
-          mma::dmma(acc[rg][u & 1], a[u].y, by[u]);
-        }
-      }
-    }
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int rg = 0; rg < 4; ++rg) mma::dmma(acc[rg], a[rg][u].y, by[u]);
   }
 #pragma unroll
   for (int rg = 0; rg < 4; ++rg) {
@@ -948,10 +1020,9 @@ __global__ void __launch_bounds__(256, OCC) k_fwd_dmma(const FwdItem *__restrict
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int m = 2 * t + h;
-        const double v = acc[rg][0][h] + acc[rg][1][h];
         if (m < mu) {
-          if (pivot) atomicAdd(&y[(int64_t)m * n + f.p0 + RB * w.rblk + r], v);
-          else atomicAdd(&b[(int64_t)m * n + rowidx[f.rptr + RB * (w.rblk - nb1) + r]], -v);
+          if (pivot) atomicAdd(&y[(int64_t)m * n + f.p0 + RB * w.rblk + r], acc[rg][h]);
+          else atomicAdd(&b[(int64_t)m * n + rowidx[f.rptr + RB * (w.rblk - nb1) + r]], -acc[rg][h]);
         }
       }
     }
@@ -974,21 +1045,21 @@ __global__ void __launch_bounds__(256, OCC) k_bwd_dmma(const BwdItem *__restrict
 #pragma unroll
     for (int q = 0; q < 4; ++q) accE[q][0] = accE[q][1] = accO[q][0] = accO[q][1] = 0.0;
     // multipliers u[row][rhs g] of a trip (B fragments), fetched one trip ahead: the struct rows need two dependent loads (index, value)
-    auto multipliers = [&](int rr, double (&ub)[2]) {
+    auto multipliers = [&](int rr, double (&ub)[4]) {
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
+      for (int ks = 0; ks < 4; ++ks) {
         const int r = rr + 4 * ks + t;
         double v = 0.0;
         if (g < mu && r < r1) v = (r < s1) ? y[(int64_t)g * n + f.p0 + r] : -x[(int64_t)g * n + rowidx[f.rptr + r - s1]];
         ub[ks] = v;
       }
     };
-    double ub[2], ubn[2];
+    double ub[4], ubn[4];
     multipliers(w.r0, ub);
-    for (int rr = w.r0; rr < r1; rr += 8) {                  // two k-steps (8 rows) per trip: 8 loads in flight per lane
-      double2 a[2][4];
+    for (int rr = w.r0; rr < r1; rr += 16) {                 // four k-steps (16 rows) per trip: 16 loads in flight per lane
+      double2 a[4][4];
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
+      for (int ks = 0; ks < 4; ++ks) {
         const int r = rr + 4 * ks + t;
         const double *rowp = P;
         int width = 0;
@@ -1008,16 +1079,16 @@ __global__ void __launch_bounds__(256, OCC) k_bwd_dmma(const BwdItem *__restrict
           a[ks][jj] = (c < width) ? ldg_stream(reinterpret_cast<const double2 *>(rowp + c)) : make_double2(0.0, 0.0);
         }
       }
-      multipliers(rr + 8, ubn);
+      multipliers(rr + 16, ubn);
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
+      for (int ks = 0; ks < 4; ++ks)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           mma::dmma(accE[jj], a[ks][jj].x, ub[ks]);
           mma::dmma(accO[jj], a[ks][jj].y, ub[ks]);
         }
-      ub[0] = ubn[0];
-      ub[1] = ubn[1];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ub[ks] = ubn[ks];
     }
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
@@ -1035,10 +1106,12 @@ __global__ void __launch_bounds__(256, OCC) k_bwd_dmma(const BwdItem *__restrict
 }
 
 // sweeps for 1 .. 8 right-hand sides on the tensor pipe (one persistent launch per level and sweep)
-// HPDDM_B200_MMA_VARIANT = reg (default: A fragments by 128-bit loads from HBM) | tma (per-warp cp.async.bulk ring, measured slower:
-// 512-byte row copies are issue-bound on the copy engine, profiles/README.md)
+// HPDDM_B200_MMA_VARIANT = reg (A fragments by 128-bit loads from HBM) | ring (per-warp shared-memory ring filled by 16-byte cp.async,
+// persistent warps) | tma (the same ring filled by one cp.async.bulk per tile row: measured issue-bound on 512-byte copies) -- A/B table
+// in profiles/README.md
 static int launch_levels_mma(Sub *s, cudaStream_t st, int mu) {
-  static const bool tma = getenv("HPDDM_B200_MMA_VARIANT") && !strcmp(getenv("HPDDM_B200_MMA_VARIANT"), "tma");
+  static const char *var = getenv("HPDDM_B200_MMA_VARIANT");
+  static const int kind = !var ? 2 : (!strcmp(var, "tma") ? 0 : (!strcmp(var, "ring") ? 1 : 2));
   static const int occ = getenv("HPDDM_B200_MMA_OCC") ? atoi(getenv("HPDDM_B200_MMA_OCC")) : 2;
   DeviceFactor &D = s->fac;
   const Symbolic &S = s->sym;
@@ -1046,20 +1119,22 @@ static int launch_levels_mma(Sub *s, cudaStream_t st, int mu) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  auto grid = [&](int64_t ni) { return (unsigned)std::min<int64_t>(sms, (ni + mma::WARPS - 1) / mma::WARPS); };
+  auto grid = [&](int64_t ni, int warps) { return (unsigned)std::min<int64_t>(sms, (ni + warps - 1) / warps); };
   for (int l = 0; l < S.nlevels; ++l) {
     const int64_t i0 = S.fwd_ptr[l], ni = S.fwd_ptr[l + 1] - i0;
     if (ni <= 0) continue;
-    if (tma) mma::k_fwd_mma<<<grid(ni), mma::WARPS * 32, mma::SMEM_F, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
-    else if (occ == 2) k_fwd_dmma<2><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
-    else k_fwd_dmma<3><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
+    if (kind == 0) mma::k_fwd_mma<0><<<grid(ni, 4), 128, mma::Cfg<0>::SMEM_F, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
+    else if (kind == 1) mma::k_fwd_mma<1><<<grid(ni, 8), 256, mma::Cfg<1>::SMEM_F, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
+    else if (occ == 3) k_fwd_dmma<3><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
+    else k_fwd_dmma<2><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, mu);
   }
   for (int l = S.nlevels - 1; l >= 0; --l) {
     const int64_t i0 = S.bwd_ptr[l], ni = S.bwd_ptr[l + 1] - i0;
     if (ni <= 0) continue;
-    if (tma) mma::k_bwd_mma<<<grid(ni), mma::WARPS * 32, mma::SMEM_B, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
-    else if (occ == 2) k_bwd_dmma<2><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
-    else k_bwd_dmma<3><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
+    if (kind == 0) mma::k_bwd_mma<0><<<grid(ni, 4), 128, mma::Cfg<0>::SMEM_B, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
+    else if (kind == 1) mma::k_bwd_mma<1><<<grid(ni, 8), 256, mma::Cfg<1>::SMEM_B, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
+    else if (occ == 3) k_bwd_dmma<3><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
+    else k_bwd_dmma<2><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.bwd + i0, ni, D.fronts, D.rowidx, D.panU, D.y, D.x, n, mu);
   }
   HB_CUDA(cudaGetLastError());
   return 0;
@@ -1078,8 +1153,10 @@ static int mma_min_mu() {
   return v;
 }
 int sptrsv_prepare(Sub *s) {  // once per factorisation, outside any stream capture: opt-in shared-memory sizes are per device
-  HB_CUDA(cudaFuncSetAttribute(mma::k_fwd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma::SMEM_F));
-  HB_CUDA(cudaFuncSetAttribute(mma::k_bwd_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma::SMEM_B));
+  HB_CUDA(cudaFuncSetAttribute(mma::k_fwd_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma::Cfg<0>::SMEM_F));
+  HB_CUDA(cudaFuncSetAttribute(mma::k_bwd_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma::Cfg<0>::SMEM_B));
+  HB_CUDA(cudaFuncSetAttribute(mma::k_fwd_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma::Cfg<1>::SMEM_F));
+  HB_CUDA(cudaFuncSetAttribute(mma::k_bwd_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mma::Cfg<1>::SMEM_B));
   HB_CUDA(cudaFuncSetAttribute(k_fwd<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 8 * FCH * sizeof(K))));
   HB_CUDA(cudaFuncSetAttribute(k_fwd<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)2 * 8 * FCH * sizeof(K))));
   return persistent_tables(s);
@@ -1127,7 +1204,7 @@ int sptrsv_solve(Sub *s, const K *b, K *x, int mu, const double *scale, bool acc
 #ifndef HB_COMPLEX
     if (tensor) return launch_levels_mma(s, st, mu);
 #endif
-    if (mu == 1 && persistent_on()) return launch_persistent(s, st);
+    if (mu == 1 && persistent_on(S)) return launch_persistent(s, st);
     return mu == 1 ? launch_levels<1>(s, st) : (mu == 2 ? launch_levels<2>(s, st) : launch_levels<4>(s, st));
   };
   static const bool use_graph = getenv("HPDDM_B200_NO_GRAPH") == nullptr;
