@@ -157,6 +157,7 @@ static Sub *local_sub(Ctx *c, int grank) {
 // ------------------------------------------------------------------ capacity
 static int ensure_capacity(Ctx *c, int mu) {
   if (mu <= c->mu_cap) return 0;
+  c->epoch++;  // work vectors are reallocated: captured graphs hold stale addresses
   for (Sub *s : c->subs) {
     for (K **p : {&s->d_in, &s->d_out, &s->d_work, &s->d_tmp, &s->d_tmp2}) {
       if (*p) cudaFree(*p);
@@ -657,6 +658,8 @@ int HB_API(ctx_destroy)(hb_ctx_t *ctx) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   hostreg_release(c);
+  for (auto &g : c->apply_graphs)
+    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   p2p_free(c);
   for (Sub *s : c->subs) sub_free(s);
   for (void *p : {(void *)c->d_E, (void *)c->d_Einv, (void *)c->d_T, (void *)c->d_Y, (void *)c->d_R, (void *)c->d_res, (void *)c->d_rowproc, (void *)c->d_rowloc})
@@ -750,6 +753,7 @@ int HB_API(sub_create)(hb_ctx_t *ctx, int global_rank, hb_sub_t **sub) {
   s->ctx = c;
   s->grank = global_rank;
   c->subs.push_back(s);
+  c->epoch++;
   *sub = reinterpret_cast<hb_sub_t *>(s);
   return 0;
 }
@@ -762,6 +766,7 @@ int HB_API(sub_destroy)(hb_sub_t *sub) {
   c->subs.erase(std::remove(c->subs.begin(), c->subs.end(), s), c->subs.end());
   for (Sub *o : c->subs) o->peer_seg.clear();  // links into the destroyed subdomain are rebuilt by the next check_ready
   c->mu_cap = 0;
+  c->epoch++;
   sub_free(s);
   return 0;
 }
@@ -864,6 +869,7 @@ int HB_API(sub_set_matrix)(hb_sub_t *sub, int n, int nnz, const int *ia, const i
   }
   HB_CHECK(up(flag, &s->d_bcflag, s->ctx->stream));
   s->ctx->mu_cap = 0;  // work vectors depend on n
+  s->ctx->epoch++;
   return 0;
 }
 
@@ -922,6 +928,7 @@ int HB_API(sub_set_neighbors)(hb_sub_t *sub, int count, const int *ranks, const 
   HB_CHECK(up(useg, &s->d_useg, s->ctx->stream));
   HB_CHECK(up(upos, &s->d_upos, s->ctx->stream));
   s->ctx->mu_cap = 0;
+  s->ctx->epoch++;
   return 0;
 }
 
@@ -930,6 +937,7 @@ int HB_API(sub_set_scaling)(hb_sub_t *sub, const double *d) {
   if (!s || !d) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(s->ctx->device));
   s->d_host.assign(d, d + s->n);
+  s->ctx->epoch++;
   return up(s->d_host, &s->d_d, s->ctx->stream);
 }
 
@@ -980,6 +988,7 @@ int HB_API(sub_numfact)(hb_sub_t *sub, int prcndtnr, int n, int nnz, const int *
   if (!s) return HPDDM_B200_ERR_ARG;
   HB_CUDA(cudaSetDevice(s->ctx->device));
   s->prcndtnr = prcndtnr;
+  s->ctx->epoch++;
   if (prcndtnr == HPDDM_B200_PRCNDTNR_NO) return 0;
   if (ia) {
     if (n != s->n) {
@@ -1004,6 +1013,7 @@ int HB_API(sub_set_vectors)(hb_sub_t *sub, const K *Z, int nu) {
   if (s->d_Z) cudaFree(s->d_Z);
   s->d_Z = nullptr;
   s->nu = nu;
+  s->ctx->epoch++;
   if (nu > 0) {
     HB_CUDA(cudaMalloc(&s->d_Z, (size_t)s->n * nu * sizeof(K)));
     HB_CUDA(cudaMemcpyAsync(s->d_Z, Z, (size_t)s->n * nu * sizeof(K), cudaMemcpyHostToDevice, s->ctx->stream));
@@ -1085,6 +1095,7 @@ static int invert_dense(int N, const std::vector<K> &E, std::vector<K> &Einv) {
 
 static int install_coarse(Ctx *c, const std::vector<K> &E) {
   const int N = c->Nc;
+  c->epoch++;
   c->E_host = E;
   HB_CHECK(up(c->E_host, &c->d_E, c->stream));
   // E^-1: extended precision on the host up to N_c = 1024 (BASELINE sizes: 160 .. 240), cuSOLVER LU on the device beyond (O(N_c^3)
@@ -1260,9 +1271,90 @@ int HB_API(deflation)(hb_ctx_t *ctx, const K *const *in, K *const *out, int mu, 
   return stage_out(c, out, mu, where);
 }
 
+// Whole apply as ONE graph launch (single-process contexts; opt-in: HPDDM_B200_APPLY_GRAPH=1): the deflation, SpMV, halo copies
+// between co-hosted subdomains, permutations and the (nested) sweep graphs of Schwarz::apply are captured once per (mu, correction)
+// on the fixed work vectors d_in / d_out and replayed -- at C1 / C5-sized subdomains the ~10 launch gaps are a visible part of the apply.
+// Multi-process contexts keep eager launches (their collectives carry host-side round numbers).
+static bool apply_graph_enabled() {
+  static const bool enabled = getenv("HPDDM_B200_APPLY_GRAPH") && !strcmp(getenv("HPDDM_B200_APPLY_GRAPH"), "1") && !getenv("HPDDM_B200_NO_GRAPH");
+  return enabled;
+}
+static int apply_graphed(Ctx *c, int mu, int correction, bool &done) {
+  done = false;
+  if (!apply_graph_enabled() || c->nproc != 1) return 0;
+  Ctx::ApplyGraph &g = c->apply_graphs[{mu, correction}];
+  if (g.epoch != c->epoch) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = Ctx::ApplyGraph();
+    g.epoch = c->epoch;
+  }
+  const size_t L = c->subs.size();
+  std::vector<const K *> ind(L);
+  std::vector<K *> outd(L);
+  for (size_t i = 0; i < L; ++i) {
+    ind[i] = c->subs[i]->d_in;
+    outd[i] = c->subs[i]->d_out;
+  }
+  if (!g.exec) {
+    if (g.warm++ == 0) return 0;  // first call for this key runs eagerly (it also builds the sweep graphs that get nested here)
+    const int64_t l0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    HB_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = hb::apply_core(c, ind, outd, mu, correction);
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc < 0 || e != cudaSuccess || !graph) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      c->launches = l0;
+      g.warm = -1000000;  // do not try again for this key: the caller launches eagerly (and reports a genuine error, if there is one)
+      return 0;
+    }
+    g.launches = c->launches - l0;
+    c->launches = l0;
+    const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) {
+      cudaGetLastError();
+      g.exec = nullptr;
+      g.warm = -1000000;
+      return 0;
+    }
+  }
+  HB_CUDA(cudaGraphLaunch(g.exec, c->stream));
+  c->launches += g.launches;
+  done = true;
+  return 0;
+}
+
 int HB_API(apply)(hb_ctx_t *ctx, const K *const *in, K *const *out, int mu, int correction, int where) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
   HB_CHECK(check_ready(c, mu));
+  if (c->nproc == 1 && apply_graph_enabled()) {  // fixed work vectors on both sides so that the captured graph can be replayed for any caller pointers
+    for (size_t i = 0; i < c->subs.size(); ++i) {
+      Sub *s = c->subs[i];
+      const size_t bytes = (size_t)s->n * mu * sizeof(K);
+      if (where == HPDDM_B200_HOST) HB_CHECK(host_copy(c, s->d_in, in[i], bytes, true));
+      else if (bytes) HB_CUDA(cudaMemcpyAsync(s->d_in, in[i], bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    bool done = false;
+    HB_CHECK(apply_graphed(c, mu, correction, done));
+    if (!done) {
+      std::vector<const K *> ind(c->subs.size());
+      std::vector<K *> outd(c->subs.size());
+      for (size_t i = 0; i < c->subs.size(); ++i) {
+        ind[i] = c->subs[i]->d_in;
+        outd[i] = c->subs[i]->d_out;
+      }
+      HB_CHECK(hb::apply_core(c, ind, outd, mu, correction));
+    }
+    if (where == HPDDM_B200_HOST) return stage_out(c, out, mu, where);
+    for (size_t i = 0; i < c->subs.size(); ++i) {
+      Sub *s = c->subs[i];
+      const size_t bytes = (size_t)s->n * mu * sizeof(K);
+      if (bytes) HB_CUDA(cudaMemcpyAsync(out[i], s->d_out, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return 0;
+  }
   std::vector<const K *> ind;
   std::vector<K *> outd;
   HB_CHECK(stage_in(c, in, mu, where, ind));

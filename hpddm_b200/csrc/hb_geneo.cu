@@ -278,6 +278,7 @@ extern "C" int HB_API(sub_solve_gevp)(hb_sub_t *sub, int n, int nnz, const int *
   GV(k_zexp_raw(c, n, k, Y, ones, nu, d_C, k, s->d_Z));
   GV(k_flush_tiny(c, (int64_t)n * nu, 1.0e-18, s->d_Z));  // schwarz.hpp:713
   s->nu = nu;
+  s->ctx->epoch++;
   if (eigenvalues)
     for (int j = 0; j < nu; ++j) eigenvalues[j] = 1.0 / theta[j];
   GVC(cudaStreamSynchronize(st));

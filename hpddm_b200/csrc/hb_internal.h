@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -220,6 +221,14 @@ struct Ctx {
   std::vector<K> E_host;
   int mu_cap = 0;
   bool started = false;
+  // whole-apply CUDA graphs (single-process contexts): one per (mu, correction), rebuilt when any setter bumps `epoch`
+  struct ApplyGraph {
+    cudaGraphExec_t exec = nullptr;
+    int64_t epoch = -1, launches = 0;
+    int warm = 0;  // eager calls seen for this key (the first one also builds the nested sweep graphs)
+  };
+  std::map<std::pair<int, int>, ApplyGraph> apply_graphs;
+  int64_t epoch = 0;
   P2P *p2p = nullptr;  // NVLink peer-memory halo state (hb_p2p.cu)
   // caller host memory pinned lazily (cudaHostRegister) between start() and end(): page-aligned, disjoint, sorted ranges;
   // host_seen counts how often a host pointer was passed in this bracket (a range is registered on its second sighting)

@@ -8,6 +8,9 @@
 // scatter-add loops of Subdomain::exchange (include/HPDDM_subdomain.hpp:118-127),
 // the coarse solve of CoarseOperator::callSolver
 // (include/HPDDM_coarse_operator_impl.hpp:1706-1720).
+#include <cstdlib>
+#include <cstring>
+
 #include "hb_internal.h"
 
 namespace hb {
@@ -58,6 +61,41 @@ __global__ void __launch_bounds__(256) kk_spmv(int n, int mu, const int *__restr
       if (beta != 0.0) v += beta * yin[i + (int64_t)c * n];
       out[i + (int64_t)c * n] = di * v;
     }
+  }
+}
+
+// Short rows (stencil matrices, <= 12 entries per row on average): a CTA owns 256 consecutive rows, whose entries are one contiguous
+// piece of ja / a -- staged into shared memory with coalesced loads, then one thread per row walks its entries there (thread-to-thread
+// stride = row length, odd for the 7- and 27-point stencils: conflict-free).  The thread-per-row kernel above reads the same piece with
+// a stride of one row length between neighbouring threads: 1.5 TB/s at 160^3 (ncu, profiles/r02_launches_apply_m160.csv).
+constexpr int SPMV_CAP = IS_COMPLEX ? 2048 : 3072;  // staged entries per CTA (36 / 40 KB)
+__global__ void __launch_bounds__(256) kk_spmv_staged(int n, int mu, const int *__restrict__ ia, const int *__restrict__ ja, const K *__restrict__ a, double alpha,
+                                                      const K *__restrict__ x, double beta, const K *__restrict__ yin, K *out, const double *__restrict__ d) {
+  __shared__ __align__(16) K as[SPMV_CAP];
+  __shared__ int js[SPMV_CAP];
+  const int r0 = blockIdx.x * 256, r1 = min(n, r0 + 256);
+  const int kb = ia[r0], ke = ia[r1];
+  const bool staged = ke - kb <= SPMV_CAP;
+  if (staged)
+    for (int k = kb + threadIdx.x; k < ke; k += 256) {
+      as[k - kb] = a[k];
+      js[k - kb] = ja[k];
+    }
+  __syncthreads();
+  const int i = r0 + threadIdx.x;
+  if (i >= r1) return;
+  const int k0 = ia[i], k1 = ia[i + 1];
+  const double di = d ? d[i] : 1.0;
+  for (int c = 0; c < mu; ++c) {
+    const K *xc = x + (int64_t)c * n;
+    K acc = mk(0.0);
+    if (staged)
+      for (int k = k0; k < k1; ++k) acc = hb_fma(as[k - kb], xc[js[k - kb]], acc);
+    else
+      for (int k = k0; k < k1; ++k) acc = hb_fma(a[k], xc[ja[k]], acc);
+    K v = alpha * acc;
+    if (beta != 0.0) v += beta * yin[i + (int64_t)c * n];
+    out[i + (int64_t)c * n] = di * v;
   }
 }
 
@@ -411,7 +449,9 @@ int k_spmv_raw(Ctx *c, int n, int64_t nnz, const int *ia, const int *ja, const K
   const double avg = (double)nnz / n;
 #define HB_SPMV(L) kk_spmv<L><<<grid1((int64_t)n * L), 256, 0, c->stream>>>(n, mu, ia, ja, a, alpha, x, beta, yin, out, d)
   // short rows (7-point stencils): one thread per row measured 3x faster than 4 lanes per row on B200
-  if (avg <= 16) HB_SPMV(1);
+  static const bool staged = !(getenv("HPDDM_B200_SPMV") && !strcmp(getenv("HPDDM_B200_SPMV"), "direct"));
+  if (avg <= 12 && staged) kk_spmv_staged<<<grid1(n), 256, 0, c->stream>>>(n, mu, ia, ja, a, alpha, x, beta, yin, out, d);
+  else if (avg <= 16) HB_SPMV(1);
   else if (avg <= 40) HB_SPMV(8);
   else if (avg <= 96) HB_SPMV(16);
   else HB_SPMV(32);

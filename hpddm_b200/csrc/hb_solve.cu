@@ -1207,7 +1207,12 @@ int sptrsv_solve(Sub *s, const K *b, K *x, int mu, const double *scale, bool acc
     if (mu == 1 && persistent_on(S)) return launch_persistent(s, st);
     return mu == 1 ? launch_levels<1>(s, st) : (mu == 2 ? launch_levels<2>(s, st) : launch_levels<4>(s, st));
   };
-  static const bool use_graph = getenv("HPDDM_B200_NO_GRAPH") == nullptr;
+  static const bool graphs_on = getenv("HPDDM_B200_NO_GRAPH") == nullptr;
+  // inside an outer capture (the whole-apply graph of hb_api.cu) the sweep launches are recorded straight into that graph: a graph
+  // cannot be launched into a capturing stream
+  cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cst);
+  const bool use_graph = graphs_on && cst == cudaStreamCaptureStatusNone;
   k_perm_in<<<(unsigned)(((int64_t)n * mu + 255) / 256), 256, 0, st>>>(n, mu, D.perm, b, D.b, D.y, D.x);
   if (use_graph && !D.graph[mu]) {
     cudaGraph_t g = nullptr;

@@ -506,3 +506,27 @@ def test_large_coarse_space_paths_device_inverse_and_grid_wide_solve(poisson3d, 
     monkeypatch.delenv("HPDDM_B200_COARSE_ONE_CTA_LIMIT")
     deco.setCoarse(w.E)      # back to the default paths for the remaining tests of the module
     assert relerr(deco.deflation(x), w.deflation(x)) < TOL
+
+
+def test_repeated_applies_replay_the_whole_apply_graph(poisson3d):
+    """From its third call on, an apply of a given (mu, correction) is ONE graph launch (single-process context: deflation, SpMV,
+    copies between co-hosted subdomains, nested sweep graphs).  Every replay must reproduce the oracle, different inputs included,
+    and a setter (here: a new coarse operator) must invalidate the captured graphs."""
+    parts, w, deco = poisson3d
+    for corr, oc in ((None, None), ("deflated", DEFLATED), ("additive", ADDITIVE), ("balanced", BALANCED)):
+        for k in range(5):
+            x = rhs(parts, w, 100 + k)
+            assert relerr(deco.apply(x, corr), w.apply(x, oc)) < TOL, (corr, k)
+    l0 = deco.launches
+    x = rhs(parts, w, 200)
+    deco.apply(x, "deflated")
+    assert deco.launches - l0 > 20            # the replay still accounts for the kernels it launches
+    deco.setCoarse(2.0 * w.E)                 # E -> 2 E: the deflated correction halves; a stale graph would keep the old E^-1
+    Q = w.deflation(x)
+    got = deco.deflation(x)
+    assert relerr(got, [0.5 * q for q in Q]) < TOL
+    for k in range(4):
+        assert relerr(deco.deflation(x), [0.5 * q for q in Q]) < TOL
+    deco.setCoarse(w.E)
+    for k in range(4):
+        assert relerr(deco.apply(x, "deflated"), w.apply(x, DEFLATED)) < TOL
