@@ -370,7 +370,9 @@ def cpu_baseline(args, m=None, steps=None, reuse=False, ranks=1):
     L = _cpu_lib()
     # scipy's OpenBLAS is built for at most 128 threads *including callers*: stay well below
     avail = usable_cpus()
-    threads = max(1, min(avail // max(1, ranks), 64))   # the host cores one of `ranks` concurrent subdomain processes would get
+    # the host cores one of `ranks` concurrent subdomain processes would get, but never fewer than 16 (or all there are): the CPU
+    # factorisation of the largest-fit subdomain must stay within minutes on a box that exposes few cores
+    threads = max(1, min(64, max(avail // max(1, ranks), min(avail, 16))))
     m = m or args.m
     cache = _cache_path(m, args.nu, threads)
     if reuse and os.path.exists(cache) and time.time() - os.path.getmtime(cache) < 6 * 3600:

@@ -674,6 +674,11 @@ static int krylov_entry(Ctx *c, const K *const *b, K *const *x, int mu, int wher
     cudaStreamSynchronize(c->stream);
     release();
   }
+  if (rc == 0) {  // DEVICE-pointer callers included: a peer-memory collective or a persistent sweep that gave up waiting must not pass silently
+    cudaStreamSynchronize(c->stream);
+    for (Sub *s : c->subs) HB_CHECK(sptrsv_check(s));
+    HB_CHECK(p2p_check(c));
+  }
   return rc;
 }
 

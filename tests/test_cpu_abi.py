@@ -158,3 +158,23 @@ def test_bench_default_size_rule_is_shared_by_both_arms(monkeypatch):
     assert bench.default_cells() == 128
     monkeypatch.setenv("HPDDM_B200_BENCH_M", "96")
     assert bench.default_cells() == 96
+
+
+def test_full_seam_binary_is_built_from_the_unmodified_driver_and_fails_loudly_without_a_gpu(tmp_path):
+    """oracle/_ref/schwarz_b200_full = the reference's examples/schwarz.cpp compiled against HPDDM::Schwarz<HPDDM::B200Sub, ...>
+    (hpddm_b200/host/HPDDM_B200_schwarz.hpp).  Without a CUDA device it must stop with the library's "no CPU fallback" error, never
+    compute on the host."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "schwarz_b200_full")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/schwarz_b200_full not built (needs /root/reference at build time)")
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: the GPU suite runs this binary for real")
+    except ImportError:
+        pass
+    res = subprocess.run([exe, "-hpddm_verbosity=1", "-Nx", "20", "-Ny", "20"], env=dict(os.environ, HPDDM_SHIM_NP="2"), cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    out = res.stdout + res.stderr
+    assert res.returncode != 0 and "no CPU fallback" in out, out[-1500:]
+    assert "converges after" not in out
