@@ -64,10 +64,10 @@ __global__ void __launch_bounds__(256) kk_spmv(int n, int mu, const int *__restr
   }
 }
 
-// Short rows (stencil matrices, <= 12 entries per row on average): a CTA owns 256 consecutive rows, whose entries are one contiguous
-// piece of ja / a -- staged into shared memory with coalesced loads, then one thread per row walks its entries there (thread-to-thread
-// stride = row length, odd for the 7- and 27-point stencils: conflict-free).  The thread-per-row kernel above reads the same piece with
-// a stride of one row length between neighbouring threads: 1.5 TB/s at 160^3 (ncu, profiles/r02_launches_apply_m160.csv).
+// Experimental variant for short rows (stencil matrices, <= 12 entries per row on average): a CTA owns 256 consecutive rows, whose
+// entries are one contiguous piece of ja / a -- staged into shared memory with coalesced loads, then one thread per row walks its
+// entries there.  Motivated by the cold-cache ncu figure of the thread-per-row kernel (1.5 TB/s at 160^3), but slower than it in the
+// live (warm, back-to-back) measurement: kept opt-in for re-measurement.
 constexpr int SPMV_CAP = IS_COMPLEX ? 2048 : 3072;  // staged entries per CTA (36 / 40 KB)
 __global__ void __launch_bounds__(256) kk_spmv_staged(int n, int mu, const int *__restrict__ ia, const int *__restrict__ ja, const K *__restrict__ a, double alpha,
                                                       const K *__restrict__ x, double beta, const K *__restrict__ yin, K *out, const double *__restrict__ d) {
@@ -449,7 +449,9 @@ int k_spmv_raw(Ctx *c, int n, int64_t nnz, const int *ia, const int *ja, const K
   const double avg = (double)nnz / n;
 #define HB_SPMV(L) kk_spmv<L><<<grid1((int64_t)n * L), 256, 0, c->stream>>>(n, mu, ia, ja, a, alpha, x, beta, yin, out, d)
   // short rows (7-point stencils): one thread per row measured 3x faster than 4 lanes per row on B200
-  static const bool staged = !(getenv("HPDDM_B200_SPMV") && !strcmp(getenv("HPDDM_B200_SPMV"), "direct"));
+  // staged variant: opt-in (HPDDM_B200_SPMV=staged) -- live A/B (profiles/README.md): 12.7 vs 8.6 us at 64^3, 0.28 vs 0.16 ms at 160^3 for
+  // SpMV + D-scale: the thread-per-row kernel wins (its strided reads hit L1 / L2; the staged one pays two passes and 36 KB per CTA)
+  static const bool staged = getenv("HPDDM_B200_SPMV") && !strcmp(getenv("HPDDM_B200_SPMV"), "staged");
   if (avg <= 12 && staged) kk_spmv_staged<<<grid1(n), 256, 0, c->stream>>>(n, mu, ia, ja, a, alpha, x, beta, yin, out, d);
   else if (avg <= 16) HB_SPMV(1);
   else if (avg <= 40) HB_SPMV(8);
