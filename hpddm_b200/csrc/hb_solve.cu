@@ -165,6 +165,55 @@ __device__ __forceinline__ K ld_cg(const K *p) {
 // through L1 instead of being staged in shared memory, so that one pass covers the whole item width (up to FCH columns) for
 // all MU columns: the shuffle reduction (reduce8) runs once per R = 8 / MU rows x FCH columns instead of once per FCH / MU
 // columns -- it dominated the staged variant at MU = 4 (profiles/README.md).
+// Narrow fronts (row width 8, 16 or 32: the small separators of the leaf-side levels, thousands per level).  The generic forward item
+// gives such a front 8 rows x (width / 2) lanes per step -- 4 to 16 active lanes; ncu at 160^3 (profiles/r02_ncu_full_sptrsv_m160.csv)
+// shows those levels at 1.8-3.9 TB/s.  A block of rows of a narrow panel is CONTIGUOUS (row stride = width), so k_fwd_narrow reads
+// it as a flat array: every lane one 128-bit load per step, 32 / G rows per step with G = width / 2 lanes per row, a G-lane shuffle
+// reduction, one RED per row.  Same item list as k_fwd_blk<1>: each of the two kernels skips the other's items (levels that have only
+// one kind get only that launch).
+__host__ __device__ inline bool hb_narrow_front(int s1) {
+  const int l = hb_ldp(s1);
+  return !IS_COMPLEX && (l == 8 || l == 16 || l == 32);
+}
+#ifndef HB_COMPLEX
+__global__ void __launch_bounds__(256) k_fwd_narrow(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts, const int *__restrict__ rowidx,
+                                                    const double *__restrict__ pan, double *b, double *y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t it = (int64_t)blockIdx.x * 8 + warp;
+  if (it >= nitems) return;
+  const FwdItem w = items[it];
+  const Front f = fronts[w.front];
+  const int s1 = f.s1;
+  if (!hb_narrow_front(s1)) return;
+  const int stride = hb_ldp(s1);  // one pivot block (s1 <= 32): block 0 of the trapezoid has the full width too
+  const bool pivot = w.rblk == 0;
+  const double *base = pivot ? pan + f.poff : pan + f.poff + hb_upd_off(s1) + (int64_t)(w.rblk - 1) * RB * stride;
+  const int nrows = pivot ? s1 : min(RB, f.s2 - RB * (w.rblk - 1));
+  const int G = stride >> 1, rpl = 32 / G;  // lanes per row, rows per warp-wide load
+  const int sub = lane % G, rsub = lane / G;
+  const double *bc = b + f.p0;
+  const double2 bz = make_double2(2 * sub < s1 ? __ldg(bc + 2 * sub) : 0.0, 2 * sub + 1 < s1 ? __ldg(bc + 2 * sub + 1) : 0.0);
+  const double2 *flat = reinterpret_cast<const double2 *>(base) + lane;
+  const int *rows = rowidx + f.rptr + (pivot ? 0 : RB * (w.rblk - 1));
+  const int nloads = (nrows + rpl - 1) / rpl;
+  for (int q0 = 0; q0 < nloads; q0 += 8) {
+    double2 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = ((q0 + u) * rpl + rsub < nrows) ? ldg_stream(flat + 32 * (q0 + u)) : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      double v = fma(t[u].x, bz.x, t[u].y * bz.y);
+      for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const int r = (q0 + u) * rpl + rsub;
+      if (sub == 0 && r < nrows) {
+        if (pivot) atomicAdd(&y[f.p0 + r], v);
+        else atomicAdd(&b[rows[r]], -v);
+      }
+    }
+  }
+}
+#endif
+
 template <int MU, bool COHERENT>
 __device__ __forceinline__ void fwd_blk_item(const FwdItem &w, int lane, const Front *__restrict__ fronts, const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n) {
   constexpr int R = 8 / MU, JU = MU;
@@ -188,10 +237,10 @@ __device__ __forceinline__ void fwd_blk_item(const FwdItem &w, int lane, const F
   }
   const int nc = min(cmax, w.c0 + w.cw) - w.c0;  // columns of this item
   if (nc <= 0) return;
+  const K *bc = b + f.p0 + w.c0;  // column m of the right-hand-side block: bc + m * n
   const int nv = (nc + VE - 1) / VE;
   const int st2 = stride / VE;  // row stride in 128-bit vectors
   const int rsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  const K *bc = b + f.p0 + w.c0;  // column m of the right-hand-side block: bc + m * n
   for (int r = 0; r < nrows; r += R) {
     const double2 *p = reinterpret_cast<const double2 *>(base + (int64_t)r * stride + w.c0);
     const int nr = min(R, nrows - r);
@@ -228,11 +277,13 @@ __device__ __forceinline__ void fwd_blk_item(const FwdItem &w, int lane, const F
 
 template <int MU>
 __global__ void __launch_bounds__(256, (IS_COMPLEX || MU == 4) ? 2 : (MU == 1 ? 4 : 3)) k_fwd_blk(const FwdItem *__restrict__ items, int64_t nitems, const Front *__restrict__ fronts,
-                                                                     const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n) {
+                                                                     const int *__restrict__ rowidx, const K *__restrict__ pan, K *b, K *y, int n, int skip_narrow = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t it = (int64_t)blockIdx.x * 8 + warp;
   if (it >= nitems) return;
-  fwd_blk_item<MU, false>(items[it], lane, fronts, rowidx, pan, b, y, n);
+  const FwdItem w = items[it];
+  if (MU == 1 && skip_narrow && hb_narrow_front(fronts[w.front].s1)) return;  // k_fwd_narrow takes these
+  fwd_blk_item<MU, false>(w, lane, fronts, rowidx, pan, b, y, n);
 }
 
 // Backward sweep work item.  NJ = slabs of 32 * VE columns covered per pass (NJ * MU <= 4 128-bit
@@ -465,7 +516,19 @@ static int launch_levels(Sub *s, cudaStream_t st) {
   for (int l = 0; l < S.nlevels; ++l) {
     const int64_t i0 = S.fwd_ptr[l], ni = S.fwd_ptr[l + 1] - i0;
     if (ni <= 0) continue;
-    if (MU == 1 && fwd1_l1) k_fwd_blk<1><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
+    if (MU == 1 && fwd1_l1) {
+      // HPDDM_B200_NARROW=1: items of narrow fronts go to k_fwd_narrow, the rest to the generic kernel
+      int64_t narrow = 0;
+#ifndef HB_COMPLEX
+      // opt-in: same-box A/B (profiles/README.md) 8.398 -> 8.434 ms at 128^3, 0.720 -> 0.734 ms at 64^3, 20.21 -> 20.26 ms at 160^3 -- the
+      // narrow levels hold 0.5 GB of 60, and the second launch per level costs what the better lane use gains
+      static const bool narrow_on = getenv("HPDDM_B200_NARROW") && !strcmp(getenv("HPDDM_B200_NARROW"), "1");
+      if (narrow_on)
+        for (int64_t q = i0; q < i0 + ni; ++q) narrow += hb_narrow_front(S.fronts[S.fwd[q].front].s1);
+      if (narrow > 0) k_fwd_narrow<<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y);
+#endif
+      if (narrow < ni) k_fwd_blk<1><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n, narrow > 0 ? 1 : 0);
+    }
     else if (MU > 1 && wide) k_fwd<(MU > 1 ? MU : 2), 2><<<(unsigned)((ni + 7) / 8), 256, smem2, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
     else if (blk) k_fwd_blk<(MU > 1 ? MU : 2)><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
     else k_fwd<MU><<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(D.fwd + i0, ni, D.fronts, D.rowidx, D.panL, D.b, D.y, n);
