@@ -76,7 +76,7 @@ static int nccl_load() {
       return HPDDM_B200_ERR_NCCL;                                                          \
     }                                                                                      \
   } while (0)
-constexpr int NCCL_INT32 = 2, NCCL_F64 = 8, NCCL_SUM = 0;
+constexpr int NCCL_F64 = 8, NCCL_SUM = 0;
 
 static int need_nccl(Ctx *c) {
   if (c->nccl) return 0;
