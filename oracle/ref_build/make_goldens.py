@@ -50,6 +50,22 @@ CASES = {
                                                               "-generate_random_rhs", "2", "-penalise", "1"]),
     "small_40x40_p4_penalised_bgmres_mu4": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "bgmres", "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "4", "-penalise", "1"]),
     "complex_40x40_p4_penalised_ras": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40", "-penalise", "1"]),
+    # IterativeMethod::GCRODR (GCRODR.hpp:35-444; the Krylov method of BASELINE config 5): restarted cycles with a recycled subspace,
+    # successive solves reusing the pair (U, C) kept in A.storage() (-solves N, see ref_driver.cpp), several right-hand sides,
+    # a two-level preconditioner, complex scalars; verbosity 3 keeps the reference's residual history in the golden's log
+    "small_40x40_p4_gcrodr_m8_k4_solves3": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "gcrodr", "-hpddm_gmres_restart", "8", "-hpddm_recycle", "4",
+                                                           "-Nx", "40", "-Ny", "40", "-solves", "3", "-hpddm_verbosity", "3"]),
+    "small_40x40_p4_gcrodr_m40_k10_solves2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "gcrodr", "-hpddm_recycle", "10",
+                                                             "-Nx", "40", "-Ny", "40", "-solves", "2", "-hpddm_verbosity", "3"]),
+    "small_40x40_p4_gcrodr_m8_k3_mu2_solves2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "gcrodr", "-hpddm_gmres_restart", "8", "-hpddm_recycle", "3",
+                                                               "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "2", "-solves", "2", "-hpddm_verbosity", "3"]),
+    "small_40x40_p4_gcrodr_m6_k2_twolevel_solves2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3",
+                                                                    "-hpddm_krylov_method", "gcrodr", "-hpddm_gmres_restart", "6", "-hpddm_recycle", "2", "-hpddm_tol", "1e-9",
+                                                                    "-Nx", "40", "-Ny", "40", "-solves", "2", "-hpddm_verbosity", "3"]),
+    "small_40x40_p4_gcrodr_m8_k3_sr_solves2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "gcrodr", "-hpddm_gmres_restart", "8", "-hpddm_recycle", "3",
+                                                              "-hpddm_recycle_target", "SR", "-hpddm_tol", "1e-7", "-Nx", "40", "-Ny", "40", "-solves", "2", "-hpddm_verbosity", "3"]),
+    "complex_40x40_p4_gcrodr_m8_k3_solves2": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "gcrodr", "-hpddm_gmres_restart", "8", "-hpddm_recycle", "3",
+                                                                     "-Nx", "40", "-Ny", "40", "-solves", "2", "-hpddm_verbosity", "3"]),
     # complex scalars (the reference's FORCE_COMPLEX build; damped-Helmholtz-like shift of the generator's matrix, see ref_driver.cpp)
     "complex_40x40_p4_ras": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-Nx", "40", "-Ny", "40"]),
     "complex_40x40_p4_twolevel_nu3": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_schwarz_coarse_correction", "deflated", "-deflation_vectors", "3", "-Nx", "40", "-Ny", "40"]),

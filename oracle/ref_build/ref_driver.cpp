@@ -46,6 +46,7 @@ int main(int argc, char **argv) {
              std::forward_as_tuple("nonuniform=(0|1)", "Use a different number of eigenpairs to compute on each subdomain.", HPDDM::Option::Arg::argument),
              std::forward_as_tuple("deflation_vectors=<0>", "Number of analytic deflation vectors per subdomain (golden runs).", HPDDM::Option::Arg::integer),
              std::forward_as_tuple("penalise=(0|1)", "Impose non-homogeneous Dirichlet data on the side y = 0 by penalisation (golden runs).", HPDDM::Option::Arg::argument),
+             std::forward_as_tuple("solves=<1>", "Number of successive solves with the same operator (golden runs of the recycling drivers).", HPDDM::Option::Arg::positive),
              std::forward_as_tuple("prefix=<string>", "Use a prefix.", HPDDM::Option::Arg::argument)});
   std::string out = getenv("HPDDM_REF_DUMP") ? getenv("HPDDM_REF_DUMP") : "golden";
   out += "_" + std::to_string(rankWorld) + ".bin";
@@ -190,6 +191,29 @@ int main(int argc, char **argv) {
   dumpd("sol", sol, (long long)mu * ndof);
   dumpd("residual", storage.data(), 2 * mu);
   if (rankWorld == 0) printf("ref_driver: %d ranks, ndof %d, nu %d, it %d, residual %.3e / %.3e\n", sizeWorld, ndof, nu, it, storage[1], storage[0]);
+  // -solves N: N - 1 further solves with the same operator and new right-hand sides, zero initial guess -- the recycled subspace
+  // (U, C) kept in A.storage() by GCRO-DR (GCRODR.hpp:64-69,94-130,245) is reused: f_s[:, nu] = (1 + nu / 2) A w_s + f[:, nu] / 4 with
+  // w_s a consistent vector (linear combinations of consistent vectors stay consistent)
+  const int solves = opt.app().find("solves") != opt.app().cend() ? (int)opt.app()["solves"] : 1;
+  for (int sidx = 2; sidx <= solves; ++sidx) {
+    std::vector<K> ws(ndof), Aw(ndof), fs((size_t)mu * ndof);
+    for (int i = 0; i < ndof; ++i) ws[i] = cplx_probe(std::cos(0.19 * sidx * i + 0.07 * rankWorld) + 0.25, std::sin(0.13 * i) + 0.1 * rankWorld);
+    A.exchange<true>(ws.data(), 1);
+    bool alloc = A.setBuffer();
+    A.GMV(ws.data(), Aw.data(), 1);
+    A.clearBuffer(alloc);
+    for (int c = 0; c < mu; ++c)
+      for (int i = 0; i < ndof; ++i) fs[(size_t)c * ndof + i] = K(1.0 + 0.5 * c) * Aw[i] + K(0.25) * f[(size_t)c * ndof + i];
+    std::fill_n(sol, (size_t)mu * ndof, K());
+    int its = HPDDM::IterativeMethod::solve(A, fs.data(), sol, mu, A.getCommunicator());
+    A.computeResidual(sol, fs.data(), storage.data(), mu);
+    const std::string tag = std::to_string(sidx);
+    dumpd(("f" + tag).c_str(), fs.data(), (long long)mu * ndof);
+    dumpi(("iterations" + tag).c_str(), &its, 1);
+    dumpd(("sol" + tag).c_str(), sol, (long long)mu * ndof);
+    dumpd(("residual" + tag).c_str(), storage.data(), 2 * mu);
+    if (rankWorld == 0) printf("ref_driver: solve %d, it %d, residual %.3e / %.3e\n", sidx, its, storage[1], storage[0]);
+  }
   fclose(g_out);
   delete[] d;
   delete MatNeumann;

@@ -42,7 +42,15 @@ def load(name):
                 sym=arg_value(args, "symmetric_csr", "0") == "1", nu=int(arg_value(args, "deflation_vectors", 0)),
                 restart=int(arg_value(args, "hpddm_gmres_restart", 40)), max_it=int(arg_value(args, "hpddm_max_it", 100)),
                 tol=float(arg_value(args, "hpddm_tol", 1e-6)), method=arg_value(args, "hpddm_schwarz_method", "ras"),
-                krylov=arg_value(args, "hpddm_krylov_method", "gmres"), penalised=arg_value(args, "penalise", "0") == "1")
+                krylov=arg_value(args, "hpddm_krylov_method", "gmres"), penalised=arg_value(args, "penalise", "0") == "1",
+                recycle=int(arg_value(args, "hpddm_recycle", 0)), solves=int(arg_value(args, "solves", 1)),
+                recycle_target=arg_value(args, "hpddm_recycle_target", "SM"))
+    # -solves N (recycling drivers): right-hand side / solution / iteration count of solve s >= 2 as f{s}, sol{s}, iterations{s}
+    for r in range(P):
+        n = parts[r]["ndof"]
+        for s in range(2, meta["solves"] + 1):
+            for key in (f"f{s}", f"sol{s}"):
+                ref[r][key] = np.asfortranarray(ref[r][key].reshape(-1, n).T)
     return parts, ref, meta
 
 

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from hpddm_b200.examples.generate import generate2d
+from oracle.gcrodr import gcrodr
 from oracle.krylov import OracleOperator, bgmres, cg, gmres
 from oracle.schwarz import ADDITIVE, BALANCED, DEFLATED, SchwarzWorld
 from tests.golden_util import cases, col, complexify, load, penalise
@@ -65,6 +66,22 @@ def test_oracle_reproduces_the_reference(name):
             assert max(rel(got[r], ref[r][key]) for r in range(P)) < TOL, key
         corr = DEFLATED
     b = [parts[r]["f"].copy() for r in range(P)]
+    if meta["krylov"] == "gcrodr":
+        # IterativeMethod::GCRODR over successive solves that share the recycled pair (U, C): identical iteration counts and
+        # solutions for every solve of the sequence (the first one builds the pair, the later ones start from it)
+        state = None
+        for s in range(1, meta["solves"] + 1):
+            tag = "" if s == 1 else str(s)
+            bs = b if s == 1 else [ref[r]["f" + tag].copy() for r in range(P)]
+            it, x, state = gcrodr(OracleOperator(w, corr), bs, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"], recycle=meta["recycle"], state=state,
+                                  target=meta["recycle_target"])
+            assert it == int(ref[0]["iterations" + tag][0]), (s, it)
+            assert max(rel(x[r], ref[r]["sol" + tag]) for r in range(P)) < 1e-9, s
+            res = w.compute_residual(x, bs)
+            gold = ref[0]["residual" + tag].reshape(-1, 2)
+            assert np.abs(res[:, 0] - gold[:, 0]).max() < 1e-10 * gold[:, 0].max()
+            assert np.all(np.abs(res[:, 1] - gold[:, 1]) < 1e-5 * gold[:, 1])
+        return
     if meta["krylov"] == "cg":
         it, x = cg(OracleOperator(w, corr), b, max_it=meta["max_it"], tol=meta["tol"])
     elif meta["krylov"] == "bgmres":
