@@ -82,6 +82,9 @@ _SIGS = {
     "hpddm_b200_solve": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
     "hpddm_b200_solve_bgmres": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
     "hpddm_b200_solve_cg": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
+    "hpddm_b200_solve_gcrodr": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
+    "hpddm_b200_recycle_dim": (C.c_int, [_P]),
+    "hpddm_b200_recycle_destroy": (C.c_int, [_P]),
 }
 # the complex instantiation exports the same set under the hpddm_b200z_ prefix, with identical
 # argument shapes (scalars travel behind pointers)

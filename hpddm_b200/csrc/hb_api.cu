@@ -658,6 +658,7 @@ int HB_API(ctx_destroy)(hb_ctx_t *ctx) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   hostreg_release(c);
+  gcrodr_release(c);
   for (auto &g : c->apply_graphs)
     if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   p2p_free(c);
@@ -765,6 +766,7 @@ int HB_API(sub_destroy)(hb_sub_t *sub) {
   cudaStreamSynchronize(c->stream);
   c->subs.erase(std::remove(c->subs.begin(), c->subs.end(), s), c->subs.end());
   for (Sub *o : c->subs) o->peer_seg.clear();  // links into the destroyed subdomain are rebuilt by the next check_ready
+  gcrodr_release(c);                            // a recycled pair belongs to the decomposition it was built on
   c->mu_cap = 0;
   c->epoch++;
   sub_free(s);

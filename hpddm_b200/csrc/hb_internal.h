@@ -238,6 +238,7 @@ struct Ctx {
   std::vector<HostRange> hostreg;
   std::unordered_map<uintptr_t, int> host_seen;
   int64_t hostreg_calls = 0;  // successful cudaHostRegister calls (statistics / tests)
+  void *recycled = nullptr;   // GCRO-DR: recycled pair (U, C) kept between solves (hb_krylov.cu, released by gcrodr_release)
 };
 
 // ---------------------------------------------------------------- kernels (launchers)
@@ -318,5 +319,6 @@ int k_scal_copy(Ctx *c, int64_t n, double a, const K *x, K *y);                 
 // block Krylov helpers: W (n x mu) += sign * V (n x k, ld n) * H (k x mu, ld ldh, device) ; W <- W * R (R mu x mu upper, device)
 int k_vupdate_blk(Ctx *c, int n, int k, int mu, const K *V, const K *H, int ldh, double sign, K *W);
 int k_rmul_upper(Ctx *c, int n, int mu, const K *R, K *W);
+void gcrodr_release(Ctx *c);  // frees the recycled pair of the GCRO-DR driver, if any
 
 }  // namespace hb

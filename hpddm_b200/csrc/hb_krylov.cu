@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "hb_gcrodr.h"
 #include "hb_internal.h"
 
 namespace hb {
@@ -630,6 +631,162 @@ int bgmres_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *
 #undef KRC
 }
 
+
+// ------------------------------------------------------------------ GCRO-DR
+// IterativeMethod::GCRODR (include/HPDDM_GCRODR.hpp:35-444).  The driver is hb_gcrodr.cpp (host logic: Hessenberg matrices, rotations,
+// harmonic Ritz problems -- checked on the CPU against goldens of the unmodified reference through tests/native/gcrodr_host.cpp); this is
+// its vector space: Krylov basis, recycled pair (U, C) and every product stay in HBM, built from the kernels of the drivers above.
+namespace {
+
+struct RecycledDev {  // Ctx::recycled: the pair survives between solves like the reference's A.storage() (HPDDM_option.hpp:445-454)
+  gcro::Recycled r;
+  std::vector<int> n;  // subdomain sizes it was built for
+};
+
+struct DeviceBackend : gcro::Backend {
+  Ctx *c;
+  int mu, correction, cap;
+  K *d_T = nullptr, *d_h = nullptr;
+  RecycledDev *rec;
+  DeviceBackend(Ctx *c_, int mu_, int correction_, int cap_, RecycledDev *rec_) : c(c_), mu(mu_), correction(correction_), cap(cap_), rec(rec_) {}
+  ~DeviceBackend() override {
+    cudaFree(d_T);
+    cudaFree(d_h);
+  }
+  int init() {
+    HB_CUDA(cudaMalloc(&d_T, (size_t)cap * mu * sizeof(K)));
+    HB_CUDA(cudaMalloc(&d_h, (size_t)cap * sizeof(K)));
+    return 0;
+  }
+  size_t subs() const override { return c->subs.size(); }
+  int64_t rows(size_t q) const override { return c->subs[q]->n; }
+  K *colp(const gcro::Vec &v, size_t q, int nu) const { return v[q] + (size_t)nu * c->subs[q]->n; }
+  int alloc(gcro::Vec &v, int blocks) override {
+    v.assign(c->subs.size(), nullptr);
+    for (size_t q = 0; q < v.size(); ++q) {
+      const size_t bytes = std::max<size_t>((size_t)c->subs[q]->n * mu * blocks, 1) * sizeof(K);
+      cudaError_t e = cudaMalloc(&v[q], bytes);
+      if (e == cudaSuccess) e = cudaMemsetAsync(v[q], 0, bytes, c->stream);
+      if (e != cudaSuccess) {
+        set_error("CUDA error %s while allocating %zu bytes of Krylov vectors (GCRO-DR)", cudaGetErrorString(e), bytes);
+        release(v);
+        return e == cudaErrorMemoryAllocation ? HPDDM_B200_ERR_NOMEM : HPDDM_B200_ERR_CUDA;
+      }
+    }
+    return 0;
+  }
+  void release(gcro::Vec &v) override {
+    if (v.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (K *p : v) cudaFree(p);
+    v.clear();
+  }
+  gcro::Recycled &recycled() override { return rec->r; }
+  int start(const gcro::Vec &b, const gcro::Vec &x) override {  // Schwarz::start (schwarz.hpp:496-514): penalised rows + exchange(x)
+    for (size_t q = 0; q < c->subs.size(); ++q) {
+      Sub *s = c->subs[q];
+      HB_CHECK(k_bc(c, s, mu, b[q], x[q]));
+      HB_CHECK(k_scale(c, s->n, mu, s->d_d, x[q], x[q]));
+    }
+    return halo(c, x.data(), mu);
+  }
+  int rhs_norms(const gcro::Vec &b, std::vector<double> &out) override {
+    const std::vector<const K *> cb(b.begin(), b.end());
+    out.resize(mu);
+    return hb::rhs_norms(c, cb, mu, out);
+  }
+  int apply(const gcro::Vec &in, const gcro::Vec &out) override {
+    const std::vector<const K *> cin(in.begin(), in.end());
+    return apply_core(c, cin, out, mu, correction);
+  }
+  int gmv(const gcro::Vec &in, const gcro::Vec &out) override {
+    const std::vector<const K *> cin(in.begin(), in.end());
+    return gmv_core(c, cin, out, mu);
+  }
+  int dots(int count, const gcro::Vec &basis, const gcro::Vec &w, std::vector<K> &out) override {
+    if (count > cap) {
+      set_error("GCRO-DR: %d products exceed the staging capacity %d", count, cap);
+      return HPDDM_B200_ERR_STATE;
+    }
+    return hb::dots(c, count, mu, basis, w, d_T, out);
+  }
+  int combine_col(int nu, int count, const gcro::Vec &basis, const K *coef, double alpha, const gcro::Vec &w) override {
+    if (count <= 0) return 0;
+    if (count > cap) {
+      set_error("GCRO-DR: %d coefficients exceed the staging capacity %d", count, cap);
+      return HPDDM_B200_ERR_STATE;
+    }
+    // pageable source: the call returns once the coefficients are staged, the caller may reuse `coef`; the copy and the kernels
+    // that read d_h are ordered on the context's stream
+    HB_CUDA(cudaMemcpyAsync(d_h, coef, (size_t)count * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+    for (size_t q = 0; q < c->subs.size(); ++q)
+      HB_CHECK(k_vupdate(c, c->subs[q], count, colp(basis, q, nu), (int64_t)mu * c->subs[q]->n, d_h, alpha, colp(w, q, nu)));
+    return 0;
+  }
+  int scal_col(int nu, double a, const gcro::Vec &in, const gcro::Vec &out) override {
+    for (size_t q = 0; q < c->subs.size(); ++q) HB_CHECK(k_scal_copy(c, c->subs[q]->n, a, colp(in, q, nu), colp(out, q, nu)));
+    return 0;
+  }
+  int axpy_col(int nu, double a, const gcro::Vec &in, const gcro::Vec &out) override {
+    for (size_t q = 0; q < c->subs.size(); ++q) HB_CHECK(k_axpy(c, c->subs[q]->n, a, colp(in, q, nu), colp(out, q, nu)));
+    return 0;
+  }
+  int zero_col(int nu, const gcro::Vec &out) override {
+    for (size_t q = 0; q < c->subs.size(); ++q)
+      if (c->subs[q]->n) HB_CUDA(cudaMemsetAsync(colp(out, q, nu), 0, (size_t)c->subs[q]->n * sizeof(K), c->stream));
+    return 0;
+  }
+};
+
+}  // namespace
+
+void gcrodr_release(Ctx *c) {
+  RecycledDev *rd = static_cast<RecycledDev *>(c->recycled);
+  if (!rd) return;
+  cudaStreamSynchronize(c->stream);
+  for (K *p : rd->r.U) cudaFree(p);
+  for (K *p : rd->r.C) cudaFree(p);
+  delete rd;
+  c->recycled = nullptr;
+}
+
+int gcrodr_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *> &x, int mu, int correction, int restart, int recycle, int target, int strategy,
+                  int max_it, double tol, int *iterations, double *rel_residual) {
+  if (recycle <= 0) return gmres_device(c, b, x, mu, correction, restart, max_it, tol, iterations, rel_residual);  // GCRODR.hpp:50-55
+  RecycledDev *rd = static_cast<RecycledDev *>(c->recycled);
+  std::vector<int> sizes;
+  for (Sub *s : c->subs) sizes.push_back(s->n);
+  if (rd && rd->n != sizes) {  // the decomposition changed under the stored pair
+    gcrodr_release(c);
+    rd = nullptr;
+  }
+  if (!rd) {
+    rd = new RecycledDev();
+    rd->n = sizes;
+    c->recycled = rd;
+  }
+  const int m = std::min(restart, max_it);
+  DeviceBackend be(c, mu, correction, m + 2, rd);
+  HB_CHECK(be.init());
+  gcro::Params p;
+  p.mu = mu;
+  p.restart = restart;
+  p.recycle = recycle;
+  p.max_it = max_it;
+  p.tol = tol;
+  p.target = target;
+  p.strategy = strategy;
+  gcro::Vec bv(b.size());
+  for (size_t q = 0; q < b.size(); ++q) bv[q] = const_cast<K *>(b[q]);  // the driver only reads b
+  const int rc = gcro::run(be, bv, x, p, iterations, rel_residual);
+  cudaStreamSynchronize(c->stream);
+  if (rc == gcro::ERR_EIGENSOLVER) {
+    set_error("solve_gcrodr: the harmonic Ritz eigenproblem of a cycle could not be solved (QR iteration did not converge or singular pencil)");
+    return HPDDM_B200_ERR_NUMERIC;
+  }
+  return rc;
+}
+
 }  // namespace hb
 
 using namespace hb;
@@ -724,4 +881,30 @@ extern "C" int HB_API(solve_bgmres)(hb_ctx_t *ctx, const K *const *b, K *const *
   return krylov_entry(c, b, x, mu, where, [&](const std::vector<const K *> &bd, const std::vector<K *> &xd) {
     return bgmres_device(c, bd, xd, mu, correction, std::min(restart, max_it), max_it, tol, iterations, rel_residual);
   });
+}
+
+extern "C" int HB_API(solve_gcrodr)(hb_ctx_t *ctx, const K *const *b, K *const *x, int mu, int correction, int restart, int recycle, int recycle_target,
+                                       int recycle_strategy, int max_it, double tol, int where, int *iterations, double *rel_residual) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !iterations || restart < 1 || max_it < 1 || mu < 1 || recycle_target < 0 || recycle_target > 5 || recycle_strategy < 0 || recycle_strategy > 1) {
+    set_error("solve_gcrodr: bad arguments");
+    return HPDDM_B200_ERR_ARG;
+  }
+  *iterations = 0;
+  return krylov_entry(c, b, x, mu, where, [&](const std::vector<const K *> &bd, const std::vector<K *> &xd) {
+    return gcrodr_device(c, bd, xd, mu, correction, restart, recycle, recycle_target, recycle_strategy, max_it, tol, iterations, rel_residual);
+  });
+}
+
+extern "C" int HB_API(recycle_dim)(hb_ctx_t *ctx) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  return c && c->recycled ? static_cast<RecycledDev *>(c->recycled)->r.k : 0;
+}
+
+extern "C" int HB_API(recycle_destroy)(hb_ctx_t *ctx) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c) return HPDDM_B200_ERR_ARG;
+  cudaSetDevice(c->device);
+  gcrodr_release(c);
+  return 0;
 }

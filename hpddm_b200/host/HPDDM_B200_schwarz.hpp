@@ -336,7 +336,10 @@ public:
     const K          *bb[1] = {f};
     K                *xx[1] = {x};
     int               it = 0, rc;
-    if (method == HPDDM_KRYLOV_METHOD_BGMRES) rc = A_::solve_bgmres(ctx_, bb, xx, mu, correction(), restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
+    if (method == HPDDM_KRYLOV_METHOD_GCRODR)  // -hpddm_recycle / _recycle_target / _recycle_strategy as IterativeMethod::options reads them (iterative.hpp:215-217)
+      rc = A_::solve_gcrodr(ctx_, bb, xx, mu, correction(), restart, opt.val<int>(prefix + "recycle", 0), opt.val<char>(prefix + "recycle_target", HPDDM_RECYCLE_TARGET_SM),
+                            opt.val<char>(prefix + "recycle_strategy", HPDDM_RECYCLE_STRATEGY_A), max_it, tol, HPDDM_B200_HOST, &it, nullptr);
+    else if (method == HPDDM_KRYLOV_METHOD_BGMRES) rc = A_::solve_bgmres(ctx_, bb, xx, mu, correction(), restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     else if (method == HPDDM_KRYLOV_METHOD_CG) rc = A_::solve_cg(ctx_, bb, xx, mu, correction(), max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     else rc = A_::solve(ctx_, bb, xx, mu, correction(), restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     return rc < 0 ? rc : it;

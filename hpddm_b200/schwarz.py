@@ -347,6 +347,27 @@ class Decomposition:
                                              capi.HOST, C.byref(it), capi.ptr(res)))
         return it.value, x, res
 
+    # IterativeMethod::GCRODR (include/HPDDM_GCRODR.hpp:35-444) on the device: Krylov basis and recycled pair (U, C) in HBM; the pair
+    # stays in the context between calls (the reference keeps it in A.storage()), recycle_destroy() drops it
+    RECYCLE_TARGET = {"SM": 0, "LM": 1, "SR": 2, "LR": 3, "SI": 4, "LI": 5}
+
+    def solve_gcrodr(self, b, x0=None, correction="__default__", restart=40, recycle=10, max_it=100, tol=1e-6, target="SM", strategy="A"):
+        corr = self.correction if correction == "__default__" else correction
+        b = [_f(v, self.dtype) for v in b]
+        x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v, self.dtype).copy(order="F") for v in x0]
+        mu = b[0].shape[1]
+        it = C.c_int(0)
+        res = np.zeros(mu)
+        self.api.check(self.api.solve_gcrodr(self.ctx, capi.ptr_array(b), capi.ptr_array(x), mu, capi.CORRECTION[corr], int(restart), int(recycle),
+                                             self.RECYCLE_TARGET[target], {"A": 0, "B": 1}[strategy], int(max_it), float(tol), capi.HOST, C.byref(it), capi.ptr(res)))
+        return it.value, x, res
+
+    def recycle_dim(self):
+        return int(self.api.recycle_dim(self.ctx))
+
+    def recycle_destroy(self):
+        self.api.check(self.api.recycle_destroy(self.ctx))
+
     # IterativeMethod::CG (include/HPDDM_CG.hpp:31-168) on the device (falls back to GMRES like the reference when the
     # preconditioner is not symmetric: RAS / ORAS or a deflated correction)
     def solve_cg(self, b, x0=None, correction="__default__", max_it=100, tol=1e-6):

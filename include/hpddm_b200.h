@@ -231,6 +231,29 @@ int hpddm_b200_solve_cg(hpddm_b200_ctx *ctx, const double *const *b, double *con
 int hpddm_b200_solve_bgmres(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int correction, int restart, int max_it, double tol, int where,
                             int *iterations, double *rel_residual);
 
+/* IterativeMethod::GCRODR (include/HPDDM_GCRODR.hpp:35-444; the Krylov method of BASELINE config 5) with the Krylov basis and the
+ * recycled pair (U, C = A M^-1 U, C^H D C = I) resident in HBM and the reference defaults (iterative.hpp:197-218): right
+ * preconditioning, classical Gram-Schmidt, CholQR.  restart = -hpddm_gmres_restart, recycle = -hpddm_recycle (clipped to restart - 1;
+ * <= 0 runs GMRES as the reference does, GCRODR.hpp:50-55), recycle_target = HPDDM_B200_RECYCLE_TARGET_* (-hpddm_recycle_target),
+ * recycle_strategy = HPDDM_B200_RECYCLE_STRATEGY_* (-hpddm_recycle_strategy).  Every right-hand side has its own Krylov space and
+ * pair, all columns share each preconditioner apply / operator product.  The pair stays in the context between calls the way the
+ * reference keeps it in A.storage() (HPDDM_option.hpp:445-454): the first solve builds it from the harmonic Ritz vectors of its first
+ * GMRES(m) cycle, later solves start from it (GCRODR.hpp:94-130); hpddm_b200_recycle_destroy drops it (Subdomain::destroy does the
+ * same in the reference); a pair built for another number of right-hand sides or another decomposition is dropped and rebuilt. */
+#define HPDDM_B200_RECYCLE_TARGET_SM 0 /* HPDDM_define.hpp:169-174 */
+#define HPDDM_B200_RECYCLE_TARGET_LM 1
+#define HPDDM_B200_RECYCLE_TARGET_SR 2
+#define HPDDM_B200_RECYCLE_TARGET_LR 3
+#define HPDDM_B200_RECYCLE_TARGET_SI 4
+#define HPDDM_B200_RECYCLE_TARGET_LI 5
+#define HPDDM_B200_RECYCLE_STRATEGY_A 0 /* HPDDM_define.hpp:166-167 */
+#define HPDDM_B200_RECYCLE_STRATEGY_B 1
+int hpddm_b200_solve_gcrodr(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int correction, int restart, int recycle, int recycle_target,
+                            int recycle_strategy, int max_it, double tol, int where, int *iterations, double *rel_residual);
+/* dimension k of the stored pair (0: none) / release it */
+int hpddm_b200_recycle_dim(hpddm_b200_ctx *ctx);
+int hpddm_b200_recycle_destroy(hpddm_b200_ctx *ctx);
+
 /* ---- host-only planning entry points (no GPU needed): the N > 1 logic the hot path uses, exposed so that CPU-only multi-process
  * tests exercise the product's own code.  coarse_layout: offsets[nproc + 1] of the process blocks of the coarse vector and the padded
  * block length of the communication layout.  halo_schedule: the ordered NCCL sends / receives of one halo round for the `nlocal`

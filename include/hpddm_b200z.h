@@ -196,6 +196,12 @@ int hpddm_b200z_solve_cg(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpd
 int hpddm_b200z_solve_bgmres(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpddm_b200_z *const *x, int mu, int correction, int restart, int max_it, double tol,
                              int where, int *iterations, double *rel_residual);
 
+/* IterativeMethod::GCRODR (include/HPDDM_GCRODR.hpp:35-444); see hpddm_b200_solve_gcrodr (targets / strategies: HPDDM_B200_RECYCLE_*) */
+int hpddm_b200z_solve_gcrodr(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpddm_b200_z *const *x, int mu, int correction, int restart, int recycle,
+                             int recycle_target, int recycle_strategy, int max_it, double tol, int where, int *iterations, double *rel_residual);
+int hpddm_b200z_recycle_dim(hpddm_b200z_ctx *ctx);
+int hpddm_b200z_recycle_destroy(hpddm_b200z_ctx *ctx);
+
 /* ---- host-only planning entry points (no GPU needed): the N > 1 logic the hot path uses, exposed so that CPU-only multi-process
  * tests exercise the product's own code.  coarse_layout: offsets[nproc + 1] of the process blocks of the coarse vector and the padded
  * block length of the communication layout.  halo_schedule: the ordered NCCL sends / receives of one halo round for the `nlocal`

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from hpddm_b200 import KrylovOperator
+from oracle.gcrodr import gcrodr
 from oracle.krylov import cg, gmres
 from oracle.schwarz import SchwarzWorld
 from tests.golden_util import cases, col, load
@@ -57,7 +58,19 @@ def test_cuda_path_reproduces_the_reference(name):
     # tests/test_golden_reference.py): +-1 iteration there, exact counts everywhere else
     sensitive = meta["krylov"] == "bgmres" and it_ref > meta["restart"]
     slack, xtol = (1, 1e-5) if sensitive else (0, 1e-7)
-    if meta["krylov"] != "bgmres":   # host-driven: the restated reference driver on top of the C ABI hot path
+    if meta["krylov"] == "gcrodr":
+        # IterativeMethod::GCRODR, host-driven on top of the C ABI hot path (the restated driver of oracle/gcrodr.py, pinned by these
+        # goldens on the CPU): every solve of the sequence sharing the recycled pair reproduces the reference's count and solution.
+        # The device-resident driver (hpddm_b200[z]_solve_gcrodr) has its own file: tests/test_gpu_gcrodr.py.
+        state = None
+        for s in range(1, meta["solves"] + 1):
+            tag = "" if s == 1 else str(s)
+            bs = b if s == 1 else [ref[r]["f" + tag].copy() for r in range(P)]
+            it, x, state = gcrodr(KrylovOperator(deco, corr), bs, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"], recycle=meta["recycle"], state=state,
+                                  target=meta["recycle_target"])
+            assert it == int(ref[0]["iterations" + tag][0]), (s, it)
+            assert max(rel(x[r], ref[r]["sol" + tag]) for r in range(P)) < 1e-7, s
+    elif meta["krylov"] != "bgmres":   # host-driven: the restated reference driver on top of the C ABI hot path
         if meta["krylov"] == "cg":
             it, x = cg(KrylovOperator(deco, corr), b, max_it=meta["max_it"], tol=meta["tol"])
         else:
@@ -65,7 +78,9 @@ def test_cuda_path_reproduces_the_reference(name):
         assert it == it_ref                                   # identical Krylov iteration count
         assert max(rel(x[r], ref[r]["sol"]) for r in range(P)) < 1e-7
     # device-resident driver (hpddm_b200[z]_solve: all right-hand sides advance together, Krylov basis in HBM)
-    if meta["krylov"] == "cg":
+    if meta["krylov"] == "gcrodr":
+        it_dev, x_dev = it_ref, [ref[r]["sol"] for r in range(P)]   # see tests/test_gpu_gcrodr.py
+    elif meta["krylov"] == "cg":
         it_dev, x_dev, res = deco.solve_cg(b, correction=corr, max_it=meta["max_it"], tol=meta["tol"])
     elif meta["krylov"] == "bgmres":
         it_dev, x_dev, res = deco.solve_bgmres(b, correction=corr, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])
