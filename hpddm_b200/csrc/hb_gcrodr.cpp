@@ -444,7 +444,16 @@ int run(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iteration
       GC(be.scal_col(nu, -1.0, vi, vi));
       GC(be.axpy_col(nu, 1.0, b, vi));
     }
-    if (j == 1 && haveU) {  // GCRODR.hpp:94-130: C = A M^-1 U, CholQR, r <- (I - C C^H D) r, x += M^-1 U C^H D r
+    if (j == 1 && haveU && p.same_system) {  // GCRODR.hpp:115-129 with id[4] / 4 != 0: C still is A M^-1 U; r <- (I - C C^H D) r, x += M^-1 (U C^H D r)
+      GC(be.dots(k, rec.C, vi, hv));
+      for (int nu = 0; nu < mu; ++nu) {
+        GC(be.zero_col(nu, work));
+        GC(be.combine_col(nu, k, rec.C, &hv[(size_t)nu * k], -1.0, vi));
+        GC(be.combine_col(nu, k, rec.U, &hv[(size_t)nu * k], 1.0, work));
+      }
+      GC(be.apply(work, z));
+      for (int nu = 0; nu < mu; ++nu) GC(be.axpy_col(nu, 1.0, z, x));
+    } else if (j == 1 && haveU) {  // GCRODR.hpp:94-130: C = A M^-1 U, CholQR, r <- (I - C C^H D) r, x += M^-1 U C^H D r
       GC(be.alloc(pt, k));
       for (int c = 0; c < k; ++c) {
         Vec uc = block(be, rec.U, c, mu), pc = block(be, pt, c, mu), cc = block(be, rec.C, c, mu);
@@ -569,7 +578,7 @@ int run(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iteration
     }
     // updateSolRecycling (iterative.hpp:338-393): y = R^-1 s, x += M^-1 (U (C^H D r - B y) + V y)
     std::vector<K> cr;
-    if (haveU) {
+    if (haveU && !p.same_system) {
       GC(be.dots(k, rec.C, v(shift), hv));
       cr = hv;
     }
@@ -589,7 +598,7 @@ int run(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iteration
       if (haveU) {
         std::vector<zc> su(k);
         for (int c = 0; c < k; ++c) {
-          su[c] = resnorm[nu] * to_z(cr[(size_t)nu * k + c]);
+          su[c] = p.same_system ? zc(0.0) : resnorm[nu] * to_z(cr[(size_t)nu * k + c]);  // iterative.hpp:351: `same` drops C^H D r
           for (int l = shift; l < dim; ++l) su[c] -= cn.B(c, l) * y[l - shift];
         }
         GC(be.combine_col(nu, k, rec.U, tok(su, 0, k), 1.0, work));
@@ -606,7 +615,9 @@ int run(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iteration
       Vec last = v(m);
       for (int nu = 0; nu < mu; ++nu) GC(be.scal_col(nu, 1.0 / col[nu].save(i, i - 1).real(), last, last));
     }
-    if (!haveU) {  // GCRODR.hpp:242-316: the first pair, from the harmonic Ritz vectors of GMRES(m)
+    if (p.same_system > 1) {
+      // GCRODR.hpp:239: id[4] / 4 <= 1 guards both branches below -- the stored pair is used as is
+    } else if (!haveU) {  // GCRODR.hpp:242-316: the first pair, from the harmonic Ritz vectors of GMRES(m)
       int dim = 0;
       bool first = true;
       for (int nu = 0; nu < mu; ++nu)

@@ -52,6 +52,11 @@ struct Params {
   double tol = 1e-6;
   int target = 0;    // HPDDM_RECYCLE_TARGET_SM .. LI (HPDDM_define.hpp:169-174)
   int strategy = 0;  // HPDDM_RECYCLE_STRATEGY_A / B (HPDDM_define.hpp:166-167)
+  // -hpddm_recycle_same_system as IterativeMethod::options reads it (iterative.hpp:217; the reference raises the option from 1 to 2
+  // after a converged solve, GCRODR.hpp:435): 0 = the operator may have changed, C = A M^-1 U is recomputed when a later solve starts;
+  // 1 = same operator: the pair is built / updated, C^H D r is taken as zero in the solution update (iterative.hpp:351); 2 = same
+  // operator, the stored pair is used as is (no product with A M^-1, no update)
+  int same_system = 0;
 };
 
 // b, x: one block vector each (x holds the initial guess).  Returns 0 or a negative error code of the backend; iterations as the

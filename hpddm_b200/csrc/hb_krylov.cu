@@ -751,7 +751,7 @@ void gcrodr_release(Ctx *c) {
 }
 
 int gcrodr_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *> &x, int mu, int correction, int restart, int recycle, int target, int strategy,
-                  int max_it, double tol, int *iterations, double *rel_residual) {
+                  int same_system, int max_it, double tol, int *iterations, double *rel_residual) {
   if (recycle <= 0) return gmres_device(c, b, x, mu, correction, restart, max_it, tol, iterations, rel_residual);  // GCRODR.hpp:50-55
   RecycledDev *rd = static_cast<RecycledDev *>(c->recycled);
   std::vector<int> sizes;
@@ -776,6 +776,7 @@ int gcrodr_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *
   p.tol = tol;
   p.target = target;
   p.strategy = strategy;
+  p.same_system = same_system;
   gcro::Vec bv(b.size());
   for (size_t q = 0; q < b.size(); ++q) bv[q] = const_cast<K *>(b[q]);  // the driver only reads b
   const int rc = gcro::run(be, bv, x, p, iterations, rel_residual);
@@ -884,15 +885,17 @@ extern "C" int HB_API(solve_bgmres)(hb_ctx_t *ctx, const K *const *b, K *const *
 }
 
 extern "C" int HB_API(solve_gcrodr)(hb_ctx_t *ctx, const K *const *b, K *const *x, int mu, int correction, int restart, int recycle, int recycle_target,
-                                       int recycle_strategy, int max_it, double tol, int where, int *iterations, double *rel_residual) {
+                                       int recycle_strategy, int recycle_same_system, int max_it, double tol, int where, int *iterations,
+                                       double *rel_residual) {
   Ctx *c = reinterpret_cast<Ctx *>(ctx);
-  if (!c || !iterations || restart < 1 || max_it < 1 || mu < 1 || recycle_target < 0 || recycle_target > 5 || recycle_strategy < 0 || recycle_strategy > 1) {
+  if (!c || !iterations || restart < 1 || max_it < 1 || mu < 1 || recycle_target < 0 || recycle_target > 5 || recycle_strategy < 0 || recycle_strategy > 1 ||
+      recycle_same_system < 0 || recycle_same_system > 2) {
     set_error("solve_gcrodr: bad arguments");
     return HPDDM_B200_ERR_ARG;
   }
   *iterations = 0;
   return krylov_entry(c, b, x, mu, where, [&](const std::vector<const K *> &bd, const std::vector<K *> &xd) {
-    return gcrodr_device(c, bd, xd, mu, correction, restart, recycle, recycle_target, recycle_strategy, max_it, tol, iterations, rel_residual);
+    return gcrodr_device(c, bd, xd, mu, correction, restart, recycle, recycle_target, recycle_strategy, recycle_same_system, max_it, tol, iterations, rel_residual);
   });
 }
 

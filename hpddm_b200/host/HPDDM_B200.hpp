@@ -110,10 +110,10 @@ struct Api;
     {                                                                                                                                              \
       return P_##_solve_cg(c, b, x, mu, corr, it, tol, w, its, res);                                                                               \
     }                                                                                                                                              \
-    static int solve_gcrodr(ctx_t *c, const K_ *const *b, K_ *const *x, int mu, int corr, int m, int k, int target, int strategy, int it,          \
-                            double tol, int w, int *its, double *res)                                                                              \
+    static int solve_gcrodr(ctx_t *c, const K_ *const *b, K_ *const *x, int mu, int corr, int m, int k, int target, int strategy, int same,        \
+                            int it, double tol, int w, int *its, double *res)                                                                      \
     {                                                                                                                                              \
-      return P_##_solve_gcrodr(c, b, x, mu, corr, m, k, target, strategy, it, tol, w, its, res);                                                   \
+      return P_##_solve_gcrodr(c, b, x, mu, corr, m, k, target, strategy, same, it, tol, w, its, res);                                             \
     }                                                                                                                                              \
     static int recycle_destroy(ctx_t *c) { return P_##_recycle_destroy(c); }                                                                       \
   }
@@ -375,7 +375,7 @@ public:
     const K *bb[1] = {f};
     K       *xx[1] = {x};
     int      it = 0, rc;
-    if (method == 4) rc = A_::solve_gcrodr(ctx_, bb, xx, mu, correction_, restart, recycle, 0, 0, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
+    if (method == 4) rc = A_::solve_gcrodr(ctx_, bb, xx, mu, correction_, restart, recycle, 0, 0, 0, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     else if (method == 1) rc = A_::solve_bgmres(ctx_, bb, xx, mu, correction_, restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     else if (method == 2) rc = A_::solve_cg(ctx_, bb, xx, mu, correction_, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     else rc = A_::solve(ctx_, bb, xx, mu, correction_, restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);

@@ -351,7 +351,8 @@ class Decomposition:
     # stays in the context between calls (the reference keeps it in A.storage()), recycle_destroy() drops it
     RECYCLE_TARGET = {"SM": 0, "LM": 1, "SR": 2, "LR": 3, "SI": 4, "LI": 5}
 
-    def solve_gcrodr(self, b, x0=None, correction="__default__", restart=40, recycle=10, max_it=100, tol=1e-6, target="SM", strategy="A"):
+    def solve_gcrodr(self, b, x0=None, correction="__default__", restart=40, recycle=10, max_it=100, tol=1e-6, target="SM", strategy="A", same_system=0):
+        """same_system: the value of -hpddm_recycle_same_system (0: operator may have changed; 1: same operator, pair built / updated; 2: pair used as is)"""
         corr = self.correction if correction == "__default__" else correction
         b = [_f(v, self.dtype) for v in b]
         x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v, self.dtype).copy(order="F") for v in x0]
@@ -359,7 +360,7 @@ class Decomposition:
         it = C.c_int(0)
         res = np.zeros(mu)
         self.api.check(self.api.solve_gcrodr(self.ctx, capi.ptr_array(b), capi.ptr_array(x), mu, capi.CORRECTION[corr], int(restart), int(recycle),
-                                             self.RECYCLE_TARGET[target], {"A": 0, "B": 1}[strategy], int(max_it), float(tol), capi.HOST, C.byref(it), capi.ptr(res)))
+                                             self.RECYCLE_TARGET[target], {"A": 0, "B": 1}[strategy], int(same_system), int(max_it), float(tol), capi.HOST, C.byref(it), capi.ptr(res)))
         return it.value, x, res
 
     def recycle_dim(self):

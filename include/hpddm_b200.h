@@ -235,7 +235,10 @@ int hpddm_b200_solve_bgmres(hpddm_b200_ctx *ctx, const double *const *b, double 
  * recycled pair (U, C = A M^-1 U, C^H D C = I) resident in HBM and the reference defaults (iterative.hpp:197-218): right
  * preconditioning, classical Gram-Schmidt, CholQR.  restart = -hpddm_gmres_restart, recycle = -hpddm_recycle (clipped to restart - 1;
  * <= 0 runs GMRES as the reference does, GCRODR.hpp:50-55), recycle_target = HPDDM_B200_RECYCLE_TARGET_* (-hpddm_recycle_target),
- * recycle_strategy = HPDDM_B200_RECYCLE_STRATEGY_* (-hpddm_recycle_strategy).  Every right-hand side has its own Krylov space and
+ * recycle_strategy = HPDDM_B200_RECYCLE_STRATEGY_* (-hpddm_recycle_strategy), recycle_same_system = the value of -hpddm_recycle_same_system as
+ * IterativeMethod::options reads it (iterative.hpp:217): 0 = the operator may have changed since the pair was built (C = A M^-1 U is recomputed and
+ * re-orthonormalised when a later solve starts), 1 = same operator, pair still built / updated, 2 = same operator, stored pair used as is (the
+ * reference raises its option from 1 to 2 after a converged solve, GCRODR.hpp:435; here the caller passes the value).  Every right-hand side has its own Krylov space and
  * pair, all columns share each preconditioner apply / operator product.  The pair stays in the context between calls the way the
  * reference keeps it in A.storage() (HPDDM_option.hpp:445-454): the first solve builds it from the harmonic Ritz vectors of its first
  * GMRES(m) cycle, later solves start from it (GCRODR.hpp:94-130); hpddm_b200_recycle_destroy drops it (Subdomain::destroy does the
@@ -249,7 +252,7 @@ int hpddm_b200_solve_bgmres(hpddm_b200_ctx *ctx, const double *const *b, double 
 #define HPDDM_B200_RECYCLE_STRATEGY_A 0 /* HPDDM_define.hpp:166-167 */
 #define HPDDM_B200_RECYCLE_STRATEGY_B 1
 int hpddm_b200_solve_gcrodr(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int correction, int restart, int recycle, int recycle_target,
-                            int recycle_strategy, int max_it, double tol, int where, int *iterations, double *rel_residual);
+                            int recycle_strategy, int recycle_same_system, int max_it, double tol, int where, int *iterations, double *rel_residual);
 /* dimension k of the stored pair (0: none) / release it */
 int hpddm_b200_recycle_dim(hpddm_b200_ctx *ctx);
 int hpddm_b200_recycle_destroy(hpddm_b200_ctx *ctx);

@@ -66,8 +66,11 @@ def _combine(blocks, coef, nu, out):
         out[r][:, nu] = acc
 
 
-def gcrodr(op, b, x0=None, tol=1e-6, max_it=100, restart=40, recycle=0, state=None, target="SM", strategy="A", verbose=False):
-    """Returns (iterations, x, state)."""
+def gcrodr(op, b, x0=None, tol=1e-6, max_it=100, restart=40, recycle=0, state=None, target="SM", strategy="A", same_system=0, verbose=False):
+    """Returns (iterations, x, state).  same_system = value of -hpddm_recycle_same_system as IterativeMethod::options reads it
+    (iterative.hpp:217; the reference raises it from 1 to 2 after a converged solve, GCRODR.hpp:435): 0 = the operator may have
+    changed (C = A M^-1 U recomputed at the start of a later solve), 1 = same operator, the pair is still built / updated, C^H D r
+    is taken as zero in the solution update, 2 = same operator, the stored pair is used as is (no product with A M^-1, no update)."""
     if recycle <= 0:                                              # GCRODR.hpp:50-55
         it, x, _ = gmres(op, b, x0=x0, tol=tol, max_it=max_it, restart=restart)
         return it, x, state
@@ -93,7 +96,17 @@ def gcrodr(op, b, x0=None, tol=1e-6, max_it=100, restart=40, recycle=0, state=No
         Ax = op.GMV(x)
         v = [None] * (m + 1)
         v[i] = [np.asfortranarray(b[r] - Ax[r]).astype(dtype) for r in range(P)]
-        if j == 1 and U is not None:                              # GCRODR.hpp:94-130: C = A M^-1 U, CholQR, projection
+        if j == 1 and U is not None and same_system:              # GCRODR.hpp:115-129 with id[4] / 4 != 0: C is still A M^-1 U
+            h = np.array([op.dot(C[c], v[i]) for c in range(k)])
+            wk = zeros()
+            for c in range(k):
+                for r in range(P):
+                    v[i][r] -= C[c][r] * h[c][None, :]
+                    wk[r] += U[c][r] * h[c][None, :]
+            corr = op.apply(wk)
+            for r in range(P):
+                x[r] += corr[r]
+        elif j == 1 and U is not None:                            # GCRODR.hpp:94-130: C = A M^-1 U, CholQR, projection
             pt = [op.apply(U[c]) for c in range(k)]
             C = [op.GMV(pt[c]) for c in range(k)]
             G = np.array([[op.dot(C[a], C[c]) for c in range(k)] for a in range(k)])      # k x k x mu
@@ -183,7 +196,9 @@ def gcrodr(op, b, x0=None, tol=1e-6, max_it=100, restart=40, recycle=0, state=No
                 continue
             y = sla.solve_triangular(R[shift:dim, shift:dim, nu], s[shift:dim, nu]) if dim > shift else np.zeros(0, dtype=dtype)
             if U is not None:
-                su = np.array([resnorm[nu] * op.dot(C[c], v[shift])[nu] for c in range(k)]) - B[:k, shift:dim, nu] @ y
+                su = -(B[:k, shift:dim, nu] @ y)                    # iterative.hpp:351: `same` drops the C^H D r term
+                if not same_system:
+                    su = su + np.array([resnorm[nu] * op.dot(C[c], v[shift])[nu] for c in range(k)])
                 _combine(U[:k] + v[shift:dim], np.concatenate([su, y]), nu, work)
             else:
                 _combine(v[:dim], y, nu, work)
@@ -197,7 +212,9 @@ def gcrodr(op, b, x0=None, tol=1e-6, max_it=100, restart=40, recycle=0, state=No
                 i -= k
             for r in range(P):
                 v[m][r] = v[m][r] / save[i, i - 1][None, :]
-        if U is None:                                             # GCRODR.hpp:242-316: first pair from GMRES(m)
+        if same_system > 1:                                       # GCRODR.hpp:239: id[4] / 4 <= 1 guards both branches below
+            pass
+        elif U is None:                                           # GCRODR.hpp:242-316: first pair from GMRES(m)
             nz = conv[conv != 0]
             dim = abs(int(nz.min())) if len(nz) else 0
             if j < k or dim < k:

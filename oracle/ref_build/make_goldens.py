@@ -64,6 +64,10 @@ CASES = {
                                                                     "-Nx", "40", "-Ny", "40", "-solves", "2", "-hpddm_verbosity", "3"]),
     "small_40x40_p4_gcrodr_m8_k3_sr_solves2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "gcrodr", "-hpddm_gmres_restart", "8", "-hpddm_recycle", "3",
                                                               "-hpddm_recycle_target", "SR", "-hpddm_tol", "1e-7", "-Nx", "40", "-Ny", "40", "-solves", "2", "-hpddm_verbosity", "3"]),
+    # -hpddm_recycle_same_system: the reference raises the option from 1 to 2 after the first converged solve -> solves 2 and 3 use the
+    # stored pair as is (no A M^-1 U product, no update of the pair)
+    "small_40x40_p4_gcrodr_m12_k4_same_solves3": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "gcrodr", "-hpddm_gmres_restart", "12", "-hpddm_recycle", "4",
+                                                                 "-hpddm_recycle_same_system", "1", "-Nx", "40", "-Ny", "40", "-solves", "3", "-hpddm_verbosity", "3"]),
     "complex_40x40_p4_gcrodr_m8_k3_solves2": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "gcrodr", "-hpddm_gmres_restart", "8", "-hpddm_recycle", "3",
                                                                      "-Nx", "40", "-Ny", "40", "-solves", "2", "-hpddm_verbosity", "3"]),
     # complex scalars (the reference's FORCE_COMPLEX build; damped-Helmholtz-like shift of the generator's matrix, see ref_driver.cpp)

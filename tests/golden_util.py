@@ -44,7 +44,7 @@ def load(name):
                 tol=float(arg_value(args, "hpddm_tol", 1e-6)), method=arg_value(args, "hpddm_schwarz_method", "ras"),
                 krylov=arg_value(args, "hpddm_krylov_method", "gmres"), penalised=arg_value(args, "penalise", "0") == "1",
                 recycle=int(arg_value(args, "hpddm_recycle", 0)), solves=int(arg_value(args, "solves", 1)),
-                recycle_target=arg_value(args, "hpddm_recycle_target", "SM"))
+                recycle_target=arg_value(args, "hpddm_recycle_target", "SM"), same_system=int(arg_value(args, "hpddm_recycle_same_system", 0)))
     # -solves N (recycling drivers): right-hand side / solution / iteration count of solve s >= 2 as f{s}, sol{s}, iterations{s}
     for r in range(P):
         n = parts[r]["ndof"]

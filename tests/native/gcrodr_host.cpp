@@ -106,7 +106,8 @@ extern "C" {
 
 // state: in/out opaque handle of the recycled pair (nullptr on the first solve); counts[0 / 1] = apply / GMV calls of this solve
 int gcrodr_host_run(int P, const int *n, const double *const *d, op_cb apply, op_cb gmv, op_cb start, norm_cb norms, void *user, K *const *b, K *const *x, int mu,
-                    int restart, int recycle, int max_it, double tol, int target, int strategy, int *iterations, double *rel_residual, void **state, long *counts) {
+                    int restart, int recycle, int max_it, double tol, int target, int strategy, int same_system, int *iterations, double *rel_residual, void **state,
+                    long *counts) {
   HostBackend be;
   be.P = P;
   be.mu = mu;
@@ -127,6 +128,7 @@ int gcrodr_host_run(int P, const int *n, const double *const *d, op_cb apply, op
   p.tol = tol;
   p.target = target;
   p.strategy = strategy;
+  p.same_system = same_system;
   const Vec bv(b, b + P), xv(x, x + P);
   const int rc = gcro::run(be, bv, xv, p, iterations, rel_residual);
   if (counts) {

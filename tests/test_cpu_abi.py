@@ -79,6 +79,26 @@ def test_host_cpp_header_compiles_and_links():
         subprocess.check_call([exe])
 
 
+@pytest.mark.parametrize("flags", [[], ["-DFORCE_COMPLEX"]])
+def test_full_seam_instantiates_its_device_resident_solve(flags, tmp_path):
+    """hpddm_b200/host/HPDDM_B200_schwarz.hpp against the reference's headers: the unmodified driver never calls solveOnDevice (it goes
+    through IterativeMethod::solve), so this member -- the device-resident GMRES / BGMRES / CG / GCRO-DR dispatch on -hpddm_krylov_method --
+    is instantiated here, for both scalar types.  Needs the reference tree (absent on the GPU box: skipped there)."""
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "include")):
+        pytest.skip("reference tree not present")
+    src = tmp_path / "seam_inst.cpp"
+    src.write_text('#include "schwarz.hpp"\n'
+                   "template <class T> int inst(T &A) { K *f = nullptr, *x = nullptr; return A.solveOnDevice(f, x, 1); }\n"
+                   "int main() { volatile bool run = false; if (run) { HPDDM::Schwarz<SUBDOMAIN, COARSEOPERATOR, symCoarse, K> A; return inst(A); } return 0; }\n")
+    host = os.path.join(ROOT, "hpddm_b200", "host")
+    subprocess.check_call(["g++", "-O0", "-std=c++11", "-w", "-DDLAPACK", "-DB200SUB", "-DB200SCHWARZ", "-DGENERAL_CO", "-DHPDDM_NUMBERING='C'"] + flags +
+                          ["-I", os.path.join(ROOT, "oracle", "ref_build"), "-I", os.path.join(ref, "include"), "-I", os.path.join(ref, "examples"), "-I", os.path.join(ROOT, "include"),
+                           "-I", host, "-include", os.path.join(host, "HPDDM_B200.hpp"), "-include", os.path.join(host, "HPDDM_B200_schwarz.hpp"), "-c", str(src),
+                           "-o", str(tmp_path / "seam_inst.o")])
+
+
 def test_ctypes_signatures_match_the_headers():
     """every declaration of include/hpddm_b200.h / hpddm_b200z.h: same number of arguments and same scalar/pointer kind as
     the argtypes of hpddm_b200/capi.py (a wrong binding would corrupt the stack silently)"""

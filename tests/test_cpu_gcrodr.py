@@ -32,7 +32,7 @@ def harness(tmp_path_factory):
         lib = C.CDLL(so)
         lib.gcrodr_host_run.restype = C.c_int
         lib.gcrodr_host_run.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), OP_CB, OP_CB, OP_CB, NORM_CB, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_void_p),
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_long)]
         lib.gcrodr_host_free.argtypes = [C.c_void_p]
         lib.gcrodr_host_recycled_dim.argtypes = [C.c_void_p]
@@ -84,7 +84,7 @@ class HostGcrodr:
                 return -1
         self.cb_norm = NORM_CB(norm_cb)
 
-    def solve(self, b, restart, recycle, max_it=100, tol=1e-6, target="SM", strategy="A"):
+    def solve(self, b, restart, recycle, max_it=100, tol=1e-6, target="SM", strategy="A", same_system=0):
         bs = [np.array(v, dtype=self.dtype, order="F", copy=True) for v in b]
         xs = [np.zeros_like(v, order="F") for v in bs]
         arr = lambda vs: (C.c_void_p * self.P)(*[v.ctypes.data for v in vs])
@@ -93,7 +93,7 @@ class HostGcrodr:
         counts = (C.c_long * 2)()
         nn = (C.c_int * self.P)(*self.n)
         rc = self.lib.gcrodr_host_run(self.P, nn, arr(self.d), self.cb_apply, self.cb_gmv, self.cb_start, self.cb_norm, None, arr(bs), arr(xs), self.mu, restart, recycle,
-                                      max_it, tol, TARGETS[target], 0 if strategy == "A" else 1, C.byref(it), rel.ctypes.data_as(C.POINTER(C.c_double)), C.byref(self.state), counts)
+                                      max_it, tol, TARGETS[target], 0 if strategy == "A" else 1, same_system, C.byref(it), rel.ctypes.data_as(C.POINTER(C.c_double)), C.byref(self.state), counts)
         if self.error is not None:
             raise self.error
         assert rc == 0, rc
@@ -131,11 +131,12 @@ def test_product_driver_reproduces_the_reference_gcrodr(harness, name):
     for s in range(1, meta["solves"] + 1):
         tag = "" if s == 1 else str(s)
         b = [parts[r]["f"] if s == 1 else ref[r]["f" + tag] for r in range(P)]
-        it, x, res, _ = h.solve(b, meta["restart"], meta["recycle"], max_it=meta["max_it"], tol=meta["tol"], target=meta["recycle_target"])
+        it, x, res, _ = h.solve(b, meta["restart"], meta["recycle"], max_it=meta["max_it"], tol=meta["tol"], target=meta["recycle_target"],
+                                same_system=min(s, 2) if meta["same_system"] else 0)
         assert it == int(ref[0]["iterations" + tag][0]), (s, it)                       # the reference's iteration count
         assert max(rel(x[r], ref[r]["sol" + tag]) for r in range(P)) < 1e-8, s          # and its solution
         assert np.all(res <= meta["tol"])
-    assert harness["real"].gcrodr_host_recycled_dim(h.state) == min(meta["recycle"], meta["restart"] - 1)
+    assert h.lib.gcrodr_host_recycled_dim(h.state) == min(meta["recycle"], meta["restart"] - 1)
     h.close()
 
 

@@ -67,7 +67,7 @@ def test_cuda_path_reproduces_the_reference(name):
             tag = "" if s == 1 else str(s)
             bs = b if s == 1 else [ref[r]["f" + tag].copy() for r in range(P)]
             it, x, state = gcrodr(KrylovOperator(deco, corr), bs, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"], recycle=meta["recycle"], state=state,
-                                  target=meta["recycle_target"])
+                                  target=meta["recycle_target"], same_system=min(s, 2) if meta["same_system"] else 0)
             assert it == int(ref[0]["iterations" + tag][0]), (s, it)
             assert max(rel(x[r], ref[r]["sol" + tag]) for r in range(P)) < 1e-7, s
     elif meta["krylov"] != "bgmres":   # host-driven: the restated reference driver on top of the C ABI hot path

@@ -35,7 +35,7 @@ def main(name):
         tag = "" if s == 1 else str(s)
         b = [parts[r]["f"] if s == 1 else ref[r]["f" + tag] for r in range(P)]
         it, x, res = deco.solve_gcrodr(b, correction=corr, restart=meta["restart"], recycle=meta["recycle"], max_it=meta["max_it"], tol=meta["tol"],
-                                       target=meta["recycle_target"])
+                                       target=meta["recycle_target"], same_system=min(s, 2) if meta["same_system"] else 0)
         gold = [ref[r]["sol" + tag] for r in range(P)]
         out["its"].append(int(it))
         out["ref"].append(int(ref[0]["iterations" + tag][0]))
