@@ -286,3 +286,21 @@ def test_reference_known_answer_40X_sequence(harness, jacobi):
         assert np.abs(np.array(got) - want).max() <= (3 if jacobi else 0), (got, want.tolist())
     if not jacobi:
         assert got_oracle == want.tolist() and got_product == want.tolist()
+
+
+def test_reference_40X_sequence_three_identical_columns(harness):
+    """the reference's test line also runs -mu 3 (the right-hand side copied three times, examples/driver.cpp:119-120): every column has
+    its own Krylov space and recycled pair, so each must take exactly the single-column count -- first three systems of the sequence"""
+    z, mats, rhs = _sequence_40x()
+    n = mats[0].shape[0]
+    h = None
+    for i in range(3):
+        op = _CsrOperator(mats[i], False)
+        if h is None:
+            h = HostGcrodr(harness["real"], op, [n], [np.ones(n)], 3, np.float64)
+        h.op = op
+        b = np.asfortranarray(np.repeat(rhs[i], 3, axis=1))
+        it, x, _, _ = h.solve([b], 40, 20, max_it=1000, tol=1e-10)
+        assert it == int(z["gcrodr_40_20_tol1e10"][i])
+        assert np.abs(x[0][:, 1] - x[0][:, 0]).max() == 0 and np.abs(x[0][:, 2] - x[0][:, 0]).max() == 0
+    h.close()
