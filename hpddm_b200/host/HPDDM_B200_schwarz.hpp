@@ -325,6 +325,14 @@ public:
     for (int i = 0; i < cnt; ++i) map[static_cast<unsigned int>(idx[i])] = val[i];
     return map;
   }
+  /* OptionsPrefix::destroy (include/HPDDM_option.hpp:431-443): drops the recycled Krylov subspace -- the host one of the reference's
+   * GCRO-DR drivers (A.storage()) and the device one of solveOnDevice (kept in the context) */
+  template <bool reset = true>
+  void destroy()
+  {
+    Subdomain<K>::template destroy<reset>();
+    if (ctx_) A_::recycle_destroy(ctx_);
+  }
   /* device-resident counterpart of IterativeMethod::solve: see B200Schwarz::solve (HPDDM_B200.hpp) */
   int solveOnDevice(const K *const f, K *const x, const unsigned short mu = 1) const
   {

@@ -90,7 +90,7 @@ def test_full_seam_instantiates_its_device_resident_solve(flags, tmp_path):
         pytest.skip("reference tree not present")
     src = tmp_path / "seam_inst.cpp"
     src.write_text('#include "schwarz.hpp"\n'
-                   "template <class T> int inst(T &A) { K *f = nullptr, *x = nullptr; return A.solveOnDevice(f, x, 1); }\n"
+                   "template <class T> int inst(T &A) { K *f = nullptr, *x = nullptr; A.destroy(); return A.solveOnDevice(f, x, 1); }\n"
                    "int main() { volatile bool run = false; if (run) { HPDDM::Schwarz<SUBDOMAIN, COARSEOPERATOR, symCoarse, K> A; return inst(A); } return 0; }\n")
     host = os.path.join(ROOT, "hpddm_b200", "host")
     subprocess.check_call(["g++", "-O0", "-std=c++11", "-w", "-DDLAPACK", "-DB200SUB", "-DB200SCHWARZ", "-DGENERAL_CO", "-DHPDDM_NUMBERING='C'"] + flags +
