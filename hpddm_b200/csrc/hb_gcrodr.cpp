@@ -629,7 +629,11 @@ int run(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iteration
       if (j < k || dim < k) k = dim;
       if (k > 0 && dim > 0) {
         GC(be.alloc(rec.U, k));
-        GC(be.alloc(rec.C, k));
+        const int rc_c = be.alloc(rec.C, k);
+        if (rc_c < 0) {  // never leave half a pair behind
+          be.release(rec.U);
+          GC(rc_c);
+        }
         rec.k = k;
         rec.mu = mu;
         for (int nu = 0; nu < mu; ++nu) {
@@ -652,6 +656,9 @@ int run(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iteration
           std::vector<zc> th;
           M X;
           if (!eig(Hm, th, X)) {
+            be.release(rec.U);  // no pair rather than a partly built one
+            be.release(rec.C);
+            rec.k = rec.mu = 0;
             cleanup();
             return ERR_EIGENSOLVER;
           }
