@@ -716,9 +716,11 @@ struct DeviceBackend : gcro::Backend {
       set_error("GCRO-DR: %d coefficients exceed the staging capacity %d", count, cap);
       return HPDDM_B200_ERR_STATE;
     }
-    // pageable source: the call returns once the coefficients are staged, the caller may reuse `coef`; the copy and the kernels
-    // that read d_h are ordered on the context's stream
+    // the driver reuses `coef` right after this call: wait for the copy (a pageable source is staged before cudaMemcpyAsync returns, but a
+    // heap block that shares a page with a range the caller pinned would make the copy truly asynchronous); the kernels that read d_h are
+    // ordered behind it on the context's stream.  A few microseconds next to a preconditioner apply.
     HB_CUDA(cudaMemcpyAsync(d_h, coef, (size_t)count * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t q = 0; q < c->subs.size(); ++q)
       HB_CHECK(k_vupdate(c, c->subs[q], count, colp(basis, q, nu), (int64_t)mu * c->subs[q]->n, d_h, alpha, colp(w, q, nu)));
     return 0;

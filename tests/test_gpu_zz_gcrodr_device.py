@@ -4,7 +4,9 @@ reference's iteration count and solution.
 
 Status of this file (round 2): the driver's logic (hb_gcrodr.cpp) is verified on the CPU against the same goldens through a host
 vector backend (tests/test_cpu_gcrodr.py); its DEVICE backend (hb_krylov.cu: DeviceBackend, a thin layer over the kernels of the
-GMRES / BGMRES drivers) was written after this round's GPU budget was spent and has not run on hardware yet.  Each case therefore
+GMRES / BGMRES drivers) and the exported entry points are verified on the CPU against a host stand-in for the CUDA runtime and the
+kernel launchers (tests/test_cpu_krylov_mock.py: the reference's own 40X known-answer test, block splits, complex scalars) -- but
+they were written after this round's GPU budget was spent and have not run on hardware yet.  Each case therefore
 runs in its own process with a timeout and is marked xfail(strict=False): an XPASS in the report means the device path reproduced the
 reference on the B200; a failure is recorded without stopping the (verified) rest of the suite, which is why the file sorts last.
 The host-driven GCRO-DR on top of the GPU apply is a gating test (tests/test_gpu_golden.py)."""
