@@ -212,6 +212,10 @@ void krylov_mock_set_values(const K *a) {
     for (int p = g.ia[i]; p < g.ia[i + 1]; ++p)
       if (g.ja[p] == i) g.diag[i] = a[p];
 }
+// Prcndtnr of every block (HPDDM_B200_PRCNDTNR_*): solve_cg runs CG only for the symmetric ones, like the reference (CG.hpp:41-44)
+void krylov_mock_set_prcndtnr(void *ctx, int value) {
+  for (Sub *s : static_cast<Ctx *>(ctx)->subs) s->prcndtnr = value;
+}
 long krylov_mock_launches(void *ctx) { return (long)static_cast<Ctx *>(ctx)->launches; }
 const char *krylov_mock_error() { return g.err; }
 void krylov_mock_destroy(void *ctx) {

@@ -17,7 +17,7 @@ from oracle.krylov import bgmres, cg, gmres
 from tests.test_cpu_gcrodr import _CsrOperator, _sequence_40x
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HOST, NONE = 0, 0   # HPDDM_B200_HOST, HPDDM_B200_CORRECTION_NONE
+HOST, NONE = 0, -1   # HPDDM_B200_HOST, HPDDM_B200_CORRECTION_NONE
 
 
 @pytest.fixture(scope="module")
@@ -35,6 +35,7 @@ def mock(tmp_path_factory):
         lib.krylov_mock_set_values.argtypes = [C.c_void_p]
         lib.krylov_mock_destroy.argtypes = [C.c_void_p]
         lib.krylov_mock_launches.argtypes = [C.c_void_p]
+        lib.krylov_mock_set_prcndtnr.argtypes = [C.c_void_p, C.c_int]
         lib.krylov_mock_launches.restype = C.c_long
         lib.krylov_mock_error.restype = C.c_char_p
         out[name] = (lib, prefix)
@@ -144,7 +145,7 @@ def test_exported_gcrodr_entry_point_three_columns_and_same_system(mock):
 
 
 def _poisson2d(m, shift=0.0):
-    T = sp.diags([-1, 2, -1], [-1, 0, 1], shape=(m, m))
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(m, m))
     A = sp.kronsum(T, T).tocsr()
     return (A + shift * sp.identity(m * m)).tocsr()
 
@@ -178,6 +179,13 @@ def test_gmres_cg_bgmres_drivers_on_the_mock(mock):
     d = MockDeco(mock, A, (150, n - 150), jacobi=True)
     it0, x0, _ = gmres(op, [b], restart=15, max_it=300, tol=1e-8)
     it, x, _ = d.solve(b, restart=15, max_it=300, tol=1e-8)
+    assert it == it0 and np.abs(x - x0[0]).max() <= 1e-8 * np.abs(x0[0]).max()
+    # CG: only for symmetric preconditioners (Prcndtnr SY = 1: ASM); with the default (GE: RAS) the entry point forwards to GMRES(40)
+    it_ge, _, _ = d.solve_cg(b, max_it=300, tol=1e-8)
+    assert it_ge == gmres(op, [b], restart=40, max_it=300, tol=1e-8)[0]
+    d.lib.krylov_mock_set_prcndtnr(d.ctx, 1)
+    it0, x0 = cg(op, [b], max_it=300, tol=1e-8)
+    it, x, _ = d.solve_cg(b, max_it=300, tol=1e-8)
     assert it == it0 and np.abs(x - x0[0]).max() <= 1e-8 * np.abs(x0[0]).max()
     it0, x0 = bgmres(op, [b], restart=15, max_it=300, tol=1e-8)
     it, x, _ = d.solve_bgmres(b, restart=15, max_it=300, tol=1e-8)
