@@ -312,3 +312,241 @@ def gcrodr(op, b, x0=None, tol=1e-6, max_it=100, restart=40, recycle=0, state=No
         if converged:
             break
     return min(j, max_it), x, dict(U=U, C=C, k=k, mu=mu)
+
+
+def bgcrodr(op, b, x0=None, tol=1e-6, max_it=100, restart=40, recycle=0, state=None, target="SM", strategy="A", same_system=0, verbose=False):
+    """IterativeMethod::BGCRODR (include/HPDDM_GCRODR.hpp:445-907) with the reference defaults (iterative.hpp:192-218): right
+    preconditioning, block classical Gram-Schmidt, CholQR, no deflation of right-hand sides (deflation_tol = -1), no enlarged Krylov
+    space, recycle target SM, strategy A.  One block Krylov space and ONE recycled pair (U, C) of mu * k columns for all right-hand
+    sides: block Arnoldi with Householder-reduced block Hessenberg matrix as in BGMRES (BlockArnoldi, iterative.hpp:714-737, with
+    `shift` = k), orthogonalisation of every new block against C, the block versions of the first pair (GCRODR.hpp:674-760), of the
+    solution update (updateSolRecycling, iterative.hpp:372-391) and of the generalised harmonic Ritz update (GCRODR.hpp:761-884).
+    U, C: lists of k blocks (per-rank lists of n x mu arrays); column c of the n x (mu k) matrix is column c % mu of block c // mu.
+    Returns (iterations, x, state)."""
+    from scipy.linalg import lapack
+    from oracle.krylov import bgmres
+    if recycle <= 0:                                              # GCRODR.hpp:460-465
+        it, x = bgmres(op, b, x0=x0, tol=tol, max_it=max_it, restart=restart)
+        return it, x, state
+    P = len(b)
+    mu = b[0].shape[1]
+    dtype = np.result_type(*[v.dtype for v in b])
+    cplx = np.issubdtype(dtype, np.complexfloating)
+    geqrf = lapack.zgeqrf if cplx else lapack.dgeqrf
+    mqr = lapack.zunmqr if cplx else lapack.dormqr
+    m = min(restart, max_it)
+    k = min(m - 1, recycle)
+    U = C = None
+    if state is not None and state.get("U") is not None:
+        assert state["mu"] == mu
+        U, C, k = state["U"], state["C"], state["k"]
+    x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [np.array(v, order="F", copy=True) for v in x0]
+    x = op.start(b, x)
+    norm = _rhs_norm(op, b)
+    norm = np.where(norm < 1e-12, 1.0, norm)
+    ldh = mu * (m + 1)
+
+    def gram(X, W):                                               # stacked X_c^H D W, (len(X) mu) x mu
+        return np.vstack([op.gram(Xc, W) for Xc in X]) if len(X) else np.zeros((0, mu), dtype=dtype)
+
+    def combine(X, coef):                                         # [X_0 X_1 ...] (n x len(X) mu) times coef -> one block of coef.shape[1] columns
+        return [sum(X[c][r] @ coef[c * mu:(c + 1) * mu] for c in range(len(X))) for r in range(P)]
+
+    def split(Mat):                                               # per-rank n x (q mu) -> q blocks
+        return [[np.asfortranarray(Mat[r][:, c * mu:(c + 1) * mu]) for r in range(P)] for c in range(Mat[0].shape[1] // mu)]
+
+    def cholqr(W, update=True):
+        G = op.gram(W, W)
+        try:
+            R = np.linalg.cholesky(G).conj().T
+        except np.linalg.LinAlgError:
+            return None
+        if update:
+            Rinv = sla.solve_triangular(R, np.eye(mu, dtype=dtype))
+            for r in range(P):
+                W[r] = np.asfortranarray(W[r] @ Rinv)
+        return R
+
+    j = 1
+    dim = mu * m
+    while j <= max_it:
+        shift = k if U is not None else 0
+        Ax = op.GMV(x)
+        v0 = [np.asfortranarray(b[r] - Ax[r]).astype(dtype) for r in range(P)]
+        if j == 1 and U is not None:                              # GCRODR.hpp:515-556
+            bK = mu * k
+            if not same_system:
+                pt = [op.apply(U[c]) for c in range(k)]
+                C = [op.GMV(pt[c]) for c in range(k)]
+                G = np.hstack([gram(C, C[c]) for c in range(k)])   # bK x bK
+                R = np.linalg.cholesky(G).conj().T
+                Rinv = sla.solve_triangular(R, np.eye(bK, dtype=dtype))
+                C, pt, U = (split(combine(blk, Rinv)) for blk in (C, pt, U))
+            Hc = gram(C, v0)
+            corr = combine(C, Hc)
+            for r in range(P):
+                v0[r] -= corr[r]
+            if not same_system:
+                upd = combine(pt, Hc)
+            else:
+                upd = op.apply(combine(U, Hc))
+            for r in range(P):
+                x[r] += upd[r]
+        R0 = cholqr(v0)
+        if R0 is None:
+            raise RuntimeError("BGCRODR: rank-deficient block residual (the reference falls back to GCRODR)")
+        v = [None] * (m + 1)
+        v[shift] = v0
+        H = np.zeros((ldh, m * mu), dtype=dtype)
+        tau = [None] * m
+        s = np.zeros((ldh, mu), dtype=dtype)
+        s[shift * mu:(shift + 1) * mu] = np.triu(R0)
+        save = np.zeros((ldh, m * mu), dtype=dtype)               # unreduced block Hessenberg matrix of this cycle, indices relative to shift
+        Bm = np.zeros((max(k, 1) * mu, m * mu), dtype=dtype)       # C^H D A M^-1 v_i
+
+        def apply_q(kk, Cm, trans):
+            blk = np.asfortranarray(H[kk * mu:(kk + 2) * mu, kk * mu:(kk + 1) * mu])
+            out, _, info = mqr("L", ("C" if cplx else "T") if trans else "N", blk, tau[kk], np.asfortranarray(Cm[kk * mu:(kk + 2) * mu]), 64 * mu)
+            Cm[kk * mu:(kk + 2) * mu] = out
+
+        i = shift
+        conv_now = False
+        while i < m and j <= max_it:
+            z = op.apply(v[i])
+            w = op.GMV(z)
+            if U is not None:
+                hB = gram(C, w)
+                corr = combine(C, hB)
+                for r in range(P):
+                    w[r] = w[r] - corr[r]
+                Bm[:k * mu, i * mu:(i + 1) * mu] = hB
+            Hc = np.zeros((ldh, mu), dtype=dtype)
+            prods = gram(v[shift:i + 1], w)
+            Hc[shift * mu:(i + 1) * mu] = prods
+            corr = combine(v[shift:i + 1], prods)
+            w = [np.asfortranarray(w[r] - corr[r]) for r in range(P)]
+            R = cholqr(w, update=i < m - 1)
+            if R is None:
+                raise RuntimeError("BGCRODR: breakdown in BlockArnoldi (the reference falls back to GCRODR)")
+            Hc[(i + 1) * mu:(i + 2) * mu] = np.triu(R)
+            save[:(i + 2 - shift) * mu, (i - shift) * mu:(i - shift + 1) * mu] = Hc[shift * mu:(i + 2) * mu]
+            v[i + 1] = w
+            for kk in range(shift, i):
+                apply_q(kk, Hc, True)
+            blk, t, _, info = geqrf(np.asfortranarray(Hc[i * mu:(i + 2) * mu]))
+            Hc[i * mu:(i + 2) * mu] = blk
+            H[:, i * mu:(i + 1) * mu] = Hc
+            tau[i] = t
+            apply_q(i, s, True)
+            i += 1
+            res = s[i * mu:(i + 1) * mu]
+            pt_ = np.array([np.linalg.norm(res[:nu + 1, nu]) for nu in range(mu)])
+            if verbose:
+                print(f"BGCRODR: {j:3d} {(pt_ / norm).max():.6e}")
+            if np.all(_converged(pt_, norm, tol)):
+                dim = mu * i
+                conv_now = True
+                break
+            j += 1
+        if not conv_now and j != max_it + 1 and i == m:
+            converged = False
+        else:
+            converged = True
+            if j == max_it + 1:
+                rem = (max_it - m) % (m - k) if U is not None else max_it % m
+                if rem:
+                    dim = mu * (rem + (k if U is not None else 0))
+        # updateSolRecycling, block form (iterative.hpp:372-391)
+        da = dim - mu * shift
+        Y = sla.solve_triangular(np.triu(H[shift * mu:shift * mu + da, shift * mu:shift * mu + da]), s[shift * mu:shift * mu + da]) if da > 0 else np.zeros((0, mu), dtype=dtype)
+        if U is not None:
+            top = -(Bm[:k * mu, shift * mu:shift * mu + da] @ Y)
+            if not same_system:
+                r0 = [np.asfortranarray(v[shift][r] @ np.triu(R0)) for r in range(P)]      # the block residual V_k R_0
+                top = top + gram(C, r0)
+            work = combine(U[:k] + v[shift:shift + da // mu], np.vstack([top, Y]))
+        else:
+            work = combine(v[:da // mu], Y)
+        corr = op.apply(work)
+        for r in range(P):
+            x[r] += corr[r]
+        if not conv_now and i == m:                               # GCRODR.hpp:658-661: the last block is normalised here
+            irel = m - shift
+            Rl = np.triu(save[irel * mu:(irel + 1) * mu, (irel - 1) * mu:irel * mu])
+            Rli = sla.solve_triangular(Rl, np.eye(mu, dtype=dtype))
+            v[m] = [np.asfortranarray(v[m][r] @ Rli) for r in range(P)]
+        if same_system > 1:
+            pass
+        elif U is None:                                           # GCRODR.hpp:674-760
+            db = min(j, m)
+            if db < k:
+                k = db
+            bK = mu * k
+            df = db * mu
+            Rd = save[db * mu:(db + 1) * mu, (db - 1) * mu:db * mu]
+            Rx = save[db * mu:(db + 1) * mu, (m - 1) * mu:m * mu]  # GCRODR.hpp:682: block column m - 1 (zero when the cycle stopped before m)
+            sb = np.zeros((ldh, mu), dtype=dtype)
+            sb[(db - 1) * mu:db * mu] = Rd.conj().T @ Rx
+            sb[:df] = sla.solve_triangular(np.triu(H[:df, :df]), sb[:df], trans="C")
+            for kk in range(db - 1, -1, -1):
+                apply_q(kk, sb, False)
+            Hbar = save[:df + mu, :df].copy()
+            Mh = Hbar[:df].copy()
+            Mh[:, df - mu:df] += sb[:df]
+            w_, X = sla.eig(Mh)
+            q = _order(w_, target)
+            vr = _ggev_columns(w_, X, q, bK, cplx).astype(dtype)
+            Q, Rr = np.linalg.qr(Hbar @ vr)
+            Yc = vr @ np.linalg.inv(Rr)
+            U = split(combine(v[:db], Yc))
+            C = split(combine(v[:db + 1], Q))
+        elif j > m - k:                                           # GCRODR.hpp:761-884
+            bK = mu * k
+            diff = dim - bK
+            nb = diff // mu
+            W = C[:k] + v[k:k + nb + 1]
+            if strategy == "A":
+                un = np.concatenate([np.real(np.diag(op.gram(U[c], U[c]))) for c in range(k)])
+                Du = 1.0 / np.sqrt(un)
+                Wt = np.hstack([gram(W, U[c]) for c in range(k)]) * Du[None, :]
+            else:
+                Du = np.ones(bK)
+            Hbar = save[:diff + mu, :diff]
+            G = np.zeros((dim + mu, dim), dtype=dtype)
+            G[:bK, :bK] = np.diag(Du)
+            G[:bK, bK:] = Bm[:bK, k * mu:k * mu + diff]
+            G[bK:, bK:] = Hbar
+            Am = G.conj().T @ G
+            Bmat = np.zeros((dim, dim), dtype=dtype)
+            if strategy == "A":
+                Bmat[:, :bK] = G.conj().T @ Wt
+            else:
+                Bmat[:bK, :bK] = np.eye(bK)
+                Bmat[bK:, :bK] = Bm[:bK, k * mu:k * mu + diff].conj().T
+            Bmat[bK:, bK:] = Hbar[:diff].conj().T
+            w_, X = sla.eig(Am, Bmat)
+            q = _order(w_, target)
+            vr = _ggev_columns(w_, X, q, bK, cplx).astype(dtype)
+            Q, Rr = np.linalg.qr(G @ vr)
+            Yc = vr @ np.linalg.inv(Rr)
+            Yc[:bK] *= Du[:, None]
+            Un = split(combine(U[:k] + v[k:k + nb], Yc))
+            Cn = split(combine(W, Q))
+            U, C = Un, Cn
+        if converged:
+            break
+    return min(j, max_it), x, dict(U=U, C=C, k=k, mu=mu)
+
+
+def _ggev_columns(w, X, q, count, cplx):
+    """first `count` entries of the ordering q as LAPACK's real eigenvector storage (column p = Re, p + 1 = Im of a conjugate pair)"""
+    if cplx:
+        return X[:, q[:count]]
+    cols = []
+    for jj in q[:count]:
+        if abs(w[jj].imag) < 1e-12 * max(1.0, abs(w[jj])) or not np.isfinite(w[jj]):
+            cols.append(X[:, jj].real)
+        else:
+            p = jj if w[jj].imag > 0 else jj - 1
+            cols.append(X[:, p].real if jj == p else X[:, p].imag)
+    return np.array(cols).T

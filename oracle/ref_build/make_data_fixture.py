@@ -47,15 +47,16 @@ def main():
             systems.append((np.array(tok[3:3 + nnz], dtype=np.float64), np.array(tok[4 + 2 * nnz + n:4 + 2 * nnz + 2 * n], dtype=np.float64)))
         drv = os.path.join(ROOT, "oracle", "_ref", "driver_ref")
         counts = {}
-        for key, extra in (("plain", []), ("diagonal_scaling", ["-diagonal_scaling", "1"])):
-            out = subprocess.run([drv, f"-path={tmp}", "-hpddm_krylov_method", "gcrodr", "-hpddm_verbosity", "1"] + extra, env=dict(os.environ, HPDDM_SHIM_NP="1"),
+        for key, extra in (("plain", []), ("diagonal_scaling", ["-diagonal_scaling", "1"]), ("block", [])):
+            method = "bgcrodr" if key == "block" else "gcrodr"   # (the pattern below also matches "BGCRODR converges ...")
+            out = subprocess.run([drv, f"-path={tmp}", "-hpddm_krylov_method", method, "-hpddm_verbosity", "1"] + extra, env=dict(os.environ, HPDDM_SHIM_NP="1"),
                                  capture_output=True, text=True, timeout=600)
             counts[key] = [int(v) for v in re.findall(r"GCRODR converges after (\d+) iteration", out.stdout)]
             total = int(re.search(r"Total number of iterations: (\d+)", out.stdout).group(1))
             assert out.returncode == 0 and len(counts[key]) == 10 and sum(counts[key]) == total, out.stdout[-500:]   # returncode 0 = inside the reference's window
-            print("driver_ref gcrodr", key, counts[key], total)
+            print("driver_ref", method, key, counts[key], total)
     np.savez_compressed(os.path.join(OUT, "refdata_40X_sequence.npz"), n=n, ia=ia, ja=ja, a=np.array([s_[0] for s_ in systems]), rhs=np.array([s_[1] for s_ in systems]),
-                        numbering="F", gcrodr_40_20_tol1e10=np.array(counts["plain"]), gcrodr_40_20_tol1e10_diagonal_scaling=np.array(counts["diagonal_scaling"]),
+                        numbering="F", gcrodr_40_20_tol1e10=np.array(counts["plain"]), gcrodr_40_20_tol1e10_diagonal_scaling=np.array(counts["diagonal_scaling"]), bgcrodr_40_20_tol1e10=np.array(counts["block"]),
                         source="examples/data/40X.tar.gz:400.txt-409.txt; counts: unmodified examples/driver.cpp (oracle/_ref/driver_ref)")
     with tarfile.open(os.path.join(DATA, "mini.tar.gz")) as t:
         txt = t.extractfile("mini.mtx").read().decode()

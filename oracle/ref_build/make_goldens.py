@@ -68,6 +68,15 @@ CASES = {
     # stored pair as is (no A M^-1 U product, no update of the pair)
     "small_40x40_p4_gcrodr_m12_k4_same_solves3": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "gcrodr", "-hpddm_gmres_restart", "12", "-hpddm_recycle", "4",
                                                                  "-hpddm_recycle_same_system", "1", "-Nx", "40", "-Ny", "40", "-solves", "3", "-hpddm_verbosity", "3"]),
+    # IterativeMethod::BGCRODR (GCRODR.hpp:445-907): one block Krylov space and one recycled pair of mu k columns for all right-hand sides
+    "small_40x40_p4_bgcrodr_m8_k3_mu2_solves3": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "bgcrodr", "-hpddm_gmres_restart", "8", "-hpddm_recycle", "3",
+                                                                "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "2", "-solves", "3", "-hpddm_verbosity", "3"]),
+    "small_40x40_p4_bgcrodr_m40_k5_mu3_solves2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "bgcrodr", "-hpddm_recycle", "5",
+                                                                 "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "3", "-solves", "2", "-hpddm_verbosity", "3"]),
+    "small_40x40_p4_bgcrodr_m8_k4_solves2": dict(np=4, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "bgcrodr", "-hpddm_gmres_restart", "8", "-hpddm_recycle", "4",
+                                                            "-Nx", "40", "-Ny", "40", "-solves", "2", "-hpddm_verbosity", "3"]),
+    "complex_40x40_p4_bgcrodr_m8_k2_mu2_solves2": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "bgcrodr", "-hpddm_gmres_restart", "8", "-hpddm_recycle", "2",
+                                                                          "-Nx", "40", "-Ny", "40", "-generate_random_rhs", "2", "-solves", "2", "-hpddm_verbosity", "3"]),
     "complex_40x40_p4_gcrodr_m8_k3_solves2": dict(np=4, z=True, args=["-hpddm_schwarz_method", "ras", "-hpddm_krylov_method", "gcrodr", "-hpddm_gmres_restart", "8", "-hpddm_recycle", "3",
                                                                      "-Nx", "40", "-Ny", "40", "-solves", "2", "-hpddm_verbosity", "3"]),
     # complex scalars (the reference's FORCE_COMPLEX build; damped-Helmholtz-like shift of the generator's matrix, see ref_driver.cpp)

@@ -70,6 +70,8 @@ def test_cuda_path_reproduces_the_reference(name):
                                   target=meta["recycle_target"], same_system=min(s, 2) if meta["same_system"] else 0)
             assert it == int(ref[0]["iterations" + tag][0]), (s, it)
             assert max(rel(x[r], ref[r]["sol" + tag]) for r in range(P)) < 1e-7, s
+    elif meta["krylov"] == "bgcrodr":
+        pass   # block recycling driver: pinned on the CPU (tests/test_golden_reference.py); this golden checks the hot-path entry points above
     elif meta["krylov"] != "bgmres":   # host-driven: the restated reference driver on top of the C ABI hot path
         if meta["krylov"] == "cg":
             it, x = cg(KrylovOperator(deco, corr), b, max_it=meta["max_it"], tol=meta["tol"])
@@ -78,8 +80,8 @@ def test_cuda_path_reproduces_the_reference(name):
         assert it == it_ref                                   # identical Krylov iteration count
         assert max(rel(x[r], ref[r]["sol"]) for r in range(P)) < 1e-7
     # device-resident driver (hpddm_b200[z]_solve: all right-hand sides advance together, Krylov basis in HBM)
-    if meta["krylov"] == "gcrodr":
-        it_dev, x_dev = it_ref, [ref[r]["sol"] for r in range(P)]   # see tests/test_gpu_gcrodr.py
+    if meta["krylov"] in ("gcrodr", "bgcrodr"):
+        it_dev, x_dev = it_ref, [ref[r]["sol"] for r in range(P)]   # see tests/test_gpu_zz_gcrodr_device.py
     elif meta["krylov"] == "cg":
         it_dev, x_dev, res = deco.solve_cg(b, correction=corr, max_it=meta["max_it"], tol=meta["tol"])
     elif meta["krylov"] == "bgmres":
