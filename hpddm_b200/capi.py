@@ -83,6 +83,7 @@ _SIGS = {
     "hpddm_b200_solve_bgmres": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
     "hpddm_b200_solve_cg": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
     "hpddm_b200_solve_gcrodr": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
+    "hpddm_b200_solve_bgcrodr": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int), _P]),
     "hpddm_b200_recycle_dim": (C.c_int, [_P]),
     "hpddm_b200_recycle_destroy": (C.c_int, [_P]),
 }

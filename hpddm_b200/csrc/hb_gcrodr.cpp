@@ -355,6 +355,47 @@ M select_columns(const std::vector<zc> &th, const M &X, const std::vector<int> &
   return V;
 }
 
+// LAPACK-convention Householder tools (zlarfg, zlarf, zgeqr2, zunm2r) on column-major zc data: the block driver keeps the reflectors of
+// its 2 mu x mu reductions the way geqrf does, because the reference's convergence test reads single entries of Q^H applied to the
+// block residual (checkBlockConvergence, iterative.hpp:139-146)
+void larfg(int n, zc &alpha, zc *x, zc &tau) {
+  double xn = 0.0;
+  for (int i = 0; i < n - 1; ++i) xn += std::norm(x[i]);
+  xn = std::sqrt(xn);
+  if (n <= 0 || (xn == 0.0 && alpha.imag() == 0.0)) {
+    tau = 0.0;
+    return;
+  }
+  const double beta = -std::copysign(std::sqrt(std::norm(alpha) + xn * xn), alpha.real());
+  tau = zc((beta - alpha.real()) / beta, -alpha.imag() / beta);
+  const zc scal = zc(1.0) / (alpha - beta);
+  for (int i = 0; i < n - 1; ++i) x[i] *= scal;
+  alpha = beta;
+}
+void larf_left(int m, int nc, const zc *v1, zc t, zc *Cm, int ldc) {  // C <- (I - t v v^H) C, v = (1; v1)
+  if (t == zc(0.0)) return;
+  for (int j = 0; j < nc; ++j) {
+    zc *cj = Cm + (size_t)j * ldc;
+    zc w = cj[0];
+    for (int r = 1; r < m; ++r) w += std::conj(v1[r - 1]) * cj[r];
+    w *= t;
+    cj[0] -= w;
+    for (int r = 1; r < m; ++r) cj[r] -= v1[r - 1] * w;
+  }
+}
+void geqr2(int m, int n, zc *A, int lda, zc *tau) {
+  for (int i = 0; i < std::min(m, n); ++i) {
+    larfg(m - i, A[i + (size_t)i * lda], A + i + 1 + (size_t)i * lda, tau[i]);
+    if (i < n - 1) larf_left(m - i, n - i - 1, A + i + 1 + (size_t)i * lda, std::conj(tau[i]), A + i + (size_t)(i + 1) * lda, lda);
+  }
+}
+void unm2r_left(bool conj_trans, int m, int nc, int k, const zc *A, int lda, const zc *tau, zc *Cm, int ldc) {  // C <- Q^H C or Q C
+  if (conj_trans)
+    for (int i = 0; i < k; ++i) larf_left(m - i, nc, A + i + 1 + (size_t)i * lda, std::conj(tau[i]), Cm + i, ldc);
+  else
+    for (int i = k - 1; i >= 0; --i) larf_left(m - i, nc, A + i + 1 + (size_t)i * lda, tau[i], Cm + i, ldc);
+}
+
 Vec block(const Backend &be, const Vec &base, int r, int mu) {
   Vec out(base.size());
   for (size_t q = 0; q < base.size(); ++q) out[q] = base[q] + (size_t)r * mu * be.rows(q);
@@ -387,6 +428,11 @@ bool eig_general(int n, const double *a, double *w, double *x) {
   return true;
 }
 
+#define HB_GC_RET(call)      \
+  do {                       \
+    const int r__ = (call);  \
+    if (r__ < 0) return r__; \
+  } while (0)
 #define GC(call)             \
   do {                       \
     const int r__ = (call);  \
@@ -401,7 +447,7 @@ int run(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iteration
   const int m = std::min(p.restart, max_it);  // iterative.hpp:210
   int k = std::min(m - 1, p.recycle);         // iterative.hpp:215
   Recycled &rec = be.recycled();
-  if (rec.k > 0 && rec.mu != mu) {  // the reference re-interprets a pair stored for another number of right-hand sides
+  if (rec.k > 0 && (rec.mu != mu || rec.block)) {  // the reference re-interprets a pair stored for another number of right-hand sides
     be.release(rec.U);              // (GCRODR.hpp:66-67); here such a pair is dropped and rebuilt
     be.release(rec.C);
     rec.k = rec.mu = 0;
@@ -636,6 +682,7 @@ int run(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iteration
         }
         rec.k = k;
         rec.mu = mu;
+        rec.block = false;
         for (int nu = 0; nu < mu; ++nu) {
           Column &cn = col[nu];
           // f = H_m^-H e_m through the stored rotations (GCRODR.hpp:250-255), last column of H_m += h_{m+1,m}^2 f
@@ -752,6 +799,380 @@ int run(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iteration
   *iterations = std::min(j, max_it);
   if (rel_residual)
     for (int nu = 0; nu < mu; ++nu) rel_residual[nu] = p.tol > 0.0 ? res[nu] / norm[nu] : res[nu];
+  return 0;
+}
+
+// ------------------------------------------------------------------ block driver
+int run_block(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iterations, double *rel_residual) {
+  const int mu = p.mu, max_it = p.max_it;
+  const int m = std::min(p.restart, max_it);
+  int k = std::min(m - 1, p.recycle);
+  const int ldh = mu * (m + 1);
+  Recycled &rec = be.recycled();
+  if (rec.k > 0 && (rec.mu != mu || !rec.block)) {  // a pair of another shape (other mu, or one pair per column): dropped and rebuilt
+    be.release(rec.U);
+    be.release(rec.C);
+    rec.k = rec.mu = 0;
+  }
+  bool haveU = rec.k > 0;
+  if (haveU) k = rec.k;
+  Vec V, z, work, pt, scratch;
+  auto cleanup = [&]() {
+    be.release(V);
+    be.release(z);
+    be.release(work);
+    be.release(pt);
+    be.release(scratch);
+  };
+  GC(be.alloc(V, m + 1));
+  GC(be.alloc(z, 1));
+  GC(be.alloc(work, 1));
+  GC(be.alloc(scratch, 1));
+  std::vector<K> hv, coef;
+  std::vector<double> norm(mu), last(mu, 0.0);
+  auto v = [&](int r) { return block(be, V, r, mu); };
+  // rows [r0, r0 + nr) x columns [c0, c0 + nc) of a dense matrix as a contiguous K array (ld nr)
+  auto sub = [&](const M &A, int r0, int nr, int c0, int nc) {
+    coef.resize((size_t)nr * nc);
+    for (int c = 0; c < nc; ++c)
+      for (int r = 0; r < nr; ++r) coef[r + (size_t)c * nr] = from_z(A(r0 + r, c0 + c));
+    return coef.data();
+  };
+  auto to_m = [&](int nr, int nc) {  // hv (nr x nc, ld nr) -> M
+    M A(nr, nc);
+    for (size_t i = 0; i < (size_t)nr * nc; ++i) A.a[i] = to_z(hv[i]);
+    return A;
+  };
+  auto zero_blk = [&](const Vec &w) -> int {
+    for (int nu = 0; nu < mu; ++nu) HB_GC_RET(be.zero_col(nu, w));
+    return 0;
+  };
+  auto copy_blk = [&](const Vec &in, const Vec &out) -> int {
+    for (int nu = 0; nu < mu; ++nu) HB_GC_RET(be.scal_col(nu, 1.0, in, out));
+    return 0;
+  };
+  // w <- w T for a mu x mu matrix T (through the scratch block)
+  auto rmul = [&](const Vec &w, const M &T) -> int {
+    HB_GC_RET(zero_blk(scratch));
+    HB_GC_RET(be.combine_blk(1, w, sub(T, 0, mu, 0, mu), 1.0, scratch));
+    return copy_blk(scratch, w);
+  };
+  // CholQR of one block (IterativeMethod::QR, HPDDM_QR_CHOLQR): R upper; w <- w R^-1 if update.  1 = not positive definite
+  auto cholqr = [&](const Vec &w, bool update, M &R) -> int {
+    HB_GC_RET(be.gram(1, w, w, hv));
+    if (!chol_upper(to_m(mu, mu), R)) return 1;
+    if (update) {
+      M I(mu, mu);
+      for (int a = 0; a < mu; ++a) I(a, a) = 1.0;
+      HB_GC_RET(rmul(w, solve_right_upper(I, R)));
+    }
+    return 0;
+  };
+  auto fallback = [&]() {  // GCRODR.hpp:896-906: rank-deficient block -> the non-block driver, from the current iterate
+    cleanup();
+    return run(be, b, x, p, iterations, rel_residual);
+  };
+  GC(be.start(b, x));
+  GC(be.rhs_norms(b, norm));
+  for (int nu = 0; nu < mu; ++nu)
+    if (norm[nu] < 1e-12) norm[nu] = 1.0;
+  int j = 1, dim = mu * m;
+  while (j <= max_it) {
+    const int shift = haveU ? k : 0;
+    Vec v0 = v(shift);
+    GC(be.gmv(x, v0));
+    for (int nu = 0; nu < mu; ++nu) {
+      GC(be.scal_col(nu, -1.0, v0, v0));
+      GC(be.axpy_col(nu, 1.0, b, v0));
+    }
+    if (j == 1 && haveU) {  // GCRODR.hpp:515-556
+      const int bK = mu * k;
+      if (!p.same_system) {
+        GC(be.alloc(pt, k));
+        for (int c = 0; c < k; ++c) {
+          GC(be.apply(block(be, rec.U, c, mu), block(be, pt, c, mu)));
+          GC(be.gmv(block(be, pt, c, mu), block(be, rec.C, c, mu)));
+        }
+        M G(bK, bK), R;
+        for (int c = 0; c < k; ++c) {
+          GC(be.gram(k, rec.C, block(be, rec.C, c, mu), hv));
+          for (int cc = 0; cc < mu; ++cc)
+            for (int r = 0; r < bK; ++r) G(r, c * mu + cc) = to_z(hv[r + (size_t)cc * bK]);
+        }
+        if (chol_upper(G, R)) {
+          M I(bK, bK);
+          for (int a = 0; a < bK; ++a) I(a, a) = 1.0;
+          const M Rinv = solve_right_upper(I, R);
+          Vec *blks[3] = {&rec.C, &pt, &rec.U};
+          for (Vec *blk : blks)
+            for (int c = k - 1; c >= 0; --c) {  // block upper triangular: column block c only needs the old blocks l <= c
+              GC(zero_blk(scratch));
+              GC(be.combine_blk(c + 1, *blk, sub(Rinv, 0, (c + 1) * mu, c * mu, mu), 1.0, scratch));
+              GC(copy_blk(scratch, block(be, *blk, c, mu)));
+            }
+        }
+      }
+      GC(be.gram(k, rec.C, v0, hv));
+      const std::vector<K> hc(hv);
+      GC(be.combine_blk(k, rec.C, hc.data(), -1.0, v0));
+      if (!p.same_system) {
+        GC(be.combine_blk(k, pt, hc.data(), 1.0, x));
+        be.release(pt);
+      } else {
+        GC(zero_blk(work));
+        GC(be.combine_blk(k, rec.U, hc.data(), 1.0, work));
+        GC(be.apply(work, z));
+        for (int nu = 0; nu < mu; ++nu) GC(be.axpy_col(nu, 1.0, z, x));
+      }
+    }
+    M R0;
+    {
+      const int rc = cholqr(v0, true, R0);
+      GC(rc);
+      if (rc == 1) return fallback();
+    }
+    M H(ldh, m * mu), s(ldh, mu), save(ldh, m * mu), Bm(std::max(k, 1) * mu, m * mu);
+    std::vector<zc> tau((size_t)m * mu, zc(0.0));
+    for (int c = 0; c < mu; ++c)
+      for (int r = 0; r <= c; ++r) s(shift * mu + r, c) = R0(r, c);
+    int i = shift;
+    bool conv_now = false;
+    while (i < m && j <= max_it) {
+      Vec w = v(i + 1);
+      GC(be.apply(v(i), z));
+      GC(be.gmv(z, w));
+      if (haveU) {  // orthogonalisation against C (GCRODR.hpp:616)
+        GC(be.gram(k, rec.C, w, hv));
+        for (int c = 0; c < mu; ++c)
+          for (int r = 0; r < k * mu; ++r) Bm(r, i * mu + c) = to_z(hv[r + (size_t)c * k * mu]);
+        const std::vector<K> hb(hv);
+        GC(be.combine_blk(k, rec.C, hb.data(), -1.0, w));
+      }
+      M Hc(ldh, mu);
+      const int cnt = i + 1 - shift;  // BlockArnoldi (iterative.hpp:714-737): block classical Gram-Schmidt, all products first
+      GC(be.gram(cnt, v(shift), w, hv));
+      for (int c = 0; c < mu; ++c)
+        for (int r = 0; r < cnt * mu; ++r) Hc(shift * mu + r, c) = to_z(hv[r + (size_t)c * cnt * mu]);
+      {
+        const std::vector<K> hp(hv);
+        GC(be.combine_blk(cnt, v(shift), hp.data(), -1.0, w));
+      }
+      M R;
+      {
+        const int rc = cholqr(w, i < m - 1, R);
+        GC(rc);
+        if (rc == 1) return fallback();
+      }
+      for (int c = 0; c < mu; ++c)
+        for (int r = 0; r <= c; ++r) Hc((i + 1) * mu + r, c) = R(r, c);
+      for (int c = 0; c < mu; ++c)
+        for (int r = 0; r < (i + 2 - shift) * mu; ++r) save(r, (i - shift) * mu + c) = Hc(shift * mu + r, c);
+      for (int kk = shift; kk < i; ++kk) unm2r_left(true, 2 * mu, mu, mu, &H(kk * mu, kk * mu), ldh, &tau[(size_t)kk * mu], &Hc(kk * mu, 0), ldh);
+      geqr2(2 * mu, mu, &Hc(i * mu, 0), ldh, &tau[(size_t)i * mu]);
+      for (int c = 0; c < mu; ++c)
+        for (int r = 0; r < ldh; ++r) H(r, i * mu + c) = Hc(r, c);
+      unm2r_left(true, 2 * mu, mu, mu, &H(i * mu, i * mu), ldh, &tau[(size_t)i * mu], &s(i * mu, 0), ldh);
+      ++i;
+      bool all = true;
+      for (int nu = 0; nu < mu; ++nu) {  // checkBlockConvergence<5>, t <= 1 (iterative.hpp:139-146): a partial norm, kept
+        double nrm = 0.0;
+        for (int r = 0; r <= nu; ++r) nrm += std::norm(s(i * mu + r, nu));
+        last[nu] = std::sqrt(nrm);
+        all = all && (p.tol > 0.0 ? last[nu] / norm[nu] <= p.tol : last[nu] <= -p.tol);
+      }
+      if (all) {
+        dim = mu * i;
+        conv_now = true;
+        break;
+      }
+      ++j;
+    }
+    bool done;
+    if (!conv_now && j != max_it + 1 && i == m)
+      done = false;
+    else {
+      done = true;
+      if (j == max_it + 1) {
+        const int rem = haveU ? (max_it - m) % (m - k) : max_it % m;
+        if (rem) dim = mu * (rem + (haveU ? k : 0));
+      }
+    }
+    // updateSolRecycling, block form (iterative.hpp:372-391): Y = R^-1 S, x += M^-1 ([U V] [C^H D r - B Y; Y])
+    const int da = dim - mu * shift;
+    M Y(std::max(da, 0), mu);
+    for (int c = 0; c < mu; ++c)
+      for (int r = da - 1; r >= 0; --r) {
+        zc acc = s(shift * mu + r, c);
+        for (int l = r + 1; l < da; ++l) acc -= H(shift * mu + r, shift * mu + l) * Y(l, c);
+        Y(r, c) = acc / H(shift * mu + r, shift * mu + r);
+      }
+    GC(zero_blk(work));
+    if (haveU) {
+      const int bK = mu * k;
+      M top(bK, mu);
+      if (!p.same_system) {  // C^H D (V_k R_0): the block residual at the start of the cycle
+        GC(copy_blk(v(shift), z));
+        GC(rmul(z, R0));
+        GC(be.gram(k, rec.C, z, hv));
+        top = to_m(bK, mu);
+      }
+      for (int c = 0; c < mu; ++c)
+        for (int r = 0; r < bK; ++r)
+          for (int l = 0; l < da; ++l) top(r, c) -= Bm(r, shift * mu + l) * Y(l, c);
+      GC(be.combine_blk(k, rec.U, sub(top, 0, bK, 0, mu), 1.0, work));
+    }
+    if (da > 0) GC(be.combine_blk(da / mu, v(shift), sub(Y, 0, da, 0, mu), 1.0, work));
+    GC(be.apply(work, z));
+    for (int nu = 0; nu < mu; ++nu) GC(be.axpy_col(nu, 1.0, z, x));
+    if (!conv_now && i == m) {  // GCRODR.hpp:658-661: the last block is normalised here (BlockArnoldi leaves it as is when i == m - 1)
+      const int ir = m - shift;
+      M Rl(mu, mu), I(mu, mu);
+      for (int c = 0; c < mu; ++c) {
+        I(c, c) = 1.0;
+        for (int r = 0; r <= c; ++r) Rl(r, c) = save(ir * mu + r, (ir - 1) * mu + c);
+      }
+      GC(rmul(v(m), solve_right_upper(I, Rl)));
+    }
+    if (p.same_system > 1) {
+      // GCRODR.hpp:663: id[4] / 4 <= 1 guards both branches below
+    } else if (!haveU) {  // GCRODR.hpp:674-760: first pair
+      const int db = std::min(j, m);
+      if (db < k) k = db;
+      const int bK = mu * k, df = db * mu;
+      if (k > 0) {
+        // last block column of H_m += first df rows of Q [R^-H E; 0], E = e_db (R_db^H R_x)   (GCRODR.hpp:682-692)
+        M sb(ldh, mu);
+        for (int c = 0; c < mu; ++c)
+          for (int r = 0; r < mu; ++r) {
+            zc acc(0.0);
+            for (int l = 0; l < mu; ++l) acc += std::conj(save(db * mu + l, (db - 1) * mu + r)) * save(db * mu + l, (m - 1) * mu + c);
+            sb((db - 1) * mu + r, c) = acc;
+          }
+        for (int c = 0; c < mu; ++c)  // trtrs("U", transc): R^H X = sb, forward substitution
+          for (int r = 0; r < df; ++r) {
+            zc acc = sb(r, c);
+            for (int l = 0; l < r; ++l) acc -= std::conj(H(l, r)) * sb(l, c);
+            sb(r, c) = acc / std::conj(H(r, r));
+          }
+        for (int kk = db - 1; kk >= 0; --kk) unm2r_left(false, 2 * mu, mu, mu, &H(kk * mu, kk * mu), ldh, &tau[(size_t)kk * mu], &sb(kk * mu, 0), ldh);
+        M Hbar(df + mu, df), Mh(df, df);
+        for (int c = 0; c < df; ++c)
+          for (int r = 0; r < df + mu; ++r) Hbar(r, c) = save(r, c);
+        for (int c = 0; c < df; ++c)
+          for (int r = 0; r < df; ++r) Mh(r, c) = Hbar(r, c);
+        for (int c = 0; c < mu; ++c)
+          for (int r = 0; r < df; ++r) Mh(r, df - mu + c) += sb(r, c);
+        std::vector<zc> th;
+        M X;
+        if (!eig(Mh, th, X)) {
+          cleanup();
+          return ERR_EIGENSOLVER;
+        }
+        const M vr = select_columns(th, X, order(th, p.target), bK);
+        M Q, Rr;
+        qr(mul(Hbar, vr), Q, Rr);
+        const M Yc = solve_right_upper(vr, Rr);
+        GC(be.alloc(rec.U, k));
+        const int rc_c = be.alloc(rec.C, k);
+        if (rc_c < 0) {
+          be.release(rec.U);
+          GC(rc_c);
+        }
+        rec.k = k;
+        rec.mu = mu;
+        rec.block = true;
+        for (int c = 0; c < k; ++c) {
+          GC(be.combine_blk(db, v(0), sub(Yc, 0, df, c * mu, mu), 1.0, block(be, rec.U, c, mu)));
+          GC(be.combine_blk(db + 1, v(0), sub(Q, 0, df + mu, c * mu, mu), 1.0, block(be, rec.C, c, mu)));
+        }
+        haveU = true;
+      }
+    } else if (j > m - k) {  // GCRODR.hpp:761-884: new pair from [U, V]
+      const int bK = mu * k, diff = dim - bK, nb = diff / mu;
+      if (nb >= 1) {
+        std::vector<double> Du(bK, 1.0);
+        M Wt(dim + mu, bK);
+        if (p.strategy == 0) {
+          for (int c = 0; c < k; ++c) {
+            Vec uc = block(be, rec.U, c, mu);
+            GC(be.gram(1, uc, uc, hv));
+            for (int cc = 0; cc < mu; ++cc) Du[c * mu + cc] = 1.0 / std::sqrt(hb_real(hv[cc + (size_t)cc * mu]));
+            GC(be.gram(k, rec.C, uc, hv));
+            for (int cc = 0; cc < mu; ++cc)
+              for (int r = 0; r < bK; ++r) Wt(r, c * mu + cc) = Du[c * mu + cc] * to_z(hv[r + (size_t)cc * bK]);
+            GC(be.gram(nb + 1, v(k), uc, hv));
+            for (int cc = 0; cc < mu; ++cc)
+              for (int r = 0; r < diff + mu; ++r) Wt(bK + r, c * mu + cc) = Du[c * mu + cc] * to_z(hv[r + (size_t)cc * (diff + mu)]);
+          }
+        }
+        M G(dim + mu, dim), Hbar(diff + mu, diff);
+        for (int c = 0; c < diff; ++c)
+          for (int r = 0; r < diff + mu; ++r) Hbar(r, c) = save(r, c);
+        for (int c = 0; c < bK; ++c) G(c, c) = Du[c];
+        for (int c = 0; c < diff; ++c) {
+          for (int r = 0; r < bK; ++r) G(r, bK + c) = Bm(r, k * mu + c);
+          for (int r = 0; r < diff + mu; ++r) G(bK + r, bK + c) = Hbar(r, c);
+        }
+        const M Am = mul(G, G, true);
+        M Bmat(dim, dim);
+        if (p.strategy == 0) {
+          const M GW = mul(G, Wt, true);
+          for (int c = 0; c < bK; ++c)
+            for (int r = 0; r < dim; ++r) Bmat(r, c) = GW(r, c);
+        } else {
+          for (int c = 0; c < bK; ++c) {
+            Bmat(c, c) = 1.0;
+            for (int r = 0; r < diff; ++r) Bmat(bK + r, c) = std::conj(Bm(c, k * mu + r));
+          }
+        }
+        for (int c = 0; c < diff; ++c)
+          for (int r = 0; r < diff; ++r) Bmat(bK + r, bK + c) = std::conj(Hbar(c, r));
+        M T = Bmat;
+        std::vector<zc> muv, th(dim);
+        M X;
+        if (!lu_solve(Am, T) || !eig(T, muv, X)) {
+          cleanup();
+          return ERR_EIGENSOLVER;
+        }
+        for (int q = 0; q < dim; ++q) th[q] = std::abs(muv[q]) > 0.0 ? zc(1.0) / muv[q] : zc(std::numeric_limits<double>::infinity(), 0.0);
+        const M vr = select_columns(th, X, order(th, p.target), bK);
+        M Q, Rr;
+        qr(mul(G, vr), Q, Rr);
+        M Yc = solve_right_upper(vr, Rr);
+        for (int c = 0; c < bK; ++c)
+          for (int r = 0; r < bK; ++r) Yc(r, c) *= Du[r];
+        // U <- [U, v_k ..] Yc, C <- [C, v_k .. v_{k+nb}] Q, through fresh blocks (the outputs alias the inputs)
+        Vec Un, Cn;
+        GC(be.alloc(Un, k));
+        const int rc_c = be.alloc(Cn, k);
+        if (rc_c < 0) {
+          be.release(Un);
+          GC(rc_c);
+        }
+        int rc = 0;
+        for (int c = 0; c < k && rc >= 0; ++c) {
+          rc = be.combine_blk(k, rec.U, sub(Yc, 0, bK, c * mu, mu), 1.0, block(be, Un, c, mu));
+          if (rc >= 0) rc = be.combine_blk(nb, v(k), sub(Yc, bK, diff, c * mu, mu), 1.0, block(be, Un, c, mu));
+          if (rc >= 0) rc = be.combine_blk(k, rec.C, sub(Q, 0, bK, c * mu, mu), 1.0, block(be, Cn, c, mu));
+          if (rc >= 0) rc = be.combine_blk(nb + 1, v(k), sub(Q, bK, diff + mu, c * mu, mu), 1.0, block(be, Cn, c, mu));
+        }
+        if (rc < 0) {
+          be.release(Un);
+          be.release(Cn);
+          GC(rc);
+        }
+        be.release(rec.U);
+        be.release(rec.C);
+        rec.U = Un;
+        rec.C = Cn;
+      }
+    }
+    if (done) break;
+  }
+  cleanup();
+  *iterations = std::min(j, max_it);
+  if (rel_residual)
+    for (int nu = 0; nu < mu; ++nu) rel_residual[nu] = p.tol > 0.0 ? last[nu] / norm[nu] : last[nu];
   return 0;
 }
 

@@ -23,6 +23,7 @@ typedef std::vector<K *> Vec;
 struct Recycled {
   Vec U, C;  // k blocks each
   int k = 0, mu = 0;
+  bool block = false;  // built by the block driver: ONE pair of mu k columns for all right-hand sides (BGCRODR), not one pair per column
 };
 
 struct Backend {
@@ -43,6 +44,11 @@ struct Backend {
   virtual int scal_col(int nu, double a, const Vec &in, const Vec &out) = 0;      // out[:, nu] = a in[:, nu]
   virtual int axpy_col(int nu, double a, const Vec &in, const Vec &out) = 0;      // out[:, nu] += a in[:, nu]
   virtual int zero_col(int nu, const Vec &out) = 0;
+  // block products of the block driver: `basis` read as the n x (count mu) matrix X of its columns (ld n per subdomain)
+  // out (count mu x mu, column-major, ld count mu) = sum over subdomains and processes of X^H D w
+  virtual int gram(int count, const Vec &basis, const Vec &w, std::vector<K> &out) = 0;
+  // w (n x mu) += alpha * X coef          (coef: host, count mu x mu, column-major, ld count mu)
+  virtual int combine_blk(int count, const Vec &basis, const K *coef, double alpha, const Vec &w) = 0;
 };
 
 constexpr int ERR_EIGENSOLVER = -100;  // the QR iteration of a harmonic Ritz problem did not converge / singular pencil
@@ -63,6 +69,12 @@ struct Params {
 // reference returns them (min(j, max_it)); rel_residual[nu] = last |s| / ||b_nu|| (absolute when tol < 0).  recycle <= 0 is the
 // caller's business (the reference switches to GMRES, GCRODR.hpp:50-55).
 int run(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iterations, double *rel_residual);
+
+// IterativeMethod::BGCRODR (GCRODR.hpp:445-907) with the reference defaults: one block Krylov space and one recycled pair of mu k columns
+// for all right-hand sides, block classical Gram-Schmidt, CholQR, Householder-reduced block Hessenberg matrix (LAPACK conventions: the
+// reference's convergence test reads individual entries of the transformed block residual, iterative.hpp:139-146), no deflation of
+// right-hand sides.  A rank-deficient block continues with run(), as the reference continues with GCRODR (GCRODR.hpp:896-906).
+int run_block(Backend &be, const Vec &b, const Vec &x, const Params &p, int *iterations, double *rel_residual);
 
 // eigenvalues and unit-norm right eigenvectors of a general complex matrix (column-major n x n, interleaved re / im): complex
 // Schur form by Householder reduction + shifted QR, back-substitution.  Exposed for the CPU tests.  Returns false if the QR

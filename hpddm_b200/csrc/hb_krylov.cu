@@ -653,9 +653,9 @@ struct DeviceBackend : gcro::Backend {
     cudaFree(d_T);
     cudaFree(d_h);
   }
-  int init() {
-    HB_CUDA(cudaMalloc(&d_T, (size_t)cap * mu * sizeof(K)));
-    HB_CUDA(cudaMalloc(&d_h, (size_t)cap * sizeof(K)));
+  int init() {  // staging for products / coefficients: cap basis vectors (non-block driver) or cap blocks of mu columns (block driver)
+    HB_CUDA(cudaMalloc(&d_T, (size_t)cap * mu * mu * sizeof(K)));
+    HB_CUDA(cudaMalloc(&d_h, (size_t)cap * mu * mu * sizeof(K)));
     return 0;
   }
   size_t subs() const override { return c->subs.size(); }
@@ -738,6 +738,33 @@ struct DeviceBackend : gcro::Backend {
       if (c->subs[q]->n) HB_CUDA(cudaMemsetAsync(colp(out, q, nu), 0, (size_t)c->subs[q]->n * sizeof(K), c->stream));
     return 0;
   }
+  // block products (BGCRO-DR): the tall-skinny kernels of the BGMRES driver; a basis of `count` blocks is an n x (count mu) matrix with ld n
+  int gram(int count, const gcro::Vec &basis, const gcro::Vec &w, std::vector<K> &out) override {
+    const int rows = count * mu;
+    if (count > cap) {
+      set_error("BGCRO-DR: %d blocks exceed the staging capacity %d", count, cap);
+      return HPDDM_B200_ERR_STATE;
+    }
+    HB_CUDA(cudaMemsetAsync(d_T, 0, (size_t)rows * mu * sizeof(K), c->stream));
+    for (size_t q = 0; q < c->subs.size(); ++q) HB_CHECK(k_zt_raw(c, c->subs[q]->n, rows, basis[q], c->subs[q]->d_d, mu, w[q], d_T, rows));
+    HB_CHECK(nccl_allreduce_sum(c, reinterpret_cast<double *>(d_T), rows * mu * KD));
+    out.resize((size_t)rows * mu);
+    HB_CUDA(cudaMemcpyAsync(out.data(), d_T, (size_t)rows * mu * sizeof(K), cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  int combine_blk(int count, const gcro::Vec &basis, const K *coef, double alpha, const gcro::Vec &w) override {
+    if (count <= 0) return 0;
+    const int rows = count * mu;
+    if (count > cap) {
+      set_error("BGCRO-DR: %d blocks exceed the staging capacity %d", count, cap);
+      return HPDDM_B200_ERR_STATE;
+    }
+    HB_CUDA(cudaMemcpyAsync(d_h, coef, (size_t)rows * mu * sizeof(K), cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));  // `coef` is reused by the driver (see combine_col)
+    for (size_t q = 0; q < c->subs.size(); ++q) HB_CHECK(k_vupdate_blk(c, c->subs[q]->n, rows, mu, basis[q], d_h, rows, alpha, w[q]));
+    return 0;
+  }
 };
 
 }  // namespace
@@ -752,9 +779,17 @@ void gcrodr_release(Ctx *c) {
   c->recycled = nullptr;
 }
 
-int gcrodr_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *> &x, int mu, int correction, int restart, int recycle, int target, int strategy,
-                  int same_system, int max_it, double tol, int *iterations, double *rel_residual) {
-  if (recycle <= 0) return gmres_device(c, b, x, mu, correction, restart, max_it, tol, iterations, rel_residual);  // GCRODR.hpp:50-55
+// block = false: IterativeMethod::GCRODR (one Krylov space and one recycled pair per right-hand side); block = true: IterativeMethod::BGCRODR
+// (GCRODR.hpp:445-907: one block Krylov space and one pair of mu k columns for all right-hand sides)
+int gcrodr_device(Ctx *c, bool block, const std::vector<const K *> &b, const std::vector<K *> &x, int mu, int correction, int restart, int recycle, int target,
+                  int strategy, int same_system, int max_it, double tol, int *iterations, double *rel_residual) {
+  if (recycle <= 0)  // GCRODR.hpp:50-55, 460-465
+    return block ? bgmres_device(c, b, x, mu, correction, std::min(restart, max_it), max_it, tol, iterations, rel_residual)
+                 : gmres_device(c, b, x, mu, correction, restart, max_it, tol, iterations, rel_residual);
+  if (block && (size_t)(std::min(restart, max_it) + 1) * mu * 4 * sizeof(K) > 48 * 1024) {
+    set_error("solve_bgcrodr: (restart + 1) x mu = %d x %d exceeds the shared-memory staging of the block update kernel", std::min(restart, max_it) + 1, mu);
+    return HPDDM_B200_ERR_ARG;
+  }
   RecycledDev *rd = static_cast<RecycledDev *>(c->recycled);
   std::vector<int> sizes;
   for (Sub *s : c->subs) sizes.push_back(s->n);
@@ -781,7 +816,7 @@ int gcrodr_device(Ctx *c, const std::vector<const K *> &b, const std::vector<K *
   p.same_system = same_system;
   gcro::Vec bv(b.size());
   for (size_t q = 0; q < b.size(); ++q) bv[q] = const_cast<K *>(b[q]);  // the driver only reads b
-  const int rc = gcro::run(be, bv, x, p, iterations, rel_residual);
+  const int rc = block ? gcro::run_block(be, bv, x, p, iterations, rel_residual) : gcro::run(be, bv, x, p, iterations, rel_residual);
   cudaStreamSynchronize(c->stream);
   if (rc == gcro::ERR_EIGENSOLVER) {
     set_error("solve_gcrodr: the harmonic Ritz eigenproblem of a cycle could not be solved (QR iteration did not converge or singular pencil)");
@@ -897,7 +932,22 @@ extern "C" int HB_API(solve_gcrodr)(hb_ctx_t *ctx, const K *const *b, K *const *
   }
   *iterations = 0;
   return krylov_entry(c, b, x, mu, where, [&](const std::vector<const K *> &bd, const std::vector<K *> &xd) {
-    return gcrodr_device(c, bd, xd, mu, correction, restart, recycle, recycle_target, recycle_strategy, recycle_same_system, max_it, tol, iterations, rel_residual);
+    return gcrodr_device(c, false, bd, xd, mu, correction, restart, recycle, recycle_target, recycle_strategy, recycle_same_system, max_it, tol, iterations, rel_residual);
+  });
+}
+
+extern "C" int HB_API(solve_bgcrodr)(hb_ctx_t *ctx, const K *const *b, K *const *x, int mu, int correction, int restart, int recycle, int recycle_target,
+                                        int recycle_strategy, int recycle_same_system, int max_it, double tol, int where, int *iterations,
+                                        double *rel_residual) {
+  Ctx *c = reinterpret_cast<Ctx *>(ctx);
+  if (!c || !iterations || restart < 1 || max_it < 1 || mu < 1 || recycle_target < 0 || recycle_target > 5 || recycle_strategy < 0 || recycle_strategy > 1 ||
+      recycle_same_system < 0 || recycle_same_system > 2) {
+    set_error("solve_bgcrodr: bad arguments");
+    return HPDDM_B200_ERR_ARG;
+  }
+  *iterations = 0;
+  return krylov_entry(c, b, x, mu, where, [&](const std::vector<const K *> &bd, const std::vector<K *> &xd) {
+    return gcrodr_device(c, true, bd, xd, mu, correction, restart, recycle, recycle_target, recycle_strategy, recycle_same_system, max_it, tol, iterations, rel_residual);
   });
 }
 

@@ -115,6 +115,11 @@ struct Api;
     {                                                                                                                                              \
       return P_##_solve_gcrodr(c, b, x, mu, corr, m, k, target, strategy, same, it, tol, w, its, res);                                             \
     }                                                                                                                                              \
+    static int solve_bgcrodr(ctx_t *c, const K_ *const *b, K_ *const *x, int mu, int corr, int m, int k, int target, int strategy, int same,       \
+                             int it, double tol, int w, int *its, double *res)                                                                     \
+    {                                                                                                                                              \
+      return P_##_solve_bgcrodr(c, b, x, mu, corr, m, k, target, strategy, same, it, tol, w, its, res);                                            \
+    }                                                                                                                                              \
     static int recycle_destroy(ctx_t *c) { return P_##_recycle_destroy(c); }                                                                       \
   }
 HPDDM_B200_DEFINE_API(double, hpddm_b200);
@@ -367,7 +372,7 @@ public:
     b200::check<K>(A_::compute_residual(ctx_, xx, ff, storage, mu, norm, HPDDM_B200_HOST), "compute_residual");
   }
   /* Device-resident counterpart of IterativeMethod::solve(A, f, sol, mu, comm) (include/HPDDM_iterative.hpp:1013-1111): the Krylov
-   * vectors never leave HBM.  method: 0 = GMRES (HPDDM_KRYLOV_METHOD_GMRES), 1 = BGMRES, 2 = CG, 4 = GCRODR (with `recycle` harmonic Ritz
+   * vectors never leave HBM.  method: 0 = GMRES (HPDDM_KRYLOV_METHOD_GMRES), 1 = BGMRES, 2 = CG, 4 = GCRODR, 5 = BGCRODR (with `recycle` harmonic Ritz
    * vectors kept between calls, default target / strategy) -- the values of -hpddm_krylov_method (include/HPDDM_define.hpp).  Returns the
    * iteration count like the reference's drivers (negative = error). */
   int solve(const K *const f, K *const x, const unsigned short mu = 1, int method = 0, int restart = 40, int max_it = 100, double tol = 1.0e-6, int recycle = 0) const
@@ -376,6 +381,7 @@ public:
     K       *xx[1] = {x};
     int      it = 0, rc;
     if (method == 4) rc = A_::solve_gcrodr(ctx_, bb, xx, mu, correction_, restart, recycle, 0, 0, 0, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
+    else if (method == 5) rc = A_::solve_bgcrodr(ctx_, bb, xx, mu, correction_, restart, recycle, 0, 0, 0, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     else if (method == 1) rc = A_::solve_bgmres(ctx_, bb, xx, mu, correction_, restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     else if (method == 2) rc = A_::solve_cg(ctx_, bb, xx, mu, correction_, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
     else rc = A_::solve(ctx_, bb, xx, mu, correction_, restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);

@@ -344,10 +344,11 @@ public:
     const K          *bb[1] = {f};
     K                *xx[1] = {x};
     int               it = 0, rc;
-    if (method == HPDDM_KRYLOV_METHOD_GCRODR) {  // -hpddm_recycle / _recycle_target / _recycle_strategy / _recycle_same_system as IterativeMethod::options reads them (iterative.hpp:215-217)
+    if (method == HPDDM_KRYLOV_METHOD_GCRODR || method == HPDDM_KRYLOV_METHOD_BGCRODR) {  // -hpddm_recycle / _recycle_target / _recycle_strategy / _recycle_same_system as IterativeMethod::options reads them (iterative.hpp:215-217)
       const int same = std::min(opt.val<unsigned short>(prefix + "recycle_same_system"), static_cast<unsigned short>(2));
-      rc             = A_::solve_gcrodr(ctx_, bb, xx, mu, correction(), restart, opt.val<int>(prefix + "recycle", 0), opt.val<char>(prefix + "recycle_target", HPDDM_RECYCLE_TARGET_SM),
-                                        opt.val<char>(prefix + "recycle_strategy", HPDDM_RECYCLE_STRATEGY_A), same, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
+      const int k = opt.val<int>(prefix + "recycle", 0), target = opt.val<char>(prefix + "recycle_target", HPDDM_RECYCLE_TARGET_SM), strategy = opt.val<char>(prefix + "recycle_strategy", HPDDM_RECYCLE_STRATEGY_A);
+      rc = method == HPDDM_KRYLOV_METHOD_GCRODR ? A_::solve_gcrodr(ctx_, bb, xx, mu, correction(), restart, k, target, strategy, same, max_it, tol, HPDDM_B200_HOST, &it, nullptr)
+                                                 : A_::solve_bgcrodr(ctx_, bb, xx, mu, correction(), restart, k, target, strategy, same, max_it, tol, HPDDM_B200_HOST, &it, nullptr);
       if (rc == 0 && it != 0 && it != max_it && same) (*Option::get())[prefix + "recycle_same_system"] += 1;  // GCRODR.hpp:435
     }
     else if (method == HPDDM_KRYLOV_METHOD_BGMRES) rc = A_::solve_bgmres(ctx_, bb, xx, mu, correction(), restart, max_it, tol, HPDDM_B200_HOST, &it, nullptr);

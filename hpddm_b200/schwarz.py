@@ -363,6 +363,19 @@ class Decomposition:
                                              self.RECYCLE_TARGET[target], {"A": 0, "B": 1}[strategy], int(same_system), int(max_it), float(tol), capi.HOST, C.byref(it), capi.ptr(res)))
         return it.value, x, res
 
+    # IterativeMethod::BGCRODR (include/HPDDM_GCRODR.hpp:445-907): block version, one recycled pair of mu k columns for all right-hand sides
+    def solve_bgcrodr(self, b, x0=None, correction="__default__", restart=40, recycle=10, max_it=100, tol=1e-6, target="SM", strategy="A", same_system=0):
+        corr = self.correction if correction == "__default__" else correction
+        b = [_f(v, self.dtype) for v in b]
+        x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v, self.dtype).copy(order="F") for v in x0]
+        mu = b[0].shape[1]
+        it = C.c_int(0)
+        res = np.zeros(mu)
+        self.api.check(self.api.solve_bgcrodr(self.ctx, capi.ptr_array(b), capi.ptr_array(x), mu, capi.CORRECTION[corr], int(restart), int(recycle),
+                                              self.RECYCLE_TARGET[target], {"A": 0, "B": 1}[strategy], int(same_system), int(max_it), float(tol), capi.HOST, C.byref(it),
+                                              capi.ptr(res)))
+        return it.value, x, res
+
     def recycle_dim(self):
         return int(self.api.recycle_dim(self.ctx))
 

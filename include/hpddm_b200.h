@@ -253,6 +253,13 @@ int hpddm_b200_solve_bgmres(hpddm_b200_ctx *ctx, const double *const *b, double 
 #define HPDDM_B200_RECYCLE_STRATEGY_B 1
 int hpddm_b200_solve_gcrodr(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int correction, int restart, int recycle, int recycle_target,
                             int recycle_strategy, int recycle_same_system, int max_it, double tol, int where, int *iterations, double *rel_residual);
+/* IterativeMethod::BGCRODR (include/HPDDM_GCRODR.hpp:445-907): the block version -- one block Krylov space and ONE recycled pair of mu k
+ * columns for all right-hand sides; block classical Gram-Schmidt, CholQR, Householder-reduced block Hessenberg matrix and the reference's
+ * per-column convergence test as in hpddm_b200_solve_bgmres, no deflation of right-hand sides; same arguments as hpddm_b200_solve_gcrodr
+ * (recycle <= 0 runs BGMRES, GCRODR.hpp:460-465).  A rank-deficient block continues with the non-block driver, as the reference does
+ * (GCRODR.hpp:896-906).  The block and the non-block driver do not share a stored pair: each drops and rebuilds a pair of the other kind. */
+int hpddm_b200_solve_bgcrodr(hpddm_b200_ctx *ctx, const double *const *b, double *const *x, int mu, int correction, int restart, int recycle, int recycle_target,
+                             int recycle_strategy, int recycle_same_system, int max_it, double tol, int where, int *iterations, double *rel_residual);
 /* dimension k of the stored pair (0: none) / release it */
 int hpddm_b200_recycle_dim(hpddm_b200_ctx *ctx);
 int hpddm_b200_recycle_destroy(hpddm_b200_ctx *ctx);

@@ -199,6 +199,9 @@ int hpddm_b200z_solve_bgmres(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b,
 /* IterativeMethod::GCRODR (include/HPDDM_GCRODR.hpp:35-444); see hpddm_b200_solve_gcrodr (targets / strategies: HPDDM_B200_RECYCLE_*) */
 int hpddm_b200z_solve_gcrodr(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpddm_b200_z *const *x, int mu, int correction, int restart, int recycle,
                              int recycle_target, int recycle_strategy, int recycle_same_system, int max_it, double tol, int where, int *iterations, double *rel_residual);
+/* IterativeMethod::BGCRODR (include/HPDDM_GCRODR.hpp:445-907); see hpddm_b200_solve_bgcrodr */
+int hpddm_b200z_solve_bgcrodr(hpddm_b200z_ctx *ctx, const hpddm_b200_z *const *b, hpddm_b200_z *const *x, int mu, int correction, int restart, int recycle,
+                              int recycle_target, int recycle_strategy, int recycle_same_system, int max_it, double tol, int where, int *iterations, double *rel_residual);
 int hpddm_b200z_recycle_dim(hpddm_b200z_ctx *ctx);
 int hpddm_b200z_recycle_destroy(hpddm_b200z_ctx *ctx);
 

@@ -98,6 +98,29 @@ struct HostBackend : gcro::Backend {
       for (int i = 0; i < n[q]; ++i) out[q][(size_t)nu * n[q] + i] = mk(0.0);
     return 0;
   }
+  int gram(int count, const Vec &basis, const Vec &w, std::vector<K> &out) override {
+    const int rows = count * mu;
+    out.assign((size_t)rows * mu, mk(0.0));
+    for (int q = 0; q < P; ++q)
+      for (int col = 0; col < mu; ++col)
+        for (int r = 0; r < rows; ++r) {
+          K acc = mk(0.0);
+          for (int i = 0; i < n[q]; ++i) acc = acc + d[q][i] * (hb_conj(basis[q][(size_t)r * n[q] + i]) * w[q][(size_t)col * n[q] + i]);
+          out[r + (size_t)col * rows] = out[r + (size_t)col * rows] + acc;
+        }
+    return 0;
+  }
+  int combine_blk(int count, const Vec &basis, const K *coef, double alpha, const Vec &w) override {
+    const int rows = count * mu;
+    for (int q = 0; q < P; ++q)
+      for (int col = 0; col < mu; ++col)
+        for (int i = 0; i < n[q]; ++i) {
+          K acc = mk(0.0);
+          for (int r = 0; r < rows; ++r) acc = acc + basis[q][(size_t)r * n[q] + i] * coef[r + (size_t)col * rows];
+          w[q][(size_t)col * n[q] + i] = w[q][(size_t)col * n[q] + i] + alpha * acc;
+        }
+    return 0;
+  }
 };
 
 }  // namespace
@@ -107,7 +130,7 @@ extern "C" {
 // state: in/out opaque handle of the recycled pair (nullptr on the first solve); counts[0 / 1] = apply / GMV calls of this solve
 int gcrodr_host_run(int P, const int *n, const double *const *d, op_cb apply, op_cb gmv, op_cb start, norm_cb norms, void *user, K *const *b, K *const *x, int mu,
                     int restart, int recycle, int max_it, double tol, int target, int strategy, int same_system, int *iterations, double *rel_residual, void **state,
-                    long *counts) {
+                    long *counts, int block) {
   HostBackend be;
   be.P = P;
   be.mu = mu;
@@ -130,7 +153,7 @@ int gcrodr_host_run(int P, const int *n, const double *const *d, op_cb apply, op
   p.strategy = strategy;
   p.same_system = same_system;
   const Vec bv(b, b + P), xv(x, x + P);
-  const int rc = gcro::run(be, bv, xv, p, iterations, rel_residual);
+  const int rc = block ? gcro::run_block(be, bv, xv, p, iterations, rel_residual) : gcro::run(be, bv, xv, p, iterations, rel_residual);
   if (counts) {
     counts[0] = be.calls_apply;
     counts[1] = be.calls_gmv;

@@ -22,7 +22,7 @@ void instantiate() {
   A.solveGEVP(M, 4); A.callNumfact(); K **ev = nullptr; A.setVectors(ev, 1); A.template buildTwo<0>(0);
   A.start(nullptr, (K *)nullptr, 1); A.apply((const K *)nullptr, (K *)nullptr, 1); A.template deflation<false>(nullptr, (K *)nullptr, 1);
   A.GMV(nullptr, (K *)nullptr, 1); A.template exchange<true>(nullptr, 1); A.end(); A.computeResidual(nullptr, nullptr, nullptr, 1);
-  A.solve(nullptr, (K *)nullptr, 1, 0); A.solve(nullptr, (K *)nullptr, 4, 1); A.solve(nullptr, (K *)nullptr, 1, 2); A.solve(nullptr, (K *)nullptr, 2, 4, 30, 100, 1e-8, 10);
+  A.solve(nullptr, (K *)nullptr, 1, 0); A.solve(nullptr, (K *)nullptr, 4, 1); A.solve(nullptr, (K *)nullptr, 1, 2); A.solve(nullptr, (K *)nullptr, 2, 4, 30, 100, 1e-8, 10); A.solve(nullptr, (K *)nullptr, 2, 5, 30, 100, 1e-8, 10);
   (void)A.getVectors(); A.statistics();
   (void)A.getScaling(); (void)A.getDof(); (void)A.boundaryConditions(); (void)A.prefix();
 }

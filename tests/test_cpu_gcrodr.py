@@ -34,7 +34,7 @@ def harness(tmp_path_factory):
         lib.gcrodr_host_run.restype = C.c_int
         lib.gcrodr_host_run.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), OP_CB, OP_CB, OP_CB, NORM_CB, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_void_p),
-                                        C.POINTER(C.c_long)]
+                                        C.POINTER(C.c_long), C.c_int]
         lib.gcrodr_host_free.argtypes = [C.c_void_p]
         lib.gcrodr_host_recycled_dim.argtypes = [C.c_void_p]
         lib.gcrodr_host_eig.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -85,7 +85,7 @@ class HostGcrodr:
                 return -1
         self.cb_norm = NORM_CB(norm_cb)
 
-    def solve(self, b, restart, recycle, max_it=100, tol=1e-6, target="SM", strategy="A", same_system=0):
+    def solve(self, b, restart, recycle, max_it=100, tol=1e-6, target="SM", strategy="A", same_system=0, block=False):
         bs = [np.array(v, dtype=self.dtype, order="F", copy=True) for v in b]
         xs = [np.zeros_like(v, order="F") for v in bs]
         arr = lambda vs: (C.c_void_p * self.P)(*[v.ctypes.data for v in vs])
@@ -94,7 +94,7 @@ class HostGcrodr:
         counts = (C.c_long * 2)()
         nn = (C.c_int * self.P)(*self.n)
         rc = self.lib.gcrodr_host_run(self.P, nn, arr(self.d), self.cb_apply, self.cb_gmv, self.cb_start, self.cb_norm, None, arr(bs), arr(xs), self.mu, restart, recycle,
-                                      max_it, tol, TARGETS[target], 0 if strategy == "A" else 1, same_system, C.byref(it), rel.ctypes.data_as(C.POINTER(C.c_double)), C.byref(self.state), counts)
+                                      max_it, tol, TARGETS[target], 0 if strategy == "A" else 1, same_system, C.byref(it), rel.ctypes.data_as(C.POINTER(C.c_double)), C.byref(self.state), counts, int(block))
         if self.error is not None:
             raise self.error
         assert rc == 0, rc
@@ -323,3 +323,41 @@ def test_reference_known_answer_40X_sequence_block_driver():
         got.append(it)
         assert np.linalg.norm(mats[i] @ x[0][:, 0] - rhs[i][:, 0]) <= 1e-7 * np.linalg.norm(rhs[i])
     assert got == want.tolist()
+
+
+@pytest.mark.parametrize("name", [n for n in cases() if "_bgcrodr_" in n])
+def test_product_block_driver_reproduces_the_reference_bgcrodr(harness, name):
+    """gcro::run_block (IterativeMethod::BGCRODR) on the host backend against goldens of the unmodified reference: one, two and three
+    right-hand sides, complex scalars, sequences of solves sharing the block pair"""
+    parts, ref, meta, w, op = _world(name)
+    P = meta["P"]
+    dtype = np.complex128 if meta["complex"] else np.float64
+    h = HostGcrodr(harness["complex" if meta["complex"] else "real"], op, [p["ndof"] for p in parts], w.d, meta["mu"], dtype)
+    for s in range(1, meta["solves"] + 1):
+        tag = "" if s == 1 else str(s)
+        b = [parts[r]["f"] if s == 1 else ref[r]["f" + tag] for r in range(P)]
+        it, x, res, _ = h.solve(b, meta["restart"], meta["recycle"], max_it=meta["max_it"], tol=meta["tol"], block=True)
+        assert it == int(ref[0]["iterations" + tag][0]), (s, it)
+        assert max(rel(x[r], ref[r]["sol" + tag]) for r in range(P)) < 1e-8, s
+    assert h.lib.gcrodr_host_recycled_dim(h.state) == min(meta["recycle"], meta["restart"] - 1)
+    # the two drivers do not share a pair: the non-block driver drops the block pair and builds its own
+    it, x, _, _ = h.solve([parts[r]["f"] for r in range(P)], meta["restart"], meta["recycle"], max_it=meta["max_it"], tol=meta["tol"])
+    res = w.compute_residual(x, [parts[r]["f"] for r in range(P)])
+    assert np.all(res[:, 1] <= 3 * meta["tol"] * res[:, 0])
+    h.close()
+
+
+def test_product_block_driver_passes_the_reference_known_answer_test(harness):
+    """first four systems of the 40X sequence through gcro::run_block (one right-hand side): 497 231 206 198, as the unmodified driver"""
+    z, mats, rhs = _sequence_40x()
+    n = mats[0].shape[0]
+    h = None
+    for i in range(4):
+        op = _CsrOperator(mats[i], False)
+        if h is None:
+            h = HostGcrodr(harness["real"], op, [n], [np.ones(n)], 1, np.float64)
+        h.op = op
+        it, x, _, _ = h.solve([rhs[i]], 40, 20, max_it=1000, tol=1e-10, block=True)
+        assert it == int(z["bgcrodr_40_20_tol1e10"][i])
+        assert np.linalg.norm(mats[i] @ x[0][:, 0] - rhs[i][:, 0]) <= 1e-7 * np.linalg.norm(rhs[i])
+    h.close()

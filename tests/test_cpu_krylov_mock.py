@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 import scipy.sparse as sp
 
+from oracle.gcrodr import bgcrodr as oracle_bgcrodr
 from oracle.gcrodr import gcrodr as oracle_gcrodr
 from oracle.krylov import bgmres, cg, gmres
 from tests.test_cpu_gcrodr import _CsrOperator, _sequence_40x
@@ -87,6 +88,9 @@ class MockDeco:
 
     def solve_gcrodr(self, b, restart=40, recycle=10, max_it=100, tol=1e-6, target=0, strategy=0, same_system=0):
         return self._call("solve_gcrodr", b, C.c_int(restart), C.c_int(recycle), C.c_int(target), C.c_int(strategy), C.c_int(same_system), C.c_int(max_it), C.c_double(tol))
+
+    def solve_bgcrodr(self, b, restart=40, recycle=10, max_it=100, tol=1e-6, target=0, strategy=0, same_system=0):
+        return self._call("solve_bgcrodr", b, C.c_int(restart), C.c_int(recycle), C.c_int(target), C.c_int(strategy), C.c_int(same_system), C.c_int(max_it), C.c_double(tol))
 
     def recycle_dim(self):
         return getattr(self.lib, self.prefix + "recycle_dim")(self.ctx)
@@ -191,3 +195,36 @@ def test_gmres_cg_bgmres_drivers_on_the_mock(mock):
     it, x, _ = d.solve_bgmres(b, restart=15, max_it=300, tol=1e-8)
     assert abs(it - it0) <= 1 and np.abs(x - x0[0]).max() <= 1e-6 * np.abs(x0[0]).max()
     d.close()
+
+
+def test_exported_bgcrodr_entry_point(mock):
+    """hpddm_b200[z]_solve_bgcrodr (IterativeMethod::BGCRODR: one block Krylov space, one recycled pair of mu k columns): the reference's
+    40X known-answer counts with one right-hand side on three row blocks; three right-hand sides and two solves against the oracle
+    restatement (itself pinned by goldens of the reference); complex scalars; the block and the non-block driver swap their pairs"""
+    z, mats, rhs = _sequence_40x()
+    n = mats[0].shape[0]
+    d = MockDeco(mock, mats[0], (1000, 1, 2987))
+    for i in range(4):
+        d.set_values(mats[i])
+        it, x, _ = d.solve_bgcrodr(rhs[i], restart=40, recycle=20, max_it=1000, tol=1e-10)
+        assert it == int(z["bgcrodr_40_20_tol1e10"][i]) and d.recycle_dim() == 20
+        assert np.linalg.norm(mats[i] @ x[:, 0] - rhs[i][:, 0]) <= 1e-7 * np.linalg.norm(rhs[i])
+    d.close()
+    for A, cplx in ((_poisson2d(22), False), (_poisson2d(22, -0.6 + 0.35j).astype(np.complex128), True)):
+        n = A.shape[0]
+        rs = np.random.RandomState(11)
+        dd = MockDeco(mock, A, (n - 170, 170), jacobi=True)
+        op = _CsrOperator(A, True)
+        state = None
+        for s in range(2):
+            b = np.asfortranarray(rs.uniform(size=(n, 3)) + (1j * rs.uniform(size=(n, 3)) if cplx else 0.0))
+            it0, x0, state = oracle_bgcrodr(op, [b], restart=10, recycle=3, max_it=300, tol=1e-8, state=state)
+            it, x, _ = dd.solve_bgcrodr(b, restart=10, recycle=3, max_it=300, tol=1e-8)
+            assert it == it0, (cplx, s, it, it0)
+            assert np.abs(x - x0[0]).max() <= 1e-7 * np.abs(x0[0]).max()
+        assert dd.recycle_dim() == 3
+        it, x, _ = dd.solve_gcrodr(b, restart=10, recycle=3, max_it=300, tol=1e-8)      # drops the block pair, builds one pair per column
+        assert np.abs(A @ x - b).max() <= 1e-6 * np.abs(b).max() and dd.recycle_dim() == 3
+        it, x, _ = dd.solve_bgcrodr(b, restart=10, recycle=0, max_it=300, tol=1e-8)     # recycle = 0: BGMRES (GCRODR.hpp:460-465)
+        assert it == dd.solve_bgmres(b, restart=10, max_it=300, tol=1e-8)[0]
+        dd.close()

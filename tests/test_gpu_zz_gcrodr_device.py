@@ -1,5 +1,5 @@
-"""GPU: the device-resident GCRO-DR driver (hpddm_b200[z]_solve_gcrodr: Krylov basis and recycled pair (U, C) in HBM) on the goldens
-of the unmodified reference's IterativeMethod::GCRODR -- every solve of a sequence that shares the recycled pair must give the
+"""GPU: the device-resident GCRO-DR and BGCRO-DR drivers (hpddm_b200[z]_solve_gcrodr / _solve_bgcrodr: Krylov basis and recycled pair
+(U, C) in HBM) on the goldens of the unmodified reference's IterativeMethod::GCRODR / BGCRODR -- every solve of a sequence that shares the recycled pair must give the
 reference's iteration count and solution.
 
 Status of this file (round 2): the driver's logic (hb_gcrodr.cpp) is verified on the CPU against the same goldens through a host
@@ -24,7 +24,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.xfail(strict=False, reason="device backend of the GCRO-DR driver not yet run on hardware (CPU-verified logic, see module docstring)")
-@pytest.mark.parametrize("name", [n for n in cases() if "_gcrodr_" in n])
+@pytest.mark.parametrize("name", [n for n in cases() if "_gcrodr_" in n or "_bgcrodr_" in n])
 def test_device_gcrodr_reproduces_the_reference(name):
     res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "run_gcrodr_device.py"), name], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, (res.stdout + res.stderr)[-3000:]

@@ -94,6 +94,12 @@ class FakeDecomposition:
                                    target=target, strategy=strategy, same_system=same_system)
         return it, x, np.zeros(b[0].shape[1])
 
+    def solve_bgcrodr(self, b, correction=None, restart=40, recycle=10, max_it=100, tol=1e-6, target="SM", strategy="A", same_system=0):
+        from oracle.gcrodr import bgcrodr
+        it, x, self.state = bgcrodr(OracleOperator(self.w, correction), b, restart=restart, recycle=recycle, max_it=max_it, tol=tol, state=getattr(self, "state", None),
+                                    target=target, strategy=strategy, same_system=same_system)
+        return it, x, np.zeros(b[0].shape[1])
+
     def recycle_dim(self):
         st = getattr(self, "state", None)
         return st["k"] if st and st.get("U") is not None else 0
@@ -115,7 +121,7 @@ def main(names):
     R.build_gpu_decomposition = T.build_gpu_decomposition
     for name in names or cases():
         T.test_cuda_path_reproduces_the_reference(name)
-        if "_gcrodr_" in name:
+        if "_gcrodr_" in name or "_bgcrodr_" in name:
             R.main(name)
         print("ok", name, flush=True)
 

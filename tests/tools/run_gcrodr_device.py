@@ -1,4 +1,4 @@
-"""Runs the device-resident GCRO-DR driver (hpddm_b200[z]_solve_gcrodr) on one golden of the unmodified reference and prints one
+"""Runs the device-resident GCRO-DR / BGCRO-DR driver (hpddm_b200[z]_solve_gcrodr / _solve_bgcrodr, by the golden's Krylov method) on one golden of the unmodified reference and prints one
 JSON line: iteration counts of every solve of the sequence next to the reference's, the relative error of every solution, the
 dimension of the recycled pair kept in the context, kernel launches.  Run by tests/test_gpu_zz_gcrodr_device.py in its own
 process (a fault in the driver must not take the CUDA context of the test session with it).
@@ -30,11 +30,13 @@ def main(name):
             s.setVectors(ref[r]["Z"].reshape(meta["nu"], -1).T)
         deco.buildTwo()
         corr = "deflated"
+    block = meta["krylov"] == "bgcrodr"
+    solver = deco.solve_bgcrodr if block else deco.solve_gcrodr
     out = dict(case=name, its=[], ref=[], err=[], res=[])
     for s in range(1, meta["solves"] + 1):
         tag = "" if s == 1 else str(s)
         b = [parts[r]["f"] if s == 1 else ref[r]["f" + tag] for r in range(P)]
-        it, x, res = deco.solve_gcrodr(b, correction=corr, restart=meta["restart"], recycle=meta["recycle"], max_it=meta["max_it"], tol=meta["tol"],
+        it, x, res = solver(b, correction=corr, restart=meta["restart"], recycle=meta["recycle"], max_it=meta["max_it"], tol=meta["tol"],
                                        target=meta["recycle_target"], same_system=min(s, 2) if meta["same_system"] else 0)
         gold = [ref[r]["sol" + tag] for r in range(P)]
         out["its"].append(int(it))
@@ -46,8 +48,9 @@ def main(name):
     out["recycled_dim_after_destroy"] = deco.recycle_dim()
     # recycle = 0 is GMRES (GCRODR.hpp:50-55): same count as the plain device driver
     b = [parts[r]["f"] for r in range(P)]
-    out["gmres_fallback"] = [int(deco.solve_gcrodr(b, correction=corr, restart=meta["restart"], recycle=0, max_it=meta["max_it"], tol=meta["tol"])[0]),
-                             int(deco.solve(b, correction=corr, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])[0])]
+    plain = deco.solve_bgmres if block else deco.solve
+    out["gmres_fallback"] = [int(solver(b, correction=corr, restart=meta["restart"], recycle=0, max_it=meta["max_it"], tol=meta["tol"])[0]),
+                             int(plain(b, correction=corr, restart=meta["restart"], max_it=meta["max_it"], tol=meta["tol"])[0])]
     out["launches"] = int(deco.launches)
     deco.close()
     print(json.dumps(out))
