@@ -274,6 +274,15 @@ def run_b200(args):
             t0 = time.time()
             it_k, _, res = fn(bvec, correction="deflated")
             out["krylov"][name] = {"seconds": time.time() - t0, "iterations": it_k, "max_rel_residual": float(np.max(res)), "rhs": mu}
+        # GCRO-DR(40, 10) (the Krylov method of BASELINE config 5): two consecutive solves, the second one starts from the recycled pair
+        # kept in the context (NOTE: device backend of this driver not yet measured on hardware when this line was written)
+        deco.recycle_destroy()
+        for tag in ("gcrodr_first_solve", "gcrodr_second_solve"):
+            deco.synchronize()
+            t0 = time.time()
+            it_k, _, res = deco.solve_gcrodr(bvec, correction="deflated", restart=40, recycle=10)
+            out["krylov"][tag] = {"seconds": time.time() - t0, "iterations": it_k, "max_rel_residual": float(np.max(res)), "rhs": mu, "recycled_dim": deco.recycle_dim()}
+        deco.recycle_destroy()
     if cplx or elas:
         out["cpu_baseline"] = None   # the CPU arm (oracle/cpu_ras.cpp) is the scalar Poisson workload; these benches are auxiliary
     elif args.cpu_baseline and rank == 0 and world == 1:
