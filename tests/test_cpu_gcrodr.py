@@ -28,7 +28,7 @@ def harness(tmp_path_factory):
     tmp = tmp_path_factory.mktemp("gcrodr")
     for name, flags in (("real", []), ("complex", ["-DHB_COMPLEX"])):
         so = str(tmp / f"libgcrodr_host_{name}.so")
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-Wall", "-I/usr/local/cuda/include"] + flags +
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-Wall", "-I/usr/local/cuda/include"] + os.environ.get("HB_TEST_CXXFLAGS", "").split() + flags +
                               ["-o", so, os.path.join(ROOT, "tests", "native", "gcrodr_host.cpp"), os.path.join(ROOT, "hpddm_b200", "csrc", "hb_gcrodr.cpp")])
         lib = C.CDLL(so)
         lib.gcrodr_host_run.restype = C.c_int

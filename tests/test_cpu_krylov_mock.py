@@ -28,7 +28,7 @@ def mock(tmp_path_factory):
     out = {}
     for name, flags, prefix in (("real", [], "hpddm_b200_"), ("complex", ["-DHB_COMPLEX"], "hpddm_b200z_")):
         so = str(tmp / f"libkrylov_mock_{name}.so")
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I/usr/local/cuda/include", "-I", os.path.join(ROOT, "include")] + flags +
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-Wl,-Bsymbolic", "-I/usr/local/cuda/include", "-I", os.path.join(ROOT, "include")] + os.environ.get("HB_TEST_CXXFLAGS", "").split() + flags +
                               ["-o", so, "-x", "c++", os.path.join(csrc, "hb_krylov.cu"), os.path.join(csrc, "hb_gcrodr.cpp"), os.path.join(ROOT, "tests", "native", "krylov_mock.cpp")])
         lib = C.CDLL(so)
         lib.krylov_mock_create.restype = C.c_void_p
