@@ -54,6 +54,7 @@ def main(name):
     out["launches"] = int(deco.launches)
     deco.close()
     print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":
