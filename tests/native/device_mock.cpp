@@ -422,12 +422,103 @@ int dense_inverse_device(Ctx *c, int N, const K *dE, K *dEinv) {
   return 0;
 }
 
-// ---- peer-memory fabric: one process, nothing to do
+// ---- peer-memory fabric.  One process: off.  Several processes (hpddm_b200_ctx_comm_init_host): the data plane of the stand-in is the
+// host program's own all-gather callback (torch.distributed / gloo in the tests), so that the N > 1 host logic of the library -- links
+// between subdomains, coarse layout and gather, Krylov reductions, the device drivers in lockstep on all ranks -- runs between real
+// processes on a machine without a GPU.  The halo round gathers every process' packed send buffers (k_pack layout) with a small
+// directory and copies the segments addressed to the local subdomains into their receive buffers; the unpack is the library's.
+namespace {
+int host_gather(Ctx *c, const void *send, void *recv, size_t bytes) {
+  if (c->host_allgather(send, recv, bytes, c->host_allgather_user) != 0) {
+    set_error("device stand-in: the host all-gather callback failed");
+    return HPDDM_B200_ERR_NCCL;
+  }
+  return 0;
+}
+}  // namespace
 int fabric_setup(Ctx *, int) { return 0; }
-bool fabric_on(Ctx *) { return false; }
-int p2p_halo(Ctx *, K *const *, int) { return 0; }
-int fabric_allgather(Ctx *, K *, int) { return 0; }
-int fabric_allreduce(Ctx *, double *, int, int) { return 0; }
+bool fabric_on(Ctx *c) { return c->nproc > 1 && c->host_allgather != nullptr; }
+int fabric_allgather(Ctx *c, K *buf, int count) {
+  if (!fabric_on(c)) return 0;
+  std::vector<K> mine(buf + (size_t)c->proc_rank * count, buf + (size_t)(c->proc_rank + 1) * count);
+  if (count) HB_CHECK(host_gather(c, mine.data(), buf, (size_t)count * sizeof(K)));
+  c->launches++;
+  return 1;
+}
+int fabric_allreduce(Ctx *c, double *buf, int count, int op) {  // op 0: sum in rank order, 1: max
+  if (!fabric_on(c)) return 0;
+  std::vector<double> all((size_t)c->nproc * count);
+  if (count) HB_CHECK(host_gather(c, buf, all.data(), (size_t)count * sizeof(double)));
+  for (int i = 0; i < count; ++i) {
+    double acc = all[i];
+    for (int p = 1; p < c->nproc; ++p) acc = op == 0 ? acc + all[(size_t)p * count + i] : std::max(acc, all[(size_t)p * count + i]);
+    buf[i] = acc;
+  }
+  c->launches++;
+  return 1;
+}
+int p2p_halo(Ctx *c, K *const *x, int mu) {
+  if (!fabric_on(c)) return 0;
+  // directory of this process: [nsub, then per subdomain: grank, nnb, (neighbour rank, entries, offset into the data block) ...]
+  std::vector<long long> dir(1, (long long)c->subs.size());
+  std::vector<K> data;
+  int li = 0;
+  for (Sub *s : c->subs) {
+    HB_CHECK(k_pack(c, s, mu, x[li++], s->d_send));
+    dir.push_back(s->grank);
+    dir.push_back((long long)s->nb_rank.size());
+    for (size_t i = 0; i < s->nb_rank.size(); ++i) {
+      const long long cnt = (long long)(s->nb_ptr[i + 1] - s->nb_ptr[i]) * mu;
+      dir.push_back(s->nb_rank[i]);
+      dir.push_back(cnt);
+      dir.push_back((long long)data.size());
+      data.insert(data.end(), s->d_send + (size_t)s->nb_ptr[i] * mu, s->d_send + (size_t)s->nb_ptr[i] * mu + cnt);
+    }
+  }
+  long long sizes[2] = {(long long)dir.size(), (long long)data.size()};
+  std::vector<long long> all_sizes((size_t)2 * c->nproc);
+  HB_CHECK(host_gather(c, sizes, all_sizes.data(), sizeof(sizes)));
+  long long dmax = 1, vmax = 1;
+  for (int p = 0; p < c->nproc; ++p) {
+    dmax = std::max(dmax, all_sizes[2 * p]);
+    vmax = std::max(vmax, all_sizes[2 * p + 1]);
+  }
+  dir.resize(dmax, 0);
+  data.resize(vmax, mk(0.0));
+  std::vector<long long> all_dir((size_t)dmax * c->nproc);
+  std::vector<K> all_data((size_t)vmax * c->nproc);
+  HB_CHECK(host_gather(c, dir.data(), all_dir.data(), (size_t)dmax * sizeof(long long)));
+  HB_CHECK(host_gather(c, data.data(), all_data.data(), (size_t)vmax * sizeof(K)));
+  for (Sub *s : c->subs)
+    for (size_t i = 0; i < s->nb_rank.size(); ++i) {
+      const long long want = (long long)(s->nb_ptr[i + 1] - s->nb_ptr[i]) * mu;
+      bool found = false;
+      for (int p = 0; p < c->nproc && !found; ++p) {
+        const long long *d = &all_dir[(size_t)p * dmax];
+        size_t at = 1;
+        for (long long q = 0; q < d[0] && !found; ++q) {
+          const long long grank = d[at], nnb = d[at + 1];
+          at += 2;
+          for (long long j = 0; j < nnb; ++j, at += 3)
+            if (grank == s->nb_rank[i] && d[at] == s->grank) {
+              if (d[at + 1] != want) {
+                set_error("device stand-in: subdomains %d and %d disagree on the size of their interface", s->grank, (int)grank);
+                return HPDDM_B200_ERR_STATE;
+              }
+              memcpy(s->d_recv + (size_t)s->nb_ptr[i] * mu, &all_data[(size_t)p * vmax + d[at + 2]], (size_t)want * sizeof(K));
+              found = true;
+            }
+        }
+      }
+      if (!found) {
+        set_error("device stand-in: no process holds neighbour %d of subdomain %d", s->nb_rank[i], s->grank);
+        return HPDDM_B200_ERR_STATE;
+      }
+    }
+  li = 0;
+  for (Sub *s : c->subs) HB_CHECK(k_unpack(c, s, mu, x[li++]));
+  return 1;
+}
 int p2p_check(Ctx *) { return 0; }
 void p2p_free(Ctx *) {}
 const K *p2p_last_halo_window(Ctx *) { return nullptr; }

@@ -5,7 +5,10 @@ own slice of apply / deflation / GMV / GMRES.  Exit code != 0 on mismatch.
 PARITY_SCALAR=z runs the complex instantiation (hpddm_b200z_*): 3-D Helmholtz, ORAS, plane-wave coarse vectors.
 PARITY_BOOT=nccl (default): NCCL bootstrap, collectives over the peer-memory fabric (HPDDM_B200_HALO=nccl forces NCCL everywhere);
 PARITY_BOOT=host: control plane over torch.distributed/gloo through hpddm_b200_ctx_comm_init_host, no NCCL at all;
-PARITY_SAME_GPU=1 (with PARITY_BOOT=host): every rank uses device 0 -- several processes sharing one GPU over CUDA IPC."""
+PARITY_SAME_GPU=1 (with PARITY_BOOT=host): every rank uses device 0 -- several processes sharing one GPU over CUDA IPC.
+PARITY_STANDIN=<library> (CPU, with PARITY_BOOT=host): load the host stand-in of the device layer (tests/native/device_mock.cpp, built by
+tests/tools/run_gpu_tests_on_stand_in.py) instead of libhpddm_b200.so -- the N > 1 host logic of the library between gloo processes on
+a machine without a GPU (tests/test_multiproc_cpu.py).  PARITY_GCRODR=1 adds the device GCRO-DR / BGCRO-DR drivers (two solves each)."""
 import os
 import sys
 
@@ -27,7 +30,13 @@ def main():
     boot = os.environ.get("PARITY_BOOT", "nccl")
     if os.environ.get("PARITY_SAME_GPU"):
         local = 0
-    torch.cuda.set_device(local)
+    standin = os.environ.get("PARITY_STANDIN")
+    if standin:
+        from hpddm_b200 import capi
+        capi.LIB_PATH = standin          # this process only; the product never loads the stand-in
+        local = 0
+    else:
+        torch.cuda.set_device(local)
     if boot == "host":
         dist.init_process_group("gloo")
     else:
@@ -102,6 +111,20 @@ def main():
         it_cref, x_cref = cg(OracleOperator(w, None), b2_all, tol=1e-8)
         it_cdev, x_cdev, _ = deco.solve_cg([b2_all[rank]], correction=None, tol=1e-8)
         errs["cg_dev_x"] = np.abs(x_cdev[0] - x_cref[rank]).max() / np.abs(x_cref[rank]).max()
+    if os.environ.get("PARITY_GCRODR"):
+        # recycling drivers on all ranks in lockstep: two solves sharing the pair kept in every rank's context, against the oracle
+        from oracle.gcrodr import bgcrodr, gcrodr
+        for name, fn, dev in (("gcrodr", gcrodr, deco.solve_gcrodr), ("bgcrodr", bgcrodr, deco.solve_bgcrodr)):
+            deco.recycle_destroy()
+            state = None
+            for k_solve, rhs in enumerate((b2_all, [2.0 * v[:, ::-1] + 1.0 for v in b2_all])):
+                rhs = w.exchange([np.asfortranarray(v).copy() for v in rhs]) if k_solve else rhs
+                it_o, x_o, state = fn(OracleOperator(w, DEFLATED), rhs, restart=8, recycle=3, tol=1e-8, state=state)
+                it_d, x_d, _ = dev([rhs[rank]], correction=DEFLATED, restart=8, recycle=3, tol=1e-8)
+                errs[f"{name}{k_solve}_dev_x"] = np.abs(x_d[0] - x_o[rank]).max() / np.abs(x_o[rank]).max()
+                if it_d != it_o or errs[f"{name}{k_solve}_dev_x"] > 1e-6:
+                    ok = False
+                    print(f"rank {rank}: {name} solve {k_solve}: {it_d} iterations, oracle {it_o}", flush=True)
     bad = (not ok) or it_gpu != it_ref or it_dev != it_ref or errs["gmres_dev_x"] > 1e-7 or it_bdev != it_bref or errs["bgmres_dev_x"] > 1e-7 or \
         it_cdev != it_cref or errs.get("cg_dev_x", 0.0) > 1e-6 or any(v > 1e-10 for k, v in errs.items() if not (k.startswith("gmres") or k.endswith("_dev_x"))) or errs["gmres_x"] > 1e-7
     want = os.environ.get("PARITY_EXPECT_TRANSPORT")
