@@ -263,6 +263,15 @@ public:
       b200::check<K>(A_::ctx_comm_init(ctx_, id, rank, size), "ctx_comm_init");
     }
   }
+  /* Host-bootstrapped communicator (hpddm_b200_ctx_comm_init_host): the control plane goes through the host program's own all-gather,
+   * e.g. [](const void *s, void *r, size_t bytes, void *comm) { return MPI_Allgather(s, bytes, MPI_BYTE, r, bytes, MPI_BYTE, *(MPI_Comm *)comm); },
+   * the hot-path collectives over the library's peer-memory fabric -- no NCCL needed (what the full seam does with Subdomain::communicator_) */
+  void setCommunicatorHost(int rank, int size, int (*allgather)(const void *, void *, size_t, void *), void *user)
+  {
+    rank_ = rank;
+    size_ = size;
+    if (size > 1) b200::check<K>(A_::ctx_comm_init_host(ctx_, rank, size, allgather, user), "ctx_comm_init_host");
+  }
   /* Subdomain::initialize(a, o, r) (include/HPDDM_subdomain.hpp:165-236) */
   template <class Neighbor, class Mapping>
   void initialize(MatrixCSR<K> *const &a, const Neighbor &o, const Mapping &r)

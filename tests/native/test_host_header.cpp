@@ -17,7 +17,7 @@ void instantiate() {
   S.numfact(M); S.solve((K *)nullptr, 1); S.solve((const K *)nullptr, (K *)nullptr, 1); S.inertia(M); S.deficiency();
   HPDDM::B200Schwarz<K> A;
   std::list<int> o; std::vector<std::vector<int>> r;
-  A.setCommunicator(0, 1, [](void *) {});
+  A.setCommunicator(0, 1, [](void *) {}); A.setCommunicatorHost(0, 1, nullptr, nullptr);
   A.initialize(M, o, r); A.setGridHint(1, 1); A.multiplicityScaling(nullptr); double *d = nullptr; A.initialize(d);
   A.solveGEVP(M, 4); A.callNumfact(); K **ev = nullptr; A.setVectors(ev, 1); A.template buildTwo<0>(0);
   A.start(nullptr, (K *)nullptr, 1); A.apply((const K *)nullptr, (K *)nullptr, 1); A.template deflation<false>(nullptr, (K *)nullptr, 1);

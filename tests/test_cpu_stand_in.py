@@ -40,9 +40,13 @@ def test_unmodified_reference_driver_on_both_seams_on_the_host_stand_in(tmp_path
     libdir.mkdir()
     shutil.copy(so, libdir / "libhpddm_b200.so")
     env = dict(os.environ, HPDDM_B200_TEST_STANDIN="1", LD_LIBRARY_PATH=str(libdir) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
-    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_dropin.py"), "-q", "-m", "gpu", "-p", "no:cacheprovider"],
-                         env=env, capture_output=True, text=True, timeout=1800, cwd=ROOT)
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_dropin.py"), os.path.join(ROOT, "tests", "test_gpu_zz_cpp_device_krylov.py"),
+                          "-q", "-m", "gpu", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=1800, cwd=ROOT)
     tail = (res.stdout + res.stderr)[-3000:]
     assert res.returncode == 0, tail
     m = re.search(r"(\d+) passed", res.stdout)
     assert m and int(m.group(1)) >= 20 and "failed" not in res.stdout.splitlines()[-1], tail
+    # the device-resident Krylov route of the C++ mirror under 4 MPI-shim ranks (GMRES, BGMRES, GCRO-DR, BGCRO-DR; two solves each):
+    # non-gating on the GPU, all four must pass here
+    x = re.search(r"(\d+) xpassed", res.stdout)
+    assert x and int(x.group(1)) == 4 and "xfailed" not in res.stdout.splitlines()[-1], tail
