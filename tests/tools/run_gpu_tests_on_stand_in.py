@@ -24,6 +24,32 @@ NEEDS_DEVICE = ["test_single_subdomain_direct_solve_residual", "test_pageable_ho
 
 
 def build(out_dir, extra):
+    """Compiles the stand-in (both scalar builds) and returns its path.  The result is cached per content of the sources and flags under
+    the system's temporary directory (three test modules need it); `out_dir` receives a copy."""
+    import hashlib
+    import shutil
+    csrc = os.path.join(ROOT, "hpddm_b200", "csrc")
+    h = hashlib.sha256(" ".join(extra).encode())
+    for d in (csrc, os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "native")):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".cu", ".cpp", ".h", ".hpp")):
+                h.update(f.encode())
+                h.update(open(os.path.join(d, f), "rb").read())
+    cache = os.path.join(tempfile.gettempdir(), "hpddm_b200_standin_" + h.hexdigest()[:16])
+    cached = os.path.join(cache, "libhpddm_b200_standin.so")
+    if not os.path.exists(cached):
+        work = tempfile.mkdtemp(prefix="hpddm_b200_standin_build_")
+        so = _compile(work, extra)
+        os.makedirs(cache, exist_ok=True)
+        os.replace(so, cached + f".{os.getpid()}")
+        os.replace(cached + f".{os.getpid()}", cached)     # atomic: concurrent builders race benignly
+        shutil.rmtree(work, ignore_errors=True)
+    out = os.path.join(out_dir, "libhpddm_b200_standin.so")
+    shutil.copy(cached, out)
+    return out
+
+
+def _compile(out_dir, extra):
     csrc = os.path.join(ROOT, "hpddm_b200", "csrc")
     objs = []
     for sfx, flags in (("d", []), ("z", ["-DHB_COMPLEX"])):
