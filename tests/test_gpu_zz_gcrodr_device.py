@@ -39,3 +39,52 @@ def test_device_gcrodr_reproduces_the_reference(name):
     assert out["recycled_dim"] > 0 and out["recycled_dim_after_destroy"] == 0
     assert out["gmres_fallback"][0] == out["gmres_fallback"][1]
     assert out["launches"] > 0
+
+
+@pytest.mark.xfail(strict=False, reason="device backend of the GCRO-DR / BGCRO-DR drivers not yet run on hardware (see module docstring)")
+def test_recycled_pair_life_cycle():
+    """The pair kept in the context across what can happen to it: a second solve, a new deflation space + coarse operator (C = A M^-1 U is
+    recomputed when a solve starts), another number of right-hand sides (dropped and rebuilt), the block driver and back (pairs of the
+    other kind are dropped), restart 2 / recycle >= restart / iteration limit inside the first cycle / zero right-hand side."""
+    import numpy as np
+    from oracle.generate import generate_world
+    from oracle.schwarz import SchwarzWorld
+    from tests.helpers import build_gpu_decomposition
+    parts = generate_world(8, dim=3, N=(10, 10, 10), overlap=1, mu=1, neumann=True)
+    w = SchwarzWorld(parts)
+    w.multiplicity_scaling()
+    w.numfact()
+    w.solve_gevp([p["MatNeumann"] for p in parts], nu=3)
+    w.build_coarse()
+    deco = build_gpu_decomposition(parts, w, two_level=True)
+
+    def converged(x, rhs, tol):
+        res = w.compute_residual(x, rhs)
+        return bool(np.all(res[:, 1] <= 10 * tol * res[:, 0]))
+
+    b = [np.asfortranarray(p["f"][:, :1]) for p in parts]
+    kw = dict(correction="deflated", restart=6, recycle=2, tol=1e-9)
+    for _ in range(2):
+        it, x, _ = deco.solve_gcrodr(b, **kw)
+        assert converged(x, b, 1e-9) and deco.recycle_dim() == 2
+    w.set_vectors([z[:, :2] for z in w.Z])
+    w.build_coarse()
+    for s, z in zip(deco.subs, w.Z):
+        s.setVectors(z)
+    deco.buildTwo()
+    it, x, _ = deco.solve_gcrodr(b, **kw)
+    assert converged(x, b, 1e-9)
+    b2 = [np.asfortranarray(np.hstack([v, 2.0 * v[::-1]])) for v in b]
+    for fn in (deco.solve_gcrodr, deco.solve_bgcrodr, deco.solve_gcrodr):
+        it, x, _ = fn(b2, **kw)
+        assert converged(x, b2, 1e-9) and deco.recycle_dim() == 2, fn.__name__
+    for fn in (deco.solve_gcrodr, deco.solve_bgcrodr):
+        deco.recycle_destroy()
+        it, x, _ = fn(b2, correction="deflated", restart=2, recycle=5, tol=1e-6)
+        assert converged(x, b2, 1e-6) and deco.recycle_dim() == 1
+        deco.recycle_destroy()
+        it, x, _ = fn(b2, correction="deflated", restart=3, recycle=2, max_it=2)
+        assert it == 2
+        it, x, _ = fn([0.0 * v for v in b2], correction="deflated", restart=5, recycle=2)
+        assert it == 0 and all(np.all(v == 0) for v in x)
+    deco.close()
