@@ -146,6 +146,17 @@ class Schwarz:
 class Decomposition:
     """The subdomains of this process + the collective hot-path calls."""
 
+
+    def _vecs(self, vs):
+        """one column-major n_i x mu block per local subdomain: the C ABI takes a bare pointer array, so a list of the wrong length or
+        a block with the wrong number of rows would be read out of bounds -- refused here"""
+        vs = [_f(v, self.dtype) for v in vs]
+        if len(vs) != len(self.subs):
+            raise capi.HpddmB200Error(f"{len(vs)} vectors for {len(self.subs)} local subdomains")
+        for v, s in zip(vs, self.subs):
+            if v.shape[0] != s.n or v.shape[1] != vs[0].shape[1]:
+                raise capi.HpddmB200Error(f"vector of shape {v.shape} for a subdomain of {s.n} unknowns ({vs[0].shape[1]} columns expected)")
+        return vs
     def __init__(self, device=0, dtype=np.float64):
         self.api = capi.api(dtype)
         self.dtype = self.api.dtype
@@ -260,7 +271,7 @@ class Decomposition:
         return [np.empty_like(v, order="F") for v in ins]
 
     def start(self, b, x):
-        b = [_f(v, self.dtype) for v in b]
+        b = self._vecs(b)
         x = [_f(v, self.dtype).copy(order="F") for v in x]
         mu = b[0].shape[1]
         self.api.check(self.api.start(self.ctx, capi.ptr_array(b), capi.ptr_array(x), mu, capi.HOST))
@@ -271,13 +282,13 @@ class Decomposition:
 
     def apply(self, ins, correction="__default__"):
         corr = self.correction if correction == "__default__" else correction
-        ins = [_f(v, self.dtype) for v in ins]
+        ins = self._vecs(ins)
         outs = self._outs(ins)
         self.api.check(self.api.apply(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), ins[0].shape[1], capi.CORRECTION[corr], capi.HOST))
         return outs
 
     def deflation(self, ins):
-        ins = [_f(v, self.dtype) for v in ins]
+        ins = self._vecs(ins)
         outs = self._outs(ins)
         self.api.check(self.api.deflation(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), ins[0].shape[1], capi.HOST))
         return outs
@@ -288,7 +299,7 @@ class Decomposition:
         return xs
 
     def GMV(self, ins):
-        ins = [_f(v, self.dtype) for v in ins]
+        ins = self._vecs(ins)
         outs = self._outs(ins)
         self.api.check(self.api.gmv(self.ctx, capi.ptr_array(ins), capi.ptr_array(outs), ins[0].shape[1], capi.HOST))
         return outs
@@ -299,8 +310,8 @@ class Decomposition:
         return rhs
 
     def dot(self, x, y):
-        x = [_f(v, self.dtype) for v in x]
-        y = [_f(v, self.dtype) for v in y]
+        x = self._vecs(x)
+        y = self._vecs(y)
         mu = x[0].shape[1]
         res = np.zeros(mu, dtype=self.dtype)
         self.api.check(self.api.dot(self.ctx, capi.ptr_array(x), capi.ptr_array(y), mu, capi.ptr(res), capi.HOST))
@@ -308,7 +319,7 @@ class Decomposition:
 
     # ||b|| of IterativeMethod::initializeNorm (include/HPDDM_iterative.hpp:455-468): penalised boundary rows count as b_i / HPDDM_PEN
     def rhs_norm(self, b):
-        b = [_f(v, self.dtype) for v in b]
+        b = self._vecs(b)
         mu = b[0].shape[1]
         out = np.zeros(mu)
         self.api.check(self.api.rhs_norm(self.ctx, capi.ptr_array(b), mu, capi.ptr(out), capi.HOST))
@@ -316,8 +327,8 @@ class Decomposition:
 
     # Schwarz::computeResidual (include/HPDDM_schwarz.hpp:761-803): (mu, 2) array of ||f||, ||A x - f||; norm in {"l2", "l1", "linfty"}
     def computeResidual(self, x, f, norm="l2"):
-        x = [_f(v, self.dtype) for v in x]
-        f = [_f(v, self.dtype) for v in f]
+        x = self._vecs(x)
+        f = self._vecs(f)
         mu = x[0].shape[1]
         st = np.zeros(2 * mu)
         self.api.check(self.api.compute_residual(self.ctx, capi.ptr_array(x), capi.ptr_array(f), capi.ptr(st), mu, {"l2": 0, "l1": 1, "linfty": 2}[norm], capi.HOST))
@@ -326,7 +337,7 @@ class Decomposition:
     # IterativeMethod::solve (include/HPDDM_iterative.hpp:1013-1111) with the Krylov basis resident in HBM
     def solve(self, b, x0=None, correction="__default__", restart=40, max_it=100, tol=1e-6):
         corr = self.correction if correction == "__default__" else correction
-        b = [_f(v, self.dtype) for v in b]
+        b = self._vecs(b)
         x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v, self.dtype).copy(order="F") for v in x0]
         mu = b[0].shape[1]
         it = C.c_int(0)
@@ -338,7 +349,7 @@ class Decomposition:
     # IterativeMethod::BGMRES (include/HPDDM_GMRES.hpp:160-313) on the device: one block Krylov space for all right-hand sides
     def solve_bgmres(self, b, x0=None, correction="__default__", restart=40, max_it=100, tol=1e-6):
         corr = self.correction if correction == "__default__" else correction
-        b = [_f(v, self.dtype) for v in b]
+        b = self._vecs(b)
         x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v, self.dtype).copy(order="F") for v in x0]
         mu = b[0].shape[1]
         it = C.c_int(0)
@@ -354,7 +365,7 @@ class Decomposition:
     def solve_gcrodr(self, b, x0=None, correction="__default__", restart=40, recycle=10, max_it=100, tol=1e-6, target="SM", strategy="A", same_system=0):
         """same_system: the value of -hpddm_recycle_same_system (0: operator may have changed; 1: same operator, pair built / updated; 2: pair used as is)"""
         corr = self.correction if correction == "__default__" else correction
-        b = [_f(v, self.dtype) for v in b]
+        b = self._vecs(b)
         x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v, self.dtype).copy(order="F") for v in x0]
         mu = b[0].shape[1]
         it = C.c_int(0)
@@ -366,7 +377,7 @@ class Decomposition:
     # IterativeMethod::BGCRODR (include/HPDDM_GCRODR.hpp:445-907): block version, one recycled pair of mu k columns for all right-hand sides
     def solve_bgcrodr(self, b, x0=None, correction="__default__", restart=40, recycle=10, max_it=100, tol=1e-6, target="SM", strategy="A", same_system=0):
         corr = self.correction if correction == "__default__" else correction
-        b = [_f(v, self.dtype) for v in b]
+        b = self._vecs(b)
         x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v, self.dtype).copy(order="F") for v in x0]
         mu = b[0].shape[1]
         it = C.c_int(0)
@@ -386,7 +397,7 @@ class Decomposition:
     # preconditioner is not symmetric: RAS / ORAS or a deflated correction)
     def solve_cg(self, b, x0=None, correction="__default__", max_it=100, tol=1e-6):
         corr = self.correction if correction == "__default__" else correction
-        b = [_f(v, self.dtype) for v in b]
+        b = self._vecs(b)
         x = [np.zeros_like(v, order="F") for v in b] if x0 is None else [_f(v, self.dtype).copy(order="F") for v in x0]
         mu = b[0].shape[1]
         it = C.c_int(0)

@@ -530,3 +530,18 @@ def test_repeated_applies_replay_the_whole_apply_graph(poisson3d):
     deco.setCoarse(w.E)
     for k in range(4):
         assert relerr(deco.apply(x, "deflated"), w.apply(x, DEFLATED)) < TOL
+
+
+def test_python_mirror_refuses_vector_lists_of_the_wrong_shape(poisson3d):
+    """the C ABI takes bare pointer arrays: a list with too few blocks, or a block with the wrong number of rows, would be read out of
+    bounds -- the Python mirror refuses them before the call"""
+    from hpddm_b200.capi import HpddmB200Error
+    parts, w, deco = poisson3d
+    x = [p["f"].copy() for p in parts]
+    with pytest.raises(HpddmB200Error):
+        deco.apply(x[:-1], None)
+    with pytest.raises(HpddmB200Error):
+        deco.GMV([v[:-1] for v in x])
+    with pytest.raises(HpddmB200Error):
+        deco.dot(x, [x[0]] + [np.hstack([v, v]) for v in x[1:]])      # blocks of one vector with different numbers of columns
+    assert relerr(deco.apply(x, None), w.apply([v.copy() for v in x], None)) < TOL
