@@ -46,6 +46,7 @@ int main(int argc, char **argv) {
              std::forward_as_tuple("nonuniform=(0|1)", "Use a different number of eigenpairs to compute on each subdomain.", HPDDM::Option::Arg::argument),
              std::forward_as_tuple("deflation_vectors=<0>", "Number of analytic deflation vectors per subdomain (golden runs).", HPDDM::Option::Arg::integer),
              std::forward_as_tuple("penalise=(0|1)", "Impose non-homogeneous Dirichlet data on the side y = 0 by penalisation (golden runs).", HPDDM::Option::Arg::argument),
+             std::forward_as_tuple("device_krylov=(0|1)", "Full-seam build only: device-resident Krylov solve (Schwarz<B200Sub, ...>::solveOnDevice) instead of IterativeMethod::solve.", HPDDM::Option::Arg::argument),
              std::forward_as_tuple("solves=<1>", "Number of successive solves with the same operator (golden runs of the recycling drivers).", HPDDM::Option::Arg::positive),
              std::forward_as_tuple("prefix=<string>", "Use a prefix.", HPDDM::Option::Arg::argument)});
   std::string out = getenv("HPDDM_REF_DUMP") ? getenv("HPDDM_REF_DUMP") : "golden";
@@ -184,7 +185,16 @@ int main(int argc, char **argv) {
     }
     A.end(alloc);
   }
-  int it = HPDDM::IterativeMethod::solve(A, f, sol, mu, A.getCommunicator());
+  // Built a second time against the FULL seam of the CUDA library (-DB200SUB -DB200SCHWARZ: HPDDM::Schwarz<HPDDM::B200Sub, ...>,
+  // oracle/_ref/ref_driver_b200_full): the same dumps then come from the GPU path and are compared with the goldens field by field;
+  // -device_krylov 1 routes the solves through solveOnDevice (options read like IterativeMethod::options reads them).
+#ifdef B200SCHWARZ
+  const bool device_krylov = opt.app().find("device_krylov") != opt.app().cend() && opt.app()["device_krylov"] == 1;
+#define REF_SOLVE(rhs, x) (device_krylov ? A.solveOnDevice(rhs, x, mu) : HPDDM::IterativeMethod::solve(A, rhs, x, mu, A.getCommunicator()))
+#else
+#define REF_SOLVE(rhs, x) HPDDM::IterativeMethod::solve(A, rhs, x, mu, A.getCommunicator())
+#endif
+  int it = REF_SOLVE(f, sol);
   std::vector<HPDDM::underlying_type<K>> storage(2 * mu);
   A.computeResidual(sol, f, storage.data(), mu);
   dumpi("iterations", &it, 1);
@@ -205,7 +215,7 @@ int main(int argc, char **argv) {
     for (int c = 0; c < mu; ++c)
       for (int i = 0; i < ndof; ++i) fs[(size_t)c * ndof + i] = K(1.0 + 0.5 * c) * Aw[i] + K(0.25) * f[(size_t)c * ndof + i];
     std::fill_n(sol, (size_t)mu * ndof, K());
-    int its = HPDDM::IterativeMethod::solve(A, fs.data(), sol, mu, A.getCommunicator());
+    int its = REF_SOLVE(fs.data(), sol);
     A.computeResidual(sol, fs.data(), storage.data(), mu);
     const std::string tag = std::to_string(sidx);
     dumpd(("f" + tag).c_str(), fs.data(), (long long)mu * ndof);

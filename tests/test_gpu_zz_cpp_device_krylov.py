@@ -35,3 +35,48 @@ def test_cpp_mirror_device_resident_solves_match_the_reference(tmp_path, krylov)
     want = [int(v) for v in re.findall(r"ref_driver:.*?\bit (\d+)", ref.stdout)]
     have = [int(re.search(r"b200_full_driver: 4 ranks, it (\d+)", got.stdout).group(1)), int(re.search(r"b200_full_driver: solve 2, it (\d+)", got.stdout).group(1))]
     assert len(want) == 2 and have == want, (have, want)
+
+
+# ---- the golden-vector driver itself on the FULL seam ------------------------------------------------------------------------------
+# oracle/ref_build/ref_driver.cpp -- the program that produced tests/golden/*.npz from the UNMODIFIED reference -- compiled a second
+# time with -DB200SUB -DB200SCHWARZ, i.e. on HPDDM::Schwarz<HPDDM::B200Sub, ...> (oracle/_ref/ref_driver_b200_full[_z]): every dump
+# (partition of unity, Subdomain::exchange, GMV, one-level apply, deflation, the three corrections, solutions, iteration counts of
+# every solve of a sequence) now comes from the CUDA library through the C++ seam and is compared with the golden FIELD BY FIELD.
+# Cases with random right-hand sides are not reproducible (std::random_device in the reference's generator) and are left out; so are the
+# 6-rank goldens, whose two-level outputs carry the reference's dense-LAPACK-plugin quirk (E^T y = r for a sparse coarse pattern, DESIGN.md
+# section 6) that the library deliberately does not reproduce.
+FULLDRV = os.path.join(ROOT, "oracle", "_ref", "ref_driver_b200_full")
+SEAM_CASES = [("small_40x40_p4_ras", []), ("small_40x40_p4_twolevel_nu3", []), ("small_36x36_p4_symcsr_twolevel_nu2", []),
+              ("small_40x40_p4_penalised_ras", []), ("small_40x40_p4_asm_cg", []), ("complex_40x40_p4_twolevel_nu3", []), ("complex_40x40_p4_penalised_ras", []),
+              ("small_40x40_p4_gcrodr_m8_k4_solves3", ["-device_krylov", "1"]), ("small_40x40_p4_gcrodr_m6_k2_twolevel_solves2", ["-device_krylov", "1"]),
+              ("small_40x40_p4_gcrodr_m12_k4_same_solves3", ["-device_krylov", "1"]), ("small_40x40_p4_bgcrodr_m8_k4_solves2", ["-device_krylov", "1"]),
+              ("complex_40x40_p4_gcrodr_m8_k3_solves2", ["-device_krylov", "1"]), ("small_40x40_p4_twolevel_nu3", ["-device_krylov", "1"])]
+
+
+@pytest.mark.xfail(strict=False, reason="golden driver on the full seam: not yet run on hardware (see module docstring)")
+@pytest.mark.skipif(not os.path.exists(FULLDRV), reason="oracle/_ref/ref_driver_b200_full not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("name,extra", SEAM_CASES)
+def test_golden_driver_on_the_full_seam_reproduces_every_dump(tmp_path, name, extra):
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from oracle.ref_build.make_goldens import read_dump
+    gold = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    P = int(gold["np"])
+    args = str(gold["args"]).split()
+    binary = FULLDRV + ("_z" if name.startswith("complex") else "")
+    env = dict(os.environ, HPDDM_SHIM_NP=str(P), HPDDM_REF_DUMP=str(tmp_path / "g"))
+    res = subprocess.run([binary] + args + extra, env=env, cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, (res.stdout + res.stderr)[-2000:]
+    checked = 0
+    for r in range(P):
+        got = read_dump(str(tmp_path / f"g_{r}.bin"))
+        for key, val in got.items():
+            want = gold[f"r{r}_{key}"]
+            if key.startswith("iterations") or key in ("header", "ia", "ja", "o") or key.startswith("mapping"):
+                assert np.array_equal(val, want), (r, key, val, want)
+            else:
+                tol = 1e-6 if key.startswith("sol") or key.startswith("residual") else 1e-10     # solutions: both are iterates at tol 1e-6 .. 1e-9
+                assert np.abs(val - want).max() <= tol * max(np.abs(want).max(), 1e-300), (r, key)
+            checked += 1
+    assert checked >= 15 * P
