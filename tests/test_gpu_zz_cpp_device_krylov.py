@@ -53,6 +53,12 @@ SEAM_CASES = [("small_40x40_p4_ras", []), ("small_40x40_p4_twolevel_nu3", []), (
               ("complex_40x40_p4_gcrodr_m8_k3_solves2", ["-device_krylov", "1"]), ("small_40x40_p4_twolevel_nu3", ["-device_krylov", "1"])]
 
 
+# on the GPU box six of them (every run starts 4 processes with a CUDA context each); the host stand-in run takes them all
+if os.environ.get("HPDDM_B200_TEST_STANDIN") != "1":
+    SEAM_CASES = [c for c in SEAM_CASES if c[0] in ("small_40x40_p4_penalised_ras", "complex_40x40_p4_twolevel_nu3", "small_40x40_p4_bgcrodr_m8_k4_solves2",
+                                                    "small_40x40_p4_gcrodr_m6_k2_twolevel_solves2", "complex_40x40_p4_gcrodr_m8_k3_solves2") or c == ("small_40x40_p4_twolevel_nu3", [])]
+
+
 @pytest.mark.xfail(strict=False, reason="golden driver on the full seam: not yet run on hardware (see module docstring)")
 @pytest.mark.skipif(not os.path.exists(FULLDRV), reason="oracle/_ref/ref_driver_b200_full not built (needs /root/reference at build time)")
 @pytest.mark.parametrize("name,extra", SEAM_CASES)
